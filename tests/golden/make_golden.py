@@ -1,0 +1,195 @@
+"""Generates tests/golden/*.npz by running the REFERENCE's own Python code in the build container.
+
+Run once here (``python tests/golden/make_golden.py``); the fixtures are committed because
+/root/reference does not exist on the GPU box.  Nothing is copied from the reference: its hot-path
+file is imported by path with a stub ``groundingdino._C`` (the package import chain needs
+detectron2), and the ZiRa ``RepZeroLinear`` class is executed from its AST because the file that
+defines it imports detectron2 at module scope.
+
+Sources exercised (relative to /root/reference/groundingdino/models/GroundingDINO/):
+  ms_deform_attn.py:90-130   multi_scale_deformable_attn_pytorch  (+ torch autograd for the grads)
+  ms_deform_attn.py:133-355  MultiScaleDeformableAttention (CPU branch, :345-348)
+  groundingdino_dual_zero_rep_branch.py:62-64, :105-135  RepZeroLinear (train / eval / __rep__)
+"""
+import ast
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF_DIR = "/root/reference/groundingdino/models/GroundingDINO"
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load_reference_msda():
+    pkg = types.ModuleType("groundingdino")
+    pkg.__path__ = []
+    pkg._C = types.ModuleType("groundingdino._C")
+    sys.modules["groundingdino"] = pkg
+    sys.modules["groundingdino._C"] = pkg._C
+    spec = importlib.util.spec_from_file_location("ref_msda", os.path.join(REF_DIR, "ms_deform_attn.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def load_reference_rep_zero_linear():
+    path = os.path.join(REF_DIR, "groundingdino_dual_zero_rep_branch.py")
+    tree = ast.parse(open(path).read())
+    keep = []
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "RepZeroLinear":
+            keep.append(node)
+        if isinstance(node, ast.Assign) and any(
+            isinstance(t, ast.Name) and t.id in ("zero_value", "lan_scale", "vis_scale") for t in node.targets
+        ):
+            keep.append(node)
+    ns = {"torch": torch, "nn": torch.nn, "Tensor": torch.Tensor}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return ns["RepZeroLinear"]
+
+
+def core_case(ref, seed, N, shapes, M, D, Lq, P, dtype, lo=-0.1, hi=1.1, special=False):
+    g = torch.Generator().manual_seed(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=torch.float64)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=torch.float64) * (hi - lo) + lo
+    if special:
+        # exact pixel centres, exact borders and far-outside points (guards at im2col.cuh:288, :56-78)
+        flat = loc.view(-1, 2)
+        flat[0] = torch.tensor([0.0, 0.0])
+        flat[1] = torch.tensor([1.0, 1.0])
+        flat[2] = torch.tensor([0.5, 0.5])
+        flat[3] = torch.tensor([-3.0, 0.5])
+        flat[4] = torch.tensor([0.5, 7.0])
+        flat[5] = torch.tensor([0.5 / shapes[0][1], 0.5 / shapes[0][0]])  # centre of pixel (0,0), level 0
+        flat[6] = torch.tensor([1.0 - 1e-9, 1e-9])
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, dtype=torch.float64), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, generator=g, dtype=torch.float64)
+    value, loc, aw, gout = (t.to(dtype) for t in (value, loc, aw, gout))
+    sh = torch.tensor(shapes, dtype=torch.long)
+    res = {}
+    for tag, dt in (("", dtype), ("_f64", torch.float64)):
+        v, l_, a = (t.to(dt).clone().requires_grad_(True) for t in (value, loc, aw))
+        out = ref.multi_scale_deformable_attn_pytorch(v, sh, l_, a)
+        out.backward(gout.to(dt))
+        res.update({"out" + tag: out.detach().numpy(), "grad_value" + tag: v.grad.numpy(),
+                    "grad_loc" + tag: l_.grad.numpy(), "grad_aw" + tag: a.grad.numpy()})
+    res.update(value=value.numpy(), loc=loc.numpy(), aw=aw.numpy(), grad_out=gout.numpy(),
+               shapes=np.asarray(shapes, dtype=np.int64))
+    return res
+
+
+def module_case(ref, seed, C, M, L, P, shapes, N, Lq, ref_dim, batch_first, with_mask, self_attn):
+    torch.manual_seed(seed)
+    mod = ref.MultiScaleDeformableAttention(C, M, L, P, batch_first=batch_first).double()
+    with torch.no_grad():  # make offsets / weights query-dependent (init has zero weights)
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.3)
+        mod.attention_weights.bias.normal_(0, 0.3)
+        mod.value_proj.bias.normal_(0, 0.1)
+        mod.output_proj.bias.normal_(0, 0.1)
+    S = sum(h * w for h, w in shapes)
+    if self_attn:
+        Lq = S
+    value = torch.randn(N, S, C, dtype=torch.float64)
+    query = torch.randn(N, Lq, C, dtype=torch.float64)
+    if ref_dim == 2:
+        refp = torch.rand(N, Lq, L, 2, dtype=torch.float64)
+    else:
+        refp = torch.cat([torch.rand(N, Lq, L, 2, dtype=torch.float64) * 0.8 + 0.1,
+                          torch.rand(N, Lq, L, 2, dtype=torch.float64) * 0.45 + 0.05], -1)
+    mask = None
+    if with_mask:
+        mask = torch.zeros(N, S, dtype=torch.bool)
+        mask[0, S // 2:] = True
+        mask[-1, ::7] = True
+    sh = torch.tensor(shapes, dtype=torch.long)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    q_in = query.clone().requires_grad_(True)
+    v_in = value.clone().requires_grad_(True)
+    qa, va = (q_in, v_in) if batch_first else (q_in.transpose(0, 1), v_in.transpose(0, 1))
+    out = mod(query=qa, value=va, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh,
+              level_start_index=lsi)
+    gout = torch.randn_like(out)
+    out.backward(gout)
+    res = {"query": query.numpy(), "value": value.numpy(), "reference_points": refp.numpy(),
+           "shapes": sh.numpy(), "out": out.detach().numpy(), "grad_out": gout.numpy(),
+           "grad_query": q_in.grad.numpy(), "grad_value_in": v_in.grad.numpy(),
+           "cfg": np.asarray([C, M, L, P, int(batch_first)], dtype=np.int64)}
+    if mask is not None:
+        res["mask"] = mask.numpy()
+    for k, v in mod.state_dict().items():
+        res["param." + k] = v.numpy()
+    for k, p in mod.named_parameters():
+        res["pgrad." + k] = p.grad.numpy()
+    return res
+
+
+def zira_case(RepZeroLinear, seed):
+    torch.manual_seed(seed)
+    m = RepZeroLinear(24, 16).double()
+    with torch.no_grad():  # non-trivial branch and accumulated soft-frozen weights
+        m.weight.normal_(0, 0.05)
+        m.bias.normal_(0, 0.05)
+        m.freeze_linear.weight.normal_(0, 0.2)
+        m.freeze_linear.bias.normal_(0, 0.2)
+        m.scaling.fill_(0.3)
+    x = torch.randn(5, 7, 24, dtype=torch.float64)
+    res = {"x": x.numpy()}
+    for k, v in m.state_dict().items():
+        res["pre." + k] = v.numpy().copy()
+    m.train()
+    xi = x.clone().requires_grad_(True)
+    out, loss = m(xi)
+    gout = torch.randn_like(out)
+    (out * gout).sum().add(loss * 0.1).backward()
+    res.update(train_out=out.detach().numpy(), train_loss=loss.detach().numpy().reshape(1),
+               grad_out=gout.numpy(), grad_x=xi.grad.numpy())
+    for k, p in m.named_parameters():
+        res["pgrad." + k] = p.grad.numpy().copy()
+    m.eval()
+    eo, el = m(x)
+    res.update(eval_out=eo.detach().numpy(), eval_loss=el.detach().numpy().reshape(1))
+    m.__rep__()
+    for k, v in m.state_dict().items():
+        res["post." + k] = v.detach().numpy().copy()
+    m.eval()
+    res["merged_eval_out"] = m(x)[0].detach().numpy()
+    m.train()
+    mo, ml = m(x)
+    res.update(merged_train_out=mo.detach().numpy(), merged_train_loss=ml.detach().numpy().reshape(1))
+    return res
+
+
+def main():
+    ref = load_reference_msda()
+    cases = {
+        "core_tiny_f64": core_case(ref, 11, 2, [(6, 5), (3, 3)], 2, 4, 7, 2, torch.float64, special=True),
+        "core_d32_f32": core_case(ref, 12, 1, [(9, 11), (5, 6), (3, 3), (2, 2)], 2, 32, 24, 4, torch.float32,
+                                  special=True),
+        "core_l5_f32": core_case(ref, 13, 2, [(6, 9), (3, 5), (2, 3), (1, 2), (1, 1)], 2, 32, 9, 4, torch.float32,
+                                 lo=-0.3, hi=1.3),
+        "core_oddD_f32": core_case(ref, 14, 1, [(5, 7), (3, 4)], 3, 6, 13, 3, torch.float32),
+        "core_d64_f32": core_case(ref, 15, 1, [(5, 6), (3, 3)], 2, 64, 7, 4, torch.float32),
+        "module_enc": module_case(ref, 21, 32, 4, 3, 2, [(5, 6), (3, 3), (2, 2)], 2, 0, 2, True, True, True),
+        "module_dec": module_case(ref, 22, 32, 4, 3, 2, [(5, 6), (3, 3), (2, 2)], 2, 10, 4, True, True, False),
+        "module_seqfirst": module_case(ref, 23, 32, 2, 2, 4, [(5, 4), (3, 2)], 3, 6, 2, False, False, False),
+        "module_d32": module_case(ref, 24, 64, 2, 4, 4, [(6, 8), (3, 4), (2, 2), (1, 1)], 1, 0, 2, True, False, True),
+    }
+    cases["zira_rep_linear"] = zira_case(load_reference_rep_zero_linear(), 31)
+    total = 0
+    for name, arrs in cases.items():
+        p = os.path.join(OUT, name + ".npz")
+        np.savez_compressed(p, **arrs)
+        total += os.path.getsize(p)
+        print(name, os.path.getsize(p))
+    print("total bytes", total)
+
+
+if __name__ == "__main__":
+    main()
