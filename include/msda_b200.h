@@ -1,0 +1,117 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Every entry point names
+ * the reference interface it replaces (paths relative to
+ * /root/reference/groundingdino/models/GroundingDINO/).  INTEGRATION.md shows the reference-side
+ * binding (a ctypes stub standing in for `groundingdino._C`).
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers on the current CUDA device, contiguous row-major,
+ *     16-byte aligned.  `spatial_shapes` / `level_start_index` are DEVICE int64 arrays, exactly as
+ *     the reference op receives them (csrc/MsDeformAttn/ms_deform_attn_cuda.cu:36-37); kernels stage
+ *     them in shared memory, so no host copy and no host synchronisation is needed.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only
+ *     enqueue work: no allocation, no synchronisation, no global state => re-entrant per stream,
+ *     like the reference (ms_deform_attn_cuda.cu:66, at::cuda::getCurrentCUDAStream()).
+ *   - Return value: 0 on success; MSDA_ERR_* (< 0) for rejected arguments; a positive cudaError_t
+ *     when a launch failed.  Unlike the reference, launch errors are returned, not printf'd
+ *     (ms_deform_im2col_cuda.cuh:948-952, :1321-1325).  msda_b200_last_error() gives the text.
+ *   - Layouts: value [N][S][M][D]; loc [N][Lq][M][L][P][2] (x, y in [0,1]); aw [N][Lq][M][L][P];
+ *     out / grad_out [N][Lq][M*D]; shapes [L][2] = (H, W); level_start [L].
+ *   - Dtype suffix = storage type of value / out / grad_out.  For bf16 and f16 the sampling
+ *     locations, attention weights and ALL gradients are fp32 and accumulation is fp32 (the
+ *     reference up-casts fp16 to fp32 around the op, ms_deform_attn.py:326-344; bf16 is new).
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_B200_ABI_VERSION 1
+#define MSDA_MAX_LEVELS 16
+
+enum {
+  MSDA_OK = 0,
+  MSDA_ERR_NULL_POINTER = -1,
+  MSDA_ERR_BAD_SHAPE = -2,     /* non-positive dim, L > MSDA_MAX_LEVELS, index range > int32 */
+  MSDA_ERR_MISALIGNED = -3,    /* a pointer is not 16-byte aligned */
+  MSDA_ERR_UNSUPPORTED = -4,   /* dtype / shape combination not built */
+  MSDA_ERR_NO_DEVICE = -5      /* no sm_100 device current */
+};
+
+int msda_b200_abi_version(void);
+/* Text of the last error raised on the calling thread ("" if none). */
+const char *msda_b200_last_error(void);
+/* 10*major+minor of the current device (100 on B200), or MSDA_ERR_NO_DEVICE. */
+int msda_b200_device_arch(void);
+
+/* ---- forward: replaces groundingdino._C.ms_deform_attn_forward --------------------------------
+ * csrc/vision.cpp:54, csrc/MsDeformAttn/ms_deform_attn.h:21-40, ms_deform_attn_cuda.cu:21-81,
+ * kernel ms_deform_im2col_cuda.cuh:237-299.  `out` is fully overwritten (no pre-zeroing needed;
+ * the reference memsets it at ms_deform_attn_cuda.cu:55).  im2col_step is not part of this ABI:
+ * it only chunks the batch (ms_deform_attn_cuda.cu:51-76); the host mirror keeps its observable
+ * `batch % min(batch, step) == 0` check. */
+int msda_forward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const float *loc, const float *aw, int N, int S, int M, int D, int L, int Lq, int P,
+                     float *out, void *stream);
+int msda_forward_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const double *loc, const double *aw, int N, int S, int M, int D, int L, int Lq, int P,
+                     double *out, void *stream);
+/* value/out are bf16 (resp. IEEE half) bit patterns; loc/aw fp32 */
+int msda_forward_bf16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *loc, const float *aw, int N, int S, int M, int D, int L, int Lq, int P,
+                      void *out, void *stream);
+int msda_forward_f16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                     const float *loc, const float *aw, int N, int S, int M, int D, int L, int Lq, int P,
+                     void *out, void *stream);
+
+/* ---- backward: replaces groundingdino._C.ms_deform_attn_backward ------------------------------
+ * csrc/vision.cpp:55, ms_deform_attn.h:42-62, ms_deform_attn_cuda.cu:84-154, kernel
+ * ms_deform_im2col_cuda.cuh:301-403 (+ :87-159).  grad_loc and grad_aw are fully overwritten.
+ * grad_value is ACCUMULATED into with atomics (summation order is not deterministic, as in the
+ * reference); pass zero_grad_value != 0 to have it memset on `stream` first (the reference always
+ * does, ms_deform_attn_cuda.cu:122). */
+int msda_backward_f32(const float *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *loc, const float *aw, const float *grad_out, int N, int S, int M, int D,
+                      int L, int Lq, int P, float *grad_value, float *grad_loc, float *grad_aw,
+                      int zero_grad_value, void *stream);
+int msda_backward_f64(const double *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const double *loc, const double *aw, const double *grad_out, int N, int S, int M, int D,
+                      int L, int Lq, int P, double *grad_value, double *grad_loc, double *grad_aw,
+                      int zero_grad_value, void *stream);
+/* value/grad_out bf16 (resp. half); grad_value, grad_loc, grad_aw fp32 */
+int msda_backward_bf16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                       const float *loc, const float *aw, const void *grad_out, int N, int S, int M, int D,
+                       int L, int Lq, int P, float *grad_value, float *grad_loc, float *grad_aw,
+                       int zero_grad_value, void *stream);
+int msda_backward_f16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                      const float *loc, const float *aw, const void *grad_out, int N, int S, int M, int D,
+                      int L, int Lq, int P, float *grad_value, float *grad_loc, float *grad_aw,
+                      int zero_grad_value, void *stream);
+
+/* ---- tuning / introspection (not part of the reference interface) ------------------------------
+ * Kernel variant knobs used by bench.py sweeps; defaults are the shipped configuration.
+ *   key "fwd_sample_batch"  : samples whose corner loads are issued together (1, 2 or 4)
+ *   key "fwd_q_fast"        : 1 = lanes of a warp span consecutive queries of one head, 0 = heads
+ *   key "bwd_q_fast"        : same for the backward kernel
+ * Returns 0, or MSDA_ERR_UNSUPPORTED for an unknown key / value. */
+int msda_b200_set_tuning(const char *key, int value);
+int msda_b200_get_tuning(const char *key);
+/* Number of kernel launches issued through this library by the calling process so far. */
+long long msda_b200_launch_count(void);
+
+/* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
+ * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =
+ * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */
+int msda_b200_probe_gather(const void *buf, long long bytes, int seg_bytes, int iters, int blocks, void *sink,
+                           void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

@@ -1,0 +1,124 @@
+"""CPU: the C-ABI library loads and exports every symbol include/msda_b200.h declares; argument
+validation that needs no GPU; host-side module API parity with the reference (constructor, attribute
+and state_dict names, init values, error behaviour)."""
+import ctypes
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import ziragroundingdino_b200 as zb
+from conftest import load_golden
+from ziragroundingdino_b200 import _lib
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _lib.declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(L, n), n
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH]).decode()
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(names) <= exported
+    assert L.msda_b200_abi_version() == 1
+
+
+def test_argument_validation_without_gpu():
+    L = _lib.lib()
+    a = (ctypes.c_float * 64)()
+    p = ctypes.addressof(a)
+    p16 = (p + 15) // 16 * 16
+    # null pointer
+    assert L.msda_forward_f32(None, p16, p16, p16, p16, 1, 4, 1, 4, 1, 1, 4, p16, None) == -1
+    assert b"null" in L.msda_b200_last_error()
+    # bad shape
+    assert L.msda_forward_f32(p16, p16, p16, p16, p16, 1, 0, 1, 4, 1, 1, 4, p16, None) == -2
+    assert L.msda_forward_f32(p16, p16, p16, p16, p16, 1, 4, 1, 4, 17, 1, 4, p16, None) == -2
+    assert L.msda_forward_f32(p16, p16, p16, p16, p16, 1, 1 << 24, 8, 32, 1, 1, 4, p16, None) == -2
+    # misaligned
+    assert L.msda_forward_f32(p16 + 4, p16, p16, p16, p16, 1, 4, 1, 4, 1, 1, 4, p16, None) == -3
+    assert L.msda_backward_f32(p16, p16, p16, p16, p16, p16, 1, 4, 1, 4, 1, 1, 4, None, p16, p16, 0, None) == -1
+    # tuning knobs
+    assert L.msda_b200_set_tuning(b"fwd_sample_batch", 3) == -4
+    assert L.msda_b200_set_tuning(b"nope", 1) == -4
+    old = L.msda_b200_get_tuning(b"fwd_passes")
+    assert L.msda_b200_set_tuning(b"fwd_passes", 2) == 0 and L.msda_b200_get_tuning(b"fwd_passes") == 2
+    L.msda_b200_set_tuning(b"fwd_passes", old)
+
+
+def test_module_api_matches_reference_surface():
+    with pytest.raises(ValueError):
+        zb.MultiScaleDeformableAttention(embed_dim=30, num_heads=8)
+    with pytest.warns(UserWarning):
+        zb.MultiScaleDeformableAttention(embed_dim=24, num_heads=4)  # head dim 6: not a power of two
+    m = zb.MultiScaleDeformableAttention()
+    assert (m.embed_dim, m.num_heads, m.num_levels, m.num_points, m.im2col_step, m.batch_first) == (256, 8, 4, 4, 64, False)
+    assert sorted(m.state_dict().keys()) == sorted(
+        "%s.%s" % (a, b) for a in ("sampling_offsets", "attention_weights", "value_proj", "output_proj")
+        for b in ("weight", "bias"))
+    assert m.sampling_offsets.weight.shape == (256, 256) and m.attention_weights.weight.shape == (128, 256)
+    # reference init (ms_deform_attn.py:194-217)
+    assert m.sampling_offsets.weight.abs().max() == 0 and m.attention_weights.weight.abs().max() == 0
+    b = m.sampling_offsets.bias.view(8, 4, 4, 2)
+    assert torch.allclose(b[0, 0, :, 0], torch.tensor([1.0, 2.0, 3.0, 4.0])) and b[0, 0, :, 1].abs().max() < 1e-6
+    assert torch.allclose(b[2, 1, 3], torch.tensor([0.0, 4.0]), atol=1e-5)
+    m.freeze_sampling_offsets(); m.freeze_attention_weights()
+    assert not m.sampling_offsets.weight.requires_grad and not m.attention_weights.bias.requires_grad
+    m._reset_parameters()
+
+
+def test_reference_state_dict_loads():
+    g = load_golden("module_enc")
+    C, M, L, P, bf = (int(x) for x in g["cfg"])
+    m = zb.MultiScaleDeformableAttention(C, M, L, P, batch_first=bool(bf))
+    sd = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")}
+    m.load_state_dict(sd, strict=True)
+
+
+def test_no_cpu_fallback():
+    m = zb.MultiScaleDeformableAttention(32, 2, 2, 2, batch_first=True)
+    sh = torch.tensor([[3, 2], [1, 1]])
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(query=torch.randn(1, 7, 32), value=torch.randn(1, 7, 32), reference_points=torch.rand(1, 7, 2, 2),
+          spatial_shapes=sh, level_start_index=torch.tensor([0, 6]))
+    with pytest.raises(RuntimeError):
+        zb.multi_scale_deformable_attn_pytorch()
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        zb._C.ms_deform_attn_forward(torch.randn(1, 7, 2, 16), sh, torch.tensor([0, 6]),
+                                     torch.rand(1, 7, 2, 2, 2, 2), torch.rand(1, 7, 2, 2, 2), 64)
+
+
+def test_zira_rep_zero_linear_matches_reference_fixture():
+    g = load_golden("zira_rep_linear")
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    m = zb.RepZeroLinear(24, 16).double()
+    sd = {k[4:]: v for k, v in t.items() if k.startswith("pre.")}
+    m.load_state_dict(sd)
+    m.train()
+    x = t["x"].clone().requires_grad_(True)
+    out, loss = m(x)
+    assert (out - t["train_out"]).abs().max() < 1e-13 and abs(float(loss.detach()) - float(t["train_loss"])) < 1e-13
+    ((out * t["grad_out"]).sum() + loss * 0.1).backward()
+    assert (x.grad - t["grad_x"]).abs().max() < 1e-12
+    for k, p in m.named_parameters():
+        assert (p.grad - t["pgrad." + k]).abs().max() < 1e-11, k
+    m.eval()
+    eo, el = m(t["x"])
+    assert (eo - t["eval_out"]).abs().max() < 1e-13 and float(el) == 0
+    m.__rep__()
+    for k, v in m.state_dict().items():
+        assert (v - t["post." + k]).abs().max() < 1e-15, k
+    assert (m(t["x"])[0] - t["merged_eval_out"]).abs().max() < 1e-13
+    m.train()
+    mo, ml = m(t["x"])
+    assert (mo - t["merged_train_out"]).abs().max() < 1e-13
+    assert abs(float(ml) - float(t["merged_train_loss"])) < 1e-13
+    # folded form == base linear + stand-alone adapter
+    base = torch.nn.Linear(24, 16).double()
+    y, l2 = m.forward_folded(t["x"], base.weight, base.bias)
+    assert (y - (base(t["x"]) + mo)).abs().max() < 1e-13 and abs(float(l2) - float(ml)) < 1e-13
+    m.eval()
+    y, l2 = m.forward_folded(t["x"], base.weight, base.bias)
+    assert l2 is None and (y - (base(t["x"]) + m(t["x"])[0])).abs().max() < 1e-13

@@ -1,0 +1,261 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the oracle on seeded inputs,
+against the reference-generated golden fixtures, against the reference's own CUDA op when
+oracle/_ref/ref_C.so is present, and -- at BASELINE.json's full sizes -- through size-independent
+properties (linearity in value, constant-map identity, adjointness of forward and backward).
+
+Bars (BASELINE.json north_star): fp32 forward <= 1e-5 max-abs, backward <= 1e-4 relative; bf16
+within 1e-2 of the fp32 truth evaluated on bf16-rounded inputs.  SURVEY.md section 0 item 4: at sigma=1
+inputs the reference's own CPU and CUDA fp32 paths sit ~2e-5 from fp64 truth, so the 1e-5 bar is
+checked against the C oracle (same formulation as the reference CUDA op) and, where the truth is
+fp64, value scale 0.5 is used at the big shapes; the scale is stated in each test.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import msda_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SWIN_T = [(100, 167), (50, 84), (25, 42), (13, 21)]
+SWIN_B5 = [(128, 225), (64, 113), (32, 57), (16, 29), (8, 15)]
+
+
+def _dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _mk(shapes, N, M, D, Lq, P, seed, dtype=torch.float32, lo=-0.05, hi=1.05, scale=1.0, dev=None):
+    g = torch.Generator().manual_seed(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    value = (torch.randn(N, S, M, D, generator=g) * scale).to(dtype)
+    loc = (torch.rand(N, Lq, M, L, P, 2, generator=g) * (hi - lo) + lo)
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g), -1).view(N, Lq, M, L, P)
+    gout = torch.randn(N, Lq, M * D, generator=g).to(dtype)
+    if dtype == torch.float64:
+        loc, aw = loc.double(), aw.double()
+    sh = torch.tensor(shapes, dtype=torch.long)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    return value, sh, lsi, loc, aw, gout
+
+
+def _run(value, sh, lsi, loc, aw, gout, dev):
+    import ziragroundingdino_b200 as zb
+    v, l, a = (t.to(dev).requires_grad_(True) for t in (value, loc, aw))
+    out = zb.MultiScaleDeformableAttnFunction.apply(v, sh.to(dev), lsi.to(dev), l, a, 64)
+    out.backward(gout.to(dev))
+    torch.cuda.synchronize()
+    return out.detach().cpu(), v.grad.cpu(), l.grad.cpu(), a.grad.cpu()
+
+
+def test_library_loaded_and_device_is_sm100():
+    from ziragroundingdino_b200 import _lib
+    _dev()
+    assert _lib.lib().msda_b200_device_arch() >= 100
+
+
+@pytest.mark.parametrize("name", ["core_tiny_f64", "core_d32_f32", "core_l5_f32", "core_oddD_f32", "core_d64_f32"])
+def test_golden_fixtures(name):
+    """Reference-generated vectors (tests/golden/make_golden.py), incl. border / centre / outside points."""
+    dev = _dev()
+    g = load_golden(name)
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    sh = t["shapes"]
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    out, gv, gl, ga = _run(t["value"], sh, lsi, t["loc"], t["aw"], t["grad_out"], dev)
+    f64 = g["value"].dtype == np.float64
+    assert np.abs(out.numpy() - g["out_f64"]).max() < (1e-12 if f64 else 1e-5)
+    tol = 1e-11 if f64 else 1e-4
+    assert rel_err(gv, g["grad_value_f64"]) < tol
+    assert rel_err(gl, g["grad_loc_f64"]) < tol
+    assert rel_err(ga, g["grad_aw_f64"]) < tol
+
+
+CASES = [
+    # shapes, N, M, D, Lq, P, dtype            (vector kernels: D in {16,32,64}, P == 4; others generic)
+    (SWIN_T, 2, 8, 32, 300, 4, torch.float32),
+    ([(20, 30), (10, 15), (5, 8), (3, 4)], 3, 8, 32, 777, 4, torch.float32),
+    ([(20, 30), (10, 15), (5, 8), (3, 4), (2, 2)], 1, 8, 32, 129, 4, torch.float32),   # 5 levels
+    ([(9, 7), (4, 4)], 2, 4, 64, 65, 4, torch.float32),
+    ([(9, 7), (4, 4)], 2, 5, 16, 33, 4, torch.float32),                                 # M=5: head-fast mapping
+    ([(9, 7), (4, 4)], 2, 3, 24, 31, 4, torch.float32),                                 # generic D
+    ([(9, 7), (4, 4)], 2, 2, 32, 31, 3, torch.float32),                                 # generic P
+    ([(9, 7), (4, 4)], 1, 2, 8, 17, 2, torch.float64),
+    ([(1, 1)], 1, 1, 32, 1, 4, torch.float32),                                          # degenerate 1x1 level
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "L%d_N%d_M%d_D%d_Lq%d_P%d_%s" % (
+    len(c[0]), c[1], c[2], c[3], c[4], c[5], str(c[6]).split(".")[-1]))
+def test_core_vs_c_oracle(case):
+    """CUDA vs oracle/msda_oracle.c on the same seeded inputs; locations in U(-0.05, 1.05), value sigma=1."""
+    dev = _dev()
+    shapes, N, M, D, Lq, P, dtype = case
+    value, sh, lsi, loc, aw, gout = _mk(shapes, N, M, D, Lq, P, seed=100 + Lq, dtype=dtype)
+    out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    o_out = O.c_forward(value.numpy(), sh.numpy(), loc.numpy(), aw.numpy())
+    o_gv, o_gl, o_ga = O.c_backward(value.numpy(), sh.numpy(), loc.numpy(), aw.numpy(), gout.numpy())
+    f64 = dtype == torch.float64
+    assert np.abs(out.numpy().reshape(o_out.shape) - o_out).max() < (1e-12 if f64 else 1e-5)
+    tol = 1e-11 if f64 else 1e-4
+    assert rel_err(gv, o_gv) < tol
+    assert rel_err(gl, o_gl) < tol
+    assert rel_err(ga, o_ga) < tol
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("D,P", [(32, 4), (64, 4), (128, 4), (24, 4), (32, 2)])
+def test_16bit_storage_vs_fp32_truth(dtype, D, P):
+    """bf16/f16 value & grad_out, fp32 loc/aw and fp32 accumulation; truth = fp64 oracle on the
+    16-bit-rounded inputs.  Bar 1e-2 (north_star); what remains is only the final output rounding."""
+    dev = _dev()
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    value, sh, lsi, loc, aw, gout = _mk(shapes, 2, 8, D, 200, P, seed=7, dtype=dtype)
+    out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    v64, go64 = value.double().numpy(), gout.double().numpy()
+    o_out = O.c_forward(v64, sh.numpy(), loc.double().numpy(), aw.double().numpy())
+    o_gv, o_gl, o_ga = O.c_backward(v64, sh.numpy(), loc.double().numpy(), aw.double().numpy(), go64)
+    assert out.dtype == dtype and gv.dtype == dtype and gl.dtype == torch.float32
+    assert np.abs(out.double().numpy() - o_out).max() < 1e-2
+    assert rel_err(gv.double(), o_gv) < 1e-2
+    assert rel_err(gl, o_gl) < 1e-4 and rel_err(ga, o_ga) < 1e-4   # fp32 accumulate of exact inputs
+
+
+def test_tuning_variants_agree():
+    """Every kernel variant the tuning knobs select gives the same answer."""
+    from ziragroundingdino_b200 import _lib
+    dev = _dev()
+    value, sh, lsi, loc, aw, gout = _mk([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, 32, 333, 4, seed=9)
+    base = None
+    keep = {k: _lib.get_tuning(k) for k in ("fwd_sample_batch", "fwd_q_fast", "fwd_passes", "bwd_q_fast", "bwd_passes")}
+    try:
+        for sb in (1, 2, 4):
+            for qf in (0, 1):
+                for ps in (1, 3):
+                    _lib.set_tuning(fwd_sample_batch=sb, fwd_q_fast=qf, fwd_passes=ps, bwd_q_fast=qf, bwd_passes=ps)
+                    res = _run(value, sh, lsi, loc, aw, gout, dev)
+                    if base is None:
+                        base = res
+                    else:
+                        assert torch.equal(res[0], base[0])
+                        assert rel_err(res[1], base[1]) < 1e-5   # atomics: order differs
+                        assert torch.equal(res[2], base[2]) and torch.equal(res[3], base[3])
+    finally:
+        _lib.set_tuning(**keep)
+
+
+def test_op_error_behaviour():
+    """Same observable errors as the reference op (ms_deform_attn_cuda.cu:29-53)."""
+    import ziragroundingdino_b200 as zb
+    dev = _dev()
+    value, sh, lsi, loc, aw, gout = (t.to(dev) for t in _mk([(4, 5), (2, 3)], 6, 2, 32, 9, 4, seed=1))
+    with pytest.raises(RuntimeError, match="contiguous"):
+        zb._C.ms_deform_attn_forward(value.transpose(1, 2), sh, lsi, loc, aw, 64)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        zb._C.ms_deform_attn_forward(value, sh, lsi, loc, aw, 4)      # 6 % 4 != 0
+    zb._C.ms_deform_attn_forward(value, sh, lsi, loc, aw, 3)           # 6 % 3 == 0
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        zb._C.ms_deform_attn_forward(value, sh.cpu(), lsi, loc, aw, 64)
+    # empty query set / empty batch
+    e = zb._C.ms_deform_attn_forward(value, sh, lsi, loc[:, :0].contiguous(), aw[:, :0].contiguous(), 64)
+    assert e.shape == (6, 0, 64)
+    gv, gl, ga = zb._C.ms_deform_attn_backward(value, sh, lsi, loc[:, :0].contiguous(), aw[:, :0].contiguous(),
+                                               gout[:, :0].contiguous(), 64)
+    assert gv.abs().max() == 0 and gl.numel() == 0
+
+
+def test_all_samples_outside_gives_zero():
+    dev = _dev()
+    value, sh, lsi, loc, aw, gout = _mk([(6, 7), (3, 4)], 1, 8, 32, 40, 4, seed=3)
+    loc = loc + 5.0
+    out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    assert out.abs().max() == 0 and gv.abs().max() == 0 and gl.abs().max() == 0 and ga.abs().max() == 0
+
+
+@pytest.mark.parametrize("shapes,N,tag", [(SWIN_T, 4, "config2_encoder_N4"), (SWIN_B5, 2, "config5_swinB_N2")])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_full_size_properties(shapes, N, tag, dtype):
+    """BASELINE.json full sizes (encoder self-attention, Lq = S): size-independent properties.
+      (1) constant value map + all samples inside  => output == that constant (weights sum to 1);
+      (2) linearity: f(a*v1 + v2) == a*f(v1) + f(v2);
+      (3) adjointness: <f(v), g> == <v, grad_value(g)>  (backward is the transpose of forward);
+      (4) a random 1/64 subset of queries equals the C oracle run on just that subset."""
+    import ziragroundingdino_b200 as zb
+    dev = _dev()
+    M, D, P, L = 8, 32, 4, len(shapes)
+    S = sum(h * w for h, w in shapes)
+    Lq = S
+    g = torch.Generator(device=dev).manual_seed(5)
+    sh = torch.tensor(shapes, dtype=torch.long, device=dev)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, device=dev) * 1.1 - 0.05
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, device=dev), -1).view(N, Lq, M, L, P)
+    f = lambda v, l=loc: zb._C.ms_deform_attn_forward(v, sh, lsi, l, aw, 64)
+    # (1)
+    inside = torch.rand(N, Lq, M, L, P, 2, generator=g, device=dev) * 0.8 + 0.1
+    const = torch.full((N, S, M, D), 0.75, device=dev, dtype=dtype)
+    out = f(const, inside).float()
+    assert (out - 0.75).abs().max() < (1e-5 if dtype == torch.float32 else 4e-3)
+    # (2)
+    v1 = (torch.randn(N, S, M, D, generator=g, device=dev) * 0.5)
+    v2 = (torch.randn(N, S, M, D, generator=g, device=dev) * 0.5)
+    if dtype == torch.float32:
+        lhs = f(2.0 * v1 + v2)
+        rhs = 2.0 * f(v1) + f(v2)
+        assert (lhs - rhs).abs().max() < 1e-5
+    # (3)
+    v = v1.to(dtype)
+    gout = torch.randn(N, Lq, M * D, generator=g, device=dev).to(dtype)
+    o = f(v)
+    gv, gl, ga = zb._C.ms_deform_attn_backward(v, sh, lsi, loc, aw, gout, 64)
+    lhs = (o.double() * gout.double()).sum().item()
+    rhs = (v.double() * gv.double()).sum().item()
+    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < (1e-5 if dtype == torch.float32 else 2e-3)
+    # (4)
+    idx = torch.randperm(Lq, generator=torch.Generator().manual_seed(1))[: max(Lq // 64, 8)].sort().values
+    sub_loc = loc[:1, idx.to(dev)].contiguous().cpu()
+    sub_aw = aw[:1, idx.to(dev)].contiguous().cpu()
+    want = O.c_forward(v[:1].float().cpu().numpy(), sh.cpu().numpy(), sub_loc.numpy(), sub_aw.numpy())
+    got = o[:1, idx.to(dev)].float().cpu().numpy()
+    assert np.abs(got - want).max() < (1e-5 if dtype == torch.float32 else 1e-2)
+    og = O.c_backward(v[:1].float().cpu().numpy(), sh.cpu().numpy(), sub_loc.numpy(), sub_aw.numpy(),
+                      gout[:1, idx.to(dev)].float().cpu().numpy())
+    assert rel_err(gl[:1, idx.to(dev)].cpu(), og[1]) < 1e-4
+    assert rel_err(ga[:1, idx.to(dev)].cpu(), og[2]) < 1e-4
+
+
+def test_config1_vs_fp64_truth_and_reference_cuda_op():
+    """Config 1 (N=1, Swin-T 800x1333, Lq=S): distances to fp64 truth for the new op, the C oracle and,
+    when oracle/_ref/ref_C.so is loadable, the reference's own CUDA op; new-vs-reference-CUDA must be
+    within 1e-5 (fwd) / 1e-4 rel (bwd).  Value sigma = 1, locations U(-0.05, 1.05)."""
+    import ziragroundingdino_b200 as zb
+    from oracle import build_ref
+    dev = _dev()
+    S = sum(h * w for h, w in SWIN_T)
+    value, sh, lsi, loc, aw, gout = _mk(SWIN_T, 1, 8, 32, S, 4, seed=1)
+    out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    truth = O.c_forward(value.double().numpy(), sh.numpy(), loc.double().numpy(), aw.double().numpy())
+    tgv, tgl, tga = O.c_backward(value.double().numpy(), sh.numpy(), loc.double().numpy(), aw.double().numpy(),
+                                 gout.double().numpy())
+    d_new = np.abs(out.numpy() - truth).max()
+    o32 = O.c_forward(value.numpy(), sh.numpy(), loc.numpy(), aw.numpy())
+    d_oracle = np.abs(o32 - truth).max()
+    print("config1 fwd max-abs vs fp64 truth: new=%.3e c_oracle_f32=%.3e new-vs-oracle=%.3e" % (
+        d_new, d_oracle, np.abs(out.numpy() - o32).max()))
+    assert np.abs(out.numpy() - o32).max() < 1e-5
+    assert d_new < 4e-5          # the reference's own fp32 paths sit at ~2e-5 here
+    assert rel_err(gv, tgv) < 1e-4 and rel_err(gl, tgl) < 1e-4 and rel_err(ga, tga) < 1e-4
+    ref = build_ref.load()
+    if ref is None:
+        pytest.skip("oracle/_ref/ref_C.so not built (reference sources absent at build time)")
+    v, l, a, go = (t.to(dev) for t in (value, loc, aw, gout))
+    r_out = ref.ms_deform_attn_forward(v, sh.to(dev), lsi.to(dev), l, a, 64)
+    r_gv, r_gl, r_ga = ref.ms_deform_attn_backward(v, sh.to(dev), lsi.to(dev), l, a, go, 64)
+    torch.cuda.synchronize()
+    print("config1 fwd: refCUDA-vs-truth=%.3e new-vs-refCUDA=%.3e" % (
+        np.abs(r_out.cpu().numpy() - truth).max(), (r_out.cpu() - out).abs().max().item()))
+    assert (r_out.cpu() - out).abs().max() < 1e-5
+    assert rel_err(gv, r_gv.cpu()) < 1e-4 and rel_err(gl, r_gl.cpu()) < 1e-4 and rel_err(ga, r_ga.cpu()) < 1e-4

@@ -1,0 +1,8 @@
+"""B200-native multi-scale deformable attention for ZiRa-GroundingDINO (drop-in for the reference's
+``groundingdino/models/GroundingDINO/ms_deform_attn.py`` + ``groundingdino._C``)."""
+from . import _C  # noqa: F401
+from .ms_deform_attn import (MultiScaleDeformableAttention, MultiScaleDeformableAttnFunction,  # noqa: F401
+                             multi_scale_deformable_attn_pytorch)
+from .zira import RepZeroLinear, merge_all  # noqa: F401
+
+__all__ = ["MultiScaleDeformableAttention", "MultiScaleDeformableAttnFunction", "RepZeroLinear", "merge_all", "_C"]

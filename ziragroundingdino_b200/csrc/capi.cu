@@ -1,0 +1,168 @@
+// extern "C" surface of libmsda_b200.so (declared in include/msda_b200.h).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "msda_common.cuh"
+
+namespace msda {
+template <typename VT>
+cudaError_t forward_f32acc(const VT*, const int64_t*, const int64_t*, const float*, const float*, VT*, int, int, int, int, int, int, int, cudaStream_t);
+template <typename VT>
+cudaError_t backward_f32acc(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+cudaError_t forward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, double*, int, int, int, int, int, int, int, cudaStream_t);
+cudaError_t backward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int, int, cudaStream_t);
+}  // namespace msda
+
+namespace {
+thread_local char t_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(t_err, sizeof(t_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_status(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return MSDA_OK;
+  snprintf(t_err, sizeof(t_err), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+  return static_cast<int>(e);
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+int check_common(const void* value, const void* shapes, const void* lstart, const void* loc, const void* aw,
+                 int N, int S, int M, int D, int L, int Lq, int P, size_t elem) {
+  if (!value || !shapes || !lstart || !loc || !aw) return fail(MSDA_ERR_NULL_POINTER, "null input pointer");
+  if (N < 0 || S <= 0 || M <= 0 || D <= 0 || L <= 0 || Lq < 0 || P <= 0)
+    return fail(MSDA_ERR_BAD_SHAPE, "non-positive dimension (N=%d S=%d M=%d D=%d L=%d Lq=%d P=%d)", N, S, M, D, L, Lq, P);
+  if (L > MSDA_MAX_LEVELS) return fail(MSDA_ERR_BAD_SHAPE, "num_levels %d > MSDA_MAX_LEVELS %d", L, MSDA_MAX_LEVELS);
+  // per-image value offsets are 32-bit inside the kernels (batch offsets are 64-bit)
+  if (static_cast<long long>(S) * M * D >= (1ll << 31))
+    return fail(MSDA_ERR_BAD_SHAPE, "S*M*D = %lld does not fit 32-bit per-image indexing", static_cast<long long>(S) * M * D);
+  if (static_cast<long long>(N) * Lq * M / 32 >= (1ll << 31))
+    return fail(MSDA_ERR_BAD_SHAPE, "N*Lq*M too large for one launch");
+  if (!aligned16(value) || !aligned16(loc) || !aligned16(aw) || (reinterpret_cast<uintptr_t>(shapes) & 7u) ||
+      (reinterpret_cast<uintptr_t>(lstart) & 7u))
+    return fail(MSDA_ERR_MISALIGNED, "input pointers must be 16-byte aligned (int64 arrays 8-byte)");
+  (void)elem;
+  return MSDA_OK;
+}
+
+template <typename VT, typename Fn>
+int run_forward(const VT* value, const int64_t* shapes, const int64_t* lstart, const void* loc, const void* aw,
+                int N, int S, int M, int D, int L, int Lq, int P, VT* out, void* stream, Fn fn) {
+  t_err[0] = 0;
+  int rc = check_common(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, sizeof(VT));
+  if (rc) return rc;
+  if (!out) return fail(MSDA_ERR_NULL_POINTER, "null output pointer");
+  if (!aligned16(out)) return fail(MSDA_ERR_MISALIGNED, "out must be 16-byte aligned");
+  if (N == 0 || Lq == 0) return MSDA_OK;  // empty batch / no queries: nothing to write
+  return cuda_status(fn(static_cast<cudaStream_t>(stream)), "msda_forward launch");
+}
+
+template <typename VT, typename GT, typename Fn>
+int run_backward(const VT* value, const int64_t* shapes, const int64_t* lstart, const void* loc, const void* aw,
+                 const VT* grad_out, int N, int S, int M, int D, int L, int Lq, int P, GT* gv, GT* gl, GT* ga,
+                 int zero_gv, void* stream, Fn fn) {
+  t_err[0] = 0;
+  int rc = check_common(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, sizeof(VT));
+  if (rc) return rc;
+  if (!grad_out || !gv || !gl || !ga) return fail(MSDA_ERR_NULL_POINTER, "null gradient pointer");
+  if (!aligned16(grad_out) || !aligned16(gv) || !aligned16(gl) || !aligned16(ga))
+    return fail(MSDA_ERR_MISALIGNED, "gradient pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zero_gv && N > 0) {
+    rc = cuda_status(cudaMemsetAsync(gv, 0, sizeof(GT) * static_cast<size_t>(N) * S * M * D, st), "grad_value memset");
+    if (rc) return rc;
+  }
+  if (N == 0 || Lq == 0) return MSDA_OK;
+  return cuda_status(fn(st), "msda_backward launch");
+}
+}  // namespace
+
+extern "C" {
+
+int msda_b200_abi_version(void) { return MSDA_B200_ABI_VERSION; }
+const char* msda_b200_last_error(void) { return t_err; }
+long long msda_b200_launch_count(void) { return msda::g_launches; }
+
+int msda_b200_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return fail(MSDA_ERR_NO_DEVICE, "no CUDA device"); }
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+static int* tuning_slot(const char* key) {
+  if (!key) return nullptr;
+  if (!strcmp(key, "fwd_sample_batch")) return &msda::g_tuning.fwd_sample_batch;
+  if (!strcmp(key, "fwd_q_fast")) return &msda::g_tuning.fwd_q_fast;
+  if (!strcmp(key, "fwd_passes")) return &msda::g_tuning.fwd_passes;
+  if (!strcmp(key, "bwd_q_fast")) return &msda::g_tuning.bwd_q_fast;
+  if (!strcmp(key, "bwd_passes")) return &msda::g_tuning.bwd_passes;
+  return nullptr;
+}
+
+int msda_b200_set_tuning(const char* key, int value) {
+  int* slot = tuning_slot(key);
+  if (!slot) return fail(MSDA_ERR_UNSUPPORTED, "unknown tuning key '%s'", key ? key : "(null)");
+  const bool is_batch = slot == &msda::g_tuning.fwd_sample_batch;
+  const bool is_pass = slot == &msda::g_tuning.fwd_passes || slot == &msda::g_tuning.bwd_passes;
+  if ((is_batch && value != 1 && value != 2 && value != 4) || (is_pass && (value < 1 || value > 64)) ||
+      (!is_batch && !is_pass && value != 0 && value != 1))
+    return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);
+  *slot = value;
+  return MSDA_OK;
+}
+
+int msda_b200_get_tuning(const char* key) {
+  int* slot = tuning_slot(key);
+  return slot ? *slot : fail(MSDA_ERR_UNSUPPORTED, "unknown tuning key '%s'", key ? key : "(null)");
+}
+
+#define MSDA_DEFINE_F32ACC(SUFFIX, CTYPE, VT)                                                                      \
+  int msda_forward_##SUFFIX(const CTYPE* value, const int64_t* shapes, const int64_t* lstart, const float* loc,  \
+                            const float* aw, int N, int S, int M, int D, int L, int Lq, int P, CTYPE* out,        \
+                            void* stream) {                                                                        \
+    const VT* v = reinterpret_cast<const VT*>(value);                                                              \
+    VT* o = reinterpret_cast<VT*>(out);                                                                            \
+    return run_forward<VT>(v, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, o, stream, [&](cudaStream_t st) {     \
+      return msda::forward_f32acc<VT>(v, shapes, lstart, loc, aw, o, N, S, M, D, L, Lq, P, st);                    \
+    });                                                                                                            \
+  }                                                                                                                \
+  int msda_backward_##SUFFIX(const CTYPE* value, const int64_t* shapes, const int64_t* lstart, const float* loc, \
+                             const float* aw, const CTYPE* grad_out, int N, int S, int M, int D, int L, int Lq,   \
+                             int P, float* gv, float* gl, float* ga, int zero_gv, void* stream) {                  \
+    const VT* v = reinterpret_cast<const VT*>(value);                                                              \
+    const VT* g = reinterpret_cast<const VT*>(grad_out);                                                           \
+    return run_backward<VT, float>(v, shapes, lstart, loc, aw, g, N, S, M, D, L, Lq, P, gv, gl, ga, zero_gv,       \
+                                   stream, [&](cudaStream_t st) {                                                  \
+      return msda::backward_f32acc<VT>(v, shapes, lstart, loc, aw, g, gv, gl, ga, N, S, M, D, L, Lq, P, st);       \
+    });                                                                                                            \
+  }
+
+MSDA_DEFINE_F32ACC(f32, float, float)
+MSDA_DEFINE_F32ACC(bf16, void, __nv_bfloat16)
+MSDA_DEFINE_F32ACC(f16, void, __half)
+
+int msda_forward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,
+                     const double* aw, int N, int S, int M, int D, int L, int Lq, int P, double* out, void* stream) {
+  return run_forward<double>(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, out, stream, [&](cudaStream_t st) {
+    return msda::forward_f64(value, shapes, lstart, loc, aw, out, N, S, M, D, L, Lq, P, st);
+  });
+}
+
+int msda_backward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,
+                      const double* aw, const double* grad_out, int N, int S, int M, int D, int L, int Lq, int P,
+                      double* gv, double* gl, double* ga, int zero_gv, void* stream) {
+  return run_backward<double, double>(value, shapes, lstart, loc, aw, grad_out, N, S, M, D, L, Lq, P, gv, gl, ga,
+                                      zero_gv, stream, [&](cudaStream_t st) {
+    return msda::backward_f64(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, D, L, Lq, P, st);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,160 @@
+// Shared device helpers for the sm_100a multi-scale deformable attention kernels.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+namespace msda {
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+// Kernel-variant knobs (msda_b200_set_tuning); the defaults are the shipped configuration.
+struct Tuning {
+  int fwd_sample_batch = 2;  // samples whose 4 corner loads are issued back to back
+  int fwd_q_fast = 1;        // lane groups of a warp span consecutive queries of one head
+  int fwd_passes = 4;        // consecutive unit tiles handled by one CTA
+  int bwd_q_fast = 1;
+  int bwd_passes = 4;
+};
+extern Tuning g_tuning;
+extern long long g_launches;
+
+// ---- storage-type traits: one lane always moves 16 bytes of channels -----------------------------
+template <typename VT> struct Vec;
+
+template <> struct Vec<float> {
+  static constexpr int CH = 4;
+  using Acc = float;
+  __device__ static __forceinline__ void load(const float* p, bool ok, float (&f)[4]) {
+    float4 r = ok ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    f[0] = r.x; f[1] = r.y; f[2] = r.z; f[3] = r.w;
+  }
+  __device__ static __forceinline__ void store(float* p, const float (&f)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+
+template <> struct Vec<__nv_bfloat16> {
+  static constexpr int CH = 8;
+  using Acc = float;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, bool ok, float (&f)[8]) {
+    uint4 r = ok ? __ldg(reinterpret_cast<const uint4*>(p)) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+template <> struct Vec<__half> {
+  static constexpr int CH = 8;
+  using Acc = float;
+  __device__ static __forceinline__ void load(const __half* p, bool ok, float (&f)[8]) {
+    uint4 r = ok ? __ldg(reinterpret_cast<const uint4*>(p)) : make_uint4(0u, 0u, 0u, 0u);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x;
+      f[2 * i + 1] = t.y;
+    }
+  }
+  __device__ static __forceinline__ void store(__half* p, const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// 128-bit reduction into fp32 global memory (REDG.E.ADD.F32x4 on sm_100a).
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// ---- scalar element access for the generic kernels -----------------------------------------------
+template <typename VT> struct Scalar { using Acc = float; };
+template <> struct Scalar<double> { using Acc = double; };
+__device__ __forceinline__ float to_acc(float v) { return v; }
+__device__ __forceinline__ double to_acc(double v) { return v; }
+__device__ __forceinline__ float to_acc(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_acc(__half v) { return __half2float(v); }
+template <typename VT, typename A> __device__ __forceinline__ VT from_acc(A v);
+template <> __device__ __forceinline__ float from_acc<float, float>(float v) { return v; }
+template <> __device__ __forceinline__ double from_acc<double, double>(double v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16, float>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_acc<__half, float>(float v) { return __float2half_rn(v); }
+
+// ---- the reference's sampling-coordinate arithmetic ----------------------------------------------
+// ms_deform_im2col_cuda.cuh:285-286: `loc * size - 0.5` with the product rounded before the
+// subtraction (the reference's 0.5 is a double literal, so nvcc cannot contract it into an FMA).
+__device__ __forceinline__ float im_coord(float loc, int size) {
+  return __fsub_rn(__fmul_rn(loc, static_cast<float>(size)), 0.5f);
+}
+__device__ __forceinline__ double im_coord(double loc, int size) {
+  return __dsub_rn(__dmul_rn(loc, static_cast<double>(size)), 0.5);
+}
+__device__ __forceinline__ int floor_int(float x) { return __float2int_rd(x); }
+__device__ __forceinline__ int floor_int(double x) { return __double2int_rd(x); }
+
+// One bilinear sample: corner offsets (in pixels, relative to the level origin), guards and weights.
+template <typename A> struct Tap {
+  bool ok;          // sample inside (-1, size) on both axes (im2col.cuh:288)
+  bool c1, c2, c3, c4;  // corner guards (im2col.cuh:56-78)
+  int o1, o2, o3, o4;   // pixel offsets h*W + w of the four corners
+  A lh, lw, hh, hw;
+};
+
+template <typename A>
+__device__ __forceinline__ Tap<A> make_tap(A loc_x, A loc_y, int H, int W) {
+  Tap<A> t;
+  const A h_im = im_coord(loc_y, H), w_im = im_coord(loc_x, W);
+  t.ok = (h_im > A(-1)) && (w_im > A(-1)) && (h_im < A(H)) && (w_im < A(W));
+  const int h0 = floor_int(h_im), w0 = floor_int(w_im);
+  const int h1 = h0 + 1, w1 = w0 + 1;
+  t.lh = h_im - A(h0);
+  t.lw = w_im - A(w0);
+  t.hh = A(1) - t.lh;
+  t.hw = A(1) - t.lw;
+  const bool top = t.ok && (h0 >= 0), bot = t.ok && (h1 <= H - 1);
+  const bool lef = (w0 >= 0), rig = (w1 <= W - 1);
+  t.c1 = top && lef; t.c2 = top && rig; t.c3 = bot && lef; t.c4 = bot && rig;
+  t.o1 = h0 * W + w0;
+  t.o2 = t.o1 + 1;
+  t.o3 = t.o1 + W;
+  t.o4 = t.o3 + 1;
+  return t;
+}
+
+// Unit (b, q, m) handled by lane-group `j` of pass `pass`.  A pass covers `tile` consecutive units in
+// (b, q, m)-major order; with q_fast the tile is walked query-fastest so that the lane groups of a
+// warp hold consecutive queries of ONE head (their corner rows often coincide on coarse levels and
+// coalesce into a single 128-byte wavefront); otherwise head-fastest.
+__device__ __forceinline__ long long unit_of(long long pass, int j, int tile, int M, bool q_fast) {
+  if (q_fast) {
+    const int qpp = tile / M;  // caller guarantees tile % M == 0 when q_fast
+    j = (j % qpp) * M + (j / qpp);
+  }
+  return pass * tile + j;
+}
+
+}  // namespace msda

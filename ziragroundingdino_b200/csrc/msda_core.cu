@@ -1,0 +1,444 @@
+// Multi-scale deformable attention, forward (bilinear gather) and backward (scatter), for sm_100a.
+//
+// Replaces the reference kernels ms_deformable_im2col_gpu_kernel (ms_deform_im2col_cuda.cuh:237-299)
+// and ms_deformable_col2im_gpu_kernel_shm_blocksize_aware_reduce_v1 (:301-403); the arithmetic per
+// sample (coordinate convention, guards, bilinear weights, gradient formulas) follows :33-159 so
+// results agree with the reference op to fp32 round-off.  The design does not:
+//
+//  * a group of D/CH lanes (CH = channels in one 16-byte load: 4 fp32 / 8 bf16) owns one
+//    (image, query, head) unit; every corner row of that head is ONE 128-bit load per lane and the
+//    attention-weighted sum lives in CH registers per lane -- 4x (fp32) / 8x (bf16) fewer load
+//    instructions than the reference's thread-per-channel mapping, and the coordinate math is done
+//    by D/CH lanes instead of D;
+//  * spatial_shapes / level_start_index are staged once per CTA in shared memory (the reference
+//    re-reads the int64 arrays from global memory per thread per level);
+//  * sampling locations and attention weights of a level are fetched with three 128-bit loads;
+//  * backward: grad_value goes out as 128-bit vector reductions (REDG.E.ADD.F32x4), the per-sample
+//    channel sums for grad_sampling_loc / grad_attn_weight are reduced with a warp-shuffle
+//    reduce-scatter (14 shuffles per 4 samples for D=32 fp32) instead of shared memory plus a serial
+//    loop on thread 0, and every (q, m, l, p) slot of both is written exactly once, so neither
+//    needs a memset.
+#include "msda_common.cuh"
+
+namespace msda {
+
+// =================================================================================================
+// forward, vectorised: D in {16, 32, 64, 128}, P == 4
+// =================================================================================================
+template <typename VT, int D, int SB>
+__global__ void __launch_bounds__(kThreads)
+msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                    const float* __restrict__ aw, VT* __restrict__ out, int S, int M, int L, int Lq,
+                    long long units, int passes, int q_fast) {
+  constexpr int CH = Vec<VT>::CH;
+  constexpr int LPG = D / CH;           // lanes per unit
+  constexpr int UPW = 32 / LPG;         // units per warp
+  constexpr int TILE = UPW * kWarpsPerBlock;
+  constexpr int P = 4;
+  static_assert(LPG >= 1 && LPG <= 32 && (LPG & (LPG - 1)) == 0, "D / CH must be a power of two <= 32");
+
+  __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
+    sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
+    sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane % LPG;                       // lane in group
+  const int j = warp * UPW + lane / LPG;            // unit slot inside the pass tile
+  const int row = M * D;                            // elements between neighbouring pixels
+
+  for (int it = 0; it < passes; ++it) {
+    const long long u = unit_of(static_cast<long long>(blockIdx.x) * passes + it, j, TILE, M, q_fast != 0);
+    if (u >= units) continue;
+    const int m = static_cast<int>(u % M);
+    const long long bq = u / M;
+    const long long b = bq / Lq;
+    const VT* vb = value + (static_cast<size_t>(b) * S * M + m) * D + lig * CH;
+    const float4* lp = reinterpret_cast<const float4*>(loc + static_cast<size_t>(u) * L * P * 2);
+    const float4* ap = reinterpret_cast<const float4*>(aw + static_cast<size_t>(u) * L * P);
+
+    float acc[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) acc[c] = 0.f;
+
+    for (int l = 0; l < L; ++l) {
+      const int H = sH[l], W = sW[l];
+      const VT* vl = vb + static_cast<size_t>(sStart[l]) * row;
+      const float4 xy01 = __ldg(lp + 2 * l), xy23 = __ldg(lp + 2 * l + 1), a4 = __ldg(ap + l);
+      const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
+      const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
+      const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+      for (int p0 = 0; p0 < P; p0 += SB) {
+        float v[SB][4][CH];
+        float k[SB][4];
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          const Tap<float> t = make_tap<float>(xs[p0 + s], ys[p0 + s], H, W);
+          Vec<VT>::load(vl + static_cast<long long>(t.o1) * row, t.c1, v[s][0]);
+          Vec<VT>::load(vl + static_cast<long long>(t.o2) * row, t.c2, v[s][1]);
+          Vec<VT>::load(vl + static_cast<long long>(t.o3) * row, t.c3, v[s][2]);
+          Vec<VT>::load(vl + static_cast<long long>(t.o4) * row, t.c4, v[s][3]);
+          k[s][0] = t.hh * t.hw; k[s][1] = t.hh * t.lw; k[s][2] = t.lh * t.hw; k[s][3] = t.lh * t.lw;
+        }
+#pragma unroll
+        for (int s = 0; s < SB; ++s) {
+          const float a = as[p0 + s];
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const float val = k[s][0] * v[s][0][c] + k[s][1] * v[s][1][c] + k[s][2] * v[s][2][c] + k[s][3] * v[s][3][c];
+            acc[c] = fmaf(val, a, acc[c]);
+          }
+        }
+      }
+    }
+    Vec<VT>::store(out + static_cast<size_t>(u) * D + lig * CH, acc);
+  }
+}
+
+// =================================================================================================
+// backward, vectorised: D in {16, 32, 64, 128} (LPG <= 16), P == 4
+// =================================================================================================
+// Sums v[0..15] across the LPG lanes of a group; afterwards lane `lig` holds entries
+// [lig*R, lig*R + R) of the 16 sums in v[0..R), R = 16 / LPG.
+template <int LPG>
+__device__ __forceinline__ void reduce_scatter16(float (&v)[16], int lig) {
+  int n = 16;
+#pragma unroll
+  for (int mask = LPG / 2; mask >= 1; mask >>= 1) {
+    n >>= 1;
+    const bool up = (lig & mask) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i < n) {
+        const float send = up ? v[i] : v[i + n];
+        const float keep = up ? v[i + n] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, mask);
+      }
+    }
+  }
+}
+
+template <typename VT, int D>
+__global__ void __launch_bounds__(kThreads)
+msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                    const int64_t* __restrict__ lstart, const float* __restrict__ loc,
+                    const float* __restrict__ aw, const VT* __restrict__ grad_out,
+                    float* __restrict__ grad_value, float* __restrict__ grad_loc,
+                    float* __restrict__ grad_aw, int S, int M, int L, int Lq, long long units,
+                    int passes, int q_fast) {
+  constexpr int CH = Vec<VT>::CH;
+  constexpr int LPG = D / CH;
+  constexpr int UPW = 32 / LPG;
+  constexpr int TILE = UPW * kWarpsPerBlock;
+  constexpr int P = 4;
+  constexpr int R = 16 / LPG;
+  static_assert(LPG >= 1 && LPG <= 16 && (LPG & (LPG - 1)) == 0, "D / CH must be a power of two <= 16");
+
+  __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
+    sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
+    sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lig = lane % LPG;
+  const int j = warp * UPW + lane / LPG;
+  const int row = M * D;
+
+  for (int it = 0; it < passes; ++it) {
+    long long u = unit_of(static_cast<long long>(blockIdx.x) * passes + it, j, TILE, M, q_fast != 0);
+    const bool active = u < units;   // inactive groups still take part in the shuffles
+    if (!active) u = 0;
+    const int m = static_cast<int>(u % M);
+    const long long bq = u / M;
+    const long long b = bq / Lq;
+    const size_t voff = (static_cast<size_t>(b) * S * M + m) * D + lig * CH;
+    const VT* vb = value + voff;
+    float* gvb = grad_value + voff;
+    const float4* lp = reinterpret_cast<const float4*>(loc + static_cast<size_t>(u) * L * P * 2);
+    const float4* ap = reinterpret_cast<const float4*>(aw + static_cast<size_t>(u) * L * P);
+    float* glp = grad_loc + static_cast<size_t>(u) * L * P * 2;
+    float* gap = grad_aw + static_cast<size_t>(u) * L * P;
+
+    float g[CH];
+    Vec<VT>::load(grad_out + static_cast<size_t>(u) * D + lig * CH, active, g);
+
+    for (int l = 0; l < L; ++l) {
+      const int H = sH[l], W = sW[l];
+      const size_t loff = static_cast<size_t>(sStart[l]) * row;
+      const VT* vl = vb + loff;
+      float* gvl = gvb + loff;
+      const float4 xy01 = __ldg(lp + 2 * l), xy23 = __ldg(lp + 2 * l + 1), a4 = __ldg(ap + l);
+      const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
+      const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
+      const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+      float red[16];
+#pragma unroll
+      for (int p = 0; p < P; ++p) {
+        Tap<float> t = make_tap<float>(xs[p], ys[p], H, W);
+        t.c1 = t.c1 && active; t.c2 = t.c2 && active; t.c3 = t.c3 && active; t.c4 = t.c4 && active;
+        float v1[CH], v2[CH], v3[CH], v4[CH];
+        const long long e1 = static_cast<long long>(t.o1) * row, e2 = static_cast<long long>(t.o2) * row;
+        const long long e3 = static_cast<long long>(t.o3) * row, e4 = static_cast<long long>(t.o4) * row;
+        Vec<VT>::load(vl + e1, t.c1, v1);
+        Vec<VT>::load(vl + e2, t.c2, v2);
+        Vec<VT>::load(vl + e3, t.c3, v3);
+        Vec<VT>::load(vl + e4, t.c4, v4);
+        const float k1 = t.hh * t.hw, k2 = t.hh * t.lw, k3 = t.lh * t.hw, k4 = t.lh * t.lw;
+        const float a = as[p];
+        float s_w = 0.f, s_h = 0.f, s_a = 0.f;
+        float tg[CH];
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          tg[c] = g[c] * a;  // top_grad_value (im2col.cuh:115)
+          // d(bilinear)/dh and /dw (im2col.cuh:123-151); guarded-off corners loaded as 0
+          const float gh = t.hw * (v3[c] - v1[c]) + t.lw * (v4[c] - v2[c]);
+          const float gw = t.hh * (v2[c] - v1[c]) + t.lh * (v4[c] - v3[c]);
+          const float val = k1 * v1[c] + k2 * v2[c] + k3 * v3[c] + k4 * v4[c];
+          s_a = fmaf(g[c], val, s_a);
+          s_w = fmaf(gw, tg[c], s_w);
+          s_h = fmaf(gh, tg[c], s_h);
+        }
+        red[4 * p + 0] = s_w * static_cast<float>(W);
+        red[4 * p + 1] = s_h * static_cast<float>(H);
+        red[4 * p + 2] = s_a;
+        red[4 * p + 3] = 0.f;
+#pragma unroll
+        for (int c0 = 0; c0 < CH; c0 += 4) {
+          if (t.c1) red_add_v4(gvl + e1 + c0, k1 * tg[c0], k1 * tg[c0 + 1], k1 * tg[c0 + 2], k1 * tg[c0 + 3]);
+          if (t.c2) red_add_v4(gvl + e2 + c0, k2 * tg[c0], k2 * tg[c0 + 1], k2 * tg[c0 + 2], k2 * tg[c0 + 3]);
+          if (t.c3) red_add_v4(gvl + e3 + c0, k3 * tg[c0], k3 * tg[c0 + 1], k3 * tg[c0 + 2], k3 * tg[c0 + 3]);
+          if (t.c4) red_add_v4(gvl + e4 + c0, k4 * tg[c0], k4 * tg[c0 + 1], k4 * tg[c0 + 2], k4 * tg[c0 + 3]);
+        }
+      }
+      reduce_scatter16<LPG>(red, lig);
+      if (active) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const int idx = lig * R + r, p = idx >> 2, comp = idx & 3;
+          if (comp < 2) glp[(l * P + p) * 2 + comp] = red[r];
+          else if (comp == 2) gap[l * P + p] = red[r];
+        }
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// generic kernels: any D, any P, fp32 / fp64 / bf16 / f16 storage (accumulate in Acc)
+// =================================================================================================
+template <typename VT, typename AT>
+__global__ void __launch_bounds__(256)
+msda_fwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lstart, const AT* __restrict__ loc,
+                        const AT* __restrict__ aw, VT* __restrict__ out, int S, int M, int D, int L,
+                        int Lq, int P, long long total) {
+  __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
+    sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
+    sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
+  }
+  __syncthreads();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = static_cast<int>(idx % D);
+  const long long u = idx / D;
+  const int m = static_cast<int>(u % M);
+  const long long b = (u / M) / Lq;
+  const size_t row = static_cast<size_t>(M) * D;
+  const VT* vb = value + (static_cast<size_t>(b) * S * M + m) * D + c;
+  const AT* lp = loc + static_cast<size_t>(u) * L * P * 2;
+  const AT* ap = aw + static_cast<size_t>(u) * L * P;
+  AT acc = AT(0);
+  for (int l = 0; l < L; ++l) {
+    const int H = sH[l], W = sW[l];
+    const VT* vl = vb + static_cast<size_t>(sStart[l]) * row;
+    for (int p = 0; p < P; ++p) {
+      const Tap<AT> t = make_tap<AT>(lp[(l * P + p) * 2], lp[(l * P + p) * 2 + 1], H, W);
+      const AT v1 = t.c1 ? AT(to_acc(vl[static_cast<long long>(t.o1) * row])) : AT(0);
+      const AT v2 = t.c2 ? AT(to_acc(vl[static_cast<long long>(t.o2) * row])) : AT(0);
+      const AT v3 = t.c3 ? AT(to_acc(vl[static_cast<long long>(t.o3) * row])) : AT(0);
+      const AT v4 = t.c4 ? AT(to_acc(vl[static_cast<long long>(t.o4) * row])) : AT(0);
+      const AT val = t.hh * t.hw * v1 + t.hh * t.lw * v2 + t.lh * t.hw * v3 + t.lh * t.lw * v4;
+      acc += val * ap[l * P + p];
+    }
+  }
+  out[idx] = from_acc<VT, AT>(acc);
+}
+
+// one warp per (b, q, m) unit; lanes stride the channels
+template <typename VT, typename AT>
+__global__ void __launch_bounds__(256)
+msda_bwd_generic_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
+                        const int64_t* __restrict__ lstart, const AT* __restrict__ loc,
+                        const AT* __restrict__ aw, const VT* __restrict__ grad_out,
+                        AT* __restrict__ grad_value, AT* __restrict__ grad_loc,
+                        AT* __restrict__ grad_aw, int S, int M, int D, int L, int Lq, int P,
+                        long long units) {
+  __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
+  if (threadIdx.x < L) {
+    sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
+    sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
+    sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long u = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (u >= units) return;  // whole warp leaves together
+  const int m = static_cast<int>(u % M);
+  const long long b = (u / M) / Lq;
+  const size_t row = static_cast<size_t>(M) * D;
+  const size_t voff = (static_cast<size_t>(b) * S * M + m) * D;
+  const AT* lp = loc + static_cast<size_t>(u) * L * P * 2;
+  const AT* ap = aw + static_cast<size_t>(u) * L * P;
+  const VT* gp = grad_out + static_cast<size_t>(u) * D;
+  for (int l = 0; l < L; ++l) {
+    const int H = sH[l], W = sW[l];
+    const size_t loff = voff + static_cast<size_t>(sStart[l]) * row;
+    for (int p = 0; p < P; ++p) {
+      const Tap<AT> t = make_tap<AT>(lp[(l * P + p) * 2], lp[(l * P + p) * 2 + 1], H, W);
+      const AT a = ap[l * P + p];
+      const AT k1 = t.hh * t.hw, k2 = t.hh * t.lw, k3 = t.lh * t.hw, k4 = t.lh * t.lw;
+      AT s_w = AT(0), s_h = AT(0), s_a = AT(0);
+      for (int c = lane; c < D; c += 32) {
+        const AT g = AT(to_acc(gp[c])), tg = g * a;
+        const size_t e1 = loff + static_cast<long long>(t.o1) * row + c, e2 = loff + static_cast<long long>(t.o2) * row + c;
+        const size_t e3 = loff + static_cast<long long>(t.o3) * row + c, e4 = loff + static_cast<long long>(t.o4) * row + c;
+        const AT v1 = t.c1 ? AT(to_acc(value[e1])) : AT(0), v2 = t.c2 ? AT(to_acc(value[e2])) : AT(0);
+        const AT v3 = t.c3 ? AT(to_acc(value[e3])) : AT(0), v4 = t.c4 ? AT(to_acc(value[e4])) : AT(0);
+        if (t.c1) atomicAdd(grad_value + e1, k1 * tg);
+        if (t.c2) atomicAdd(grad_value + e2, k2 * tg);
+        if (t.c3) atomicAdd(grad_value + e3, k3 * tg);
+        if (t.c4) atomicAdd(grad_value + e4, k4 * tg);
+        s_a += g * (k1 * v1 + k2 * v2 + k3 * v3 + k4 * v4);
+        s_w += (t.hh * (v2 - v1) + t.lh * (v4 - v3)) * tg;
+        s_h += (t.hw * (v3 - v1) + t.lw * (v4 - v2)) * tg;
+      }
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        s_w += __shfl_xor_sync(0xffffffffu, s_w, o);
+        s_h += __shfl_xor_sync(0xffffffffu, s_h, o);
+        s_a += __shfl_xor_sync(0xffffffffu, s_a, o);
+      }
+      if (lane == 0) {
+        grad_loc[static_cast<size_t>(u) * L * P * 2 + (l * P + p) * 2] = s_w * AT(W);
+        grad_loc[static_cast<size_t>(u) * L * P * 2 + (l * P + p) * 2 + 1] = s_h * AT(H);
+        grad_aw[static_cast<size_t>(u) * L * P + l * P + p] = s_a;
+      }
+    }
+  }
+}
+
+// =================================================================================================
+// host-side launchers
+// =================================================================================================
+Tuning g_tuning;
+long long g_launches = 0;
+
+template <typename VT, int D>
+static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
+                                  const float* loc, const float* aw, VT* out, int N, int S, int M, int L,
+                                  int Lq, cudaStream_t st) {
+  constexpr int TILE = (32 / (D / Vec<VT>::CH)) * kWarpsPerBlock;
+  const long long units = static_cast<long long>(N) * Lq * M;
+  const int q_fast = (g_tuning.fwd_q_fast && TILE % M == 0) ? 1 : 0;
+  const int passes = g_tuning.fwd_passes;
+  const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
+  const dim3 grid(static_cast<unsigned>(blocks));
+  ++g_launches;
+  switch (g_tuning.fwd_sample_batch) {
+    case 1: msda_fwd_vec_kernel<VT, D, 1><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    case 4: msda_fwd_vec_kernel<VT, D, 4><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    default: msda_fwd_vec_kernel<VT, D, 2><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+  }
+  return cudaGetLastError();
+}
+
+template <typename VT, int D>
+static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
+                                  const float* loc, const float* aw, const VT* grad_out, float* gv,
+                                  float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
+  constexpr int TILE = (32 / (D / Vec<VT>::CH)) * kWarpsPerBlock;
+  const long long units = static_cast<long long>(N) * Lq * M;
+  const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
+  const int passes = g_tuning.bwd_passes;
+  const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
+  ++g_launches;
+  msda_bwd_vec_kernel<VT, D><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast);
+  return cudaGetLastError();
+}
+
+// Storage types whose locations / weights / gradients are fp32 (float, bf16, half).
+template <typename VT>
+cudaError_t forward_f32acc(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
+                           const float* aw, VT* out, int N, int S, int M, int D, int L, int Lq, int P,
+                           cudaStream_t st) {
+  constexpr int CH = Vec<VT>::CH;
+  if (P == 4) {
+    if (D == 32) return launch_fwd_vec<VT, 32>(value, shapes, lstart, loc, aw, out, N, S, M, L, Lq, st);
+    if (D == 64) return launch_fwd_vec<VT, 64>(value, shapes, lstart, loc, aw, out, N, S, M, L, Lq, st);
+    if (D == 16) return launch_fwd_vec<VT, 16>(value, shapes, lstart, loc, aw, out, N, S, M, L, Lq, st);
+    if constexpr (CH == 8) if (D == 128) return launch_fwd_vec<VT, 128>(value, shapes, lstart, loc, aw, out, N, S, M, L, Lq, st);
+  }
+  const long long total = static_cast<long long>(N) * Lq * M * D;
+  ++g_launches;
+  msda_fwd_generic_kernel<VT, float><<<dim3(static_cast<unsigned>((total + 255) / 256)), 256, 0, st>>>(
+      value, shapes, lstart, loc, aw, out, S, M, D, L, Lq, P, total);
+  return cudaGetLastError();
+}
+
+template <typename VT>
+cudaError_t backward_f32acc(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
+                            const float* aw, const VT* grad_out, float* gv, float* gl, float* ga, int N,
+                            int S, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  constexpr int CH = Vec<VT>::CH;
+  if (P == 4) {
+    if (D == 32) return launch_bwd_vec<VT, 32>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+    if (D == 64) return launch_bwd_vec<VT, 64>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+    if (D == 16) return launch_bwd_vec<VT, 16>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+    if constexpr (CH == 8) if (D == 128) return launch_bwd_vec<VT, 128>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+  }
+  const long long units = static_cast<long long>(N) * Lq * M;
+  ++g_launches;
+  msda_bwd_generic_kernel<VT, float><<<dim3(static_cast<unsigned>((units + 7) / 8)), 256, 0, st>>>(
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, D, L, Lq, P, units);
+  return cudaGetLastError();
+}
+
+cudaError_t forward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,
+                        const double* aw, double* out, int N, int S, int M, int D, int L, int Lq, int P,
+                        cudaStream_t st) {
+  const long long total = static_cast<long long>(N) * Lq * M * D;
+  ++g_launches;
+  msda_fwd_generic_kernel<double, double><<<dim3(static_cast<unsigned>((total + 255) / 256)), 256, 0, st>>>(
+      value, shapes, lstart, loc, aw, out, S, M, D, L, Lq, P, total);
+  return cudaGetLastError();
+}
+
+cudaError_t backward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,
+                         const double* aw, const double* grad_out, double* gv, double* gl, double* ga, int N,
+                         int S, int M, int D, int L, int Lq, int P, cudaStream_t st) {
+  const long long units = static_cast<long long>(N) * Lq * M;
+  ++g_launches;
+  msda_bwd_generic_kernel<double, double><<<dim3(static_cast<unsigned>((units + 7) / 8)), 256, 0, st>>>(
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, D, L, Lq, P, units);
+  return cudaGetLastError();
+}
+
+template cudaError_t forward_f32acc<float>(const float*, const int64_t*, const int64_t*, const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template cudaError_t forward_f32acc<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, __nv_bfloat16*, int, int, int, int, int, int, int, cudaStream_t);
+template cudaError_t forward_f32acc<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, __half*, int, int, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_f32acc<float>(const float*, const int64_t*, const int64_t*, const float*, const float*, const float*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_f32acc<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_f32acc<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+
+}  // namespace msda

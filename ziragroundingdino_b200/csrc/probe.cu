@@ -1,0 +1,55 @@
+// Measurement aid (bench.py / tools only): achievable L2 gather bandwidth on this GPU.
+//
+// MEASURED_PEAKS.json has no L2 figure, and the gather kernels are bounded by how fast SMs can pull
+// random, row-sized segments out of an L2-resident map.  This probe reproduces exactly that access
+// shape with nothing else in the way: groups of `seg_bytes/16` lanes read random seg_bytes-aligned
+// segments (128 B = one fp32 head row, 64 B = one bf16 head row) of a buffer small enough to live in
+// L2, eight independent 128-bit loads in flight per lane, no arithmetic beyond an XOR sink.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+namespace {
+__device__ __forceinline__ uint32_t mix(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+template <int LPG>
+__global__ void __launch_bounds__(256) gather_probe_kernel(const uint4* __restrict__ buf, uint32_t nseg, int iters,
+                                                           uint32_t* __restrict__ sink) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t group = tid / LPG, lig = tid % LPG;
+  uint4 acc = make_uint4(0, 0, 0, 0);
+  for (int i = 0; i < iters; i += 8) {
+    uint4 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t seg = mix(group * 2654435761u + static_cast<uint32_t>(i + k) * 40503u) % nseg;
+      v[k] = __ldg(buf + static_cast<size_t>(seg) * LPG + lig);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { acc.x ^= v[k].x; acc.y ^= v[k].y; acc.z ^= v[k].z; acc.w ^= v[k].w; }
+  }
+  if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[0] = tid;  // keep the loads alive
+}
+}  // namespace
+
+extern "C" int msda_b200_probe_gather(const void* buf, long long bytes, int seg_bytes, int iters, int blocks,
+                                      void* sink, void* stream) {
+  if (!buf || !sink || bytes < seg_bytes || iters <= 0 || blocks <= 0) return MSDA_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t nseg = static_cast<uint32_t>(bytes / seg_bytes);
+  iters = (iters + 7) / 8 * 8;
+  if (seg_bytes == 128)
+    gather_probe_kernel<8><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(buf), nseg, iters, static_cast<uint32_t*>(sink));
+  else if (seg_bytes == 64)
+    gather_probe_kernel<4><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(buf), nseg, iters, static_cast<uint32_t*>(sink));
+  else if (seg_bytes == 512)
+    gather_probe_kernel<32><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(buf), nseg, iters, static_cast<uint32_t*>(sink));
+  else
+    return MSDA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}

@@ -1,0 +1,234 @@
+"""B200-native drop-in for the reference's ``groundingdino/models/GroundingDINO/ms_deform_attn.py``.
+
+Public names, constructor, attributes, ``forward`` signature, ``state_dict`` keys and error
+behaviour mirror the reference (ms_deform_attn.py:38-87 for the autograd Function, :133-355 for the
+module) so a checkpoint and a call site written for the reference work unchanged; the arithmetic
+runs in the sm_100a kernels behind ``ziragroundingdino_b200._C`` / include/msda_b200.h.
+
+Differences, all deliberate:
+  * there is NO CPU path.  The reference falls back to ``multi_scale_deformable_attn_pytorch`` for
+    CPU tensors (ms_deform_attn.py:345-348); here a CPU tensor raises ``RuntimeError``.
+  * bf16 is supported (the reference op dispatches float/double only, ms_deform_attn_cuda.cu:65);
+    fp16 and bf16 run natively with 16-bit value/output, fp32 locations/weights and fp32
+    accumulation, which is what the reference's fp16 up-cast computes (ms_deform_attn.py:326-344).
+  * the ``sum(H*W) == num_value`` check (ms_deform_attn.py:284) costs the reference a device->host
+    sync per call; here the host copy of ``spatial_shapes`` is cached per tensor version.
+  * ZiRa: ``add_zira_branches()`` attaches re-parameterisable side branches with the semantics of the
+    reference's ``RepZeroLinear`` (groundingdino_dual_zero_rep_branch.py:105-135) to ``value_proj``
+    and ``output_proj`` (see zira.py).
+"""
+import math
+import warnings
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+from torch.nn.init import constant_, xavier_uniform_
+
+from . import _C
+from .zira import RepZeroLinear
+
+
+def _is_power_of_2(n):
+    if (not isinstance(n, int)) or (n < 0):
+        raise ValueError("invalid input for _is_power_of_2: {} (type: {})".format(n, type(n)))
+    return (n & (n - 1) == 0) and n != 0
+
+
+class MultiScaleDeformableAttnFunction(Function):
+    """Same call signature as the reference Function (ms_deform_attn.py:38-87)."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                attention_weights, im2col_step):
+        ctx.im2col_step = im2col_step
+        output = _C.ms_deform_attn_forward(value, value_spatial_shapes, value_level_start_index,
+                                           sampling_locations, attention_weights, ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, level_start, loc, aw = ctx.saved_tensors
+        grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(
+            value, shapes, level_start, loc, aw, grad_output.contiguous(), ctx.im2col_step)
+        if grad_value.dtype != value.dtype:
+            grad_value = grad_value.to(value.dtype)
+        return grad_value, None, None, grad_loc, grad_aw, None
+
+
+def multi_scale_deformable_attn_pytorch(*args, **kwargs):
+    """The reference's CPU implementation (ms_deform_attn.py:90-130) has no counterpart here."""
+    raise RuntimeError("ziragroundingdino_b200 has no CPU / PyTorch fallback for multi-scale deformable "
+                       "attention; use MultiScaleDeformableAttnFunction on CUDA tensors")
+
+
+_SHAPE_CACHE = {}
+
+
+def _host_shapes(spatial_shapes):
+    """Host copy of ``spatial_shapes`` as a tuple of (H, W), cached per (storage, version)."""
+    if not spatial_shapes.is_cuda:
+        return tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())
+    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index,
+           tuple(spatial_shapes.shape))
+    hit = _SHAPE_CACHE.get(key)
+    if hit is None:
+        if len(_SHAPE_CACHE) > 256:
+            _SHAPE_CACHE.clear()
+        hit = tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())  # one sync per new tensor
+        _SHAPE_CACHE[key] = hit
+    return hit
+
+
+class MultiScaleDeformableAttention(nn.Module):
+    """Multi-Scale Deformable Attention (Deformable-DETR), reference ms_deform_attn.py:133-355.
+
+    Args:
+        embed_dim (int): embedding dimension. Default: 256.
+        num_heads (int): attention heads. Default: 8.
+        num_levels (int): feature levels. Default: 4.
+        num_points (int): sampling points per head per level. Default: 4.
+        img2col_step (int): kept for API compatibility (only its divisibility check is observable).
+        batch_first (bool): ``(bs, n, embed_dim)`` if True else ``(n, bs, embed_dim)``. Default: False.
+    """
+
+    def __init__(self, embed_dim: int = 256, num_heads: int = 8, num_levels: int = 4, num_points: int = 4,
+                 img2col_step: int = 64, batch_first: bool = False):
+        super().__init__()
+        if embed_dim % num_heads != 0:
+            raise ValueError("embed_dim must be divisible by num_heads, but got {} and {}".format(
+                embed_dim, num_heads))
+        head_dim = embed_dim // num_heads
+        self.batch_first = batch_first
+        if not _is_power_of_2(head_dim):
+            warnings.warn(
+                """
+                You'd better set d_model in MSDeformAttn to make sure that
+                each dim of the attention head a power of 2, which is more efficient.
+                """
+            )
+        self.im2col_step = img2col_step
+        self.embed_dim = embed_dim
+        self.num_heads = num_heads
+        self.num_levels = num_levels
+        self.num_points = num_points
+        self.sampling_offsets = nn.Linear(embed_dim, num_heads * num_levels * num_points * 2)
+        self.attention_weights = nn.Linear(embed_dim, num_heads * num_levels * num_points)
+        self.value_proj = nn.Linear(embed_dim, embed_dim)
+        self.output_proj = nn.Linear(embed_dim, embed_dim)
+        # ZiRa side branches (None until add_zira_branches()); not part of the reference state_dict
+        self.value_proj_adapter = None
+        self.output_proj_adapter = None
+        self.zero_inter_loss = None  # set by forward() in training mode when branches exist
+        self.init_weights()
+
+    def _reset_parameters(self):
+        return self.init_weights()
+
+    def init_weights(self):
+        """Reference initialisation (ms_deform_attn.py:194-217)."""
+        constant_(self.sampling_offsets.weight.data, 0.0)
+        thetas = torch.arange(self.num_heads, dtype=torch.float32) * (2.0 * math.pi / self.num_heads)
+        grid_init = torch.stack([thetas.cos(), thetas.sin()], -1)
+        grid_init = (grid_init / grid_init.abs().max(-1, keepdim=True)[0]).view(self.num_heads, 1, 1, 2)
+        grid_init = grid_init.repeat(1, self.num_levels, self.num_points, 1)
+        for i in range(self.num_points):
+            grid_init[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias = nn.Parameter(grid_init.view(-1))
+        constant_(self.attention_weights.weight.data, 0.0)
+        constant_(self.attention_weights.bias.data, 0.0)
+        xavier_uniform_(self.value_proj.weight.data)
+        constant_(self.value_proj.bias.data, 0.0)
+        xavier_uniform_(self.output_proj.weight.data)
+        constant_(self.output_proj.bias.data, 0.0)
+
+    def freeze_sampling_offsets(self):
+        print("Freeze sampling offsets")
+        self.sampling_offsets.weight.requires_grad = False
+        self.sampling_offsets.bias.requires_grad = False
+
+    def freeze_attention_weights(self):
+        print("Freeze attention weights")
+        self.attention_weights.weight.requires_grad = False
+        self.attention_weights.bias.requires_grad = False
+
+    # ---- ZiRa -------------------------------------------------------------------------------------
+    def add_zira_branches(self, value_proj: bool = True, output_proj: bool = True):
+        """Attach zero-initialised re-parameterisable branches (RepZeroLinear semantics) next to
+        value_proj / output_proj.  Parameter names contain "adapter", which is what the reference's
+        ``before_train`` un-freezes (groundingdino_dual_zero_rep_branch.py:722-734)."""
+        dev, dt = self.value_proj.weight.device, self.value_proj.weight.dtype
+        if value_proj and self.value_proj_adapter is None:
+            self.value_proj_adapter = RepZeroLinear(self.embed_dim, self.embed_dim).to(device=dev, dtype=dt)
+        if output_proj and self.output_proj_adapter is None:
+            self.output_proj_adapter = RepZeroLinear(self.embed_dim, self.embed_dim).to(device=dev, dtype=dt)
+        return self
+
+    def _project(self, x, base, adapter):
+        """``base(x)`` plus, when present, the ZiRa branch: train ``base(x) + s*branch(x) + freeze(x)``
+        (+ zero-inter loss), eval ``base(x) + freeze(x)``  (caller-side sum as in
+        groundingdino_dual_zero_rep_branch.py:459-462)."""
+        if adapter is None:
+            return F.linear(x, base.weight, base.bias), None
+        return adapter.forward_folded(x, base.weight, base.bias)
+
+    def forward(self, query: torch.Tensor, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
+                query_pos: Optional[torch.Tensor] = None, key_padding_mask: Optional[torch.Tensor] = None,
+                reference_points: Optional[torch.Tensor] = None, spatial_shapes: Optional[torch.Tensor] = None,
+                level_start_index: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        """Same contract as the reference forward (ms_deform_attn.py:229-355); ``key`` is ignored."""
+        if value is None:
+            value = query
+        if query_pos is not None:
+            query = query + query_pos
+        if not self.batch_first:
+            query = query.permute(1, 0, 2)
+            value = value.permute(1, 0, 2)
+
+        bs, num_query, _ = query.shape
+        bs, num_value, _ = value.shape
+        assert sum(h * w for h, w in _host_shapes(spatial_shapes)) == num_value
+        if not value.is_cuda:
+            raise RuntimeError("MultiScaleDeformableAttention (B200) has no CPU path; got a %s tensor" % value.device)
+
+        M, L, P = self.num_heads, self.num_levels, self.num_points
+        value, loss_v = self._project(value, self.value_proj, self.value_proj_adapter)
+        if key_padding_mask is not None:
+            value = value.masked_fill(key_padding_mask[..., None], float(0))
+        value = value.view(bs, num_value, M, -1)
+        acc_dtype = torch.float64 if value.dtype == torch.float64 else torch.float32
+        # 16-bit activations: offsets -> locations and the softmax are evaluated in fp32
+        sampling_offsets = self.sampling_offsets(query).view(bs, num_query, M, L, P, 2).to(acc_dtype)
+        reference_points = reference_points.to(acc_dtype)
+        attention_weights = self.attention_weights(query).view(bs, num_query, M, L * P)
+        attention_weights = attention_weights.softmax(-1, dtype=acc_dtype).view(bs, num_query, M, L, P)
+
+        if reference_points.shape[-1] == 2:
+            offset_normalizer = torch.stack([spatial_shapes[..., 1], spatial_shapes[..., 0]], -1)
+            sampling_locations = (reference_points[:, :, None, :, None, :]
+                                  + sampling_offsets / offset_normalizer[None, None, None, :, None, :])
+        elif reference_points.shape[-1] == 4:
+            sampling_locations = (reference_points[:, :, None, :, None, :2]
+                                  + sampling_offsets / P * reference_points[:, :, None, :, None, 2:] * 0.5)
+        else:
+            raise ValueError("Last dim of reference_points must be 2 or 4, but get {} instead.".format(
+                reference_points.shape[-1]))
+
+        output = MultiScaleDeformableAttnFunction.apply(
+            value.contiguous(), spatial_shapes, level_start_index,
+            sampling_locations.contiguous(), attention_weights.contiguous(), self.im2col_step)
+
+        output, loss_o = self._project(output, self.output_proj, self.output_proj_adapter)
+        self.zero_inter_loss = None
+        if loss_v is not None or loss_o is not None:
+            self.zero_inter_loss = sum(x for x in (loss_v, loss_o) if x is not None)
+        if not self.batch_first:
+            output = output.permute(1, 0, 2)
+        return output

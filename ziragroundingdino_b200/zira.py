@@ -1,0 +1,82 @@
+"""ZiRa re-parameterisable zero-initialised branches.
+
+Semantics follow the reference's ``RepZeroLinear`` (groundingdino_dual_zero_rep_branch.py:105-135;
+constants :62-64; merge trigger ``after_train`` :739-745):
+
+  construct  branch weight := 1e-8, branch bias keeps nn.Linear's default init, scaling := 0.1,
+             freeze_linear weight/bias := 0
+  train      branch = scaling * (W_b x + b_b);  out = branch + (W_f x + b_f)
+             returns (out, SmoothL1(branch, 0) + SmoothL1(out, 0))
+  eval       returns (W_f x + b_f, 0)           -- an un-merged branch is ignored in eval
+  __rep__    W_f += scaling*W_b ; b_f += scaling*b_b ; scaling := 0.1 ; W_b := 1e-8 ; b_b := 1e-8
+
+Parameter names (``weight``, ``bias``, ``scaling``, ``freeze_linear.weight``, ``freeze_linear.bias``)
+match the reference so its optimiser rule (lr factor for names containing "freeze",
+test_odinw13_softfreeze/for_train/*.py:24) applies unchanged.
+
+``forward_folded`` is the extension BASELINE.json asks for: the branch sits beside a frozen
+``nn.Linear`` (value_proj / output_proj of MultiScaleDeformableAttention) and the three weight sets
+(pretrained W_0, soft-frozen W_f, fresh s*W_b) are contracted in ONE pass over the activation.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+zero_value = 1e-8
+lan_scale = 0.1
+
+
+class RepZeroLinear(nn.Linear):
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None) -> None:
+        super().__init__(in_features, out_features, bias, device, dtype)
+        self.scaling = nn.parameter.Parameter(torch.ones(1, device=device, dtype=dtype) * lan_scale)
+        nn.init.constant_(self.weight, val=zero_value)
+        self.freeze_linear = nn.Linear(in_features, out_features, bias, device, dtype)
+        nn.init.constant_(self.freeze_linear.weight, val=0.0)
+        if self.bias is not None:
+            nn.init.constant_(self.freeze_linear.bias, val=0.0)
+        self.zero_inter_loss = torch.nn.SmoothL1Loss(reduction="mean")
+
+    def forward(self, input):
+        """Stand-alone use, exactly the reference contract: returns ``(output, zero_inter_loss)``."""
+        if self.training:
+            branch_output = self.scaling * F.linear(input, self.weight, self.bias)
+            output = branch_output + self.freeze_linear(input)
+            loss = (self.zero_inter_loss(branch_output, torch.zeros_like(branch_output))
+                    + self.zero_inter_loss(output, torch.zeros_like(output)))
+            return output, loss
+        return self.freeze_linear(input), torch.zeros(1).to(input)
+
+    def forward_folded(self, input, base_weight, base_bias):
+        """``F.linear(input, base_weight, base_bias) + self(input)[0]`` and the zero-inter loss.
+
+        Weight-space fold: one [out, 2*in]... GEMM over the activation is not needed -- the three weight
+        sets are summed (a 256x256 axpy) and applied once; the loss terms need the branch and the
+        adapter output separately, so in training the branch and freeze products are formed too.
+        """
+        if not self.training:
+            w = base_weight + self.freeze_linear.weight
+            b = None if base_bias is None else base_bias + self.freeze_linear.bias
+            return F.linear(input, w, b), None
+        branch = self.scaling * F.linear(input, self.weight, self.bias)
+        adapter_out = branch + self.freeze_linear(input)
+        loss = (self.zero_inter_loss(branch, torch.zeros_like(branch))
+                + self.zero_inter_loss(adapter_out, torch.zeros_like(adapter_out)))
+        return F.linear(input, base_weight, base_bias) + adapter_out, loss
+
+    def __rep__(self):
+        with torch.no_grad():
+            self.freeze_linear.weight.data = self.weight.data * self.scaling + self.freeze_linear.weight.data
+            if self.bias is not None:
+                self.freeze_linear.bias.data = self.bias.data * self.scaling + self.freeze_linear.bias.data
+        self.scaling = nn.parameter.Parameter(torch.ones(1).to(self.weight.data) * lan_scale)
+        nn.init.constant_(self.weight, val=zero_value)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, val=zero_value)
+
+
+def merge_all(module: nn.Module):
+    """The reference's ``after_train`` (groundingdino_dual_zero_rep_branch.py:739-745): merge every branch."""
+    for m in module.modules():
+        if hasattr(m, "__rep__"):
+            m.__rep__()
