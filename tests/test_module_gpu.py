@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 def _load_module(g, dtype, dev):
     import ziragroundingdino_b200 as zb
     C, M, L, P, bf = (int(x) for x in g["cfg"])
-    m = zb.MultiScaleDeformableAttention(C, M, L, P, batch_first=bool(bf))
+    m = zb.MultiScaleDeformableAttention(C, M, L, P, batch_first=bool(bf)).double()  # fixtures are fp64
     m.load_state_dict({k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
     return m.to(device=dev, dtype=dtype), (C, M, L, P, bool(bf))
 

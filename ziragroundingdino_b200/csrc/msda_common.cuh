@@ -14,11 +14,11 @@ constexpr int kThreads = kWarpsPerBlock * 32;
 
 // Kernel-variant knobs (msda_b200_set_tuning); the defaults are the shipped configuration.
 struct Tuning {
-  int fwd_sample_batch = 2;  // samples whose 4 corner loads are issued back to back
+  int fwd_sample_batch = 4;  // samples whose 4 corner loads are issued back to back
   int fwd_q_fast = 1;        // lane groups of a warp span consecutive queries of one head
-  int fwd_passes = 4;        // consecutive unit tiles handled by one CTA
+  int fwd_passes = 1;        // consecutive unit tiles handled by one CTA
   int bwd_q_fast = 1;
-  int bwd_passes = 4;
+  int bwd_passes = 1;
 };
 extern Tuning g_tuning;
 extern long long g_launches;

@@ -18,6 +18,8 @@
 //    reduce-scatter (14 shuffles per 4 samples for D=32 fp32) instead of shared memory plus a serial
 //    loop on thread 0, and every (q, m, l, p) slot of both is written exactly once, so neither
 //    needs a memset.
+#include <type_traits>
+
 #include "msda_common.cuh"
 
 namespace msda {
@@ -169,6 +171,32 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
 
     float g[CH];
     Vec<VT>::load(grad_out + static_cast<size_t>(u) * D + lig * CH, active, g);
+    // Channels this lane REDUCES into grad_value.  fp32: the 4 it loads.  16-bit storage: a lane
+    // loads 8 contiguous channels (16 B) but the fp32 gradient of those is 32 B, so issuing them as
+    // two 16-byte reductions would leave every 32-byte L2 sector half written per instruction.
+    // Instead the lane reduces channels [4*lig, +4) and [4*LPG + 4*lig, +4): each instruction of the
+    // group then covers a contiguous 16*LPG bytes.  Costs one extra 2 x 8-byte load of grad_out per unit.
+    float gr[CH];
+    if constexpr (CH == 4) {
+#pragma unroll
+      for (int c = 0; c < CH; ++c) gr[c] = g[c];
+    } else {
+      const VT* gp = grad_out + static_cast<size_t>(u) * D;
+      const uint2 lo = active ? __ldg(reinterpret_cast<const uint2*>(gp + 4 * lig)) : make_uint2(0u, 0u);
+      const uint2 hi = active ? __ldg(reinterpret_cast<const uint2*>(gp + 4 * LPG + 4 * lig)) : make_uint2(0u, 0u);
+      const uint32_t w[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if constexpr (sizeof(VT) == 2 && !std::is_same<VT, __half>::value) {
+          gr[2 * i] = __uint_as_float(w[i] << 16);
+          gr[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        } else {
+          const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+          gr[2 * i] = t2.x;
+          gr[2 * i + 1] = t2.y;
+        }
+      }
+    }
 
     for (int l = 0; l < L; ++l) {
       const int H = sH[l], W = sW[l];
@@ -212,10 +240,13 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         red[4 * p + 3] = 0.f;
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 4) {
-          if (t.c1) red_add_v4(gvl + e1 + c0, k1 * tg[c0], k1 * tg[c0 + 1], k1 * tg[c0 + 2], k1 * tg[c0 + 3]);
-          if (t.c2) red_add_v4(gvl + e2 + c0, k2 * tg[c0], k2 * tg[c0 + 1], k2 * tg[c0 + 2], k2 * tg[c0 + 3]);
-          if (t.c3) red_add_v4(gvl + e3 + c0, k3 * tg[c0], k3 * tg[c0 + 1], k3 * tg[c0 + 2], k3 * tg[c0 + 3]);
-          if (t.c4) red_add_v4(gvl + e4 + c0, k4 * tg[c0], k4 * tg[c0 + 1], k4 * tg[c0 + 2], k4 * tg[c0 + 3]);
+          // element offset of this 4-channel slice relative to the lane's load slice (see `gr` above)
+          const int ro = (CH == 4) ? 0 : ((c0 == 0 ? 4 * lig : 4 * LPG + 4 * lig) - CH * lig);
+          const float r0 = gr[c0] * a, r1 = gr[c0 + 1] * a, r2 = gr[c0 + 2] * a, r3 = gr[c0 + 3] * a;
+          if (t.c1) red_add_v4(gvl + e1 + ro, k1 * r0, k1 * r1, k1 * r2, k1 * r3);
+          if (t.c2) red_add_v4(gvl + e2 + ro, k2 * r0, k2 * r1, k2 * r2, k2 * r3);
+          if (t.c3) red_add_v4(gvl + e3 + ro, k3 * r0, k3 * r1, k3 * r2, k3 * r3);
+          if (t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
         }
       }
       reduce_scatter16<LPG>(red, lig);
