@@ -105,6 +105,33 @@ int msda_b200_get_tuning(const char *key);
 /* Number of kernel launches issued through this library by the calling process so far. */
 long long msda_b200_launch_count(void);
 
+/* ---- projections: replace the four nn.Linear calls of MultiScaleDeformableAttention.forward ------
+ * (ms_deform_attn.py:184-187 parameters; :286 value_proj, :290 sampling_offsets, :293 attention_weights,
+ * :350 output_proj) and the elementwise passes between them, as tcgen05/TMA GEMMs over 16-bit (bf16, or
+ * IEEE half when is_half != 0) activations with fp32 accumulation.  X is [R, K] row-major, W is the
+ * nn.Linear weight [Nout, K] row-major, bias fp32.  K % 64 == 0; Nout % 32 == 0; Nout <= 1024.
+ *
+ * msda_linear_16: out[r, :] = X[r, :] W^T + bias, rows with row_mask[r] != 0 written as zero (the
+ *   masked_fill of :287-288; pass NULL for none).  out is 16-bit (out_f32 == 0) or fp32, leading
+ *   dimension out_ld elements.  Also used for the dgrad products (pass W^T as `w`).
+ * msda_query_proj_16: the sampling_offsets and attention_weights linears share their input, so they run as
+ *   ONE GEMM against w_cat = [W_offsets; W_attention] ([3*M*L*P, K]); the epilogue turns offsets into
+ *   sampling locations (:306-319; ref is [R, L, ref_dim], ref_dim 2 or 4) and logits into softmax
+ *   weights (:296), writing loc_out [R, M, L, P, 2] and aw_out [R, M, L, P] in fp32 -- exactly the two
+ *   tensors msda_forward_* consumes.  Needs (L*P) | 32 and M*L*P % 32 == 0.
+ * msda_query_bwd_prep_16 / msda_cast_mask_16: elementwise backward companions (see proj_elementwise.cu). */
+int msda_linear_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out,
+                   int out_ld, int out_f32, const uint8_t *row_mask, int is_half, void *stream);
+int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_cat, const float *ref, int ref_dim,
+                       const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
+                       float *aw_out, int is_half, void *stream);
+int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const float *aw, const float *ref, int ref_dim,
+                           const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int is_half,
+                           void *stream);
+int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, int cols, void *out, int is_half,
+                      void *stream);
+const char *msda_b200_gemm_last_error(void);
+
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
  * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =
  * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */

@@ -1,0 +1,180 @@
+"""GPU: the tcgen05/TMA projection GEMMs and their fused epilogues against fp64 PyTorch references of
+the same ops on the same (16-bit-rounded) inputs; fp32 accumulation => tolerance 1e-4 relative on fp32
+outputs, one 16-bit rounding (2^-8 bf16, 2^-11 f16) on 16-bit outputs."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(dtype).to(DEV)
+
+
+@pytest.mark.parametrize("R", [1, 127, 128, 129, 1000, 22223, 4 * 22223 + 5])
+@pytest.mark.parametrize("K,Nout", [(256, 256), (256, 128), (384, 256), (64, 32), (256, 384), (512, 64)])
+def test_linear16_fp32_out(R, K, Nout):
+    from ziragroundingdino_b200 import fused
+    if R > 30000 and (K, Nout) != (256, 256):
+        pytest.skip("large R only for the model shape")
+    x, w = _rand((R, K), torch.bfloat16, 1), _rand((Nout, K), torch.bfloat16, 2, 0.06)
+    b = _rand((Nout,), torch.float32, 3)
+    y = fused.linear16(x, w, b, out_f32=True)
+    ref = x.double() @ w.double().t() + b.double()
+    assert y.shape == (R, Nout) and y.dtype == torch.float32
+    assert rel_err(y.cpu(), ref.cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("dtype,eps", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)])
+def test_linear16_16bit_out_and_row_mask(dtype, eps):
+    from ziragroundingdino_b200 import fused
+    R, K, Nout = 3001, 256, 256
+    x, w, b = _rand((R, K), dtype, 4), _rand((Nout, K), dtype, 5, 0.06), _rand((Nout,), torch.float32, 6)
+    mask = (torch.arange(R, device=DEV) % 5 == 0).to(torch.uint8)
+    y = fused.linear16(x, w, b, row_mask=mask)
+    ref = (x.double() @ w.double().t() + b.double()) * (1 - mask.double())[:, None]
+    assert y.dtype == dtype
+    assert (y.double() - ref).abs().max().item() <= eps * ref.abs().max().item() * 1.01
+    assert y[mask.bool()].abs().max().item() == 0
+    y2 = fused.linear16(x, w, None)                      # no bias, no mask
+    assert rel_err(y2.double().cpu(), (x.double() @ w.double().t()).cpu()) < 2 * eps
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("M,L,P", [(8, 4, 4), (4, 2, 4), (8, 4, 2), (16, 2, 1)])
+def test_query_proj16(ref_dim, M, L, P):
+    from ziragroundingdino_b200 import fused
+    R, K = 2500, 256
+    n_aw = M * L * P
+    q = _rand((R, K), torch.bfloat16, 7)
+    w = _rand((3 * n_aw, K), torch.bfloat16, 8, 0.05)
+    b = _rand((3 * n_aw,), torch.float32, 9)
+    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)][:L], device=DEV)
+    g = torch.Generator().manual_seed(10)
+    ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
+    loc, aw = fused.query_proj16(q, w, b, ref, ref_dim, shapes, M, L, P)
+    pre = q.double() @ w.double().t() + b.double()
+    off = pre[:, :2 * n_aw].view(R, M, L, P, 2)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).double()
+        want_loc = ref.double()[:, None, :, None, :] + off / norm[None, None, :, None, :]
+    else:
+        want_loc = ref.double()[:, None, :, None, :2] + off / P * ref.double()[:, None, :, None, 2:] * 0.5
+    want_aw = pre[:, 2 * n_aw:].view(R, M, L * P).softmax(-1).view(R, M, L, P)
+    assert (loc.double() - want_loc).abs().max().item() < 1e-5
+    assert (aw.double() - want_aw).abs().max().item() < 1e-5
+    assert (aw.sum((-1, -2)) - 1).abs().max().item() < 1e-5
+
+
+def test_backward_elementwise_kernels():
+    from ziragroundingdino_b200 import fused
+    R, M, L, P = 777, 8, 4, 4
+    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)], device=DEV)
+    g = torch.Generator().manual_seed(11)
+    gl = torch.randn(R, M, L, P, 2, generator=g).to(DEV)
+    ga = torch.randn(R, M, L, P, generator=g).to(DEV)
+    aw = torch.randn(R, M, L * P, generator=g).softmax(-1).view(R, M, L, P).to(DEV)
+    for ref_dim in (2, 4):
+        ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
+        out = fused.query_bwd_prep16(gl, ga, aw, ref, ref_dim, shapes, R, M, L, P, torch.bfloat16)
+        if ref_dim == 2:
+            norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
+            d_off = gl / norm[None, None, :, None, :]
+        else:
+            d_off = gl * ref[:, None, :, None, 2:] * 0.5 / P
+        a2, g2 = aw.view(R, M, L * P), ga.view(R, M, L * P)
+        d_logit = a2 * (g2 - (g2 * a2).sum(-1, keepdim=True))
+        want = torch.cat([d_off.reshape(R, -1), d_logit.reshape(R, -1)], 1)
+        assert (out.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() * 1.01
+    x = torch.randn(999, 256, generator=g).to(DEV)
+    mask = (torch.arange(999, device=DEV) % 3 == 0).to(torch.uint8)
+    y = fused.cast_mask16(x, mask, torch.bfloat16)
+    assert torch.equal(y, (x * (1 - mask.float())[:, None]).to(torch.bfloat16))
+    assert torch.equal(fused.cast_mask16(x, None, torch.float16), x.half())
+
+
+def _module_inputs(N, shapes, C, dtype, Lq=None, ref_dim=2, seed=0):
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import synthetic as syn
+    torch.manual_seed(seed)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    sh, lsi = syn.level_tensors(shapes, DEV)
+    m = zb.MultiScaleDeformableAttention(C, 8, L, 4, batch_first=True)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.02)
+        m.attention_weights.weight.normal_(0, 0.05)
+        m.value_proj.bias.normal_(0, 0.1)
+    m = m.to(DEV).to(dtype)
+    src = torch.randn(N, S, C, device=DEV).to(dtype)
+    if Lq is None:
+        refp = syn.encoder_reference_points(shapes, torch.ones(N, L, 2, device=DEV), DEV)
+        query = (src.float() + torch.randn(N, S, C, device=DEV) * 0.5).to(dtype)
+    else:
+        refp = torch.rand(N, Lq, L, ref_dim, device=DEV) * 0.5 + 0.2
+        query = torch.randn(N, Lq, C, device=DEV).to(dtype)
+    mask = torch.zeros(N, S, dtype=torch.bool, device=DEV)
+    mask[0, S - S // 5:] = True
+    return m, query, src, refp, sh, lsi, mask
+
+
+@pytest.mark.parametrize("case", ["encoder", "decoder4"])
+def test_module_fused_vs_unfused_and_oracle(case):
+    """bf16 module: fused tcgen05 path vs the unfused path (cuBLAS linears + torch elementwise) and vs the
+    fp64 oracle restatement of the reference module on the bf16-rounded weights/inputs (bar 1e-2)."""
+    import ziragroundingdino_b200 as zb
+    from oracle import msda_oracle as O
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(2, shapes, 256, torch.bfloat16,
+                                                        Lq=None if case == "encoder" else 300, ref_dim=4)
+    for p in m.parameters():
+        p.requires_grad_(True)
+    outs, grads = {}, {}
+    for fused_on in (True, False):
+        zb.MultiScaleDeformableAttention.fused_enabled = fused_on
+        try:
+            q, v = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+            m.zero_grad()
+            n0 = zb._lib.launch_count()
+            y = m(query=q, value=v, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+            gy = torch.randn(y.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)).to(y.dtype)
+            y.backward(gy)
+            outs[fused_on] = y.detach().float()
+            grads[fused_on] = dict(q=q.grad.float(), v=v.grad.float(), **{k: p.grad.float() for k, p in m.named_parameters()})
+            launches = zb._lib.launch_count() - n0
+            assert launches == (10 if fused_on else 2), launches
+        finally:
+            zb.MultiScaleDeformableAttention.fused_enabled = True
+    params = {k: p.detach().double().cpu() for k, p in m.state_dict().items()}
+    truth = O.module_forward(params, query.double().cpu(), src.double().cpu(), mask.cpu(), refp.double().cpu(), sh.cpu(), 8, 4, 4)
+    scale = truth.abs().max().item()
+    assert (outs[True].double().cpu() - truth).abs().max().item() < 1e-2 * scale
+    assert (outs[False].double().cpu() - truth).abs().max().item() < 2e-2 * scale
+    for k in grads[True]:
+        a, b = grads[True][k], grads[False][k]
+        assert (a - b).abs().max().item() < 4e-2 * b.abs().max().item() + 1e-6, k
+
+
+def test_module_fused_f16_and_eval_fold():
+    import ziragroundingdino_b200 as zb
+    shapes = [(12, 16), (6, 8), (3, 4), (2, 2)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(1, shapes, 256, torch.float16)
+    m.add_zira_branches()
+    with torch.no_grad():
+        m.value_proj_adapter.freeze_linear.weight.normal_(0, 0.02)
+        m.output_proj_adapter.freeze_linear.bias.normal_(0, 0.1)
+    m.eval()
+    kw = dict(query=query, value=src, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    y_f = m(**kw)
+    zb.MultiScaleDeformableAttention.fused_enabled = False
+    try:
+        y_u = m(**kw)
+    finally:
+        zb.MultiScaleDeformableAttention.fused_enabled = True
+    assert y_f.dtype == torch.float16
+    assert (y_f.float() - y_u.float()).abs().max().item() < 1e-2 * y_u.float().abs().max().item()

@@ -247,7 +247,14 @@ def test_config1_vs_fp64_truth_and_reference_cuda_op():
         d_new, d_oracle, np.abs(out.numpy() - o32).max()))
     assert np.abs(out.numpy() - o32).max() < 1e-5
     assert d_new < 4e-5          # the reference's own fp32 paths sit at ~2e-5 here
-    assert rel_err(gv, tgv) < 1e-4 and rel_err(gl, tgl) < 1e-4 and rel_err(ga, tga) < 1e-4
+    ogv, ogl, oga = O.c_backward(value.numpy(), sh.numpy(), loc.numpy(), aw.numpy(), gout.numpy())
+    assert rel_err(gv, ogv) < 1e-4 and rel_err(gl, ogl) < 1e-4 and rel_err(ga, oga) < 1e-4
+    # vs fp64 truth: grad_value / grad_attn_weight are continuous in loc; grad_sampling_loc is not (floor):
+    # a sample within fp32 round-off of a pixel boundary legitimately lands in the neighbouring cell, so
+    # that comparison is made on the fraction of slots that agree.
+    assert rel_err(gv, tgv) < 1e-4 and rel_err(ga, tga) < 1e-4
+    bad = np.abs(gl.numpy().astype(np.float64) - tgl) > 1e-4 * np.abs(tgl).max()
+    assert bad.mean() < 1e-5, bad.mean()
     ref = build_ref.load()
     if ref is None:
         pytest.skip("oracle/_ref/ref_C.so not built (reference sources absent at build time)")

@@ -98,9 +98,10 @@ def main():
         emit(f, kind="env", gpu=torch.cuda.get_device_name(0), sms=torch.cuda.get_device_properties(0).multi_processor_count)
         if "--no-probe" not in sys.argv:
             probe(f)
-        core(f, "c1_f32_local_N1", syn.SWIN_T_800x1333, 1, torch.float32, "local")
+        quick = "--quick" in sys.argv
+        core(f, "c1_f32_local_N1", syn.SWIN_T_800x1333, 1, torch.float32, "local", full=not quick)
         core(f, "c1_f32_uniform_N1", syn.SWIN_T_800x1333, 1, torch.float32, "uniform", full=False)
-        core(f, "c2_bf16_local_N4", syn.SWIN_T_800x1333, 4, torch.bfloat16, "local")
+        core(f, "c2_bf16_local_N4", syn.SWIN_T_800x1333, 4, torch.bfloat16, "local", full=not quick)
         core(f, "c2_bf16_uniform_N4", syn.SWIN_T_800x1333, 4, torch.bfloat16, "uniform", full=False)
         core(f, "c2_f32_local_N4", syn.SWIN_T_800x1333, 4, torch.float32, "local", full=False)
         core(f, "dec_bf16_local_N4", syn.SWIN_T_800x1333, 4, torch.bfloat16, "local", Lq=900, full=False)

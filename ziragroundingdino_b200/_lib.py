@@ -44,6 +44,11 @@ def lib():
     for sfx in ("f32", "f64", "bf16", "f16"):
         getattr(L, "msda_forward_" + sfx).argtypes = _FWD
         getattr(L, "msda_backward_" + sfx).argtypes = _BWD
+    L.msda_b200_gemm_last_error.restype = ctypes.c_char_p
+    L.msda_linear_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp]
+    L.msda_query_proj_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]
+    L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _vp]
+    L.msda_cast_mask_16.argtypes = [_vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     _lib = L
     return L
@@ -51,7 +56,7 @@ def lib():
 
 def check(rc, what):
     if rc != 0:
-        msg = lib().msda_b200_last_error().decode()
+        msg = lib().msda_b200_last_error().decode() or lib().msda_b200_gemm_last_error().decode()
         raise RuntimeError("%s failed (status %d): %s" % (what, rc, msg))
 
 

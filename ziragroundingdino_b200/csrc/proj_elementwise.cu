@@ -1,0 +1,110 @@
+// Elementwise companions of the projection GEMMs (backward side of ms_deform_attn.py:286-325).
+//
+//  * query_bwd_prep: turns the core op's grad_sampling_loc / grad_attn_weight into the gradient of the
+//    stacked [sampling_offsets | attention_weights] pre-activations, in the 16-bit type the dgrad GEMM
+//    consumes: d_off = grad_loc / (W_l, H_l)            (2-d reference points, :306-311)
+//              d_off = grad_loc * ref_wh * 0.5 / P      (4-d reference boxes,  :312-319)
+//              d_logit = aw * (grad_aw - sum_j grad_aw_j * aw_j)   over each run of L*P (softmax, :296)
+//  * cast_mask: fp32 grad_value -> 16-bit with padded rows zeroed (backward of masked_fill, :287-288).
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+namespace msda {
+extern long long g_launches;
+}
+
+namespace {
+
+__device__ __forceinline__ uint16_t to16(float v, bool is_half) {
+  if (is_half) { __half h = __float2half_rn(v); return *reinterpret_cast<uint16_t*>(&h); }
+  __nv_bfloat16 h = __float2bfloat16_rn(v);
+  return *reinterpret_cast<uint16_t*>(&h);
+}
+
+// one thread per (row, head): 2*L*P offset gradients + L*P logit gradients
+__global__ void __launch_bounds__(256)
+query_bwd_prep_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_aw, const float* __restrict__ aw,
+                      const float* __restrict__ ref, const int64_t* __restrict__ shapes, long long R, int M, int L, int P,
+                      int ref_dim, int is_half, uint16_t* __restrict__ out) {
+  __shared__ float s_norm[MSDA_MAX_LEVELS * 2];
+  if (threadIdx.x < L) {
+    s_norm[2 * threadIdx.x] = static_cast<float>(shapes[2 * threadIdx.x + 1]);
+    s_norm[2 * threadIdx.x + 1] = static_cast<float>(shapes[2 * threadIdx.x]);
+  }
+  __syncthreads();
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= R * M) return;
+  const long long row = idx / M;
+  const int m = static_cast<int>(idx % M);
+  const int lp = L * P, n_aw = M * lp, n_loc = 2 * n_aw, ld = n_loc + n_aw;
+  const float* gl = grad_loc + row * n_loc + m * lp * 2;
+  const float* ga = grad_aw + row * n_aw + m * lp;
+  const float* a = aw + row * n_aw + m * lp;
+  const float* rp = ref + row * L * ref_dim;
+  uint16_t* o_off = out + row * ld + m * lp * 2;
+  uint16_t* o_aw = out + row * ld + n_loc + m * lp;
+  float dot = 0.f;
+  for (int j = 0; j < lp; ++j) dot = fmaf(ga[j], a[j], dot);
+  for (int j = 0; j < lp; ++j) o_aw[j] = to16(a[j] * (ga[j] - dot), is_half != 0);
+  for (int l = 0; l < L; ++l) {
+    float sx, sy;
+    if (ref_dim == 2) { sx = 1.f / s_norm[2 * l]; sy = 1.f / s_norm[2 * l + 1]; }
+    else { sx = rp[l * 4 + 2] * 0.5f / P; sy = rp[l * 4 + 3] * 0.5f / P; }
+    for (int p = 0; p < P; ++p) {
+      const int j = (l * P + p) * 2;
+      o_off[j] = to16(gl[j] * sx, is_half != 0);
+      o_off[j + 1] = to16(gl[j + 1] * sy, is_half != 0);
+    }
+  }
+}
+
+// 8 elements per thread; `cols` (row length) must be a multiple of 8
+__global__ void __launch_bounds__(256)
+cast_mask_kernel(const float* __restrict__ in, const uint8_t* __restrict__ row_mask, long long n8, int cols8, int is_half,
+                 uint4* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const bool zero = row_mask != nullptr && row_mask[i / cols8] != 0;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+  uint4 w;
+  const bool h = is_half != 0;
+  w.x = to16(a.x, h) | (static_cast<uint32_t>(to16(a.y, h)) << 16);
+  w.y = to16(a.z, h) | (static_cast<uint32_t>(to16(a.w, h)) << 16);
+  w.z = to16(b.x, h) | (static_cast<uint32_t>(to16(b.y, h)) << 16);
+  w.w = to16(b.z, h) | (static_cast<uint32_t>(to16(b.w, h)) << 16);
+  out[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
+}
+}  // namespace
+
+extern "C" {
+
+int msda_query_bwd_prep_16(const float* grad_loc, const float* grad_aw, const float* aw, const float* ref, int ref_dim,
+                           const int64_t* spatial_shapes, long long R, int M, int L, int P, void* out, int is_half,
+                           void* stream) {
+  if (!grad_loc || !grad_aw || !aw || !ref || !spatial_shapes || !out) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || M <= 0 || L <= 0 || L > MSDA_MAX_LEVELS || P <= 0 || (ref_dim != 2 && ref_dim != 4)) return MSDA_ERR_BAD_SHAPE;
+  const long long n = R * M;
+  ++msda::g_launches;
+  query_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      grad_loc, grad_aw, aw, ref, spatial_shapes, R, M, L, P, ref_dim, is_half, static_cast<uint16_t*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+int msda_cast_mask_16(const float* in, const uint8_t* row_mask, long long rows, int cols, void* out, int is_half,
+                      void* stream) {
+  if (!in || !out) return MSDA_ERR_NULL_POINTER;
+  if (rows <= 0 || cols <= 0 || cols % 8) return MSDA_ERR_BAD_SHAPE;
+  const long long n8 = rows * (cols / 8);
+  ++msda::g_launches;
+  cast_mask_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      in, row_mask, n8, cols / 8, is_half, static_cast<uint4*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+}  // extern "C"

@@ -1,0 +1,462 @@
+// tcgen05 / TMA projection GEMMs for the MultiScaleDeformableAttention module (sm_100a only).
+//
+// Replaces the four nn.Linear calls of the reference module and the elementwise passes around them
+// (ms_deform_attn.py:286-325): value_proj + key-padding mask (:286-289), sampling_offsets ->
+// sampling locations (:290-292, :306-319), attention_weights -> softmax (:293-303) and output_proj
+// (:350).  Every one of them is Y[R, Nout] = X[R, K] * W[Nout, K]^T with K = 256: left of the B200
+// ridge, i.e. bound by reading X and writing Y, so the design goal is ONE pass over the activation
+// with everything else folded into the epilogue, not peak MMA rate.
+//
+// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+//   warp 0     TMA producer: cp.async.bulk.tensor 128x64 (A) and block_n x 64 (B) bf16 boxes, 128B swizzle,
+//              into a 4-stage shared-memory ring; completion on mbarriers (expect_tx).
+//   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n,
+//              K=16) four times per stage; tcgen05.commit releases the stage and, after the last K
+//              block, publishes the accumulator.  Also owns the TMEM allocation (2 x block_n columns).
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers (thread = one output row, 32
+//              consecutive columns), bias + {mask | sampling-location | softmax} math, direct 16-byte
+//              stores.  Double-buffered accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/msda_b200.h"
+
+namespace msda {
+extern long long g_launches;
+}
+
+namespace pg {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int SMEM_A = BLOCK_M * BLOCK_K * 2;   // 16 KiB
+constexpr int MAX_N = 1024;              // widest stacked weight handled by one launch
+constexpr int THREADS = 192;
+constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
+
+enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1 };
+
+struct EpiParams {
+  int mode;
+  // EPI_STORE: out[row * out_ld + col] = acc + bias[col]  (row zeroed when row_mask[row] != 0)
+  void* out;
+  int out_ld;
+  int out_f32;             // 1: fp32 output, 0: same 16-bit type as the inputs
+  int out_half;            // 16-bit output is IEEE half instead of bf16
+  const float* bias;       // [Nout] fp32, may be null
+  const uint8_t* row_mask; // [R] or null
+  // EPI_QUERY: columns [0, n_loc) are sampling offsets laid out (m, l, p, xy); columns [n_loc, n_loc + n_aw)
+  // are attention logits laid out (m, l*p).
+  float* loc_out;          // [R, n_loc]
+  float* aw_out;           // [R, n_aw]
+  const float* ref;        // [R, L, ref_dim]
+  const int64_t* shapes;   // device [L, 2] (H, W)
+  int ref_dim, L, P, n_loc, n_aw;
+};
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile with 128-byte swizzle: rows are 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile, int k_byte_offset) {
+  const uint32_t addr = smem_u32(smem_tile) + k_byte_offset;
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);        // start address, bits [0,14)
+  d |= static_cast<uint64_t>(0) << 16;                      // leading byte offset: unused for swizzled K-major
+  d |= static_cast<uint64_t>((1024 >> 4) & 0x3fff) << 32;   // stride byte offset, bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                      // layout: SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, 16-bit inputs (bf16 or half)
+__host__ __device__ inline uint32_t umma_idesc(int m, int n, bool half_in) {
+  const uint32_t fmt = half_in ? 0u : 1u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, bool half_out) {
+  if (half_out) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ---- epilogue bodies: one thread = one row, 32 consecutive columns starting at global column gc -----
+__device__ __forceinline__ void epi_store(const EpiParams& ep, const float (&v)[32], long long row, int gc) {
+  const bool zero = ep.row_mask != nullptr && ep.row_mask[row] != 0;
+  if (ep.out_f32) {
+    float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + row * ep.out_ld + gc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o[i] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + row * ep.out_ld + gc);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      uint4 w;
+      w.x = pack16(v[8 * i], v[8 * i + 1], ep.out_half != 0);
+      w.y = pack16(v[8 * i + 2], v[8 * i + 3], ep.out_half != 0);
+      w.z = pack16(v[8 * i + 4], v[8 * i + 5], ep.out_half != 0);
+      w.w = pack16(v[8 * i + 6], v[8 * i + 7], ep.out_half != 0);
+      o[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
+    }
+  }
+}
+
+// sampling locations (ms_deform_attn.py:306-319): columns are (m, l, p, xy)
+__device__ __forceinline__ void epi_loc(const EpiParams& ep, const float (&v)[32], long long row, int gc,
+                                        const float* s_norm) {
+  const float* rp = ep.ref + row * ep.L * ep.ref_dim;
+  float4* o = reinterpret_cast<float4*>(ep.loc_out + row * ep.n_loc + gc);
+  float r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int idx = gc + j, xy = idx & 1, l = (idx / (2 * ep.P)) % ep.L;
+    if (ep.ref_dim == 2) {
+      r[j] = rp[l * 2 + xy] + __fdiv_rn(v[j], s_norm[l * 2 + xy]);
+    } else {
+      r[j] = rp[l * 4 + xy] + __fdiv_rn(v[j], static_cast<float>(ep.P)) * rp[l * 4 + 2 + xy] * 0.5f;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+}
+
+// softmax over each run of L*P logits (ms_deform_attn.py:293-303); 32 % (L*P) == 0 is guaranteed by the host
+template <int LP>
+__device__ __forceinline__ void softmax_runs(float (&v)[32]) {
+#pragma unroll
+  for (int g0 = 0; g0 < 32; g0 += LP) {
+    float mx = v[g0];
+#pragma unroll
+    for (int j = 1; j < LP; ++j) mx = fmaxf(mx, v[g0 + j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < LP; ++j) { v[g0 + j] = __expf(v[g0 + j] - mx); sum += v[g0 + j]; }
+    const float inv = __fdividef(1.f, sum);
+#pragma unroll
+    for (int j = 0; j < LP; ++j) v[g0 + j] *= inv;
+  }
+}
+
+__device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32], long long row, int gc) {
+  const int lp = ep.L * ep.P;
+  if (lp == 16) softmax_runs<16>(v);
+  else if (lp == 32) softmax_runs<32>(v);
+  else if (lp == 8) softmax_runs<8>(v);
+  else if (lp == 4) softmax_runs<4>(v);
+  else if (lp == 2) softmax_runs<2>(v);
+  else softmax_runs<1>(v);
+  float4* o = reinterpret_cast<float4*>(ep.aw_out + row * ep.n_aw + (gc - ep.n_loc));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+
+// ---- the kernel -----------------------------------------------------------------------------------
+__global__ void __launch_bounds__(THREADS, 1)
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int Nout,
+                 int K, int block_n, int half_in, EpiParams ep) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = SMEM_A + block_n * BLOCK_K * 2;
+  uint8_t* aux = smem + STAGES * stage_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(aux + 256);
+  float* s_norm = s_bias + MAX_N;   // (W_l, H_l) as floats
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_k = K / BLOCK_K;
+  const int num_n = Nout / block_n;
+  const int num_m = (R + BLOCK_M - 1) / BLOCK_M;
+  const int num_tiles = num_m * num_n;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < static_cast<uint32_t>(2 * block_n)) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < Nout; i += THREADS) s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
+  if (ep.mode == EPI_QUERY && threadIdx.x < ep.L) {
+    s_norm[2 * threadIdx.x] = static_cast<float>(ep.shapes[2 * threadIdx.x + 1]);      // W
+    s_norm[2 * threadIdx.x + 1] = static_cast<float>(ep.shapes[2 * threadIdx.x]);      // H
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_idx = (t / num_n) * BLOCK_M, n_idx = (t % num_n) * block_n;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          mbar_expect_tx(full_bar + stage, static_cast<uint32_t>(stage_bytes));
+          tma_load_2d(&tmA, full_bar + stage, sa, kb * BLOCK_K, m_idx);
+          tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, kb * BLOCK_K, n_idx);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = umma_idesc(BLOCK_M, block_n, half_in != 0);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      mbar_wait(tempty_bar + acc, acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * block_n);
+      for (int kb = 0; kb < num_k; ++kb) {
+        mbar_wait(full_bar + stage, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint8_t* sa = smem + stage * stage_bytes;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(sa, k * UMMA_K * 2);
+            const uint64_t db = umma_desc_sw128(sa + SMEM_A, k * UMMA_K * 2);
+            umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);                      // smem stage free once these MMAs retire
+          if (kb == num_k - 1) umma_commit(tfull_bar + acc);    // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    const int quarter = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_idx = (t / num_n) * BLOCK_M, n_idx = (t % num_n) * block_n;
+      mbar_wait(tfull_bar + acc, acc_phase);
+      tc_fence_after();
+      const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * block_n);
+      for (int c0 = 0; c0 < block_n; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c0, r);
+        const int gc = n_idx + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[gc + j];
+        if (row < R) {
+          if (ep.mode == EPI_STORE) epi_store(ep, v, row, gc);
+          else if (gc < ep.n_loc) epi_loc(ep, v, row, gc, s_norm);
+          else epi_softmax(ep, v, row, gc);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- host side ------------------------------------------------------------------------------------
+thread_local char t_err[256] = "";
+
+static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// row-major [rows, cols] 16-bit matrix, box = box_rows x 64 columns, 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows, bool half_in) {
+  auto fn = encode_fn();
+  if (!fn) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled unavailable"); return MSDA_ERR_NO_DEVICE; }
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
+  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, half_in ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return MSDA_ERR_BAD_SHAPE; }
+  return 0;
+}
+
+static int launch(const void* x, const void* w, long long R, int K, int Nout, int block_n, bool half_in,
+                  const EpiParams& ep, cudaStream_t st) {
+  if (!x || !w) { snprintf(t_err, sizeof(t_err), "null operand"); return MSDA_ERR_NULL_POINTER; }
+  if (R <= 0 || R >= (1ll << 31) || K <= 0 || K % BLOCK_K || Nout <= 0 || Nout > MAX_N || block_n % 32 || block_n > 256 ||
+      block_n < 32 || Nout % block_n) {
+    snprintf(t_err, sizeof(t_err), "unsupported GEMM shape R=%lld K=%d Nout=%d block_n=%d", R, K, Nout, block_n);
+    return MSDA_ERR_UNSUPPORTED;
+  }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15u) {
+    snprintf(t_err, sizeof(t_err), "operands must be 16-byte aligned");
+    return MSDA_ERR_MISALIGNED;
+  }
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, x, R, K, BLOCK_M, half_in);
+  if (rc) return rc;
+  rc = make_map(&tmB, w, Nout, K, block_n, half_in);
+  if (rc) return rc;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int smem = STAGES * (SMEM_A + block_n * BLOCK_K * 2) + AUX_BYTES + 1024;
+  static int configured = 0;
+  if (configured < smem) {
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+    configured = 200 * 1024;
+  }
+  const long long tiles = ((R + BLOCK_M - 1) / BLOCK_M) * (Nout / block_n);
+  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  ++msda::g_launches;
+  linear_tc_kernel<<<grid, THREADS, smem, st>>>(tmA, tmB, static_cast<int>(R), Nout, K, block_n, half_in ? 1 : 0, ep);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "linear_tc_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  return 0;
+}
+
+}  // namespace pg
+
+extern "C" {
+
+const char* msda_b200_gemm_last_error(void) { return pg::t_err; }
+
+int msda_linear_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out,
+                   int out_ld, int out_f32, const uint8_t* row_mask, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out) { snprintf(pg::t_err, sizeof(pg::t_err), "null output"); return MSDA_ERR_NULL_POINTER; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = out; ep.out_ld = out_ld; ep.out_f32 = out_f32; ep.out_half = is_half; ep.bias = bias; ep.row_mask = row_mask;
+  int block_n = 128;
+  if (Nout % 128) block_n = (Nout % 64 == 0) ? 64 : 32;
+  return pg::launch(x, w, R, K, Nout, block_n, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_cat, const float* ref, int ref_dim,
+                       const int64_t* spatial_shapes, long long R, int K, int M, int L, int P, float* loc_out,
+                       float* aw_out, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!ref || !spatial_shapes || !loc_out || !aw_out) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  const int n_aw = M * L * P, n_loc = 2 * n_aw, lp = L * P;
+  if ((ref_dim != 2 && ref_dim != 4) || L > MSDA_MAX_LEVELS || lp > 32 || 32 % lp || n_aw % 32) {
+    snprintf(pg::t_err, sizeof(pg::t_err), "fused query projection needs L*P dividing 32 and M*L*P %% 32 == 0 (L=%d P=%d M=%d)", L, P, M);
+    return MSDA_ERR_UNSUPPORTED;
+  }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_QUERY;
+  ep.bias = bias_cat; ep.loc_out = loc_out; ep.aw_out = aw_out; ep.ref = ref; ep.shapes = spatial_shapes;
+  ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
+  int block_n = (n_aw % 128 == 0) ? 128 : (n_aw % 64 == 0 ? 64 : 32);
+  return pg::launch(query, w_cat, R, K, n_loc + n_aw, block_n, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

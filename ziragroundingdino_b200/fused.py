@@ -1,0 +1,136 @@
+"""Fused 16-bit execution of ``MultiScaleDeformableAttention.forward`` (reference ms_deform_attn.py:281-350).
+
+Five launches replace the reference's ~20 eager ops per call:
+
+  value_proj + key-padding mask ............ msda_linear_16        (tcgen05 GEMM, mask in the epilogue)
+  sampling_offsets | attention_weights ..... msda_query_proj_16    (ONE tcgen05 GEMM; epilogue = sampling
+                                             locations + softmax, fp32 out)
+  bilinear gather .......................... msda_forward_{bf16,f16}
+  output_proj .............................. msda_linear_16
+
+and the backward is: dgrad GEMM, scatter kernel, one elementwise prep kernel (softmax / location
+backward + down-cast), dgrad GEMM (K = 3*M*L*P), mask+cast kernel, dgrad GEMM.  Weight gradients, only
+needed when the module's own linears are trainable (they are frozen in the ZiRa configuration,
+groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:50), are plain library GEMMs.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _C, _lib
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def linear16(x2d, w, bias_f32=None, row_mask=None, out_f32=False):
+    """x2d [R, K] (bf16/f16, contiguous) @ w[Nout, K]^T + bias -> [R, Nout]."""
+    R, K = x2d.shape
+    Nout = w.shape[0]
+    assert x2d.is_contiguous() and w.is_contiguous() and w.dtype == x2d.dtype and w.shape[1] == K
+    out = torch.empty((R, Nout), dtype=torch.float32 if out_f32 else x2d.dtype, device=x2d.device)
+    if R == 0:
+        return out
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_16(x2d.data_ptr(), w.data_ptr(), 0 if bias_f32 is None else bias_f32.data_ptr(), R, K,
+                                       Nout, out.data_ptr(), Nout, 1 if out_f32 else 0,
+                                       0 if row_mask is None else row_mask.data_ptr(),
+                                       1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_linear_16")
+    return out
+
+
+def query_proj16(q2d, w_cat, bias_cat_f32, ref, ref_dim, spatial_shapes, M, L, P):
+    """-> (loc [R, M, L, P, 2] fp32, aw [R, M, L, P] fp32)."""
+    R, K = q2d.shape
+    loc = torch.empty((R, M, L, P, 2), dtype=torch.float32, device=q2d.device)
+    aw = torch.empty((R, M, L, P), dtype=torch.float32, device=q2d.device)
+    if R == 0:
+        return loc, aw
+    with torch.cuda.device(q2d.device):
+        rc = _lib.lib().msda_query_proj_16(q2d.data_ptr(), w_cat.data_ptr(), bias_cat_f32.data_ptr(), ref.data_ptr(), ref_dim,
+                                           spatial_shapes.data_ptr(), R, K, M, L, P, loc.data_ptr(), aw.data_ptr(),
+                                           1 if q2d.dtype == torch.float16 else 0, _stream(q2d))
+    _lib.check(rc, "msda_query_proj_16")
+    return loc, aw
+
+
+def query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, R, M, L, P, dtype):
+    out = torch.empty((R, 3 * M * L * P), dtype=dtype, device=aw.device)
+    with torch.cuda.device(aw.device):
+        rc = _lib.lib().msda_query_bwd_prep_16(grad_loc.data_ptr(), grad_aw.data_ptr(), aw.data_ptr(), ref.data_ptr(), ref_dim,
+                                               spatial_shapes.data_ptr(), R, M, L, P, out.data_ptr(),
+                                               1 if dtype == torch.float16 else 0, _stream(aw))
+    _lib.check(rc, "msda_query_bwd_prep_16")
+    return out
+
+
+def cast_mask16(x_f32_2d, row_mask, dtype):
+    rows, cols = x_f32_2d.shape
+    out = torch.empty((rows, cols), dtype=dtype, device=x_f32_2d.device)
+    with torch.cuda.device(x_f32_2d.device):
+        rc = _lib.lib().msda_cast_mask_16(x_f32_2d.data_ptr(), 0 if row_mask is None else row_mask.data_ptr(), rows, cols,
+                                          out.data_ptr(), 1 if dtype == torch.float16 else 0, _stream(x_f32_2d))
+    _lib.check(rc, "msda_cast_mask_16")
+    return out
+
+
+def supported(embed_dim, M, L, P, dtype):
+    lp = L * P
+    return (dtype in (torch.bfloat16, torch.float16) and embed_dim % 64 == 0 and embed_dim <= 1024 and lp <= 32
+            and 32 % lp == 0 and (M * lp) % 32 == 0 and 3 * M * lp <= 1024 and (3 * M * lp) % 64 == 0)
+
+
+class FusedMSDeformAttnFunction(Function):
+    """Whole-module forward/backward on 16-bit activations. Inputs are batch-first and contiguous."""
+
+    @staticmethod
+    def forward(ctx, query, value_in, row_mask, reference_points, spatial_shapes, level_start_index, w_v, b_v, w_off,
+                b_off, w_aw, b_aw, w_o, b_o, M, L, P, im2col_step):
+        N, Lq, C = query.shape
+        S = value_in.shape[1]
+        dt = query.dtype
+        q2d = query.reshape(N * Lq, C)
+        v2d = value_in.reshape(N * S, C)
+        ref = reference_points.to(torch.float32).contiguous()
+        ref_dim = ref.shape[-1]
+        w_cat = torch.cat([w_off, w_aw], 0)
+        b_cat = torch.cat([b_off, b_aw], 0).float()
+        value = linear16(v2d, w_v, b_v.float(), row_mask).view(N, S, M, C // M)
+        loc, aw = query_proj16(q2d, w_cat, b_cat, ref, ref_dim, spatial_shapes, M, L, P)
+        loc = loc.view(N, Lq, M, L, P, 2)
+        aw = aw.view(N, Lq, M, L, P)
+        core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
+        out = linear16(core.view(N * Lq, C), w_o, b_o.float()).view(N, Lq, C)
+        ctx.dims = (N, Lq, S, C, M, L, P, ref_dim, im2col_step)
+        ctx.wgrad = any(ctx.needs_input_grad[i] for i in range(6, 14))
+        ctx.save_for_backward(query if ctx.wgrad else None, value_in if ctx.wgrad else None, row_mask, ref, spatial_shapes,
+                              level_start_index, w_v, w_cat, w_o, value, loc, aw, core if ctx.wgrad else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        (query, value_in, row_mask, ref, spatial_shapes, level_start_index, w_v, w_cat, w_o, value, loc, aw,
+         core) = ctx.saved_tensors
+        N, Lq, S, C, M, L, P, ref_dim, im2col_step = ctx.dims
+        dt = value.dtype
+        g2d = grad_out.contiguous().view(N * Lq, C)
+        d_core = linear16(g2d, w_o.t().contiguous())
+        grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
+                                                                   d_core.view(N, Lq, C), im2col_step)
+        dq_cat = query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * Lq, M, L, P, dt)
+        d_query = linear16(dq_cat, w_cat.t().contiguous()).view(N, Lq, C) if ctx.needs_input_grad[0] else None
+        gv16 = cast_mask16(grad_value.view(N * S, C), row_mask, dt)
+        d_value_in = linear16(gv16, w_v.t().contiguous()).view(N, S, C) if ctx.needs_input_grad[1] else None
+        grads = [None] * 8
+        if ctx.wgrad:  # plain library GEMMs; the module's own linears are frozen in the ZiRa configuration
+            n_loc = 2 * M * L * P
+            q2d, v2d = query.reshape(N * Lq, C), value_in.reshape(N * S, C)
+            dw_cat = dq_cat.t() @ q2d
+            db_cat = dq_cat.float().sum(0)
+            grads = [gv16.t() @ v2d, gv16.float().sum(0).to(dt), dw_cat[:n_loc], db_cat[:n_loc].to(dt), dw_cat[n_loc:],
+                     db_cat[n_loc:].to(dt), g2d.t() @ core.view(N * Lq, C), g2d.float().sum(0).to(dt)]
+            grads = [g if ctx.needs_input_grad[6 + i] else None for i, g in enumerate(grads)]
+        return (d_query, d_value_in, None, None, None, None, *grads, None, None, None, None)

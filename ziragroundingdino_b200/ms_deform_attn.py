@@ -28,7 +28,7 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 from torch.nn.init import constant_, xavier_uniform_
 
-from . import _C
+from . import _C, fused
 from .zira import RepZeroLinear
 
 
@@ -179,6 +179,38 @@ class MultiScaleDeformableAttention(nn.Module):
             return F.linear(x, base.weight, base.bias), None
         return adapter.forward_folded(x, base.weight, base.bias)
 
+    # ---- fused 16-bit path (tcgen05 GEMMs with fused epilogues; see fused.py) ---------------------
+    fused_enabled = True  # class-level switch used by tests / benchmarks for A/B runs
+
+    def _use_fused(self, value, reference_points):
+        if not (self.fused_enabled and value.is_cuda and fused.supported(self.embed_dim, self.num_heads, self.num_levels,
+                                                                        self.num_points, value.dtype)):
+            return False
+        if reference_points.shape[-1] not in (2, 4) or reference_points.requires_grad:
+            return False
+        # un-merged ZiRa branches in training mode need the branch activations for the zero-inter loss
+        has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None
+        return not (has_branch and self.training)
+
+    def _effective(self, base, adapter):
+        """Eval-mode weights of a projection: pretrained + accumulated soft-frozen ZiRa weights
+        (the un-merged branch is ignored in eval, groundingdino_dual_zero_rep_branch.py:126-127)."""
+        if adapter is None:
+            return base.weight, base.bias
+        return base.weight + adapter.freeze_linear.weight, base.bias + adapter.freeze_linear.bias
+
+    def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+        w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
+        w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
+        row_mask = None
+        if key_padding_mask is not None:
+            row_mask = key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
+        self.zero_inter_loss = None
+        return fused.FusedMSDeformAttnFunction.apply(
+            query.contiguous(), value.contiguous(), row_mask, reference_points, spatial_shapes, level_start_index,
+            w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+            self.attention_weights.bias, w_o, b_o, self.num_heads, self.num_levels, self.num_points, self.im2col_step)
+
     def forward(self, query: torch.Tensor, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
                 query_pos: Optional[torch.Tensor] = None, key_padding_mask: Optional[torch.Tensor] = None,
                 reference_points: Optional[torch.Tensor] = None, spatial_shapes: Optional[torch.Tensor] = None,
@@ -199,6 +231,12 @@ class MultiScaleDeformableAttention(nn.Module):
             raise RuntimeError("MultiScaleDeformableAttention (B200) has no CPU path; got a %s tensor" % value.device)
 
         M, L, P = self.num_heads, self.num_levels, self.num_points
+        if self._use_fused(value, reference_points):
+            output = self._forward_fused(query, value, key_padding_mask, reference_points, spatial_shapes,
+                                         level_start_index)
+            if not self.batch_first:
+                output = output.permute(1, 0, 2)
+            return output
         value, loss_v = self._project(value, self.value_proj, self.value_proj_adapter)
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], float(0))
