@@ -1,0 +1,299 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+
+Workload (configs[1], "config 2"): GroundingDINO Swin-T 6-layer deformable encoder, forward + backward,
+4 images per GPU padded to 800x1333 (levels 100x167, 50x84, 25x42, 13x21; S = 22 223 tokens/image), bf16,
+as it runs inside a ZiRa incremental fine-tuning step: the twelve... here six encoder MSDeformAttn layers and
+their FFNs are FROZEN (groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:50), the only trainable
+parameters are a ZiRa RepZeroLinear branch at the transformer input (stand-in for the reference's
+input_proj adapters, groundingdino_dual_zero_rep_branch.py:487-523), so backward carries activation
+gradients through every layer (grad_value / grad_sampling_loc / grad_attn_weight + dgrad GEMMs) and weight
+gradients only for the branch.  With N > 1 GPUs each rank runs its own 4 images (weak scaling) and the
+branch gradients are all-reduced in ONE flat NCCL bucket per step.
+
+One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step
+with pinned-host inputs copied in and the loss read back every step.  `roofline` is for the dominant
+kernel (the backward scatter); `cpu_baseline` is the reference's CPU path (oracle port) on a bounded sample.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMAGES_PER_GPU = 4
+NUM_LAYERS = 6
+METRIC = "encoder6_msdeformattn_fwd_bwd_images_per_s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    return ap.parse_args()
+
+
+def workload_config(n_gpus):
+    return {"workload": "config2: GroundingDINO Swin-T 6-layer deformable encoder (MSDeformAttn + residual/LN + FFN 256-2048-256) "
+                        "fwd+bwd, frozen layers, trainable ZiRa input branch",
+            "images_per_gpu": IMAGES_PER_GPU, "global_batch": IMAGES_PER_GPU * n_gpus, "image": "800x1333",
+            "levels": [[100, 167], [50, 84], [25, 42], [13, 21]], "tokens_per_image": 22223, "d_model": 256, "heads": 8,
+            "points": 4, "layers": NUM_LAYERS, "padding": "per-image valid fraction 0.6-1.0 of the canvas",
+            "parallelism": "dp%d" % n_gpus, "omitted": "Swin backbone, BERT, text fusion/text layers, decoder, criterion",
+            "l2": "working set per step > 126 MB L2 (activations of 6 layers x 4 images); no explicit flush"}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU path on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_images_per_s(budget_s, threads):
+    """One image through as many of the 6 layers as fit the time budget; throughput normalised to 6."""
+    from oracle import cpu_encoder
+    from ziragroundingdino_b200 import synthetic as syn
+    t1 = cpu_encoder.timed_step(syn.SWIN_T_800x1333, 1, threads)       # also the warm-up
+    layers = max(1, min(NUM_LAYERS, int(budget_s / max(t1, 1e-3))))
+    t = cpu_encoder.timed_step(syn.SWIN_T_800x1333, layers, threads)
+    per_image = t * NUM_LAYERS / layers
+    return 1.0 / per_image, layers, t
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, sample = [], None
+    total = max(1, args.steps)
+    budget = min(30.0, 150.0 / (total + args.warmup))
+    for i in range(args.warmup + total):
+        ips, layers, t = cpu_images_per_s(budget, threads)
+        sample = "1 image x %d of 6 encoder layers fwd+bwd per step (fp32, torch CPU, grid_sample core)" % layers
+        if i >= args.warmup:
+            vals.append(ips)
+    v = sum(vals) / len(vals)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        self.p.wait()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], None, set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx = float(c[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        os.unlink(self.f.name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import _lib, encoder, synthetic as syn
+    from ziragroundingdino_b200.dp import FlatGradBucket
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().msda_b200_device_arch() >= 100
+
+    shapes = syn.SWIN_T_800x1333
+    S = sum(h * w for h, w in shapes)
+    N, C, dt = IMAGES_PER_GPU, 256, torch.bfloat16
+    torch.manual_seed(1234 + rank)
+    enc = encoder.DeformableEncoder(NUM_LAYERS).to(dev)
+    with torch.no_grad():
+        for layer in enc.layers:   # query-dependent offsets / weights, as in a trained model
+            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+            layer.self_attn.attention_weights.weight.normal_(0, 0.02)
+    enc = enc.to(dt)
+    for p in enc.parameters():
+        p.requires_grad_(False)
+    base_in = torch.nn.Linear(C, C).to(dev).to(dt)
+    for p in base_in.parameters():
+        p.requires_grad_(False)
+    branch = zb.RepZeroLinear(C, C).to(dev).to(dt)
+    branch.train()
+    params = [p for p in branch.parameters()]
+    bucket = FlatGradBucket(params, world)
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+
+    sh, lsi = syn.level_tensors(shapes, dev)
+    g = torch.Generator().manual_seed(99 + rank)
+    mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g)
+    host_feat = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
+    host_pos = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
+    host_mask = mask.cpu().pin_memory()
+    feat, pos = host_feat.to(dev), host_pos.to(dev)
+    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def step(feat_, pos_, mask_):
+        src, zloss = branch.forward_folded(feat_, base_in.weight, base_in.bias)
+        out = enc(src, pos_, shapes, sh, lsi, valid, mask_)
+        loss = out.float().square().mean() + 0.1 * zloss.float()
+        loss.backward()
+        bucket.all_reduce()
+        torch.nn.utils.clip_grad_norm_(params, 0.1)
+        opt.step()
+        opt.zero_grad(set_to_none=False)
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    # ---- device-resident timing ---------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(feat, pos, mask)
+    sampler = ClockSampler(local) if rank == 0 else None
+    n0 = _lib.launch_count()
+    ms = timed(lambda: step(feat, pos, mask), args.steps)
+    launches = _lib.launch_count() - n0
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end: pinned host inputs in, loss out, every step --------------------------------------
+    def e2e_step():
+        f = host_feat.to(dev, non_blocking=True)
+        p = host_pos.to(dev, non_blocking=True)
+        m = host_mask.to(dev, non_blocking=True)
+        loss = step(f, p, m)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = host_feat.numel() * 2 + host_pos.numel() * 2 + host_mask.numel()
+
+    # ---- the dominant kernel alone: backward scatter of one layer (CUDA events on the launching stream) ----
+    inp = syn.core_inputs(shapes, N, dtype=dt, regime="local", device=dev, seed=5)
+    cargs = (inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"])
+    ab = syn.algorithmic_bytes(*inp["dims"], 2)
+
+    def kernel_us(fn, reps=10):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) * 1e3 / reps
+
+    us_fwd = kernel_us(lambda: zb._C.ms_deform_attn_forward(*cargs, 64))
+    us_bwd = kernel_us(lambda: zb._C.ms_deform_attn_backward(*cargs, inp["grad_out"], 64))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    images = IMAGES_PER_GPU * world * args.steps
+    value = images / (ms / 1e3)
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic", "config": workload_config(world), "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "images": N,
+                                   "fwd_l2_algorithmic_gbps": ab["fwd_l2"] / us_fwd / 1e3,
+                                   "bwd_l2_algorithmic_gbps": ab["bwd_l2"] / us_bwd / 1e3},
+        "roofline": {"kernel": "msda_bwd_vec_kernel<bf16,32>", "bound": "hbm", "achieved": ab["bwd_hbm"] / us_bwd / 1e3,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ab["bwd_hbm"] / us_bwd / 1e3 / hbm_peak, "traffic": None,
+                     "peak_source": peak_src,
+                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by L1TEX/L2 reduction "
+                             "throughput, not HBM -- see DESIGN.md and profiles/"},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        ips, layers, t = cpu_images_per_s(20.0, threads)
+        out["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
+                               "sample": "1 image x %d of 6 encoder layers fwd+bwd (fp32, torch CPU, grid_sample core), %.1f s" % (layers, t)}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

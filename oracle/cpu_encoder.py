@@ -1,0 +1,58 @@
+"""TEST INFRASTRUCTURE ONLY -- the reference's CPU path for the benchmark workload.
+
+One image through ``layers`` deformable encoder layers, forward + backward, in fp32 on the host cores,
+built from the oracle's restatement of the reference module (oracle/msda_oracle.py: module_forward with
+the grid_sample core = ms_deform_attn.py:90-130, :281-350) plus the residual/LayerNorm/FFN of
+transformer_for_adapter.py:876-907.  Used by bench.py for ``cpu_baseline`` and ``--impl reference``.
+"""
+import time
+
+import torch
+import torch.nn.functional as F
+
+from . import msda_oracle as O
+
+
+def make_layer_params(d_model=256, d_ffn=2048, M=8, L=4, P=4, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    return {
+        "value_proj.weight": r(d_model, d_model, std=0.06), "value_proj.bias": torch.zeros(d_model),
+        "sampling_offsets.weight": r(M * L * P * 2, d_model), "sampling_offsets.bias": r(M * L * P * 2, std=2.0),
+        "attention_weights.weight": r(M * L * P, d_model), "attention_weights.bias": torch.zeros(M * L * P),
+        "output_proj.weight": r(d_model, d_model, std=0.06), "output_proj.bias": torch.zeros(d_model),
+        "linear1.weight": r(d_ffn, d_model, std=0.06), "linear1.bias": torch.zeros(d_ffn),
+        "linear2.weight": r(d_model, d_ffn, std=0.02), "linear2.bias": torch.zeros(d_model),
+        "norm1.weight": torch.ones(d_model), "norm1.bias": torch.zeros(d_model),
+        "norm2.weight": torch.ones(d_model), "norm2.bias": torch.zeros(d_model),
+    }
+
+
+def encoder_layer(p, src, pos, refp, shapes, mask, M, L, P):
+    src2 = O.module_forward(p, src + pos, src, mask, refp, shapes, M, L, P)
+    src = F.layer_norm(src + src2, (src.shape[-1],), p["norm1.weight"], p["norm1.bias"])
+    ffn = F.linear(F.relu(F.linear(src, p["linear1.weight"], p["linear1.bias"])), p["linear2.weight"], p["linear2.bias"])
+    return F.layer_norm(src + ffn, (src.shape[-1],), p["norm2.weight"], p["norm2.bias"])
+
+
+def timed_step(shapes, layers, threads, d_model=256, M=8, P=4, seed=0):
+    """Returns seconds for one image through `layers` layers fwd+bwd on `threads` host threads."""
+    torch.set_num_threads(threads)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(seed)
+    sh = torch.tensor(shapes, dtype=torch.long)
+    params = [make_layer_params(d_model, 2048, M, L, P, seed + i) for i in range(layers)]
+    src = torch.randn(1, S, d_model, generator=g).requires_grad_(True)
+    pos = torch.randn(1, S, d_model, generator=g)
+    pts = []
+    for (h, w) in shapes:
+        ys, xs = torch.meshgrid(torch.linspace(0.5, h - 0.5, h) / h, torch.linspace(0.5, w - 0.5, w) / w, indexing="ij")
+        pts.append(torch.stack((xs.reshape(-1), ys.reshape(-1)), -1))
+    refp = torch.cat(pts, 0)[None, :, None, :].expand(1, S, L, 2).contiguous()
+    t0 = time.perf_counter()
+    x = src
+    for p in params:
+        x = encoder_layer(p, x, pos, refp, sh, None, M, L, P)
+    x.square().mean().backward()
+    return time.perf_counter() - t0

@@ -150,14 +150,30 @@ def test_module_fused_vs_unfused_and_oracle(case):
             assert launches == (10 if fused_on else 2), launches
         finally:
             zb.MultiScaleDeformableAttention.fused_enabled = True
-    params = {k: p.detach().double().cpu() for k, p in m.state_dict().items()}
-    truth = O.module_forward(params, query.double().cpu(), src.double().cpu(), mask.cpu(), refp.double().cpu(), sh.cpu(), 8, 4, 4)
+    # fp64 truth (forward and autograd backward) from the oracle's restatement of the reference module
+    params = {k: p.detach().double().cpu().requires_grad_(True) for k, p in m.state_dict().items()}
+    tq, tv = query.double().cpu().requires_grad_(True), src.double().cpu().requires_grad_(True)
+    truth = O.module_forward(params, tq, tv, mask.cpu(), refp.double().cpu(), sh.cpu(), 8, 4, 4)
+    gy64 = torch.randn(truth.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3)).to(query.dtype)
+    truth.backward(gy64.double().cpu())
+    tgrads = dict(q=tq.grad, v=tv.grad, **{k: p.grad for k, p in params.items()})
     scale = truth.abs().max().item()
-    assert (outs[True].double().cpu() - truth).abs().max().item() < 1e-2 * scale
-    assert (outs[False].double().cpu() - truth).abs().max().item() < 2e-2 * scale
+    assert (outs[True].double().cpu() - truth.detach()).abs().max().item() < 1e-2 * scale
+    assert (outs[False].double().cpu() - truth.detach()).abs().max().item() < 2e-2 * scale
+
+    def close(a, b, tol, frac):
+        """|a-b| <= tol*max|b| for all but `frac` of the entries: gradients through sampling locations are
+        discontinuous at pixel boundaries, so a 16-bit rounding upstream legitimately flips a few samples
+        into the neighbouring cell (same effect as SURVEY.md section 0 item 4, at bf16 scale)."""
+        d = (a.double().cpu() - b.double().cpu()).abs()
+        return (d > tol * b.abs().max().item() + 1e-7).double().mean().item() <= frac
+
     for k in grads[True]:
-        a, b = grads[True][k], grads[False][k]
-        assert (a - b).abs().max().item() < 4e-2 * b.abs().max().item() + 1e-6, k
+        assert close(grads[True][k], tgrads[k], 3e-2, 2e-3), "fused vs fp64 truth: " + k
+        assert close(grads[True][k], grads[False][k], 4e-2, 5e-3), "fused vs unfused: " + k
+    # the value-side gradients do not pass through the floor(): tight everywhere
+    assert rel_err(grads[True]["v"].cpu(), tgrads["v"]) < 2e-2
+    assert rel_err(grads[True]["value_proj.weight"].cpu(), tgrads["value_proj.weight"]) < 2e-2
 
 
 def test_module_fused_f16_and_eval_fold():
