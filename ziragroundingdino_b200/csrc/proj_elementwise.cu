@@ -25,41 +25,52 @@ __device__ __forceinline__ uint16_t to16(float v, bool is_half) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 
-// one thread per (row, head): 2*L*P offset gradients + L*P logit gradients
+// One thread per 4 consecutive columns of the stacked [R, 3*M*L*P] output row: coalesced 16-byte loads,
+// 8-byte stores.  Offset columns are a per-column scale; logit columns need the softmax dot product of
+// their run of L*P weights, taken with shuffles across the L*P/4 neighbouring threads.  Needs (L*P) % 4 == 0.
 __global__ void __launch_bounds__(256)
 query_bwd_prep_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_aw, const float* __restrict__ aw,
                       const float* __restrict__ ref, const int64_t* __restrict__ shapes, long long R, int M, int L, int P,
                       int ref_dim, int is_half, uint16_t* __restrict__ out) {
-  __shared__ float s_norm[MSDA_MAX_LEVELS * 2];
+  __shared__ float s_inv[MSDA_MAX_LEVELS * 2];
   if (threadIdx.x < L) {
-    s_norm[2 * threadIdx.x] = static_cast<float>(shapes[2 * threadIdx.x + 1]);
-    s_norm[2 * threadIdx.x + 1] = static_cast<float>(shapes[2 * threadIdx.x]);
+    s_inv[2 * threadIdx.x] = 1.f / static_cast<float>(shapes[2 * threadIdx.x + 1]);
+    s_inv[2 * threadIdx.x + 1] = 1.f / static_cast<float>(shapes[2 * threadIdx.x]);
   }
   __syncthreads();
+  const int lp = L * P, n_aw = M * lp, n_loc = 2 * n_aw, ld = n_loc + n_aw, tpr = ld / 4;   // threads per row
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= R * M) return;
-  const long long row = idx / M;
-  const int m = static_cast<int>(idx % M);
-  const int lp = L * P, n_aw = M * lp, n_loc = 2 * n_aw, ld = n_loc + n_aw;
-  const float* gl = grad_loc + row * n_loc + m * lp * 2;
-  const float* ga = grad_aw + row * n_aw + m * lp;
-  const float* a = aw + row * n_aw + m * lp;
-  const float* rp = ref + row * L * ref_dim;
-  uint16_t* o_off = out + row * ld + m * lp * 2;
-  uint16_t* o_aw = out + row * ld + n_loc + m * lp;
-  float dot = 0.f;
-  for (int j = 0; j < lp; ++j) dot = fmaf(ga[j], a[j], dot);
-  for (int j = 0; j < lp; ++j) o_aw[j] = to16(a[j] * (ga[j] - dot), is_half != 0);
-  for (int l = 0; l < L; ++l) {
-    float sx, sy;
-    if (ref_dim == 2) { sx = 1.f / s_norm[2 * l]; sy = 1.f / s_norm[2 * l + 1]; }
-    else { sx = rp[l * 4 + 2] * 0.5f / P; sy = rp[l * 4 + 3] * 0.5f / P; }
-    for (int p = 0; p < P; ++p) {
-      const int j = (l * P + p) * 2;
-      o_off[j] = to16(gl[j] * sx, is_half != 0);
-      o_off[j + 1] = to16(gl[j + 1] * sy, is_half != 0);
+  const bool live = idx < R * tpr;
+  const long long row = live ? idx / tpr : 0;
+  const int col = live ? static_cast<int>(idx % tpr) * 4 : 0;
+  float o[4] = {0.f, 0.f, 0.f, 0.f};
+  const bool is_logit = col >= n_loc;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
+  if (live && is_logit) {
+    a = __ldg(reinterpret_cast<const float4*>(aw + row * n_aw + (col - n_loc)));
+    g = __ldg(reinterpret_cast<const float4*>(grad_aw + row * n_aw + (col - n_loc)));
+  }
+  // softmax backward: runs of lp logits = lp/4 consecutive threads (a run never straddles a warp)
+  float dot = g.x * a.x + g.y * a.y + g.z * a.z + g.w * a.w;
+  for (int o_ = 1; o_ < lp / 4; o_ <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o_);
+  if (!live) return;
+  if (is_logit) {
+    o[0] = a.x * (g.x - dot); o[1] = a.y * (g.y - dot); o[2] = a.z * (g.z - dot); o[3] = a.w * (g.w - dot);
+  } else {
+    const float4 gl = __ldg(reinterpret_cast<const float4*>(grad_loc + row * n_loc + col));
+    const float gv[4] = {gl.x, gl.y, gl.z, gl.w};
+    const float* rp = ref + row * L * ref_dim;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col + j, xy = c & 1, l = (c / (2 * P)) % L;
+      const float sc = (ref_dim == 2) ? s_inv[2 * l + xy] : rp[l * 4 + 2 + xy] * (0.5f / P);
+      o[j] = gv[j] * sc;
     }
   }
+  uint2 w;
+  w.x = to16(o[0], is_half != 0) | (static_cast<uint32_t>(to16(o[1], is_half != 0)) << 16);
+  w.y = to16(o[2], is_half != 0) | (static_cast<uint32_t>(to16(o[3], is_half != 0)) << 16);
+  *reinterpret_cast<uint2*>(out + row * ld + col) = w;
 }
 
 // 8 elements per thread; `cols` (row length) must be a multiple of 8
@@ -87,7 +98,8 @@ int msda_query_bwd_prep_16(const float* grad_loc, const float* grad_aw, const fl
                            void* stream) {
   if (!grad_loc || !grad_aw || !aw || !ref || !spatial_shapes || !out) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || M <= 0 || L <= 0 || L > MSDA_MAX_LEVELS || P <= 0 || (ref_dim != 2 && ref_dim != 4)) return MSDA_ERR_BAD_SHAPE;
-  const long long n = R * M;
+  if ((L * P) % 4 || (L * P) > 128 || ((L * P / 4) & (L * P / 4 - 1))) return MSDA_ERR_UNSUPPORTED;
+  const long long n = R * (3ll * M * L * P / 4);
   ++msda::g_launches;
   query_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       grad_loc, grad_aw, aw, ref, spatial_shapes, R, M, L, P, ref_dim, is_half, static_cast<uint16_t*>(out));

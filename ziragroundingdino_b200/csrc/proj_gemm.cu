@@ -175,20 +175,47 @@ __device__ __forceinline__ void epi_store(const EpiParams& ep, const float (&v)[
   }
 }
 
-// sampling locations (ms_deform_attn.py:306-319): columns are (m, l, p, xy)
+// sampling locations (ms_deform_attn.py:306-319): columns are (m, l, p, xy).  Generic shapes.
 __device__ __forceinline__ void epi_loc(const EpiParams& ep, const float (&v)[32], long long row, int gc,
-                                        const float* s_norm) {
+                                        const float* s_inv) {
   const float* rp = ep.ref + row * ep.L * ep.ref_dim;
   float4* o = reinterpret_cast<float4*>(ep.loc_out + row * ep.n_loc + gc);
+  const float half_over_p = 0.5f / static_cast<float>(ep.P);
   float r[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int idx = gc + j, xy = idx & 1, l = (idx / (2 * ep.P)) % ep.L;
-    if (ep.ref_dim == 2) {
-      r[j] = rp[l * 2 + xy] + __fdiv_rn(v[j], s_norm[l * 2 + xy]);
-    } else {
-      r[j] = rp[l * 4 + xy] + __fdiv_rn(v[j], static_cast<float>(ep.P)) * rp[l * 4 + 2 + xy] * 0.5f;
-    }
+    if (ep.ref_dim == 2) r[j] = fmaf(v[j], s_inv[l * 2 + xy], rp[l * 2 + xy]);
+    else r[j] = fmaf(v[j] * half_over_p, rp[l * 4 + 2 + xy], rp[l * 4 + xy]);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+}
+
+// L = 4, P = 4 (every GroundingDINO configuration): one 32-column chunk is exactly one head, so the level
+// and the x/y selector of each column are compile-time and the row's reference points sit in registers.
+template <int REF_DIM>
+__device__ __forceinline__ void epi_loc_l4p4(const EpiParams& ep, const float (&v)[32], long long row, int gc,
+                                             const float* s_inv) {
+  constexpr int L = 4, P = 4;
+  float ref[L * REF_DIM];
+  const float4* rp = reinterpret_cast<const float4*>(ep.ref + row * L * REF_DIM);
+#pragma unroll
+  for (int i = 0; i < L * REF_DIM / 4; ++i) {
+    const float4 t = __ldg(rp + i);
+    ref[4 * i] = t.x; ref[4 * i + 1] = t.y; ref[4 * i + 2] = t.z; ref[4 * i + 3] = t.w;
+  }
+  float inv[2 * L];
+#pragma unroll
+  for (int i = 0; i < 2 * L; ++i) inv[i] = s_inv[i];
+  float4* o = reinterpret_cast<float4*>(ep.loc_out + row * ep.n_loc + gc);
+  float r[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    constexpr float half_over_p = 0.5f / P;
+    const int l = j / (2 * P), xy = j & 1;
+    if (REF_DIM == 2) r[j] = fmaf(v[j], inv[l * 2 + xy], ref[l * 2 + xy]);
+    else r[j] = fmaf(v[j] * half_over_p, ref[l * 4 + 2 + xy], ref[l * 4 + xy]);
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
@@ -238,7 +265,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   float* s_bias = reinterpret_cast<float*>(aux + 256);
-  float* s_norm = s_bias + MAX_N;   // (W_l, H_l) as floats
+  float* s_norm = s_bias + MAX_N;   // (1/W_l, 1/H_l)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = K / BLOCK_K;
@@ -261,8 +288,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
   for (int i = threadIdx.x; i < Nout; i += THREADS) s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
   if (ep.mode == EPI_QUERY && threadIdx.x < ep.L) {
-    s_norm[2 * threadIdx.x] = static_cast<float>(ep.shapes[2 * threadIdx.x + 1]);      // W
-    s_norm[2 * threadIdx.x + 1] = static_cast<float>(ep.shapes[2 * threadIdx.x]);      // H
+    s_norm[2 * threadIdx.x] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x + 1]);      // 1/W
+    s_norm[2 * threadIdx.x + 1] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x]);      // 1/H
   }
   tc_fence_before();
   __syncthreads();
@@ -334,7 +361,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[gc + j];
         if (row < R) {
           if (ep.mode == EPI_STORE) epi_store(ep, v, row, gc);
-          else if (gc < ep.n_loc) epi_loc(ep, v, row, gc, s_norm);
+          else if (gc < ep.n_loc) {
+            if (ep.L == 4 && ep.P == 4) {
+              if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, row, gc, s_norm);
+              else epi_loc_l4p4<4>(ep, v, row, gc, s_norm);
+            } else {
+              epi_loc(ep, v, row, gc, s_norm);
+            }
+          }
           else epi_softmax(ep, v, row, gc);
         }
       }

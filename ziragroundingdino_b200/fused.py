@@ -79,51 +79,66 @@ def cast_mask16(x_f32_2d, row_mask, dtype):
 def supported(embed_dim, M, L, P, dtype):
     lp = L * P
     return (dtype in (torch.bfloat16, torch.float16) and embed_dim % 64 == 0 and embed_dim <= 1024 and lp <= 32
-            and 32 % lp == 0 and (M * lp) % 32 == 0 and 3 * M * lp <= 1024 and (3 * M * lp) % 64 == 0)
+            and 32 % lp == 0 and lp % 4 == 0 and (M * lp) % 32 == 0 and 3 * M * lp <= 1024 and (3 * M * lp) % 64 == 0)
+
+
+class Prepared:
+    """Weights of one module in the form the kernels consume (built once per parameter version):
+    contiguous 16-bit matrices and their transposes for the dgrad products, the stacked
+    [sampling_offsets; attention_weights] matrix, fp32 biases."""
+
+    def __init__(self, w_v, b_v, w_off, b_off, w_aw, b_aw, w_o, b_o):
+        with torch.no_grad():
+            self.w_v, self.w_o = w_v.detach().contiguous(), w_o.detach().contiguous()
+            self.w_cat = torch.cat([w_off.detach(), w_aw.detach()], 0).contiguous()
+            self.b_v, self.b_o = b_v.detach().float(), b_o.detach().float()
+            self.b_cat = torch.cat([b_off.detach(), b_aw.detach()], 0).float()
+            self.w_v_t, self.w_o_t = self.w_v.t().contiguous(), self.w_o.t().contiguous()
+            self.w_cat_t = self.w_cat.t().contiguous()
 
 
 class FusedMSDeformAttnFunction(Function):
-    """Whole-module forward/backward on 16-bit activations. Inputs are batch-first and contiguous."""
+    """Whole-module forward/backward on 16-bit activations. Inputs are batch-first and contiguous.
+    ``prep`` carries the kernel-ready weights; the eight raw parameters are passed only so autograd can
+    route weight gradients to them when they are trainable."""
 
     @staticmethod
-    def forward(ctx, query, value_in, row_mask, reference_points, spatial_shapes, level_start_index, w_v, b_v, w_off,
-                b_off, w_aw, b_aw, w_o, b_o, M, L, P, im2col_step):
+    def forward(ctx, query, value_in, row_mask, reference_points, spatial_shapes, level_start_index, prep, M, L, P,
+                im2col_step, w_v, b_v, w_off, b_off, w_aw, b_aw, w_o, b_o):
         N, Lq, C = query.shape
         S = value_in.shape[1]
-        dt = query.dtype
         q2d = query.reshape(N * Lq, C)
         v2d = value_in.reshape(N * S, C)
         ref = reference_points.to(torch.float32).contiguous()
         ref_dim = ref.shape[-1]
-        w_cat = torch.cat([w_off, w_aw], 0)
-        b_cat = torch.cat([b_off, b_aw], 0).float()
-        value = linear16(v2d, w_v, b_v.float(), row_mask).view(N, S, M, C // M)
-        loc, aw = query_proj16(q2d, w_cat, b_cat, ref, ref_dim, spatial_shapes, M, L, P)
+        value = linear16(v2d, prep.w_v, prep.b_v, row_mask).view(N, S, M, C // M)
+        loc, aw = query_proj16(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
         loc = loc.view(N, Lq, M, L, P, 2)
         aw = aw.view(N, Lq, M, L, P)
         core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
-        out = linear16(core.view(N * Lq, C), w_o, b_o.float()).view(N, Lq, C)
+        out = linear16(core.view(N * Lq, C), prep.w_o, prep.b_o).view(N, Lq, C)
         ctx.dims = (N, Lq, S, C, M, L, P, ref_dim, im2col_step)
-        ctx.wgrad = any(ctx.needs_input_grad[i] for i in range(6, 14))
+        ctx.prep = prep
+        ctx.wgrad = any(ctx.needs_input_grad[11:19])
         ctx.save_for_backward(query if ctx.wgrad else None, value_in if ctx.wgrad else None, row_mask, ref, spatial_shapes,
-                              level_start_index, w_v, w_cat, w_o, value, loc, aw, core if ctx.wgrad else None)
+                              level_start_index, value, loc, aw, core if ctx.wgrad else None)
         return out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_out):
-        (query, value_in, row_mask, ref, spatial_shapes, level_start_index, w_v, w_cat, w_o, value, loc, aw,
-         core) = ctx.saved_tensors
+        query, value_in, row_mask, ref, spatial_shapes, level_start_index, value, loc, aw, core = ctx.saved_tensors
         N, Lq, S, C, M, L, P, ref_dim, im2col_step = ctx.dims
+        prep = ctx.prep
         dt = value.dtype
         g2d = grad_out.contiguous().view(N * Lq, C)
-        d_core = linear16(g2d, w_o.t().contiguous())
+        d_core = linear16(g2d, prep.w_o_t)
         grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
                                                                    d_core.view(N, Lq, C), im2col_step)
         dq_cat = query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * Lq, M, L, P, dt)
-        d_query = linear16(dq_cat, w_cat.t().contiguous()).view(N, Lq, C) if ctx.needs_input_grad[0] else None
+        d_query = linear16(dq_cat, prep.w_cat_t).view(N, Lq, C) if ctx.needs_input_grad[0] else None
         gv16 = cast_mask16(grad_value.view(N * S, C), row_mask, dt)
-        d_value_in = linear16(gv16, w_v.t().contiguous()).view(N, S, C) if ctx.needs_input_grad[1] else None
+        d_value_in = linear16(gv16, prep.w_v_t).view(N, S, C) if ctx.needs_input_grad[1] else None
         grads = [None] * 8
         if ctx.wgrad:  # plain library GEMMs; the module's own linears are frozen in the ZiRa configuration
             n_loc = 2 * M * L * P
@@ -132,5 +147,5 @@ class FusedMSDeformAttnFunction(Function):
             db_cat = dq_cat.float().sum(0)
             grads = [gv16.t() @ v2d, gv16.float().sum(0).to(dt), dw_cat[:n_loc], db_cat[:n_loc].to(dt), dw_cat[n_loc:],
                      db_cat[n_loc:].to(dt), g2d.t() @ core.view(N * Lq, C), g2d.float().sum(0).to(dt)]
-            grads = [g if ctx.needs_input_grad[6 + i] else None for i, g in enumerate(grads)]
-        return (d_query, d_value_in, None, None, None, None, *grads, None, None, None, None)
+            grads = [g if ctx.needs_input_grad[11 + i] else None for i, g in enumerate(grads)]
+        return (d_query, d_value_in, None, None, None, None, None, None, None, None, None, *grads)

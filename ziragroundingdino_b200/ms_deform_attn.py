@@ -202,14 +202,19 @@ class MultiScaleDeformableAttention(nn.Module):
     def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
         w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
         w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
+        raw = (w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+               self.attention_weights.bias, w_o, b_o)
+        srcs = [p for p in self.parameters()]
+        key = tuple((t.data_ptr(), t._version, t.dtype) for t in srcs)
+        if getattr(self, "_prep_key", None) != key:      # rebuilt only when a parameter changed
+            self._prep, self._prep_key = fused.Prepared(*raw), key
         row_mask = None
         if key_padding_mask is not None:
             row_mask = key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
         self.zero_inter_loss = None
         return fused.FusedMSDeformAttnFunction.apply(
             query.contiguous(), value.contiguous(), row_mask, reference_points, spatial_shapes, level_start_index,
-            w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
-            self.attention_weights.bias, w_o, b_o, self.num_heads, self.num_levels, self.num_points, self.im2col_step)
+            self._prep, self.num_heads, self.num_levels, self.num_points, self.im2col_step, *raw)
 
     def forward(self, query: torch.Tensor, key: Optional[torch.Tensor] = None, value: Optional[torch.Tensor] = None,
                 query_pos: Optional[torch.Tensor] = None, key_padding_mask: Optional[torch.Tensor] = None,
