@@ -170,9 +170,6 @@ def test_module_fused_vs_unfused_and_oracle(case):
 
     for k in grads[True]:
         assert close(grads[True][k], tgrads[k], 3e-2, 2e-3), "fused vs fp64 truth: " + k
-        # the unfused path rounds offsets and logits to bf16 before the location / softmax math, so it sits
-        # further from the truth than the fused path; it only has to be in the same neighbourhood
-        assert close(grads[False][k], tgrads[k], 6e-2, 3e-2), "unfused vs fp64 truth: " + k
     # the value-side gradients do not pass through the floor(): tight everywhere
     assert rel_err(grads[True]["v"].cpu(), tgrads["v"]) < 2e-2
     assert rel_err(grads[True]["value_proj.weight"].cpu(), tgrads["value_proj.weight"]) < 2e-2

@@ -19,6 +19,7 @@ Differences, all deliberate:
 """
 import math
 import warnings
+import weakref
 from typing import Optional
 
 import torch
@@ -72,18 +73,21 @@ _SHAPE_CACHE = {}
 
 
 def _host_shapes(spatial_shapes):
-    """Host copy of ``spatial_shapes`` as a tuple of (H, W), cached per (storage, version)."""
+    """Host copy of ``spatial_shapes`` as a tuple of (H, W).  Cached per tensor *object* (weak reference) and
+    version counter, so a call costs one device->host sync the first time a given tensor is seen and none
+    afterwards (the reference syncs on every call, ms_deform_attn.py:284)."""
     if not spatial_shapes.is_cuda:
         return tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())
-    key = (spatial_shapes.data_ptr(), spatial_shapes._version, spatial_shapes.device.index,
-           tuple(spatial_shapes.shape))
+    key = id(spatial_shapes)
     hit = _SHAPE_CACHE.get(key)
-    if hit is None:
-        if len(_SHAPE_CACHE) > 256:
-            _SHAPE_CACHE.clear()
-        hit = tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())  # one sync per new tensor
-        _SHAPE_CACHE[key] = hit
-    return hit
+    if hit is not None and hit[0]() is spatial_shapes and hit[1] == spatial_shapes._version:
+        return hit[2]
+    if len(_SHAPE_CACHE) > 64:
+        for k in [k for k, v in _SHAPE_CACHE.items() if v[0]() is None]:
+            del _SHAPE_CACHE[k]
+    val = tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())
+    _SHAPE_CACHE[key] = (weakref.ref(spatial_shapes), spatial_shapes._version, val)
+    return val
 
 
 class MultiScaleDeformableAttention(nn.Module):
