@@ -100,8 +100,6 @@ int msda_backward_f16(const void *value, const int64_t *spatial_shapes, const in
  *   key "fwd_q_fast"        : 1 = lanes of a warp span consecutive queries of one head, 0 = heads
  *   key "bwd_q_fast"        : same for the backward kernel
  *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64)
- *   key "bwd_run"           : 0 = plain scatter kernel; 4, 8, 16 = run-merging kernel (that many consecutive
- *                             queries of one head per lane group, contributions to one cell combined in registers)
  * Returns 0, or MSDA_ERR_UNSUPPORTED for an unknown key / value. */
 int msda_b200_set_tuning(const char *key, int value);
 int msda_b200_get_tuning(const char *key);

@@ -147,40 +147,6 @@ def test_tuning_variants_agree():
         _lib.set_tuning(**keep)
 
 
-@pytest.mark.parametrize("T", [4, 8, 16])
-@pytest.mark.parametrize("case", [
-    (SWIN_T, 1, 8, 32, 1237, torch.float32, "uniform"),
-    ([(20, 30), (10, 15), (5, 8), (3, 4)], 3, 8, 32, 791, torch.float32, "local"),     # Lq = S, encoder-like
-    ([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, 32, 791, torch.bfloat16, "local"),
-    ([(20, 30), (10, 15), (5, 8), (3, 4), (2, 2)], 1, 5, 16, 37, torch.float32, "uniform"),
-    ([(9, 7), (4, 4)], 2, 4, 64, 65, torch.float16, "uniform"),
-], ids=lambda c: "N%d_M%d_D%d_Lq%d_%s_%s" % (c[1], c[2], c[3], c[4], str(c[5]).split(".")[-1], c[6]))
-def test_run_merging_backward_vs_oracle(case, T):
-    """The run-merging backward kernel (bwd_run = T) against the C oracle, incl. runs cut by Lq % T != 0,
-    runs that never merge (uniform locations) and runs that merge almost always (encoder-like local offsets)."""
-    from ziragroundingdino_b200 import _lib, synthetic as syn
-    dev = _dev()
-    shapes, N, M, D, Lq, dtype, regime = case
-    if regime == "local":
-        inp = syn.core_inputs(shapes, N, M=M, D=D, dtype=dtype, regime="local", device="cpu", seed=3)
-        value, sh, lsi, loc, aw, gout = (inp[k] for k in ("value", "shapes", "level_start", "loc", "aw", "grad_out"))
-    else:
-        value, sh, lsi, loc, aw, gout = _mk(shapes, N, M, D, Lq, 4, seed=50 + Lq, dtype=dtype)
-    keep = _lib.get_tuning("bwd_run")
-    try:
-        _lib.set_tuning(bwd_run=T)
-        out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
-    finally:
-        _lib.set_tuning(bwd_run=keep)
-    v64 = value.double().numpy()
-    o_gv, o_gl, o_ga = O.c_backward(v64, sh.numpy(), loc.double().numpy(), aw.double().numpy(), gout.double().numpy())
-    tol = 1e-4 if dtype == torch.float32 else 1e-2
-    assert rel_err(gv.double(), o_gv) < tol
-    bad = np.abs(gl.double().numpy() - o_gl) > 1e-4 * np.abs(o_gl).max()     # floor() discontinuity vs fp64 truth
-    assert bad.mean() < 1e-4
-    assert rel_err(ga, o_ga) < 1e-4
-
-
 def test_op_error_behaviour():
     """Same observable errors as the reference op (ms_deform_attn_cuda.cu:29-53)."""
     import ziragroundingdino_b200 as zb

@@ -79,13 +79,6 @@ def core(f, name, shapes, N, dtype, regime, Lq=None, full=True):
             emit(f, kind="bwd", case=name, qf=qf, passes=ps, flush=flush, us=med, us_best=best,
                  l2_gbps=ab["bwd_l2"] / med / 1e3, hbm_gbps=ab["bwd_hbm"] / med / 1e3)
     _lib.set_tuning(**keep)
-    keep_run = _lib.get_tuning("bwd_run")
-    for T in (0, 4, 8, 16):
-        _lib.set_tuning(bwd_run=T)
-        for flush in (True, False):
-            med, best = timeit(bwd, flush=flush)
-            emit(f, kind="bwd_run", case=name, T=T, flush=flush, us=med, us_best=best, l2_gbps=ab["bwd_l2"] / med / 1e3)
-    _lib.set_tuning(bwd_run=keep_run)
     if dtype == torch.float32:
         from oracle import build_ref
         ref = build_ref.load()

@@ -104,7 +104,6 @@ static int* tuning_slot(const char* key) {
   if (!strcmp(key, "fwd_passes")) return &msda::g_tuning.fwd_passes;
   if (!strcmp(key, "bwd_q_fast")) return &msda::g_tuning.bwd_q_fast;
   if (!strcmp(key, "bwd_passes")) return &msda::g_tuning.bwd_passes;
-  if (!strcmp(key, "bwd_run")) return &msda::g_tuning.bwd_run;
   return nullptr;
 }
 
@@ -113,11 +112,6 @@ int msda_b200_set_tuning(const char* key, int value) {
   if (!slot) return fail(MSDA_ERR_UNSUPPORTED, "unknown tuning key '%s'", key ? key : "(null)");
   const bool is_batch = slot == &msda::g_tuning.fwd_sample_batch;
   const bool is_pass = slot == &msda::g_tuning.fwd_passes || slot == &msda::g_tuning.bwd_passes;
-  if (slot == &msda::g_tuning.bwd_run) {
-    if (value != 0 && value != 4 && value != 8 && value != 16) return fail(MSDA_ERR_UNSUPPORTED, "bwd_run must be 0, 4, 8 or 16");
-    *slot = value;
-    return MSDA_OK;
-  }
   if ((is_batch && value != 1 && value != 2 && value != 4) || (is_pass && (value < 1 || value > 64)) ||
       (!is_batch && !is_pass && value != 0 && value != 1))
     return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);

@@ -19,7 +19,6 @@ struct Tuning {
   int fwd_passes = 1;        // consecutive unit tiles handled by one CTA
   int bwd_q_fast = 1;
   int bwd_passes = 1;
-  int bwd_run = 0;           // >0: run-merging backward kernel, T = bwd_run consecutive queries per lane group
 };
 extern Tuning g_tuning;
 extern long long g_launches;

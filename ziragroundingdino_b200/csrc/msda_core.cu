@@ -428,16 +428,10 @@ cudaError_t forward_f32acc(const VT* value, const int64_t* shapes, const int64_t
 }
 
 template <typename VT>
-cudaError_t backward_run(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, float*,
-                         float*, int, int, int, int, int, int, int, int, cudaStream_t);
-
-template <typename VT>
 cudaError_t backward_f32acc(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc,
                             const float* aw, const VT* grad_out, float* gv, float* gl, float* ga, int N,
                             int S, int M, int D, int L, int Lq, int P, cudaStream_t st) {
   constexpr int CH = Vec<VT>::CH;
-  if (g_tuning.bwd_run > 0 && P == 4 && (D == 16 || D == 32 || D == 64))
-    return backward_run<VT>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, D, L, Lq, P, g_tuning.bwd_run, st);
   if (P == 4) {
     if (D == 32) return launch_bwd_vec<VT, 32>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
     if (D == 64) return launch_bwd_vec<VT, 64>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
