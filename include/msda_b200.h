@@ -131,6 +131,21 @@ int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const fl
                            void *stream);
 int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, int cols, void *out, int is_half,
                       void *stream);
+/* ZiRa training-mode projection (semantics of RepZeroLinear, groundingdino_dual_zero_rep_branch.py:119-125, beside a
+ * frozen nn.Linear): ONE GEMM over the stacked weight [W_0; W_f; W_b] -- rows interleaved in runs of 32 output
+ * features (base 0-31, soft-frozen 0-31, branch 0-31, base 32-63, ...) -- whose epilogue forms
+ *   branch = s*(x W_b^T + b_b), adapter = branch + x W_f^T + b_f, out = x W_0^T + b_0 + adapter  (masked rows -> 0)
+ * and reduces the zero-inter loss terms: loss_sums[0] += sum SmoothL1(branch), loss_sums[1] += sum SmoothL1(adapter)
+ * (caller zeroes loss_sums and divides by R*F).  bias3 = [b_0 | b_f | b_b] fp32, scaling = device scalar.  pre_out
+ * (x W_b^T + b_b) and adapter_out, both [R, F] 16-bit, are what the backward needs; either may be NULL.
+ * msda_zira_bwd_prep_16 builds the K-stacked operand [dY_eff | dO | dB] ([R, 3F]) of the dgrad GEMM
+ * (msda_linear_16 against [W_0^T | W_f^T | s W_b^T]). */
+int msda_zira_linear_16(const void *x, const void *w_stack, const float *bias3, const float *scaling, long long R, int K,
+                        int F, void *out, const uint8_t *row_mask, void *pre_out, void *adapter_out, float *loss_sums,
+                        int is_half, void *stream);
+int msda_zira_bwd_prep_16(const void *dy, const void *pre, const void *adapter, const uint8_t *row_mask,
+                          const float *scaling, const float *dloss, long long R, int F, void *out, int is_half,
+                          void *stream);
 const char *msda_b200_gemm_last_error(void);
 
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,

@@ -89,9 +89,65 @@ cast_mask_kernel(const float* __restrict__ in, const uint8_t* __restrict__ row_m
   w.w = to16(b.z, h) | (static_cast<uint32_t>(to16(b.w, h)) << 16);
   out[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
 }
+__device__ __forceinline__ float from16(uint16_t v, bool is_half) {
+  if (is_half) return __half2float(*reinterpret_cast<const __half*>(&v));
+  return __uint_as_float(static_cast<uint32_t>(v) << 16);
+}
+
+// ZiRa training-mode projection, backward prep (one pass): from the upstream gradient dY, the saved branch
+// pre-activation and adapter output, and the upstream gradient of the zero-inter loss, build the K-stacked
+// operand [dY_eff | dO | dB] of the dgrad GEMM:
+//   dY_eff = dY (0 on masked rows);  dO = dY_eff + gl * SmoothL1'(adapter);  dB = dO + gl * SmoothL1'(s * pre)
+// where gl = dLoss / (R * F) and SmoothL1'(x) = clamp(x, -1, 1).  8 features per thread.
+__global__ void __launch_bounds__(256)
+zira_bwd_prep_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ pre, const uint16_t* __restrict__ adapter,
+                     const uint8_t* __restrict__ row_mask, const float* __restrict__ scaling, const float* __restrict__ dloss,
+                     long long R, int F, int is_half, uint16_t* __restrict__ out) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int f8 = F / 8;
+  if (i >= R * f8) return;
+  const long long row = i / f8;
+  const int col = static_cast<int>(i % f8) * 8;
+  const bool h = is_half != 0;
+  const float s = __ldg(scaling);
+  const float gl = __ldg(dloss) / (static_cast<float>(R) * static_cast<float>(F));
+  const bool masked = row_mask != nullptr && row_mask[row] != 0;
+  const uint4 a = __ldg(reinterpret_cast<const uint4*>(dy + row * F + col));
+  const uint4 b = __ldg(reinterpret_cast<const uint4*>(pre + row * F + col));
+  const uint4 c = __ldg(reinterpret_cast<const uint4*>(adapter + row * F + col));
+  const uint16_t* pa = reinterpret_cast<const uint16_t*>(&a);
+  const uint16_t* pb = reinterpret_cast<const uint16_t*>(&b);
+  const uint16_t* pc = reinterpret_cast<const uint16_t*>(&c);
+  uint16_t o0[8], o1[8], o2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float dye = masked ? 0.f : from16(pa[j], h);
+    const float d_o = dye + gl * fminf(fmaxf(from16(pc[j], h), -1.f), 1.f);
+    const float d_b = d_o + gl * fminf(fmaxf(s * from16(pb[j], h), -1.f), 1.f);
+    o0[j] = to16(dye, h); o1[j] = to16(d_o, h); o2[j] = to16(d_b, h);
+  }
+  uint16_t* orow = out + row * 3 * F + col;
+  *reinterpret_cast<uint4*>(orow) = *reinterpret_cast<const uint4*>(o0);
+  *reinterpret_cast<uint4*>(orow + F) = *reinterpret_cast<const uint4*>(o1);
+  *reinterpret_cast<uint4*>(orow + 2 * F) = *reinterpret_cast<const uint4*>(o2);
+}
 }  // namespace
 
 extern "C" {
+
+int msda_zira_bwd_prep_16(const void* dy, const void* pre, const void* adapter, const uint8_t* row_mask, const float* scaling,
+                          const float* dloss, long long R, int F, void* out, int is_half, void* stream) {
+  if (!dy || !pre || !adapter || !scaling || !dloss || !out) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || F <= 0 || F % 8) return MSDA_ERR_BAD_SHAPE;
+  const long long n = R * (F / 8);
+  ++msda::g_launches;
+  zira_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(adapter), row_mask,
+      scaling, dloss, R, F, is_half, static_cast<uint16_t*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
 
 int msda_query_bwd_prep_16(const float* grad_loc, const float* grad_aw, const float* aw, const float* ref, int ref_dim,
                            const int64_t* spatial_shapes, long long R, int M, int L, int P, void* out, int is_half,

@@ -43,7 +43,7 @@ constexpr int MAX_N = 1024;              // widest stacked weight handled by one
 constexpr int THREADS = 192;
 constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
 
-enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1 };
+enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1, EPI_ZIRA = 2 };
 
 struct EpiParams {
   int mode;
@@ -61,6 +61,16 @@ struct EpiParams {
   const float* ref;        // [R, L, ref_dim]
   const int64_t* shapes;   // device [L, 2] (H, W)
   int ref_dim, L, P, n_loc, n_aw;
+  // EPI_ZIRA (training-mode ZiRa projection): the stacked weight is [W_0; W_f; W_b] interleaved in runs of 32
+  // output features, so columns [96g, 96g+32) / [+32, +64) / [+64, +96) are the base / soft-frozen / branch
+  // products of features [32g, 32g+32).  bias = [b_0 | b_f | b_b] (3F floats).
+  //   branch  = s * (x W_b^T + b_b)            adapter = branch + x W_f^T + b_f           y = x W_0^T + b_0 + adapter
+  //   loss_sums[0] += sum SmoothL1(branch), loss_sums[1] += sum SmoothL1(adapter)   (all rows, also masked ones)
+  const float* scaling;    // device scalar s
+  void* pre_out;           // [R, F] 16-bit: x W_b^T + b_b   (saved for backward; may be null)
+  void* adapter_out;       // [R, F] 16-bit: adapter          (saved for backward; may be null)
+  float* loss_sums;        // 2 floats, pre-zeroed by the caller
+  int F;
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------
@@ -251,6 +261,24 @@ __device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32],
   for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
+__device__ __forceinline__ float smooth_l1(float x) {   // beta = 1 (torch.nn.SmoothL1Loss default)
+  const float a = fabsf(x);
+  return a < 1.f ? 0.5f * x * x : a - 0.5f;
+}
+
+__device__ __forceinline__ void store16x32(void* base, long long off, const float (&v)[32], bool half_out, bool zero) {
+  uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + off);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 w;
+    w.x = pack16(v[8 * i], v[8 * i + 1], half_out);
+    w.y = pack16(v[8 * i + 2], v[8 * i + 3], half_out);
+    w.z = pack16(v[8 * i + 4], v[8 * i + 5], half_out);
+    w.w = pack16(v[8 * i + 6], v[8 * i + 7], half_out);
+    o[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
+  }
+}
+
 // ---- the kernel -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int Nout,
@@ -346,12 +374,39 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3;
     int acc = 0;
     uint32_t acc_phase = 0;
+    float zsum_b = 0.f, zsum_o = 0.f;   // EPI_ZIRA: this thread's share of the two SmoothL1 sums
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int m_idx = (t / num_n) * BLOCK_M, n_idx = (t % num_n) * block_n;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * block_n);
+      if (ep.mode == EPI_ZIRA) {
+        const float s = __ldg(ep.scaling);
+        const bool half_out = ep.out_half != 0;
+        for (int c0 = 0; c0 < block_n; c0 += 96) {
+          uint32_t r0[32], r1[32], r2[32];
+          tmem_ld32(taddr + c0, r0);
+          tmem_ld32(taddr + c0 + 32, r1);
+          tmem_ld32(taddr + c0 + 64, r2);
+          const int f0 = (n_idx + c0) / 3;     // first of the 32 features of this triple
+          float y[32], pre[32], ad[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            pre[j] = __uint_as_float(r2[j]) + s_bias[2 * ep.F + f0 + j];
+            const float br = s * pre[j];
+            ad[j] = br + __uint_as_float(r1[j]) + s_bias[ep.F + f0 + j];
+            y[j] = __uint_as_float(r0[j]) + s_bias[f0 + j] + ad[j];
+            if (row < R) { zsum_b += smooth_l1(br); zsum_o += smooth_l1(ad[j]); }
+          }
+          if (row < R) {
+            const bool zero = ep.row_mask != nullptr && ep.row_mask[row] != 0;
+            store16x32(ep.out, row * ep.out_ld + f0, y, half_out, zero);
+            if (ep.pre_out) store16x32(ep.pre_out, row * ep.F + f0, pre, half_out, false);
+            if (ep.adapter_out) store16x32(ep.adapter_out, row * ep.F + f0, ad, half_out, false);
+          }
+        }
+      } else
       for (int c0 = 0; c0 < block_n; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c0, r);
@@ -376,6 +431,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (ep.mode == EPI_ZIRA) {
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) {
+        zsum_b += __shfl_xor_sync(0xffffffffu, zsum_b, o);
+        zsum_o += __shfl_xor_sync(0xffffffffu, zsum_o, o);
+      }
+      if (lane == 0) { atomicAdd(ep.loss_sums, zsum_b); atomicAdd(ep.loss_sums + 1, zsum_o); }
     }
   }
 
@@ -491,6 +554,20 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
   int block_n = (n_aw % 128 == 0) ? 128 : (n_aw % 64 == 0 ? 64 : 32);
   return pg::launch(query, w_cat, R, K, n_loc + n_aw, block_n, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+int msda_zira_linear_16(const void* x, const void* w_stack, const float* bias3, const float* scaling, long long R, int K,
+                        int F, void* out, const uint8_t* row_mask, void* pre_out, void* adapter_out, float* loss_sums,
+                        int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out || !bias3 || !scaling || !loss_sums) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  if (F % 64 || 3 * F > pg::MAX_N) { snprintf(pg::t_err, sizeof(pg::t_err), "ZiRa projection needs F %% 64 == 0 and F <= %d", pg::MAX_N / 3); return MSDA_ERR_UNSUPPORTED; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_ZIRA;
+  ep.out = out; ep.out_ld = F; ep.out_half = is_half; ep.bias = bias3; ep.row_mask = row_mask;
+  ep.scaling = scaling; ep.pre_out = pre_out; ep.adapter_out = adapter_out; ep.loss_sums = loss_sums; ep.F = F;
+  return pg::launch(x, w_stack, R, K, 3 * F, 192, is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

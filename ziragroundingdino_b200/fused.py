@@ -149,3 +149,125 @@ class FusedMSDeformAttnFunction(Function):
                      db_cat[n_loc:].to(dt), g2d.t() @ core.view(N * Lq, C), g2d.float().sum(0).to(dt)]
             grads = [g if ctx.needs_input_grad[11 + i] else None for i, g in enumerate(grads)]
         return (d_query, d_value_in, None, None, None, None, None, None, None, None, None, *grads)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Stage-wise autograd Functions: used when the module cannot run as ONE fused Function, i.e. with
+# un-merged ZiRa branches in training mode (their GEMM has its own epilogue, loss output and backward).
+# ---------------------------------------------------------------------------------------------------
+class Linear16Function(Function):
+    """y = x W^T + b with an optional row mask (rows zeroed), x [R, K] 16-bit."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, b, row_mask):
+        ctx.save_for_backward(x2d, w, row_mask)
+        return linear16(x2d, w.contiguous(), None if b is None else b.float(), row_mask)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        x2d, w, row_mask = ctx.saved_tensors
+        gy = gy.contiguous()
+        if row_mask is not None:
+            gy = gy.masked_fill(row_mask.bool()[:, None], 0)
+        gx = linear16(gy, w.t().contiguous()) if ctx.needs_input_grad[0] else None
+        gw = gy.t() @ x2d if ctx.needs_input_grad[1] else None
+        gb = gy.float().sum(0).to(gy.dtype) if ctx.needs_input_grad[2] else None
+        return gx, gw, gb, None
+
+
+class QueryProj16Function(Function):
+    """(query, W_off, b_off, W_aw, b_aw, ref) -> (sampling locations, softmax weights), both fp32."""
+
+    @staticmethod
+    def forward(ctx, q2d, w_off, b_off, w_aw, b_aw, ref, spatial_shapes, M, L, P):
+        w_cat = torch.cat([w_off, w_aw], 0).contiguous()
+        b_cat = torch.cat([b_off, b_aw], 0).float()
+        ref = ref.to(torch.float32).contiguous()
+        loc, aw = query_proj16(q2d, w_cat, b_cat, ref, ref.shape[-1], spatial_shapes, M, L, P)
+        ctx.save_for_backward(q2d, w_cat, ref, spatial_shapes, aw)
+        ctx.dims = (M, L, P)
+        return loc, aw
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_loc, g_aw):
+        q2d, w_cat, ref, spatial_shapes, aw = ctx.saved_tensors
+        M, L, P = ctx.dims
+        R = q2d.shape[0]
+        dq_cat = query_bwd_prep16(g_loc.contiguous(), g_aw.contiguous(), aw, ref, ref.shape[-1], spatial_shapes, R, M, L, P,
+                                  q2d.dtype)
+        gq = linear16(dq_cat, w_cat.t().contiguous()) if ctx.needs_input_grad[0] else None
+        n_loc = 2 * M * L * P
+        gw = gb = None
+        if any(ctx.needs_input_grad[1:5]):
+            gw = dq_cat.t() @ q2d
+            gb = dq_cat.float().sum(0).to(q2d.dtype)
+        pick = lambda i, t: t if (t is not None and ctx.needs_input_grad[i]) else None
+        return (gq, pick(1, None if gw is None else gw[:n_loc]), pick(2, None if gb is None else gb[:n_loc]),
+                pick(3, None if gw is None else gw[n_loc:]), pick(4, None if gb is None else gb[n_loc:]), None, None, None,
+                None, None)
+
+
+def _interleave32(w0, wf, wb):
+    """[W_0; W_f; W_b] with rows interleaved in runs of 32 output features (the layout msda_zira_linear_16 expects)."""
+    F, K = w0.shape
+    return torch.stack([w0.view(F // 32, 32, K), wf.view(F // 32, 32, K), wb.view(F // 32, 32, K)], 1).reshape(3 * F, K).contiguous()
+
+
+class ZiRaLinear16Function(Function):
+    """Training-mode ZiRa projection beside a frozen linear, one tcgen05 GEMM (see msda_zira_linear_16):
+    returns (y, zero_inter_loss).  Inputs: x [R, K] 16-bit; base (w0, b0); soft-frozen (wf, bf); branch (wb, bb);
+    scaling s (1 element); optional row mask applied to y only."""
+
+    @staticmethod
+    def forward(ctx, x2d, row_mask, w0, b0, wf, bf, wb, bb, s):
+        R, K = x2d.shape
+        F = w0.shape[0]
+        dt = x2d.dtype
+        w_stack = _interleave32(w0, wf, wb)
+        bias3 = torch.cat([b0, bf, bb]).float()
+        s32 = s.detach().float().reshape(1).contiguous()
+        y = torch.empty((R, F), dtype=dt, device=x2d.device)
+        pre = torch.empty((R, F), dtype=dt, device=x2d.device)
+        adapter = torch.empty((R, F), dtype=dt, device=x2d.device)
+        sums = torch.zeros(2, dtype=torch.float32, device=x2d.device)
+        with torch.cuda.device(x2d.device):
+            rc = _lib.lib().msda_zira_linear_16(x2d.data_ptr(), w_stack.data_ptr(), bias3.data_ptr(), s32.data_ptr(), R, K, F,
+                                                y.data_ptr(), 0 if row_mask is None else row_mask.data_ptr(), pre.data_ptr(),
+                                                adapter.data_ptr(), sums.data_ptr(), 1 if dt == torch.float16 else 0,
+                                                _stream(x2d))
+        _lib.check(rc, "msda_zira_linear_16")
+        loss = (sums.sum() / (R * F)).to(dt)
+        ctx.save_for_backward(x2d, row_mask, w0, wf, wb, s32, pre, adapter)
+        return y, loss
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy, gloss):
+        x2d, row_mask, w0, wf, wb, s32, pre, adapter = ctx.saved_tensors
+        R, K = x2d.shape
+        F = w0.shape[0]
+        dt = x2d.dtype
+        gl32 = gloss.detach().float().reshape(1).contiguous()
+        stacked = torch.empty((R, 3 * F), dtype=dt, device=x2d.device)
+        with torch.cuda.device(x2d.device):
+            rc = _lib.lib().msda_zira_bwd_prep_16(gy.contiguous().data_ptr(), pre.data_ptr(), adapter.data_ptr(),
+                                                  0 if row_mask is None else row_mask.data_ptr(), s32.data_ptr(), gl32.data_ptr(),
+                                                  R, F, stacked.data_ptr(), 1 if dt == torch.float16 else 0, _stream(x2d))
+        _lib.check(rc, "msda_zira_bwd_prep_16")
+        s = s32.to(dt)
+        gx = None
+        if ctx.needs_input_grad[0]:   # dX = dY W_0 + dO W_f + dB (s W_b): one GEMM with K = 3F
+            w_t = torch.cat([w0.t(), wf.t(), (wb * s).t()], 1).contiguous()
+            gx = linear16(stacked, w_t)
+        d_y, d_o, d_b = stacked[:, :F], stacked[:, F:2 * F], stacked[:, 2 * F:]
+        need = ctx.needs_input_grad
+        gw0 = d_y.t() @ x2d if need[2] else None
+        gb0 = d_y.float().sum(0).to(dt) if need[3] else None
+        gwf = d_o.t() @ x2d if need[4] else None
+        gbf = d_o.float().sum(0).to(dt) if need[5] else None
+        gwb = (d_b.t() @ x2d) * s if need[6] else None
+        gbb = (d_b.float().sum(0) * s32).to(dt) if need[7] else None
+        gs = (d_b.float() * pre.float()).sum().reshape(1).to(dt) if need[8] else None
+        return gx, None, gw0, gb0, gwf, gbf, gwb, gbb, gs

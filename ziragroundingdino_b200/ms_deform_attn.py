@@ -192,9 +192,7 @@ class MultiScaleDeformableAttention(nn.Module):
             return False
         if reference_points.shape[-1] not in (2, 4) or reference_points.requires_grad:
             return False
-        # un-merged ZiRa branches in training mode need the branch activations for the zero-inter loss
-        has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None
-        return not (has_branch and self.training)
+        return True
 
     def _effective(self, base, adapter):
         """Eval-mode weights of a projection: pretrained + accumulated soft-frozen ZiRa weights
@@ -203,7 +201,41 @@ class MultiScaleDeformableAttention(nn.Module):
             return base.weight, base.bias
         return base.weight + adapter.freeze_linear.weight, base.bias + adapter.freeze_linear.bias
 
+    def _forward_fused_zira_train(self, query, value, key_padding_mask, reference_points, spatial_shapes,
+                                  level_start_index):
+        """Training mode with un-merged ZiRa branches: stage-wise Functions; each augmented projection is ONE
+        tcgen05 GEMM over [W_0; W_f; W_b] whose epilogue folds the three products and reduces the zero-inter loss."""
+        N, Lq, C = query.shape
+        S = value.shape[1]
+        M, L, P = self.num_heads, self.num_levels, self.num_points
+        row_mask = None
+        if key_padding_mask is not None:
+            row_mask = key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
+        losses = []
+
+        def project(x2d, base, ad, mask):
+            if ad is None:
+                return fused.Linear16Function.apply(x2d, base.weight, base.bias, mask)
+            y, zl = fused.ZiRaLinear16Function.apply(x2d, mask, base.weight, base.bias, ad.freeze_linear.weight,
+                                                     ad.freeze_linear.bias, ad.weight, ad.bias, ad.scaling)
+            losses.append(zl)
+            return y
+
+        v = project(value.reshape(N * S, C).contiguous(), self.value_proj, self.value_proj_adapter, row_mask)
+        loc, aw = fused.QueryProj16Function.apply(query.reshape(N * Lq, C).contiguous(), self.sampling_offsets.weight,
+                                                  self.sampling_offsets.bias, self.attention_weights.weight,
+                                                  self.attention_weights.bias, reference_points, spatial_shapes, M, L, P)
+        core = MultiScaleDeformableAttnFunction.apply(v.view(N, S, M, C // M), spatial_shapes, level_start_index,
+                                                      loc.view(N, Lq, M, L, P, 2), aw.view(N, Lq, M, L, P), self.im2col_step)
+        out = project(core.reshape(N * Lq, C), self.output_proj, self.output_proj_adapter, None)
+        self.zero_inter_loss = sum(losses) if losses else None
+        return out.view(N, Lq, C)
+
     def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
+        has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None
+        if has_branch and self.training:
+            return self._forward_fused_zira_train(query, value, key_padding_mask, reference_points, spatial_shapes,
+                                                  level_start_index)
         w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
         w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
         raw = (w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
