@@ -50,7 +50,7 @@ def lib():
     L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _vp]
     L.msda_cast_mask_16.argtypes = [_vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_zira_linear_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
-    L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _i, _vp]
+    L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     _lib = L
     return L

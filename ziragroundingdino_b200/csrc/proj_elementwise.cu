@@ -102,10 +102,11 @@ __device__ __forceinline__ float from16(uint16_t v, bool is_half) {
 __global__ void __launch_bounds__(256)
 zira_bwd_prep_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ pre, const uint16_t* __restrict__ adapter,
                      const uint8_t* __restrict__ row_mask, const float* __restrict__ scaling, const float* __restrict__ dloss,
-                     long long R, int F, int is_half, uint16_t* __restrict__ out) {
+                     long long R, int F, int is_half, uint16_t* __restrict__ out, float* __restrict__ ds_out) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const int f8 = F / 8;
-  if (i >= R * f8) return;
+  float ds = 0.f;   // this thread's share of d(loss)/d(scaling) = sum dB * pre, taken before dB is rounded to 16 bit
+  if (i < R * f8) {
   const long long row = i / f8;
   const int col = static_cast<int>(i % f8) * 8;
   const bool h = is_half != 0;
@@ -125,25 +126,39 @@ zira_bwd_prep_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict
     const float d_o = dye + gl * fminf(fmaxf(from16(pc[j], h), -1.f), 1.f);
     const float d_b = d_o + gl * fminf(fmaxf(s * from16(pb[j], h), -1.f), 1.f);
     o0[j] = to16(dye, h); o1[j] = to16(d_o, h); o2[j] = to16(d_b, h);
+    ds = fmaf(d_b, from16(pb[j], h), ds);
   }
   uint16_t* orow = out + row * 3 * F + col;
   *reinterpret_cast<uint4*>(orow) = *reinterpret_cast<const uint4*>(o0);
   *reinterpret_cast<uint4*>(orow + F) = *reinterpret_cast<const uint4*>(o1);
   *reinterpret_cast<uint4*>(orow + 2 * F) = *reinterpret_cast<const uint4*>(o2);
+  }
+  if (ds_out != nullptr) {   // block reduction, one atomic per CTA
+    __shared__ float s_part[8];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) ds += __shfl_xor_sync(0xffffffffu, ds, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = ds;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += s_part[w];
+      atomicAdd(ds_out, t);
+    }
+  }
 }
 }  // namespace
 
 extern "C" {
 
 int msda_zira_bwd_prep_16(const void* dy, const void* pre, const void* adapter, const uint8_t* row_mask, const float* scaling,
-                          const float* dloss, long long R, int F, void* out, int is_half, void* stream) {
+                          const float* dloss, long long R, int F, void* out, float* ds_out, int is_half, void* stream) {
   if (!dy || !pre || !adapter || !scaling || !dloss || !out) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || F <= 0 || F % 8) return MSDA_ERR_BAD_SHAPE;
   const long long n = R * (F / 8);
   ++msda::g_launches;
   zira_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(adapter), row_mask,
-      scaling, dloss, R, F, is_half, static_cast<uint16_t*>(out));
+      scaling, dloss, R, F, is_half, static_cast<uint16_t*>(out), ds_out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

@@ -251,10 +251,12 @@ class ZiRaLinear16Function(Function):
         dt = x2d.dtype
         gl32 = gloss.detach().float().reshape(1).contiguous()
         stacked = torch.empty((R, 3 * F), dtype=dt, device=x2d.device)
+        ds = torch.zeros(1, dtype=torch.float32, device=x2d.device)
         with torch.cuda.device(x2d.device):
             rc = _lib.lib().msda_zira_bwd_prep_16(gy.contiguous().data_ptr(), pre.data_ptr(), adapter.data_ptr(),
                                                   0 if row_mask is None else row_mask.data_ptr(), s32.data_ptr(), gl32.data_ptr(),
-                                                  R, F, stacked.data_ptr(), 1 if dt == torch.float16 else 0, _stream(x2d))
+                                                  R, F, stacked.data_ptr(), ds.data_ptr(), 1 if dt == torch.float16 else 0,
+                                                  _stream(x2d))
         _lib.check(rc, "msda_zira_bwd_prep_16")
         s = s32.to(dt)
         gx = None
@@ -269,5 +271,5 @@ class ZiRaLinear16Function(Function):
         gbf = d_o.float().sum(0).to(dt) if need[5] else None
         gwb = (d_b.t() @ x2d) * s if need[6] else None
         gbb = (d_b.float().sum(0) * s32).to(dt) if need[7] else None
-        gs = (d_b.float() * pre.float()).sum().reshape(1).to(dt) if need[8] else None
+        gs = ds.to(dt) if need[8] else None
         return gx, None, gw0, gb0, gwf, gbf, gwb, gbb, gs
