@@ -148,6 +148,18 @@ int msda_zira_bwd_prep_16(const void *dy, const void *pre, const void *adapter, 
                           const float *scaling, const float *dloss, long long R, int F, void *out, float *ds_out,
                           int is_half, void *stream);
 const char *msda_b200_gemm_last_error(void);
+/* A/B switch for benchmarks: 1 (default) keeps each CTA's slice of W resident in shared memory when it fits. */
+int msda_b200_gemm_set_resident(int on);
+
+/* ---- the op's immediate caller: residual + LayerNorm ------------------------------
+ * `src = norm(src + src2)` of the reference's DeformableTransformerEncoderLayer (transformer_for_adapter.py:901-902 after
+ * the attention, :882-885 after the FFN; dropout p = 0), one pass per direction over 16-bit activations [R, C] with fp32
+ * statistics.  fwd writes z = x + r (LayerNorm's saved input), y, mean[R], rstd[R]; bwd returns dz (gradient of both x
+ * and r).  C % 8 == 0, C <= 1024.  gamma / beta fp32. */
+int msda_add_layernorm_fwd_16(const void *x, const void *r, const float *gamma, const float *beta, long long R, int C,
+                              float eps, void *z, void *y, float *mean, float *rstd, int is_half, void *stream);
+int msda_add_layernorm_bwd_16(const void *dy, const void *z, const float *gamma, const float *mean, const float *rstd,
+                              long long R, int C, void *dz, int is_half, void *stream);
 
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
  * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =

@@ -272,3 +272,44 @@ def test_module_zira_train_fused_vs_unfused():
     with torch.no_grad():
         y_merged = m(query=query, value=src, **kw).float()
     assert (y_merged - yf).abs().max().item() < 2e-2 * yf.abs().max().item()
+
+
+@pytest.mark.parametrize("dtype,eps16", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)])
+@pytest.mark.parametrize("R,C", [(1000, 256), (77, 64), (5, 1024)])
+def test_add_layernorm_fused(dtype, eps16, R, C):
+    """Fused residual + LayerNorm (forward and backward) vs torch in fp64 on the same 16-bit inputs."""
+    from ziragroundingdino_b200.layer_ops import AddLayerNormFunction
+    x, r = _rand((R, C), dtype, 31), _rand((R, C), dtype, 32)
+    w, b = (_rand((C,), dtype, 33) * 0.2 + 1).requires_grad_(True), _rand((C,), dtype, 34, 0.1).requires_grad_(True)
+    xg, rg = x.clone().requires_grad_(True), r.clone().requires_grad_(True)
+    y = AddLayerNormFunction.apply(xg, rg, w, b, 1e-5)
+    gy = _rand((R, C), dtype, 35)
+    y.backward(gy)
+    xd, rd = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    wd, bd = w.detach().double().requires_grad_(True), b.detach().double().requires_grad_(True)
+    z = (x + r).double()          # the unfused sequence rounds the sum to 16 bit before LayerNorm; so does the kernel
+    z = z + (xd + rd - (xd + rd).detach())
+    yd = torch.nn.functional.layer_norm(z, (C,), wd, bd, 1e-5)
+    yd.backward(gy.double())
+    assert (y.double() - yd.detach()).abs().max().item() <= 1.5 * eps16 * yd.abs().max().item()
+    assert rel_err(xg.grad.double().cpu(), xd.grad.cpu()) < 4 * eps16
+    assert torch.equal(xg.grad, rg.grad)
+    assert rel_err(w.grad.double().cpu(), wd.grad.cpu()) < 8 * eps16
+    assert rel_err(b.grad.double().cpu(), bd.grad.cpu()) < 8 * eps16
+
+
+def test_gemm_resident_and_streaming_modes_agree():
+    """The GEMM keeps its slice of W resident in shared memory when it fits and streams it otherwise: same bits."""
+    from ziragroundingdino_b200 import _lib, fused
+    L = _lib.lib()
+    for (R, K, Nout) in [(3000, 256, 256), (1500, 384, 256), (700, 256, 384), (400, 768, 256)]:
+        x, w, b = _rand((R, K), torch.bfloat16, 41), _rand((Nout, K), torch.bfloat16, 42, 0.05), _rand((Nout,), torch.float32, 43)
+        try:
+            L.msda_b200_gemm_set_resident(1)
+            y1 = fused.linear16(x, w, b, out_f32=True)
+            L.msda_b200_gemm_set_resident(0)
+            y0 = fused.linear16(x, w, b, out_f32=True)
+        finally:
+            L.msda_b200_gemm_set_resident(1)
+        assert torch.equal(y0, y1)
+        assert rel_err(y1.cpu(), (x.double() @ w.double().t() + b.double()).cpu()) < 1e-4

@@ -1,0 +1,168 @@
+// Row N1 of SURVEY.md section 8(f): the residual + LayerNorm that follows MultiScaleDeformableAttention (and the FFN)
+// in the reference's DeformableTransformerEncoderLayer (transformer_for_adapter.py:901-902, :882-885):
+//     src = norm(src + dropout(src2))          (dropout is the identity: p = 0.0 in the ZiRa configuration)
+// as ONE pass over the activation in each direction instead of add + LayerNorm (fwd) and LayerNorm-grad + add (bwd).
+// 16-bit activations, fp32 statistics.  One warp per row; C <= 1024, C % 8 == 0.
+//   forward : z = x + r (stored, 16-bit: it is LayerNorm's saved input), y = (z - mean) * rstd * gamma + beta
+//   backward: dz = rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma,  xhat = (z - mean) * rstd
+//             (dz is the gradient of BOTH x and r)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/msda_b200.h"
+
+namespace msda {
+extern long long g_launches;
+}
+
+namespace {
+constexpr int kMaxVec = 4;   // up to 4 x 8 elements per lane = C <= 1024
+
+__device__ __forceinline__ void unpack8(const uint4& r, bool h, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (h) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      f[2 * i] = t.x; f[2 * i + 1] = t.y;
+    } else {
+      f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8], bool h) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (h) { __half2 t = __floats2half2_rn(f[2 * i], f[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    else { __nv_bfloat162 t = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, long long R, int C, float eps, int is_half, uint16_t* __restrict__ z,
+                  uint16_t* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31, nvec = C / 256 + (C % 256 ? 1 : 0);
+  const bool h = is_half != 0;
+  float v[kMaxVec][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (i < nvec && c < C) {
+      float a[8], b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + c)), h, a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(r + row * C + c)), h, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[i][j] = a[j] + b[j];
+      // LayerNorm sees the 16-bit rounded sum, exactly as the unfused add -> LayerNorm sequence does
+      const uint4 zz = pack8(v[i], h);
+      *reinterpret_cast<uint4*>(z + row * C + c) = zz;
+      unpack8(zz, h, v[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += v[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (i < nvec && c < C) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq = fmaf(d, d, sq); }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (i < nvec && c < C) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, __ldg(gamma + c + j), __ldg(beta + c + j));
+      *reinterpret_cast<uint4*>(y + row * C + c) = pack8(o, h);
+    }
+  }
+  if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+}
+
+__global__ void __launch_bounds__(256)
+add_ln_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ z, const float* __restrict__ gamma,
+                  const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long R, int C, int is_half,
+                  uint16_t* __restrict__ dz) {
+  const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+  if (row >= R) return;
+  const int lane = threadIdx.x & 31, nvec = C / 256 + (C % 256 ? 1 : 0);
+  const bool h = is_half != 0;
+  const float mean = mean_in[row], rstd = rstd_in[row];
+  float g[kMaxVec][8], xh[kMaxVec][8];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (i < nvec && c < C) {
+      float a[8], b[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + c)), h, a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(z + row * C + c)), h, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[i][j] = a[j] * __ldg(gamma + c + j);
+        xh[i][j] = (b[j] - mean) * rstd;
+        s1 += g[i][j];
+        s2 = fmaf(g[i][j], xh[i][j], s2);
+      }
+    }
+  }
+  const float m1 = warp_sum(s1) / C, m2 = warp_sum(s2) / C;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = (i * 32 + lane) * 8;
+    if (i < nvec && c < C) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (g[i][j] - m1 - xh[i][j] * m2);
+      *reinterpret_cast<uint4*>(dz + row * C + c) = pack8(o, h);
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+int msda_add_layernorm_fwd_16(const void* x, const void* r, const float* gamma, const float* beta, long long R, int C,
+                              float eps, void* z, void* y, float* mean, float* rstd, int is_half, void* stream) {
+  if (!x || !r || !gamma || !beta || !z || !y || !mean || !rstd) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || C <= 0 || C % 8 || C > 1024) return MSDA_ERR_BAD_SHAPE;
+  ++msda::g_launches;
+  add_ln_fwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(r), gamma, beta, R, C, eps, is_half,
+      static_cast<uint16_t*>(z), static_cast<uint16_t*>(y), mean, rstd);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+int msda_add_layernorm_bwd_16(const void* dy, const void* z, const float* gamma, const float* mean, const float* rstd,
+                              long long R, int C, void* dz, int is_half, void* stream) {
+  if (!dy || !z || !gamma || !mean || !rstd || !dz) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || C <= 0 || C % 8 || C > 1024) return MSDA_ERR_BAD_SHAPE;
+  ++msda::g_launches;
+  add_ln_bwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(z), gamma, mean, rstd, R, C, is_half,
+      static_cast<uint16_t*>(dz));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+}  // extern "C"

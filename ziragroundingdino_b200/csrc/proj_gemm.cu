@@ -42,6 +42,8 @@ constexpr int SMEM_A = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_N = 1024;              // widest stacked weight handled by one launch
 constexpr int THREADS = 192;
 constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
+constexpr int kMaxSmem = 227 * 1024;
+bool g_allow_resident = true;   // msda_b200_set_tuning("gemm_resident", 0|1)
 
 enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1, EPI_ZIRA = 2 };
 
@@ -282,16 +284,22 @@ __device__ __forceinline__ void store16x32(void* base, long long off, const floa
 // ---- the kernel -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int Nout,
-                 int K, int block_n, int half_in, EpiParams ep) {
+                 int K, int block_n, int b_resident, int half_in, EpiParams ep) {
+  // b_resident: the CTA owns ONE n-block for its whole life and keeps that slice of W (block_n x K) in shared
+  // memory, loaded once; only the activation tiles stream through the ring (K = 256, N <= 256: 128 KiB of W).
+  // Otherwise A and B tiles stream together (any shape).
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = SMEM_A + block_n * BLOCK_K * 2;
-  uint8_t* aux = smem + STAGES * stage_bytes;
+  const int b_tile_bytes = block_n * BLOCK_K * 2;
+  const int stage_bytes = b_resident ? SMEM_A : SMEM_A + b_tile_bytes;
+  uint8_t* smem_bres = smem + STAGES * stage_bytes;                       // resident W slice: (K/64) tiles
+  uint8_t* aux = smem_bres + (b_resident ? (K / BLOCK_K) * b_tile_bytes : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(aux + 256);
   float* s_norm = s_bias + MAX_N;   // (1/W_l, 1/H_l)
 
@@ -299,7 +307,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_k = K / BLOCK_K;
   const int num_n = Nout / block_n;
   const int num_m = (R + BLOCK_M - 1) / BLOCK_M;
-  const int num_tiles = num_m * num_n;
+  // tile enumeration: streaming mode walks (m, n) tiles n-fastest; resident mode fixes n = blockIdx.x % num_n and walks m
+  const int t_first = b_resident ? blockIdx.x / num_n : blockIdx.x;
+  const int t_step = b_resident ? gridDim.x / num_n : gridDim.x;
+  const int t_end = b_resident ? num_m : num_m * num_n;
+  const int n_fixed = (blockIdx.x % num_n) * block_n;
   uint32_t tmem_cols = 32;
   while (tmem_cols < static_cast<uint32_t>(2 * block_n)) tmem_cols <<= 1;
 
@@ -308,6 +320,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -329,14 +342,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_idx = (t / num_n) * BLOCK_M, n_idx = (t % num_n) * block_n;
+      if (b_resident && t_first < t_end) {
+        mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_k * b_tile_bytes));
+        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, bres_bar, smem_bres + kb * b_tile_bytes, kb * BLOCK_K, n_fixed);
+      }
+      for (int t = t_first; t < t_end; t += t_step) {
+        const int m_idx = (b_resident ? t : t / num_n) * BLOCK_M, n_idx = b_resident ? n_fixed : (t % num_n) * block_n;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_expect_tx(full_bar + stage, static_cast<uint32_t>(stage_bytes));
           tma_load_2d(&tmA, full_bar + stage, sa, kb * BLOCK_K, m_idx);
-          tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, kb * BLOCK_K, n_idx);
+          if (!b_resident) tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, kb * BLOCK_K, n_idx);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -346,7 +363,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t idesc = umma_idesc(BLOCK_M, block_n, half_in != 0);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    if (b_resident && t_first < t_end) mbar_wait(bres_bar, 0);
+    for (int t = t_first; t < t_end; t += t_step) {
       mbar_wait(tempty_bar + acc, acc_phase ^ 1);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * block_n);
@@ -355,10 +373,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint8_t* sa = smem + stage * stage_bytes;
+          const uint8_t* sb = b_resident ? smem_bres + kb * b_tile_bytes : sa + SMEM_A;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = umma_desc_sw128(sa, k * UMMA_K * 2);
-            const uint64_t db = umma_desc_sw128(sa + SMEM_A, k * UMMA_K * 2);
+            const uint64_t db = umma_desc_sw128(sb, k * UMMA_K * 2);
             umma_f16(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar + stage);                      // smem stage free once these MMAs retire
@@ -375,8 +394,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int acc = 0;
     uint32_t acc_phase = 0;
     float zsum_b = 0.f, zsum_o = 0.f;   // EPI_ZIRA: this thread's share of the two SmoothL1 sums
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_idx = (t / num_n) * BLOCK_M, n_idx = (t % num_n) * block_n;
+    for (int t = t_first; t < t_end; t += t_step) {
+      const int m_idx = (b_resident ? t : t / num_n) * BLOCK_M, n_idx = b_resident ? n_fixed : (t % num_n) * block_n;
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
@@ -479,6 +498,22 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int cols
   return 0;
 }
 
+// Widest n-block (multiple of `unit`, dividing Nout, <= 256 columns so two accumulators fit TMEM) whose slice of W
+// (block_n x K 16-bit) still fits in shared memory beside the activation ring; the smallest legal block otherwise.
+static int pick_block_n(int Nout, int K, int unit) {
+  int best = 0, smallest = 0;
+  for (int bn = unit; bn <= 256 && bn <= Nout; bn += unit) {
+    if (Nout % bn) continue;
+    if (!smallest) smallest = bn;
+    if (bn * K * 2 + STAGES * SMEM_A + AUX_BYTES + 1024 <= kMaxSmem) best = bn;
+  }
+  if (best) return best;
+  // nothing fits resident: largest block whose streaming stages fit
+  for (int bn = 256; bn >= unit; bn -= unit)
+    if (Nout % bn == 0 && bn % unit == 0 && STAGES * (SMEM_A + bn * BLOCK_K * 2) + AUX_BYTES + 1024 <= kMaxSmem) return bn;
+  return smallest ? smallest : unit;
+}
+
 static int launch(const void* x, const void* w, long long R, int K, int Nout, int block_n, bool half_in,
                   const EpiParams& ep, cudaStream_t st) {
   if (!x || !w) { snprintf(t_err, sizeof(t_err), "null operand"); return MSDA_ERR_NULL_POINTER; }
@@ -502,23 +537,37 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const int smem = STAGES * (SMEM_A + block_n * BLOCK_K * 2) + AUX_BYTES + 1024;
-  static int configured = 0;
-  if (configured < smem) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  // resident-W mode whenever the CTA's slice of W fits beside the activation ring
+  const int num_n = Nout / block_n;
+  const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
+  const int bres_bytes = block_n * K * 2;
+  const bool b_res = g_allow_resident && bres_bytes + STAGES * SMEM_A + AUX_BYTES + 1024 <= kMaxSmem && num_n <= sms;
+  const int smem = (b_res ? STAGES * SMEM_A + bres_bytes : STAGES * (SMEM_A + block_n * BLOCK_K * 2)) + AUX_BYTES + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
     if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    configured = 200 * 1024;
+    configured = true;
   }
-  const long long tiles = ((R + BLOCK_M - 1) / BLOCK_M) * (Nout / block_n);
-  const int grid = static_cast<int>(tiles < sms ? tiles : sms);
+  int grid;
+  if (b_res) {
+    long long per_n = sms / num_n;
+    if (per_n > num_m) per_n = num_m;
+    grid = static_cast<int>(per_n) * num_n;
+  } else {
+    const long long tiles = num_m * num_n;
+    grid = static_cast<int>(tiles < sms ? tiles : sms);
+  }
   ++msda::g_launches;
-  linear_tc_kernel<<<grid, THREADS, smem, st>>>(tmA, tmB, static_cast<int>(R), Nout, K, block_n, half_in ? 1 : 0, ep);
+  linear_tc_kernel<<<grid, THREADS, smem, st>>>(tmA, tmB, static_cast<int>(R), Nout, K, block_n, b_res ? 1 : 0, half_in ? 1 : 0, ep);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "linear_tc_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;
 }
 
 }  // namespace pg
+
+extern "C" int msda_b200_gemm_set_resident(int on) { pg::g_allow_resident = on != 0; return 0; }
 
 extern "C" {
 
@@ -532,9 +581,7 @@ int msda_linear_16(const void* x, const void* w, const float* bias, long long R,
   memset(&ep, 0, sizeof(ep));
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = out_ld; ep.out_f32 = out_f32; ep.out_half = is_half; ep.bias = bias; ep.row_mask = row_mask;
-  int block_n = 128;
-  if (Nout % 128) block_n = (Nout % 64 == 0) ? 64 : 32;
-  return pg::launch(x, w, R, K, Nout, block_n, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_cat, const float* ref, int ref_dim,
@@ -552,8 +599,8 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   ep.mode = pg::EPI_QUERY;
   ep.bias = bias_cat; ep.loc_out = loc_out; ep.aw_out = aw_out; ep.ref = ref; ep.shapes = spatial_shapes;
   ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
-  int block_n = (n_aw % 128 == 0) ? 128 : (n_aw % 64 == 0 ? 64 : 32);
-  return pg::launch(query, w_cat, R, K, n_loc + n_aw, block_n, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32), is_half != 0, ep,
+                    static_cast<cudaStream_t>(stream));
 }
 
 int msda_zira_linear_16(const void* x, const void* w_stack, const float* bias3, const float* scaling, long long R, int K,
@@ -567,7 +614,7 @@ int msda_zira_linear_16(const void* x, const void* w_stack, const float* bias3, 
   ep.mode = pg::EPI_ZIRA;
   ep.out = out; ep.out_ld = F; ep.out_half = is_half; ep.bias = bias3; ep.row_mask = row_mask;
   ep.scaling = scaling; ep.pre_out = pre_out; ep.adapter_out = adapter_out; ep.loss_sums = loss_sums; ep.F = F;
-  return pg::launch(x, w_stack, R, K, 3 * F, 192, is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(x, w_stack, R, K, 3 * F, pg::pick_block_n(3 * F, K, 96), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -4,8 +4,8 @@ Mirrors the reference's ``DeformableTransformerEncoderLayer`` (transformer_for_a
 sub-module names, so checkpoint keys ``transformer.encoder.layers.{i}.self_attn.*`` / ``norm1`` /
 ``linear1`` ... load unchanged) with ``use_adapter=False`` as in the ZiRa configuration
 (groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:56).  The MSDeformAttn module inside is the
-B200-native one; residual + LayerNorm + FFN are still library ops here (SURVEY.md section 8(f) row N1 --
-the next thing to fuse).  ``DeformableEncoder`` is the 6-layer stack used by bench.py (BASELINE.json
+B200-native one; residual + LayerNorm are one fused kernel per direction (layer_ops.py); the FFN GEMMs are
+still library ops.  ``DeformableEncoder`` is the 6-layer stack used by bench.py (BASELINE.json
 config 2); the text-fusion and text-encoder sub-layers of the reference encoder loop
 (transformer_for_adapter.py:563-612) are out of scope and omitted.
 """
@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .layer_ops import add_layer_norm
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 
@@ -39,16 +40,14 @@ class DeformableTransformerEncoderLayer(nn.Module):
     def forward_ffn(self, src):
         adapter_loss = src.new_zeros(1)
         src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
-        src = src + self.dropout3(src2)
-        src = self.norm2(src)
+        src = add_layer_norm(src, src2, self.norm2, self.dropout3.p, self.training)
         return src, adapter_loss
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
         src2 = self.self_attn(query=self.with_pos_embed(src, pos), reference_points=reference_points, value=src,
                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                               key_padding_mask=key_padding_mask)
-        src = src + self.dropout1(src2)
-        src = self.norm1(src)
+        src = add_layer_norm(src, src2, self.norm1, self.dropout1.p, self.training)
         return self.forward_ffn(src)
 
 
