@@ -110,7 +110,7 @@ long long msda_b200_launch_count(void);
  * (ms_deform_attn.py:184-187 parameters; :286 value_proj, :290 sampling_offsets, :293 attention_weights,
  * :350 output_proj) and the elementwise passes between them, as tcgen05/TMA GEMMs over 16-bit (bf16, or
  * IEEE half when is_half != 0) activations with fp32 accumulation.  X is [R, K] row-major, W is the
- * nn.Linear weight [Nout, K] row-major, bias fp32.  K % 64 == 0; Nout % 32 == 0; Nout <= 1024.
+ * nn.Linear weight [Nout, K] row-major, bias fp32.  K % 64 == 0; Nout % 32 == 0; Nout <= 2048.
  *
  * msda_linear_16: out[r, :] = X[r, :] W^T + bias, rows with row_mask[r] != 0 written as zero (the
  *   masked_fill of :287-288; pass NULL for none).  out is 16-bit (out_f32 == 0) or fp32, leading
@@ -123,6 +123,11 @@ long long msda_b200_launch_count(void);
  * msda_query_bwd_prep_16 / msda_cast_mask_16: elementwise backward companions (see proj_elementwise.cu). */
 int msda_linear_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out,
                    int out_ld, int out_f32, const uint8_t *row_mask, int is_half, void *stream);
+/* FFN companions (row N1; reference transformer_for_adapter.py:876-885): out = relu(x W^T + bias) when relu != 0, and
+ * out = (x W^T + bias) where gate > 0 else 0 when gate != NULL (gate: 16-bit [R, Nout]) -- the ReLU backward fused into
+ * the dgrad GEMM of linear2.  16-bit output, leading dimension Nout; Nout <= 2048. */
+int msda_linear_act_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out, int relu,
+                       const void *gate, int is_half, void *stream);
 int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_cat, const float *ref, int ref_dim,
                        const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
                        float *aw_out, int is_half, void *stream);

@@ -313,3 +313,51 @@ def test_gemm_resident_and_streaming_modes_agree():
             L.msda_b200_gemm_set_resident(1)
         assert torch.equal(y0, y1)
         assert rel_err(y1.cpu(), (x.double() @ w.double().t() + b.double()).cpu()) < 1e-4
+
+
+@pytest.mark.parametrize("dtype,eps16", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)])
+def test_ffn_fused(dtype, eps16):
+    """relu folded into the linear1 epilogue and relu-backward folded into linear2's dgrad epilogue, vs torch fp64."""
+    from ziragroundingdino_b200.layer_ops import FFN16Function
+    R, C, Fh = 1111, 256, 2048
+    x = _rand((R, C), dtype, 51)
+    w1, b1 = _rand((Fh, C), dtype, 52, 0.06), _rand((Fh,), dtype, 53, 0.1)
+    w2, b2 = _rand((C, Fh), dtype, 54, 0.03), _rand((C,), dtype, 55, 0.1)
+    leaves = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    y = FFN16Function.apply(*leaves)
+    gy = _rand((R, C), dtype, 56)
+    y.backward(gy)
+    d = [t.double().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    h = torch.relu(torch.nn.functional.linear(d[0], d[1], d[2]))
+    h16 = h.detach().to(dtype).double()                    # the fused path stores h in 16 bit, like the unfused one
+    yd = torch.nn.functional.linear(h + (h16 - h.detach()), d[3], d[4])
+    yd.backward(gy.double())
+    assert (y.double() - yd.detach()).abs().max().item() <= 3 * eps16 * yd.abs().max().item()
+    for n, a, b in zip(("x", "w1", "b1", "w2", "b2"), leaves, d):
+        assert rel_err(a.grad.double().cpu(), b.grad.cpu()) < 6 * eps16, n
+
+
+def test_encoder_layer_fused_vs_library_ops():
+    """Encoder layer with the fused residual+LayerNorm / FFN pieces vs the same layer on library ops (bf16)."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import encoder, layer_ops
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(2, shapes, 256, torch.bfloat16)
+    torch.manual_seed(7)
+    layer = encoder.DeformableTransformerEncoderLayer(256, 2048, 0.0).to(DEV).to(torch.bfloat16)
+    pos = (query.float() - src.float()).to(torch.bfloat16)
+    outs = []
+    for fused_on in (True, False):
+        x = src.clone().requires_grad_(True)
+        if fused_on:
+            y, _ = layer(x, pos, refp, sh, lsi, mask)
+        else:
+            src2 = layer.self_attn(query=x + pos, reference_points=refp, value=x, spatial_shapes=sh, level_start_index=lsi,
+                                   key_padding_mask=mask)
+            z = layer.norm1(x + src2)
+            y = layer.norm2(z + layer.linear2(torch.relu(layer.linear1(z))))
+        y.float().square().mean().backward()
+        outs.append((y.detach().float(), x.grad.float()))
+    assert (outs[0][0] - outs[1][0]).abs().max().item() < 3e-2 * outs[1][0].abs().max().item()
+    d = (outs[0][1] - outs[1][1]).abs()
+    assert (d > 5e-2 * outs[1][1].abs().max().item()).float().mean().item() < 5e-3

@@ -39,9 +39,9 @@ constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int SMEM_A = BLOCK_M * BLOCK_K * 2;   // 16 KiB
-constexpr int MAX_N = 1024;              // widest stacked weight handled by one launch
+constexpr int MAX_N = 2048;              // widest (stacked) weight handled by one launch
 constexpr int THREADS = 192;
-constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
+constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8 + 4 * 32 * (128 + 16);
 constexpr int kMaxSmem = 227 * 1024;
 bool g_allow_resident = true;   // msda_b200_set_tuning("gemm_resident", 0|1)
 
@@ -56,6 +56,8 @@ struct EpiParams {
   int out_half;            // 16-bit output is IEEE half instead of bf16
   const float* bias;       // [Nout] fp32, may be null
   const uint8_t* row_mask; // [R] or null
+  int relu;                // max(., 0) after the bias
+  const void* gate;        // optional 16-bit [R, out_ld]: out = acc where gate > 0 else 0 (ReLU backward fused in a dgrad)
   // EPI_QUERY: columns [0, n_loc) are sampling offsets laid out (m, l, p, xy); columns [n_loc, n_loc + n_aw)
   // are attention logits laid out (m, l*p).
   float* loc_out;          // [R, n_loc]
@@ -165,50 +167,84 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool half_out) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// ---- epilogue bodies: one thread = one row, 32 consecutive columns starting at global column gc -----
-__device__ __forceinline__ void epi_store(const EpiParams& ep, const float (&v)[32], long long row, int gc) {
-  const bool zero = ep.row_mask != nullptr && ep.row_mask[row] != 0;
-  if (ep.out_f32) {
-    float4* o = reinterpret_cast<float4*>(static_cast<float*>(ep.out) + row * ep.out_ld + gc);
+// ---- epilogue -------------------------------------------------------------------------------------
+// tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns per chunk), so a naive store is 32
+// lanes x 16 bytes at a row-pitch stride: every request a half-filled sector.  Each epilogue warp therefore owns a
+// private staging buffer (32 rows x up to 128 bytes, +16 bytes pitch against bank conflicts): registers -> shared
+// (row per lane), __syncwarp, shared -> global with lanes running along the row, i.e. full 64/128-byte segments.
+constexpr int STAGE_PITCH_MAX = 128 + 16;
+constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH_MAX;
+
+template <int N16>
+__device__ __forceinline__ void staged_store(uint8_t* buf, int lane, const uint4 (&regs)[N16], void* gdst_row0,
+                                             long long ld_bytes, int rows_valid) {
+  constexpr int PITCH = N16 * 16 + 16, RPI = 32 / N16;
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o[i] = zero ? make_float4(0.f, 0.f, 0.f, 0.f) : make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-  } else {
-    uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(ep.out) + row * ep.out_ld + gc);
+  for (int i = 0; i < N16; ++i) *reinterpret_cast<uint4*>(buf + lane * PITCH + i * 16) = regs[i];
+  __syncwarp();
+  const int c16 = lane % N16, rsub = lane / N16;
+  uint8_t* g = static_cast<uint8_t*>(gdst_row0);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 w;
-      w.x = pack16(v[8 * i], v[8 * i + 1], ep.out_half != 0);
-      w.y = pack16(v[8 * i + 2], v[8 * i + 3], ep.out_half != 0);
-      w.z = pack16(v[8 * i + 4], v[8 * i + 5], ep.out_half != 0);
-      w.w = pack16(v[8 * i + 6], v[8 * i + 7], ep.out_half != 0);
-      o[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
-    }
+  for (int it = 0; it < N16; ++it) {
+    const int r = it * RPI + rsub;
+    const uint4 v = *reinterpret_cast<const uint4*>(buf + r * PITCH + c16 * 16);
+    if (r < rows_valid) *reinterpret_cast<uint4*>(g + r * ld_bytes + c16 * 16) = v;
+  }
+  __syncwarp();
+}
+
+template <int N16>
+__device__ __forceinline__ void staged_load(uint8_t* buf, int lane, uint4 (&regs)[N16], const void* gsrc_row0,
+                                            long long ld_bytes, int rows_valid) {
+  constexpr int PITCH = N16 * 16 + 16, RPI = 32 / N16;
+  const int c16 = lane % N16, rsub = lane / N16;
+  const uint8_t* g = static_cast<const uint8_t*>(gsrc_row0);
+#pragma unroll
+  for (int it = 0; it < N16; ++it) {
+    const int r = it * RPI + rsub;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(g + r * ld_bytes + c16 * 16));
+    *reinterpret_cast<uint4*>(buf + r * PITCH + c16 * 16) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < N16; ++i) regs[i] = *reinterpret_cast<const uint4*>(buf + lane * PITCH + i * 16);
+  __syncwarp();
+}
+
+__device__ __forceinline__ void pack_f32(const float (&v)[32], uint4 (&o)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    o[i] = make_uint4(__float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+}
+__device__ __forceinline__ void pack_16(const float (&v)[32], bool half_out, bool zero, uint4 (&o)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[i].x = zero ? 0u : pack16(v[8 * i], v[8 * i + 1], half_out);
+    o[i].y = zero ? 0u : pack16(v[8 * i + 2], v[8 * i + 3], half_out);
+    o[i].z = zero ? 0u : pack16(v[8 * i + 4], v[8 * i + 5], half_out);
+    o[i].w = zero ? 0u : pack16(v[8 * i + 6], v[8 * i + 7], half_out);
   }
 }
 
 // sampling locations (ms_deform_attn.py:306-319): columns are (m, l, p, xy).  Generic shapes.
 __device__ __forceinline__ void epi_loc(const EpiParams& ep, const float (&v)[32], long long row, int gc,
-                                        const float* s_inv) {
+                                        const float* s_inv, float (&r)[32]) {
   const float* rp = ep.ref + row * ep.L * ep.ref_dim;
-  float4* o = reinterpret_cast<float4*>(ep.loc_out + row * ep.n_loc + gc);
   const float half_over_p = 0.5f / static_cast<float>(ep.P);
-  float r[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     const int idx = gc + j, xy = idx & 1, l = (idx / (2 * ep.P)) % ep.L;
     if (ep.ref_dim == 2) r[j] = fmaf(v[j], s_inv[l * 2 + xy], rp[l * 2 + xy]);
     else r[j] = fmaf(v[j] * half_over_p, rp[l * 4 + 2 + xy], rp[l * 4 + xy]);
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
 // L = 4, P = 4 (every GroundingDINO configuration): one 32-column chunk is exactly one head, so the level
 // and the x/y selector of each column are compile-time and the row's reference points sit in registers.
 template <int REF_DIM>
-__device__ __forceinline__ void epi_loc_l4p4(const EpiParams& ep, const float (&v)[32], long long row, int gc,
-                                             const float* s_inv) {
+__device__ __forceinline__ void epi_loc_l4p4(const EpiParams& ep, const float (&v)[32], long long row,
+                                             const float* s_inv, float (&r)[32]) {
   constexpr int L = 4, P = 4;
   float ref[L * REF_DIM];
   const float4* rp = reinterpret_cast<const float4*>(ep.ref + row * L * REF_DIM);
@@ -220,8 +256,6 @@ __device__ __forceinline__ void epi_loc_l4p4(const EpiParams& ep, const float (&
   float inv[2 * L];
 #pragma unroll
   for (int i = 0; i < 2 * L; ++i) inv[i] = s_inv[i];
-  float4* o = reinterpret_cast<float4*>(ep.loc_out + row * ep.n_loc + gc);
-  float r[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     constexpr float half_over_p = 0.5f / P;
@@ -229,8 +263,6 @@ __device__ __forceinline__ void epi_loc_l4p4(const EpiParams& ep, const float (&
     if (REF_DIM == 2) r[j] = fmaf(v[j], inv[l * 2 + xy], ref[l * 2 + xy]);
     else r[j] = fmaf(v[j] * half_over_p, ref[l * 4 + 2 + xy], ref[l * 4 + xy]);
   }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
 }
 
 // softmax over each run of L*P logits (ms_deform_attn.py:293-303); 32 % (L*P) == 0 is guaranteed by the host
@@ -250,7 +282,7 @@ __device__ __forceinline__ void softmax_runs(float (&v)[32]) {
   }
 }
 
-__device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32], long long row, int gc) {
+__device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32]) {
   const int lp = ep.L * ep.P;
   if (lp == 16) softmax_runs<16>(v);
   else if (lp == 32) softmax_runs<32>(v);
@@ -258,27 +290,11 @@ __device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32],
   else if (lp == 4) softmax_runs<4>(v);
   else if (lp == 2) softmax_runs<2>(v);
   else softmax_runs<1>(v);
-  float4* o = reinterpret_cast<float4*>(ep.aw_out + row * ep.n_aw + (gc - ep.n_loc));
-#pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 
 __device__ __forceinline__ float smooth_l1(float x) {   // beta = 1 (torch.nn.SmoothL1Loss default)
   const float a = fabsf(x);
   return a < 1.f ? 0.5f * x * x : a - 0.5f;
-}
-
-__device__ __forceinline__ void store16x32(void* base, long long off, const float (&v)[32], bool half_out, bool zero) {
-  uint4* o = reinterpret_cast<uint4*>(static_cast<uint16_t*>(base) + off);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    uint4 w;
-    w.x = pack16(v[8 * i], v[8 * i + 1], half_out);
-    w.y = pack16(v[8 * i + 2], v[8 * i + 3], half_out);
-    w.z = pack16(v[8 * i + 4], v[8 * i + 5], half_out);
-    w.w = pack16(v[8 * i + 6], v[8 * i + 7], half_out);
-    o[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
-  }
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
@@ -302,6 +318,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(aux + 256);
   float* s_norm = s_bias + MAX_N;   // (1/W_l, 1/H_l)
+  uint8_t* stage_all = reinterpret_cast<uint8_t*>(s_norm + 2 * MSDA_MAX_LEVELS);   // 4 x STAGE_BYTES_PER_WARP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = K / BLOCK_K;
@@ -391,6 +408,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else {
     // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
     const int quarter = warp & 3;
+    uint8_t* stage = stage_all + (warp - 2) * STAGE_BYTES_PER_WARP;
     int acc = 0;
     uint32_t acc_phase = 0;
     float zsum_b = 0.f, zsum_o = 0.f;   // EPI_ZIRA: this thread's share of the two SmoothL1 sums
@@ -400,9 +418,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * block_n);
+      const long long row0 = static_cast<long long>(m_idx) + quarter * 32;      // first row of this warp
+      const int rows_valid = static_cast<int>(R - row0 < 32 ? (R - row0 < 0 ? 0 : R - row0) : 32);
+      const bool live = row < R;
+      const bool half_out = ep.out_half != 0;
+      const bool zero = live && ep.row_mask != nullptr && ep.row_mask[row] != 0;
       if (ep.mode == EPI_ZIRA) {
         const float s = __ldg(ep.scaling);
-        const bool half_out = ep.out_half != 0;
         for (int c0 = 0; c0 < block_n; c0 += 96) {
           uint32_t r0[32], r1[32], r2[32];
           tmem_ld32(taddr + c0, r0);
@@ -416,13 +438,18 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const float br = s * pre[j];
             ad[j] = br + __uint_as_float(r1[j]) + s_bias[ep.F + f0 + j];
             y[j] = __uint_as_float(r0[j]) + s_bias[f0 + j] + ad[j];
-            if (row < R) { zsum_b += smooth_l1(br); zsum_o += smooth_l1(ad[j]); }
+            if (live) { zsum_b += smooth_l1(br); zsum_o += smooth_l1(ad[j]); }
           }
-          if (row < R) {
-            const bool zero = ep.row_mask != nullptr && ep.row_mask[row] != 0;
-            store16x32(ep.out, row * ep.out_ld + f0, y, half_out, zero);
-            if (ep.pre_out) store16x32(ep.pre_out, row * ep.F + f0, pre, half_out, false);
-            if (ep.adapter_out) store16x32(ep.adapter_out, row * ep.F + f0, ad, half_out, false);
+          uint4 pk[4];
+          pack_16(y, half_out, zero, pk);
+          staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.out) + row0 * ep.out_ld + f0, 2ll * ep.out_ld, rows_valid);
+          if (ep.pre_out) {
+            pack_16(pre, half_out, false, pk);
+            staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.pre_out) + row0 * ep.F + f0, 2ll * ep.F, rows_valid);
+          }
+          if (ep.adapter_out) {
+            pack_16(ad, half_out, false, pk);
+            staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.adapter_out) + row0 * ep.F + f0, 2ll * ep.F, rows_valid);
           }
         }
       } else
@@ -433,17 +460,51 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[gc + j];
-        if (row < R) {
-          if (ep.mode == EPI_STORE) epi_store(ep, v, row, gc);
-          else if (gc < ep.n_loc) {
-            if (ep.L == 4 && ep.P == 4) {
-              if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, row, gc, s_norm);
-              else epi_loc_l4p4<4>(ep, v, row, gc, s_norm);
-            } else {
-              epi_loc(ep, v, row, gc, s_norm);
+        if (ep.mode == EPI_STORE) {
+          if (ep.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          }
+          if (ep.gate != nullptr) {   // keep where the gate activation (16-bit, same shape as out) is positive: ReLU backward
+            uint4 gt[4];
+            staged_load<4>(stage, lane, gt, static_cast<const uint16_t*>(ep.gate) + row0 * ep.out_ld + gc, 2ll * ep.out_ld, rows_valid);
+            const uint16_t* gp = reinterpret_cast<const uint16_t*>(gt);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const bool pos = (gp[j] & 0x7fffu) != 0 && (gp[j] & 0x8000u) == 0;   // > 0 for bf16 and f16 alike
+              v[j] = pos ? v[j] : 0.f;
             }
           }
-          else epi_softmax(ep, v, row, gc);
+          if (ep.out_f32) {
+            if (zero) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            uint4 pk[8];
+            pack_f32(v, pk);
+            staged_store<8>(stage, lane, pk, static_cast<float*>(ep.out) + row0 * ep.out_ld + gc, 4ll * ep.out_ld, rows_valid);
+          } else {
+            uint4 pk[4];
+            pack_16(v, half_out, zero, pk);
+            staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.out) + row0 * ep.out_ld + gc, 2ll * ep.out_ld, rows_valid);
+          }
+        } else if (gc < ep.n_loc) {
+          float o[32];
+          const long long rr = live ? row : 0;
+          if (ep.L == 4 && ep.P == 4) {
+            if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, rr, s_norm, o);
+            else epi_loc_l4p4<4>(ep, v, rr, s_norm, o);
+          } else {
+            epi_loc(ep, v, rr, gc, s_norm, o);
+          }
+          uint4 pk[8];
+          pack_f32(o, pk);
+          staged_store<8>(stage, lane, pk, ep.loc_out + row0 * ep.n_loc + gc, 4ll * ep.n_loc, rows_valid);
+        } else {
+          epi_softmax(ep, v);
+          uint4 pk[8];
+          pack_f32(v, pk);
+          staged_store<8>(stage, lane, pk, ep.aw_out + row0 * ep.n_aw + (gc - ep.n_loc), 4ll * ep.n_aw, rows_valid);
         }
       }
       tc_fence_before();
@@ -581,6 +642,17 @@ int msda_linear_16(const void* x, const void* w, const float* bias, long long R,
   memset(&ep, 0, sizeof(ep));
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = out_ld; ep.out_f32 = out_f32; ep.out_half = is_half; ep.bias = bias; ep.row_mask = row_mask;
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+int msda_linear_act_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out, int relu,
+                       const void* gate, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out) { snprintf(pg::t_err, sizeof(pg::t_err), "null output"); return MSDA_ERR_NULL_POINTER; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.relu = relu; ep.gate = gate;
   return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .layer_ops import add_layer_norm
+from .layer_ops import add_layer_norm, ffn
 from .ms_deform_attn import MultiScaleDeformableAttention
 
 
@@ -39,7 +39,7 @@ class DeformableTransformerEncoderLayer(nn.Module):
 
     def forward_ffn(self, src):
         adapter_loss = src.new_zeros(1)
-        src2 = self.linear2(self.dropout2(self.activation(self.linear1(src))))
+        src2 = ffn(src, self.linear1, self.linear2, self.dropout2.p, self.training)
         src = add_layer_norm(src, src2, self.norm2, self.dropout3.p, self.training)
         return src, adapter_loss
 

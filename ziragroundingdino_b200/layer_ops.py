@@ -62,3 +62,59 @@ def add_layer_norm(x, r, norm, dropout_p=0.0, training=False):
     if training and dropout_p > 0:
         r = torch.nn.functional.dropout(r, dropout_p, True)
     return norm(x + r)
+
+
+def _linear_act16(x2d, w, bias_f32, relu=False, gate=None):
+    R, K = x2d.shape
+    Nout = w.shape[0]
+    out = torch.empty((R, Nout), dtype=x2d.dtype, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_act_16(x2d.data_ptr(), w.data_ptr(), 0 if bias_f32 is None else bias_f32.data_ptr(), R, K, Nout,
+                                           out.data_ptr(), 1 if relu else 0, 0 if gate is None else gate.data_ptr(),
+                                           1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_linear_act_16")
+    return out
+
+
+class FFN16Function(Function):
+    """``linear2(relu(linear1(x)))`` on 16-bit activations (reference transformer_for_adapter.py:880-881).
+
+    The two products with K = d_model run on the tcgen05 GEMM with the activation folded into the epilogue:
+    forward ``h = relu(x W1^T + b1)`` (no separate ReLU pass) and backward ``dh = (dy W2) * (h > 0)`` (no separate
+    threshold pass).  The two products with K = d_ffn (linear2 forward, linear1 dgrad) stay library GEMMs: their weight
+    does not fit in shared memory and a single-CTA streaming kernel would lose to cuBLAS's 2-CTA multicast one."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        shape = x.shape
+        x2d = x.reshape(-1, shape[-1]).contiguous()
+        h = _linear_act16(x2d, w1.contiguous(), b1.float(), relu=True)
+        y = torch.nn.functional.linear(h, w2, b2)
+        ctx.save_for_backward(x2d, h, w1, w2)
+        ctx.shape = shape
+        return y.view(*shape[:-1], w2.shape[0])
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x2d, h, w1, w2 = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dh = _linear_act16(dy2, w2.t().contiguous(), None, gate=h)        # (dy W2) gated by relu'(.)
+        dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
+        dw1 = dh.t() @ x2d if ctx.needs_input_grad[1] else None
+        db1 = dh.float().sum(0).to(dy.dtype) if ctx.needs_input_grad[2] else None
+        dw2 = dy2.t() @ h if ctx.needs_input_grad[3] else None
+        db2 = dy2.float().sum(0).to(dy.dtype) if ctx.needs_input_grad[4] else None
+        return dx, dw1, db1, dw2, db2
+
+
+def ffn(x, linear1, linear2, dropout_p=0.0, training=False):
+    """``linear2(dropout(relu(linear1(x))))`` -- fused when possible."""
+    d_model, d_ffn = linear1.in_features, linear1.out_features
+    if (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and not (training and dropout_p > 0) and d_model % 64 == 0
+            and d_ffn % 32 == 0 and d_ffn <= 2048 and linear1.bias is not None and linear2.bias is not None):
+        return FFN16Function.apply(x, linear1.weight, linear1.bias, linear2.weight, linear2.bias)
+    h = torch.nn.functional.relu(linear1(x))
+    if training and dropout_p > 0:
+        h = torch.nn.functional.dropout(h, dropout_p, True)
+    return linear2(h)
