@@ -40,10 +40,14 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int SMEM_A = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_N = 2048;              // widest (stacked) weight handled by one launch
-constexpr int THREADS = 192;
-constexpr int AUX_BYTES = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8 + 4 * 32 * (128 + 16);
+constexpr int EPI_WARPS = 8;
+constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int AUX_BASE = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
+constexpr int AUX_BYTES_16 = AUX_BASE + EPI_WARPS * 32 * 80;    // 16-bit outputs
+constexpr int AUX_BYTES_32 = AUX_BASE + EPI_WARPS * 32 * 144;   // fp32 outputs
 constexpr int kMaxSmem = 227 * 1024;
-bool g_allow_resident = true;   // msda_b200_set_tuning("gemm_resident", 0|1)
+bool g_allow_resident = true;
+bool g_staged_store = true;      // msda_b200_gemm_set_staged(0|1)   // msda_b200_set_tuning("gemm_resident", 0|1)
 
 enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1, EPI_ZIRA = 2 };
 
@@ -168,13 +172,15 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool half_out) {
 }
 
 // ---- epilogue -------------------------------------------------------------------------------------
-// tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns per chunk), so a naive store is 32
-// lanes x 16 bytes at a row-pitch stride: every request a half-filled sector.  Each epilogue warp therefore owns a
-// private staging buffer (32 rows x up to 128 bytes, +16 bytes pitch against bank conflicts): registers -> shared
-// (row per lane), __syncwarp, shared -> global with lanes running along the row, i.e. full 64/128-byte segments.
-constexpr int STAGE_PITCH_MAX = 128 + 16;
-constexpr int STAGE_BYTES_PER_WARP = 32 * STAGE_PITCH_MAX;
-
+// tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns per chunk).  Measured in round 1
+// (profiles/r1_gemm_ab.txt): the kernel is bound by the latency of this per-chunk instruction chain on the few epilogue
+// warps, not by the store pattern (a shared-memory transposition to coalesce the stores changed nothing) and not by
+// shared-memory traffic (resident vs streamed W changed nothing).  Hence: EIGHT epilogue warps (two per TMEM lane
+// quarter, alternating column chunks) and every mode / dtype decision a template parameter.
+// Warp-private transposition buffer (32 rows x N16*16 bytes, +16 bytes pitch against bank conflicts): registers ->
+// shared (row per lane), __syncwarp, shared -> global with lanes running along the row, so a store instruction
+// covers 32/N16 rows x N16*16 contiguous bytes instead of 32 rows x 16 bytes.  With eight epilogue warps the LSU
+// wavefront count of the direct pattern (32 per instruction) is what bounds the kernel.
 template <int N16>
 __device__ __forceinline__ void staged_store(uint8_t* buf, int lane, const uint4 (&regs)[N16], void* gdst_row0,
                                              long long ld_bytes, int rows_valid) {
@@ -190,25 +196,6 @@ __device__ __forceinline__ void staged_store(uint8_t* buf, int lane, const uint4
     const uint4 v = *reinterpret_cast<const uint4*>(buf + r * PITCH + c16 * 16);
     if (r < rows_valid) *reinterpret_cast<uint4*>(g + r * ld_bytes + c16 * 16) = v;
   }
-  __syncwarp();
-}
-
-template <int N16>
-__device__ __forceinline__ void staged_load(uint8_t* buf, int lane, uint4 (&regs)[N16], const void* gsrc_row0,
-                                            long long ld_bytes, int rows_valid) {
-  constexpr int PITCH = N16 * 16 + 16, RPI = 32 / N16;
-  const int c16 = lane % N16, rsub = lane / N16;
-  const uint8_t* g = static_cast<const uint8_t*>(gsrc_row0);
-#pragma unroll
-  for (int it = 0; it < N16; ++it) {
-    const int r = it * RPI + rsub;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(g + r * ld_bytes + c16 * 16));
-    *reinterpret_cast<uint4*>(buf + r * PITCH + c16 * 16) = v;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < N16; ++i) regs[i] = *reinterpret_cast<const uint4*>(buf + lane * PITCH + i * 16);
   __syncwarp();
 }
 
@@ -298,6 +285,7 @@ __device__ __forceinline__ float smooth_l1(float x) {   // beta = 1 (torch.nn.Sm
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
+template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int Nout,
                  int K, int block_n, int b_resident, int half_in, EpiParams ep) {
@@ -318,7 +306,6 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(aux + 256);
   float* s_norm = s_bias + MAX_N;   // (1/W_l, 1/H_l)
-  uint8_t* stage_all = reinterpret_cast<uint8_t*>(s_norm + 2 * MSDA_MAX_LEVELS);   // 4 x STAGE_BYTES_PER_WARP
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_k = K / BLOCK_K;
@@ -336,7 +323,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, EPI_WARPS); }
     mbar_init(bres_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -345,7 +332,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < Nout; i += THREADS) s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
-  if (ep.mode == EPI_QUERY && threadIdx.x < ep.L) {
+  if (MODE == EPI_QUERY && threadIdx.x < ep.L) {
     s_norm[2 * threadIdx.x] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x + 1]);      // 1/W
     s_norm[2 * threadIdx.x + 1] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x]);      // 1/H
   }
@@ -406,9 +393,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===== epilogue warps (TMEM lane quarter = warp % 4) =====
+    // ===== epilogue warps: TMEM lane quarter = warp % 4; the two warps of a quarter alternate column chunks =====
     const int quarter = warp & 3;
-    uint8_t* stage = stage_all + (warp - 2) * STAGE_BYTES_PER_WARP;
+    const int chunk_par = (warp - 2) >> 2;     // 0 or 1
+    constexpr int kStagePitch = (OUT_F32 || MODE == EPI_QUERY) ? 144 : 80;
+    uint8_t* stage = reinterpret_cast<uint8_t*>(s_norm + 2 * MSDA_MAX_LEVELS) + (warp - 2) * 32 * kStagePitch;
     int acc = 0;
     uint32_t acc_phase = 0;
     float zsum_b = 0.f, zsum_o = 0.f;   // EPI_ZIRA: this thread's share of the two SmoothL1 sums
@@ -418,14 +407,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * block_n);
-      const long long row0 = static_cast<long long>(m_idx) + quarter * 32;      // first row of this warp
-      const int rows_valid = static_cast<int>(R - row0 < 32 ? (R - row0 < 0 ? 0 : R - row0) : 32);
       const bool live = row < R;
-      const bool half_out = ep.out_half != 0;
       const bool zero = live && ep.row_mask != nullptr && ep.row_mask[row] != 0;
-      if (ep.mode == EPI_ZIRA) {
+      const long long row0 = static_cast<long long>(m_idx) + quarter * 32;
+      const int rows_valid = static_cast<int>(R - row0 < 32 ? (R - row0 < 0 ? 0 : R - row0) : 32);
+      if (MODE == EPI_ZIRA) {
         const float s = __ldg(ep.scaling);
-        for (int c0 = 0; c0 < block_n; c0 += 96) {
+        for (int c0 = chunk_par * 96; c0 < block_n; c0 += 192) {
           uint32_t r0[32], r1[32], r2[32];
           tmem_ld32(taddr + c0, r0);
           tmem_ld32(taddr + c0 + 32, r1);
@@ -441,70 +429,98 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (live) { zsum_b += smooth_l1(br); zsum_o += smooth_l1(ad[j]); }
           }
           uint4 pk[4];
-          pack_16(y, half_out, zero, pk);
+          pack_16(y, HALF_OUT, zero, pk);
           staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.out) + row0 * ep.out_ld + f0, 2ll * ep.out_ld, rows_valid);
           if (ep.pre_out) {
-            pack_16(pre, half_out, false, pk);
+            pack_16(pre, HALF_OUT, false, pk);
             staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.pre_out) + row0 * ep.F + f0, 2ll * ep.F, rows_valid);
           }
           if (ep.adapter_out) {
-            pack_16(ad, half_out, false, pk);
+            pack_16(ad, HALF_OUT, false, pk);
             staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.adapter_out) + row0 * ep.F + f0, 2ll * ep.F, rows_valid);
           }
         }
-      } else
-      for (int c0 = 0; c0 < block_n; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c0, r);
-        const int gc = n_idx + c0;
-        float v[32];
+      } else {
+        // GATE: the gate rows of a chunk are fetched one chunk AHEAD with coalesced loads (lanes along the row: 8 rows x 64
+        // bytes per instruction) and transposed through the staging buffer when the chunk is processed.
+        uint4 gnext[4];
+        const int g_c16 = lane & 3, g_rsub = lane >> 2;
+        auto gate_fetch = [&](int c) {
+          const uint8_t* g = reinterpret_cast<const uint8_t*>(static_cast<const uint16_t*>(ep.gate) + row0 * ep.out_ld + n_idx + c);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + s_bias[gc + j];
-        if (ep.mode == EPI_STORE) {
-          if (ep.relu) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + g_rsub;
+            gnext[it] = (rr < rows_valid) ? __ldg(reinterpret_cast<const uint4*>(g + rr * 2ll * ep.out_ld + g_c16 * 16)) : make_uint4(0u, 0u, 0u, 0u);
           }
-          if (ep.gate != nullptr) {   // keep where the gate activation (16-bit, same shape as out) is positive: ReLU backward
-            uint4 gt[4];
-            staged_load<4>(stage, lane, gt, static_cast<const uint16_t*>(ep.gate) + row0 * ep.out_ld + gc, 2ll * ep.out_ld, rows_valid);
-            const uint16_t* gp = reinterpret_cast<const uint16_t*>(gt);
+        };
+        if (GATE && chunk_par * 32 < block_n) gate_fetch(chunk_par * 32);
+        for (int c0 = chunk_par * 32; c0 < block_n; c0 += 64) {
+          const int gc = n_idx + c0;
+          uint4 gt[4];
+          if (GATE) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const bool pos = (gp[j] & 0x7fffu) != 0 && (gp[j] & 0x8000u) == 0;   // > 0 for bf16 and f16 alike
-              v[j] = pos ? v[j] : 0.f;
+            for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stage + (it * 8 + g_rsub) * 80 + g_c16 * 16) = gnext[it];
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) gt[i] = *reinterpret_cast<const uint4*>(stage + lane * 80 + i * 16);
+            __syncwarp();
+            if (c0 + 64 < block_n) gate_fetch(c0 + 64);
+          }
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          float v[32];
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + gc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = bp[i];
+            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+          }
+          if (MODE == EPI_STORE) {
+            if (RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-          }
-          if (ep.out_f32) {
-            if (zero) {
+            if (GATE) {   // keep where the gate activation is positive: ReLU backward fused into the dgrad
+              const uint32_t* gw = reinterpret_cast<const uint32_t*>(gt);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t w2 = gw[j], lo = w2 & 0xffffu, hi = w2 >> 16;
+                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) v[2 * j] = 0.f;
+                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) v[2 * j + 1] = 0.f;
+              }
+            }
+            if (OUT_F32) {
+              if (zero) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              }
+              uint4 pk[8];
+              pack_f32(v, pk);
+              staged_store<8>(stage, lane, pk, static_cast<float*>(ep.out) + row0 * ep.out_ld + gc, 4ll * ep.out_ld, rows_valid);
+            } else {
+              uint4 pk[4];
+              pack_16(v, HALF_OUT, zero, pk);
+              staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.out) + row0 * ep.out_ld + gc, 2ll * ep.out_ld, rows_valid);
+            }
+          } else if (gc < ep.n_loc) {
+            float o32[32];
+            const long long rr = live ? row : 0;
+            if (ep.L == 4 && ep.P == 4) {
+              if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, rr, s_norm, o32);
+              else epi_loc_l4p4<4>(ep, v, rr, s_norm, o32);
+            } else {
+              epi_loc(ep, v, rr, gc, s_norm, o32);
             }
             uint4 pk[8];
+            pack_f32(o32, pk);
+            staged_store<8>(stage, lane, pk, ep.loc_out + row0 * ep.n_loc + gc, 4ll * ep.n_loc, rows_valid);
+          } else {
+            epi_softmax(ep, v);
+            uint4 pk[8];
             pack_f32(v, pk);
-            staged_store<8>(stage, lane, pk, static_cast<float*>(ep.out) + row0 * ep.out_ld + gc, 4ll * ep.out_ld, rows_valid);
-          } else {
-            uint4 pk[4];
-            pack_16(v, half_out, zero, pk);
-            staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.out) + row0 * ep.out_ld + gc, 2ll * ep.out_ld, rows_valid);
+            staged_store<8>(stage, lane, pk, ep.aw_out + row0 * ep.n_aw + (gc - ep.n_loc), 4ll * ep.n_aw, rows_valid);
           }
-        } else if (gc < ep.n_loc) {
-          float o[32];
-          const long long rr = live ? row : 0;
-          if (ep.L == 4 && ep.P == 4) {
-            if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, rr, s_norm, o);
-            else epi_loc_l4p4<4>(ep, v, rr, s_norm, o);
-          } else {
-            epi_loc(ep, v, rr, gc, s_norm, o);
-          }
-          uint4 pk[8];
-          pack_f32(o, pk);
-          staged_store<8>(stage, lane, pk, ep.loc_out + row0 * ep.n_loc + gc, 4ll * ep.n_loc, rows_valid);
-        } else {
-          epi_softmax(ep, v);
-          uint4 pk[8];
-          pack_f32(v, pk);
-          staged_store<8>(stage, lane, pk, ep.aw_out + row0 * ep.n_aw + (gc - ep.n_loc), 4ll * ep.n_aw, rows_valid);
         }
       }
       tc_fence_before();
@@ -512,7 +528,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (ep.mode == EPI_ZIRA) {
+    if (MODE == EPI_ZIRA) {
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
         zsum_b += __shfl_xor_sync(0xffffffffu, zsum_b, o);
@@ -561,7 +577,8 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int cols
 
 // Widest n-block (multiple of `unit`, dividing Nout, <= 256 columns so two accumulators fit TMEM) whose slice of W
 // (block_n x K 16-bit) still fits in shared memory beside the activation ring; the smallest legal block otherwise.
-static int pick_block_n(int Nout, int K, int unit) {
+static int pick_block_n(int Nout, int K, int unit, bool f32_out) {
+  const int AUX_BYTES = f32_out ? AUX_BYTES_32 : AUX_BYTES_16;
   int best = 0, smallest = 0;
   for (int bn = unit; bn <= 256 && bn <= Nout; bn += unit) {
     if (Nout % bn) continue;
@@ -602,14 +619,9 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   const int num_n = Nout / block_n;
   const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
   const int bres_bytes = block_n * K * 2;
+  const int AUX_BYTES = (ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16;
   const bool b_res = g_allow_resident && bres_bytes + STAGES * SMEM_A + AUX_BYTES + 1024 <= kMaxSmem && num_n <= sms;
   const int smem = (b_res ? STAGES * SMEM_A + bres_bytes : STAGES * (SMEM_A + block_n * BLOCK_K * 2)) + AUX_BYTES + 1024;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(linear_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
-    if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
-    configured = true;
-  }
   int grid;
   if (b_res) {
     long long per_n = sms / num_n;
@@ -620,7 +632,27 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
     grid = static_cast<int>(tiles < sms ? tiles : sms);
   }
   ++msda::g_launches;
-  linear_tc_kernel<<<grid, THREADS, smem, st>>>(tmA, tmB, static_cast<int>(R), Nout, K, block_n, b_res ? 1 : 0, half_in ? 1 : 0, ep);
+  const int Ri = static_cast<int>(R), br = b_res ? 1 : 0, hi = half_in ? 1 : 0;
+  cudaError_t cfg = cudaSuccess;
+#define PG_LAUNCH(MODE, F32, HALF, RELU, GATE)                                                                            \
+  do {                                                                                                                     \
+    static bool configured = false;                                                                                        \
+    if (!configured) {                                                                                                     \
+      cfg = cudaFuncSetAttribute(linear_tc_kernel<MODE, F32, HALF, RELU, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+      configured = cfg == cudaSuccess;                                                                                     \
+    }                                                                                                                      \
+    if (cfg == cudaSuccess)                                                                                                \
+      linear_tc_kernel<MODE, F32, HALF, RELU, GATE><<<grid, THREADS, smem, st>>>(tmA, tmB, Ri, Nout, K, block_n, br, hi, ep); \
+  } while (0)
+  const bool half_out = ep.out_half != 0;
+  if (ep.mode == EPI_QUERY) PG_LAUNCH(EPI_QUERY, true, false, false, false);
+  else if (ep.mode == EPI_ZIRA) { if (half_out) PG_LAUNCH(EPI_ZIRA, false, true, false, false); else PG_LAUNCH(EPI_ZIRA, false, false, false, false); }
+  else if (ep.out_f32) PG_LAUNCH(EPI_STORE, true, false, false, false);
+  else if (ep.gate) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, false, true); else PG_LAUNCH(EPI_STORE, false, false, false, true); }
+  else if (ep.relu) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, true, false); else PG_LAUNCH(EPI_STORE, false, false, true, false); }
+  else { if (half_out) PG_LAUNCH(EPI_STORE, false, true, false, false); else PG_LAUNCH(EPI_STORE, false, false, false, false); }
+#undef PG_LAUNCH
+  if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "linear_tc_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;
@@ -629,6 +661,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
 }  // namespace pg
 
 extern "C" int msda_b200_gemm_set_resident(int on) { pg::g_allow_resident = on != 0; return 0; }
+extern "C" int msda_b200_gemm_set_staged(int) { return 0; }   // kept for ABI stability: staging was removed
 
 extern "C" {
 
@@ -642,7 +675,7 @@ int msda_linear_16(const void* x, const void* w, const float* bias, long long R,
   memset(&ep, 0, sizeof(ep));
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = out_ld; ep.out_f32 = out_f32; ep.out_half = is_half; ep.bias = bias; ep.row_mask = row_mask;
-  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, out_f32 != 0), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 int msda_linear_act_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out, int relu,
@@ -653,7 +686,7 @@ int msda_linear_act_16(const void* x, const void* w, const float* bias, long lon
   memset(&ep, 0, sizeof(ep));
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.relu = relu; ep.gate = gate;
-  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_cat, const float* ref, int ref_dim,
@@ -671,7 +704,7 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   ep.mode = pg::EPI_QUERY;
   ep.bias = bias_cat; ep.loc_out = loc_out; ep.aw_out = aw_out; ep.ref = ref; ep.shapes = spatial_shapes;
   ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
-  return pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32), is_half != 0, ep,
+  return pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
                     static_cast<cudaStream_t>(stream));
 }
 
@@ -686,7 +719,7 @@ int msda_zira_linear_16(const void* x, const void* w_stack, const float* bias3, 
   ep.mode = pg::EPI_ZIRA;
   ep.out = out; ep.out_ld = F; ep.out_half = is_half; ep.bias = bias3; ep.row_mask = row_mask;
   ep.scaling = scaling; ep.pre_out = pre_out; ep.adapter_out = adapter_out; ep.loss_sums = loss_sums; ep.F = F;
-  return pg::launch(x, w_stack, R, K, 3 * F, pg::pick_block_n(3 * F, K, 96), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+  return pg::launch(x, w_stack, R, K, 3 * F, pg::pick_block_n(3 * F, K, 96, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
