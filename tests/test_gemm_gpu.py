@@ -315,10 +315,12 @@ def test_gemm_resident_and_streaming_modes_agree():
         assert rel_err(y1.cpu(), (x.double() @ w.double().t() + b.double()).cpu()) < 1e-4
 
 
+@pytest.mark.parametrize("gate_fused", [False, True])
 @pytest.mark.parametrize("dtype,eps16", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)])
-def test_ffn_fused(dtype, eps16):
-    """relu folded into the linear1 epilogue and relu-backward folded into linear2's dgrad epilogue, vs torch fp64."""
+def test_ffn_fused(dtype, eps16, gate_fused, monkeypatch):
+    """relu folded into the linear1 epilogue and (optionally) relu-backward folded into linear2's dgrad epilogue, vs torch fp64."""
     from ziragroundingdino_b200.layer_ops import FFN16Function
+    monkeypatch.setattr(FFN16Function, "fuse_relu_backward", gate_fused)
     R, C, Fh = 1111, 256, 2048
     x = _rand((R, C), dtype, 51)
     w1, b1 = _rand((Fh, C), dtype, 52, 0.06), _rand((Fh,), dtype, 53, 0.1)

@@ -18,7 +18,6 @@ extern long long g_launches;
 }
 
 namespace {
-constexpr int kMaxVec = 4;   // up to 4 x 8 elements per lane = C <= 1024
 
 __device__ __forceinline__ void unpack8(const uint4& r, bool h, float (&f)[8]) {
   const uint32_t w[4] = {r.x, r.y, r.z, r.w};
@@ -47,13 +46,16 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// NVEC = ceil(C / 256): 8-element vectors per lane (compile-time so that C = 256 keeps 8 values, not 32, in registers)
+template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r, const float* __restrict__ gamma,
                   const float* __restrict__ beta, long long R, int C, float eps, int is_half, uint16_t* __restrict__ z,
                   uint16_t* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= R) return;
-  const int lane = threadIdx.x & 31, nvec = C / 256 + (C % 256 ? 1 : 0);
+  const int lane = threadIdx.x & 31;
+  constexpr int nvec = kMaxVec;
   const bool h = is_half != 0;
   float v[kMaxVec][8];
   float sum = 0.f;
@@ -90,21 +92,27 @@ add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r
     const int c = (i * 32 + lane) * 8;
     if (i < nvec && c < C) {
       float o[8];
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, __ldg(gamma + c + j), __ldg(beta + c + j));
+      for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
       *reinterpret_cast<uint4*>(y + row * C + c) = pack8(o, h);
     }
   }
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
 }
 
+template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 add_ln_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ z, const float* __restrict__ gamma,
                   const float* __restrict__ mean_in, const float* __restrict__ rstd_in, long long R, int C, int is_half,
                   uint16_t* __restrict__ dz) {
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= R) return;
-  const int lane = threadIdx.x & 31, nvec = C / 256 + (C % 256 ? 1 : 0);
+  const int lane = threadIdx.x & 31;
+  constexpr int nvec = kMaxVec;
   const bool h = is_half != 0;
   const float mean = mean_in[row], rstd = rstd_in[row];
   float g[kMaxVec][8], xh[kMaxVec][8];
@@ -116,9 +124,11 @@ add_ln_bwd_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ 
       float a[8], b[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(dy + row * C + c)), h, a);
       unpack8(__ldg(reinterpret_cast<const uint4*>(z + row * C + c)), h, b);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        g[i][j] = a[j] * __ldg(gamma + c + j);
+        g[i][j] = a[j] * gg[j];
         xh[i][j] = (b[j] - mean) * rstd;
         s1 += g[i][j];
         s2 = fmaf(g[i][j], xh[i][j], s2);
@@ -146,9 +156,12 @@ int msda_add_layernorm_fwd_16(const void* x, const void* r, const float* gamma, 
   if (!x || !r || !gamma || !beta || !z || !y || !mean || !rstd) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || C <= 0 || C % 8 || C > 1024) return MSDA_ERR_BAD_SHAPE;
   ++msda::g_launches;
-  add_ln_fwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(r), gamma, beta, R, C, eps, is_half,
-      static_cast<uint16_t*>(z), static_cast<uint16_t*>(y), mean, rstd);
+  const unsigned grid = static_cast<unsigned>((R + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LN_FWD(NV) add_ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(r), \
+      gamma, beta, R, C, eps, is_half, static_cast<uint16_t*>(z), static_cast<uint16_t*>(y), mean, rstd)
+  if (C <= 256) LN_FWD(1); else if (C <= 512) LN_FWD(2); else LN_FWD(4);
+#undef LN_FWD
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
@@ -158,9 +171,12 @@ int msda_add_layernorm_bwd_16(const void* dy, const void* z, const float* gamma,
   if (!dy || !z || !gamma || !mean || !rstd || !dz) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || C <= 0 || C % 8 || C > 1024) return MSDA_ERR_BAD_SHAPE;
   ++msda::g_launches;
-  add_ln_bwd_kernel<<<static_cast<unsigned>((R + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(z), gamma, mean, rstd, R, C, is_half,
-      static_cast<uint16_t*>(dz));
+  const unsigned grid = static_cast<unsigned>((R + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LN_BWD(NV) add_ln_bwd_kernel<NV><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(z), \
+      gamma, mean, rstd, R, C, is_half, static_cast<uint16_t*>(dz))
+  if (C <= 256) LN_BWD(1); else if (C <= 512) LN_BWD(2); else LN_BWD(4);
+#undef LN_BWD
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

@@ -84,6 +84,11 @@ class FFN16Function(Function):
     threshold pass).  The two products with K = d_ffn (linear2 forward, linear1 dgrad) stay library GEMMs: their weight
     does not fit in shared memory and a single-CTA streaming kernel would lose to cuBLAS's 2-CTA multicast one."""
 
+    # Measured on B200 (profiles/r1_gemm_ab.txt): the gated dgrad epilogue (287 us) does not beat cuBLAS + the
+    # elementwise threshold kernel (105 + 152 us) yet -- its extra 364 MB gate read sits in the epilogue's dependency
+    # chain -- so it is off by default; the fused bias+ReLU forward (131 vs 230 us) is on.
+    fuse_relu_backward = False
+
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
         shape = x.shape
@@ -99,7 +104,10 @@ class FFN16Function(Function):
     def backward(ctx, dy):
         x2d, h, w1, w2 = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
-        dh = _linear_act16(dy2, w2.t().contiguous(), None, gate=h)        # (dy W2) gated by relu'(.)
+        if FFN16Function.fuse_relu_backward:
+            dh = _linear_act16(dy2, w2.t().contiguous(), None, gate=h)    # (dy W2) gated by relu'(.) in the GEMM epilogue
+        else:
+            dh = torch.ops.aten.threshold_backward(dy2 @ w2, h, 0)
         dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
         dw1 = dh.t() @ x2d if ctx.needs_input_grad[1] else None
         db1 = dh.float().sum(0).to(dy.dtype) if ctx.needs_input_grad[2] else None
