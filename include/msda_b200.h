@@ -100,6 +100,8 @@ int msda_backward_f16(const void *value, const int64_t *spatial_shapes, const in
  *   key "fwd_q_fast"        : 1 = lanes of a warp span consecutive queries of one head, 0 = heads
  *   key "bwd_q_fast"        : same for the backward kernel
  *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64)
+ *   key "bwd_narrow"        : 16-bit storage, 1 = 4 channels per lane in the backward kernel (one full-line
+ *                             reduction per corner), 0 = 8 channels per lane
  * Returns 0, or MSDA_ERR_UNSUPPORTED for an unknown key / value. */
 int msda_b200_set_tuning(const char *key, int value);
 int msda_b200_get_tuning(const char *key);

@@ -106,15 +106,22 @@ def test_core_vs_c_oracle(case):
     assert rel_err(ga, o_ga) < tol
 
 
+@pytest.mark.parametrize("narrow", [1, 0])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
-@pytest.mark.parametrize("D,P", [(32, 4), (64, 4), (128, 4), (24, 4), (32, 2)])
-def test_16bit_storage_vs_fp32_truth(dtype, D, P):
+@pytest.mark.parametrize("D,P", [(32, 4), (64, 4), (128, 4), (24, 4), (32, 2), (16, 4)])
+def test_16bit_storage_vs_fp32_truth(dtype, D, P, narrow):
     """bf16/f16 value & grad_out, fp32 loc/aw and fp32 accumulation; truth = fp64 oracle on the
     16-bit-rounded inputs.  Bar 1e-2 (north_star); what remains is only the final output rounding."""
     dev = _dev()
     shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    from ziragroundingdino_b200 import _lib
     value, sh, lsi, loc, aw, gout = _mk(shapes, 2, 8, D, 200, P, seed=7, dtype=dtype)
-    out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    keep = _lib.get_tuning("bwd_narrow")
+    try:
+        _lib.set_tuning(bwd_narrow=narrow)     # 4 vs 8 channels per lane in the backward kernel
+        out, gv, gl, ga = _run(value, sh, lsi, loc, aw, gout, dev)
+    finally:
+        _lib.set_tuning(bwd_narrow=keep)
     v64, go64 = value.double().numpy(), gout.double().numpy()
     o_out = O.c_forward(v64, sh.numpy(), loc.double().numpy(), aw.double().numpy())
     o_gv, o_gl, o_ga = O.c_backward(v64, sh.numpy(), loc.double().numpy(), aw.double().numpy(), go64)

@@ -79,6 +79,13 @@ def core(f, name, shapes, N, dtype, regime, Lq=None, full=True):
             emit(f, kind="bwd", case=name, qf=qf, passes=ps, flush=flush, us=med, us_best=best,
                  l2_gbps=ab["bwd_l2"] / med / 1e3, hbm_gbps=ab["bwd_hbm"] / med / 1e3)
     _lib.set_tuning(**keep)
+    if dtype != torch.float32:
+        keep_n = _lib.get_tuning("bwd_narrow")
+        for nw in (0, 1):
+            _lib.set_tuning(bwd_narrow=nw)
+            med, best = timeit(bwd, flush=True)
+            emit(f, kind="bwd_narrow", case=name, narrow=nw, us=med, us_best=best, l2_gbps=ab["bwd_l2"] / med / 1e3)
+        _lib.set_tuning(bwd_narrow=keep_n)
     if dtype == torch.float32:
         from oracle import build_ref
         ref = build_ref.load()

@@ -104,6 +104,7 @@ static int* tuning_slot(const char* key) {
   if (!strcmp(key, "fwd_passes")) return &msda::g_tuning.fwd_passes;
   if (!strcmp(key, "bwd_q_fast")) return &msda::g_tuning.bwd_q_fast;
   if (!strcmp(key, "bwd_passes")) return &msda::g_tuning.bwd_passes;
+  if (!strcmp(key, "bwd_narrow")) return &msda::g_tuning.bwd_narrow;
   return nullptr;
 }
 

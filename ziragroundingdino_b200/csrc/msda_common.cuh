@@ -19,6 +19,7 @@ struct Tuning {
   int fwd_passes = 1;        // consecutive unit tiles handled by one CTA
   int bwd_q_fast = 1;
   int bwd_passes = 1;
+  int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
 };
 extern Tuning g_tuning;
 extern long long g_launches;
@@ -82,6 +83,30 @@ template <> struct Vec<__half> {
       w[i] = *reinterpret_cast<uint32_t*>(&h);
     }
     *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
+// Narrow variants for the backward kernel: 4 channels per lane whatever the storage type (fp32: the same 16-byte
+// load; bf16/f16: an 8-byte load).  With 4 channels per lane a unit is D/4 lanes and ONE 128-bit reduction
+// instruction covers the unit's whole D*4-byte fp32 gradient row, i.e. one request per 128-byte line instead of two
+// half-line requests -- the backward kernel is bound by L1TEX->XBAR reduction requests.
+template <typename VT> struct VecQ;
+template <> struct VecQ<float> : Vec<float> {};
+template <> struct VecQ<__nv_bfloat16> {
+  static constexpr int CH = 4;
+  __device__ static __forceinline__ void load(const __nv_bfloat16* p, bool ok, float (&f)[4]) {
+    const uint2 r = ok ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+template <> struct VecQ<__half> {
+  static constexpr int CH = 4;
+  __device__ static __forceinline__ void load(const __half* p, bool ok, float (&f)[4]) {
+    const uint2 r = ok ? __ldg(reinterpret_cast<const uint2*>(p)) : make_uint2(0u, 0u);
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
   }
 };
 

@@ -131,7 +131,7 @@ __device__ __forceinline__ void reduce_scatter16(float (&v)[16], int lig) {
   }
 }
 
-template <typename VT, int D>
+template <typename VT, int D, typename V>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -139,7 +139,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_aw, int S, int M, int L, int Lq, long long units,
                     int passes, int q_fast) {
-  constexpr int CH = Vec<VT>::CH;
+  constexpr int CH = V::CH;
   constexpr int LPG = D / CH;
   constexpr int UPW = 32 / LPG;
   constexpr int TILE = UPW * kWarpsPerBlock;
@@ -176,7 +176,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
     float* gap = grad_aw + static_cast<size_t>(u) * L * P;
 
     float g[CH];
-    Vec<VT>::load(grad_out + static_cast<size_t>(u) * D + lig * CH, active, g);
+    V::load(grad_out + static_cast<size_t>(u) * D + lig * CH, active, g);
     // Channels this lane REDUCES into grad_value.  fp32: the 4 it loads.  16-bit storage: a lane
     // loads 8 contiguous channels (16 B) but the fp32 gradient of those is 32 B, so issuing them as
     // two 16-byte reductions would leave every 32-byte L2 sector half written per instruction.
@@ -221,10 +221,10 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         float v1[CH], v2[CH], v3[CH], v4[CH];
         const long long e1 = static_cast<long long>(t.o1) * row, e2 = static_cast<long long>(t.o2) * row;
         const long long e3 = static_cast<long long>(t.o3) * row, e4 = static_cast<long long>(t.o4) * row;
-        Vec<VT>::load(vl + e1, t.c1, v1);
-        Vec<VT>::load(vl + e2, t.c2, v2);
-        Vec<VT>::load(vl + e3, t.c3, v3);
-        Vec<VT>::load(vl + e4, t.c4, v4);
+        V::load(vl + e1, t.c1, v1);
+        V::load(vl + e2, t.c2, v2);
+        V::load(vl + e3, t.c3, v3);
+        V::load(vl + e4, t.c4, v4);
         const float k1 = t.hh * t.hw, k2 = t.hh * t.lw, k3 = t.lh * t.hw, k4 = t.lh * t.lw;
         const float a = as[p];
         float s_w = 0.f, s_h = 0.f, s_a = 0.f;
@@ -399,19 +399,31 @@ static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const 
   return cudaGetLastError();
 }
 
-template <typename VT, int D>
-static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
-                                  const float* loc, const float* aw, const VT* grad_out, float* gv,
-                                  float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
-  constexpr int TILE = (32 / (D / Vec<VT>::CH)) * kWarpsPerBlock;
+template <typename VT, int D, typename V>
+static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, const int64_t* lstart,
+                                    const float* loc, const float* aw, const VT* grad_out, float* gv,
+                                    float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
+  constexpr int TILE = (32 / (D / V::CH)) * kWarpsPerBlock;
   const long long units = static_cast<long long>(N) * Lq * M;
   const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
   const int passes = g_tuning.bwd_passes;
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   ++g_launches;
-  msda_bwd_vec_kernel<VT, D><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+  msda_bwd_vec_kernel<VT, D, V><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
       value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast);
   return cudaGetLastError();
+}
+
+template <typename VT, int D>
+static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
+                                  const float* loc, const float* aw, const VT* grad_out, float* gv,
+                                  float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
+  // narrow layout needs D/4 <= 16 lanes per unit
+  if constexpr (Vec<VT>::CH == 8 && D <= 64) {
+    if (g_tuning.bwd_narrow)
+      return launch_bwd_vec_t<VT, D, VecQ<VT>>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+  }
+  return launch_bwd_vec_t<VT, D, Vec<VT>>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
 }
 
 // Storage types whose locations / weights / gradients are fp32 (float, bf16, half).

@@ -293,7 +293,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // memory, loaded once; only the activation tiles stream through the ring (K = 256, N <= 256: 128 KiB of W).
   // Otherwise A and B tiles stream together (any shape).
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // align by OFFSET, not by casting through an integer: the compiler then still knows these are shared-memory
+  // addresses and emits LDS/STS instead of generic LD/ST (which go through L1TEX address translation)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_tile_bytes = block_n * BLOCK_K * 2;
   const int stage_bytes = b_resident ? SMEM_A : SMEM_A + b_tile_bytes;
   uint8_t* smem_bres = smem + STAGES * stage_bytes;                       // resident W slice: (K/64) tiles

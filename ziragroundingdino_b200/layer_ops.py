@@ -84,10 +84,9 @@ class FFN16Function(Function):
     threshold pass).  The two products with K = d_ffn (linear2 forward, linear1 dgrad) stay library GEMMs: their weight
     does not fit in shared memory and a single-CTA streaming kernel would lose to cuBLAS's 2-CTA multicast one."""
 
-    # Measured on B200 (profiles/r1_gemm_ab.txt): the gated dgrad epilogue (287 us) does not beat cuBLAS + the
-    # elementwise threshold kernel (105 + 152 us) yet -- its extra 364 MB gate read sits in the epilogue's dependency
-    # chain -- so it is off by default; the fused bias+ReLU forward (131 vs 230 us) is on.
-    fuse_relu_backward = False
+    # Measured on B200 (profiles/r1_gemm_ab.txt, R = 88 892): fused bias+ReLU forward 115 us vs cuBLAS + ReLU kernel 230 us;
+    # gated dgrad 227 us vs cuBLAS + threshold kernel 250 us.  The switch exists for A/B runs.
+    fuse_relu_backward = True
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
