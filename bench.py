@@ -254,18 +254,40 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
 
     # ---- end to end: pinned host inputs in, loss out, every step --------------------------------------
+    # A two-deep input pipeline, as a data loader would run it: step i's host->device copies are issued on a copy
+    # stream into a staging set while step i-1 computes; at the start of step i a device-to-device copy moves the
+    # staged inputs into the buffers the captured graph reads.  Every step still copies its own 91 MB from pinned
+    # host memory and reads its loss back; the host waits for the loss of step i before it returns.
+    copy_stream = torch.cuda.Stream()
+    stage_feat, stage_pos, stage_mask = torch.empty_like(feat), torch.empty_like(pos), torch.empty_like(mask)
+    staged_ready, staged_free = torch.cuda.Event(), torch.cuda.Event()
+
+    def prefetch():
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(staged_free)           # previous contents consumed
+            stage_feat.copy_(host_feat, non_blocking=True)
+            stage_pos.copy_(host_pos, non_blocking=True)
+            stage_mask.copy_(host_mask, non_blocking=True)
+            staged_ready.record(copy_stream)
+
+    staged_free.record(torch.cuda.current_stream())
+    prefetch()
+
     def e2e_step():
-        if graph is not None:   # the graph reads the static device buffers: refill them from pinned host memory
-            feat.copy_(host_feat, non_blocking=True)
-            pos.copy_(host_pos, non_blocking=True)
-            mask.copy_(host_mask, non_blocking=True)
+        cur = torch.cuda.current_stream()
+        cur.wait_event(staged_ready)
+        feat.copy_(stage_feat, non_blocking=True)
+        pos.copy_(stage_pos, non_blocking=True)
+        mask.copy_(stage_mask, non_blocking=True)
+        staged_free.record(cur)
+        prefetch()                                        # next step's inputs travel while this step computes
+        if graph is not None:
             run()
             loss = static_loss
         else:
-            loss = step(host_feat.to(dev, non_blocking=True), host_pos.to(dev, non_blocking=True),
-                        host_mask.to(dev, non_blocking=True))
+            loss = step(feat, pos, mask)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        cur.synchronize()
 
     for _ in range(2):
         e2e_step()

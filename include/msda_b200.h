@@ -157,7 +157,8 @@ int msda_zira_bwd_prep_16(const void *dy, const void *pre, const void *adapter, 
 const char *msda_b200_gemm_last_error(void);
 /* A/B switch for benchmarks: 1 (default) keeps each CTA's slice of W resident in shared memory when it fits. */
 int msda_b200_gemm_set_resident(int on);
-/* A/B switch: 1 (default) transposes 16-bit epilogue stores through shared memory so they leave coalesced. */
+/* A/B switch: 1 (default) stores the epilogue through TMA from 128B-swizzled tiles; 0 = shared-memory transposition +
+ * coalesced st.global. */
 int msda_b200_gemm_set_staged(int on);
 
 /* ---- the op's immediate caller: residual + LayerNorm ------------------------------

@@ -299,20 +299,27 @@ def test_add_layernorm_fused(dtype, eps16, R, C):
 
 
 def test_gemm_resident_and_streaming_modes_agree():
-    """The GEMM keeps its slice of W resident in shared memory when it fits and streams it otherwise: same bits."""
+    """The GEMM keeps its slice of W resident in shared memory when it fits and streams it otherwise, and stores its
+    epilogue through TMA or through st.global: same bits in every combination."""
     from ziragroundingdino_b200 import _lib, fused
     L = _lib.lib()
-    for (R, K, Nout) in [(3000, 256, 256), (1500, 384, 256), (700, 256, 384), (400, 768, 256)]:
+    for (R, K, Nout) in [(3000, 256, 256), (1500, 384, 256), (700, 256, 384), (400, 768, 256), (333, 256, 2048), (129, 256, 96)]:
         x, w, b = _rand((R, K), torch.bfloat16, 41), _rand((Nout, K), torch.bfloat16, 42, 0.05), _rand((Nout,), torch.float32, 43)
+        mask = (torch.arange(R, device=DEV) % 3 == 0).to(torch.uint8)
+        ref = (x.double() @ w.double().t() + b.double())
+        outs = []
         try:
-            L.msda_b200_gemm_set_resident(1)
-            y1 = fused.linear16(x, w, b, out_f32=True)
-            L.msda_b200_gemm_set_resident(0)
-            y0 = fused.linear16(x, w, b, out_f32=True)
+            for res in (1, 0):
+                for tma in (1, 0):
+                    L.msda_b200_gemm_set_resident(res); L.msda_b200_gemm_set_staged(tma)
+                    outs.append((fused.linear16(x, w, b, out_f32=True), fused.linear16(x, w, b, row_mask=mask)))
         finally:
-            L.msda_b200_gemm_set_resident(1)
-        assert torch.equal(y0, y1)
-        assert rel_err(y1.cpu(), (x.double() @ w.double().t() + b.double()).cpu()) < 1e-4
+            L.msda_b200_gemm_set_resident(1); L.msda_b200_gemm_set_staged(1)
+        for y32, y16 in outs[1:]:
+            assert torch.equal(y32, outs[0][0]) and torch.equal(y16, outs[0][1])
+        assert rel_err(outs[0][0].cpu(), ref.cpu()) < 1e-4
+        want16 = ref * (1 - mask.double())[:, None]
+        assert (outs[0][1].double() - want16).abs().max().item() <= 2 ** -8 * ref.abs().max().item() * 1.01
 
 
 @pytest.mark.parametrize("gate_fused", [False, True])

@@ -63,4 +63,4 @@ else:
             for name, fn in cases.items():
                 if "cublas" in name and (staged, res) != (1, 1):
                     continue
-                print("staged=%d resident=%d  %-36s cold %7.1f us   warm %7.1f us" % (staged, res, name, timeit(fn, True), timeit(fn, False)))
+                print("tma_store=%d resident=%d  %-36s cold %7.1f us   warm %7.1f us" % (staged, res, name, timeit(fn, True), timeit(fn, False)))

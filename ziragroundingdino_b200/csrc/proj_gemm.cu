@@ -37,7 +37,7 @@ namespace pg {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;              // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
+constexpr int STAGES = 4;                // maximum ring depth; the host may pick 3 to make room for the store tiles
 constexpr int SMEM_A = BLOCK_M * BLOCK_K * 2;   // 16 KiB
 constexpr int MAX_N = 2048;              // widest (stacked) weight handled by one launch
 constexpr int EPI_WARPS = 8;
@@ -45,8 +45,11 @@ constexpr int THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue
 constexpr int AUX_BASE = 256 + MAX_N * 4 + MSDA_MAX_LEVELS * 8;
 constexpr int AUX_BYTES_16 = AUX_BASE + EPI_WARPS * 32 * 80;    // 16-bit outputs
 constexpr int AUX_BYTES_32 = AUX_BASE + EPI_WARPS * 32 * 144;   // fp32 outputs
+constexpr int TMA_TILE_BYTES = 32 * 128;                        // one epilogue warp's 128B-swizzled store tile
+constexpr int AUX_BYTES_TMA = AUX_BASE + EPI_WARPS * TMA_TILE_BYTES;
 constexpr int kMaxSmem = 227 * 1024;
 bool g_allow_resident = true;
+bool g_tma_store = true;         // msda_b200_gemm_set_staged(0) turns the TMA-store epilogue off (A/B)
 bool g_staged_store = true;      // msda_b200_gemm_set_staged(0|1)   // msda_b200_set_tuning("gemm_resident", 0|1)
 
 enum EpiMode { EPI_STORE = 0, EPI_QUERY = 1, EPI_ZIRA = 2 };
@@ -109,6 +112,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// 16-byte chunk j of row r inside a 32 x 128-byte tile laid out for CU_TENSOR_MAP_SWIZZLE_128B
+__device__ __forceinline__ uint8_t* swz(uint8_t* tile, int r, int j) { return tile + r * 128 + ((j ^ (r & 7)) << 4); }
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
@@ -285,10 +299,11 @@ __device__ __forceinline__ float smooth_l1(float x) {   // beta = 1 (torch.nn.Sm
 }
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE>
+template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE, bool TMA_OUT>
 __global__ void __launch_bounds__(THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int R, int Nout,
-                 int K, int block_n, int b_resident, int half_in, EpiParams ep) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int R, int Nout,
+                 int K, int block_n, int b_resident, int stages, int half_in, EpiParams ep) {
   // b_resident: the CTA owns ONE n-block for its whole life and keeps that slice of W (block_n x K) in shared
   // memory, loaded once; only the activation tiles stream through the ring (K = 256, N <= 256: 128 KiB of W).
   // Otherwise A and B tiles stream together (any shape).
@@ -298,8 +313,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int b_tile_bytes = block_n * BLOCK_K * 2;
   const int stage_bytes = b_resident ? SMEM_A : SMEM_A + b_tile_bytes;
-  uint8_t* smem_bres = smem + STAGES * stage_bytes;                       // resident W slice: (K/64) tiles
-  uint8_t* aux = smem_bres + (b_resident ? (K / BLOCK_K) * b_tile_bytes : 0);
+  uint8_t* smem_bres = smem + stages * stage_bytes;                       // resident W slice: (K/64) tiles
+  uint8_t* tma_tiles = smem_bres + (b_resident ? (K / BLOCK_K) * b_tile_bytes : 0);   // 1024-aligned (all sizes above are)
+  uint8_t* aux = tma_tiles + (TMA_OUT ? EPI_WARPS * TMA_TILE_BYTES : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -360,7 +376,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(full_bar + stage, static_cast<uint32_t>(stage_bytes));
           tma_load_2d(&tmA, full_bar + stage, sa, kb * BLOCK_K, m_idx);
           if (!b_resident) tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, kb * BLOCK_K, n_idx);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -390,7 +406,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (kb == num_k - 1) umma_commit(tfull_bar + acc);    // accumulator complete
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -440,6 +456,111 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ep.adapter_out) {
             pack_16(ad, HALF_OUT, false, pk);
             staged_store<4>(stage, lane, pk, static_cast<uint16_t*>(ep.adapter_out) + row0 * ep.F + f0, 2ll * ep.F, rows_valid);
+          }
+        }
+      } else if (TMA_OUT && MODE == EPI_STORE) {
+        // ---- 16-bit output through TMA: 64 columns (128 bytes per row) per step, written into this warp's
+        // 128B-swizzled 32 x 128-byte tile (conflict-free STS), then ONE cp.async.bulk.tensor store.  Rows >= R are
+        // clipped by the tensor map.  The two warps of a lane quarter alternate 64-column groups.
+        uint8_t* tile = tma_tiles + (warp - 2) * TMA_TILE_BYTES;
+        uint4 gnext[8];
+        const int g_j = lane & 7, g_rsub = lane >> 3;           // gate fetch: 8 lanes along a 128-byte row, 4 rows per instr
+        auto gate_fetch = [&](int c) {
+          const uint8_t* g = reinterpret_cast<const uint8_t*>(static_cast<const uint16_t*>(ep.gate) + row0 * ep.out_ld + n_idx + c);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + g_rsub;
+            gnext[it] = (rr < rows_valid) ? __ldg(reinterpret_cast<const uint4*>(g + rr * 2ll * ep.out_ld + g_j * 16)) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        };
+        if (GATE && chunk_par * 64 < block_n) gate_fetch(chunk_par * 64);
+        for (int c0 = chunk_par * 64; c0 < block_n; c0 += 128) {
+          const int gc = n_idx + c0;
+          if (lane == 0) tma_store_wait_read();      // the previous store of this warp has finished reading the tile
+          __syncwarp();
+          uint4 gt[8];
+          if (GATE) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(swz(tile, it * 4 + g_rsub, g_j)) = gnext[it];
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) gt[j] = *reinterpret_cast<const uint4*>(swz(tile, lane, j));
+            __syncwarp();
+            if (c0 + 128 < block_n) gate_fetch(c0 + 128);
+          }
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            tmem_ld32(taddr + c0 + 32 * hf, r);
+            float v[32];
+            const float4* bp = reinterpret_cast<const float4*>(s_bias + gc + 32 * hf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = bp[i];
+              v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+            }
+            if (RELU) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (GATE) {
+              const uint32_t* gw = reinterpret_cast<const uint32_t*>(gt) + 16 * hf;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const uint32_t w2 = gw[j], lo = w2 & 0xffffu, hi = w2 >> 16;
+                if (!((lo & 0x7fffu) != 0 && (lo & 0x8000u) == 0)) v[2 * j] = 0.f;
+                if (!((hi & 0x7fffu) != 0 && (hi & 0x8000u) == 0)) v[2 * j + 1] = 0.f;
+              }
+            }
+            uint4 pk[4];
+            pack_16(v, HALF_OUT, zero, pk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(tile, lane, 4 * hf + i)) = pk[i];
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmC, tile, gc, static_cast<int>(row0));
+        }
+      } else if (TMA_OUT && MODE == EPI_QUERY) {
+        // ---- fp32 sampling locations / softmax weights through TMA: 32 columns (128 bytes per row) per step
+        uint8_t* tile = tma_tiles + (warp - 2) * TMA_TILE_BYTES;
+        for (int c0 = chunk_par * 32; c0 < block_n; c0 += 64) {
+          const int gc = n_idx + c0;
+          uint32_t r[32];
+          tmem_ld32(taddr + c0, r);
+          float v[32], o32[32];
+          const float4* bp = reinterpret_cast<const float4*>(s_bias + gc);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = bp[i];
+            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+          }
+          const bool is_loc = gc < ep.n_loc;
+          if (is_loc) {
+            const long long rr = live ? row : 0;
+            if (ep.L == 4 && ep.P == 4) {
+              if (ep.ref_dim == 2) epi_loc_l4p4<2>(ep, v, rr, s_norm, o32);
+              else epi_loc_l4p4<4>(ep, v, rr, s_norm, o32);
+            } else {
+              epi_loc(ep, v, rr, gc, s_norm, o32);
+            }
+          } else {
+            epi_softmax(ep, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) o32[j] = v[j];
+          }
+          if (lane == 0) tma_store_wait_read();
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(swz(tile, lane, i)) = make_float4(o32[4 * i], o32[4 * i + 1], o32[4 * i + 2], o32[4 * i + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (is_loc) tma_store_2d(&tmC, tile, gc, static_cast<int>(row0));
+            else tma_store_2d(&tmC2, tile, gc - ep.n_loc, static_cast<int>(row0));
           }
         }
       } else {
@@ -530,6 +651,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) mbar_arrive(tempty_bar + acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (TMA_OUT && lane == 0) tma_store_wait_all();
     if (MODE == EPI_ZIRA) {
 #pragma unroll
       for (int o = 16; o >= 1; o >>= 1) {
@@ -562,16 +684,19 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-// row-major [rows, cols] 16-bit matrix, box = box_rows x 64 columns, 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* base, long long rows, int cols, int box_rows, bool half_in) {
+// row-major [rows, cols] matrix of `esize`-byte elements, box = box_rows x box_cols (box_cols * esize == 128),
+// 128-byte swizzle.  dtype: 0 bf16, 1 f16, 2 f32.
+static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols, int dtype) {
   auto fn = encode_fn();
   if (!fn) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled unavailable"); return MSDA_ERR_NO_DEVICE; }
+  const int esize = dtype == 2 ? 4 : 2;
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
-  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * 2};
-  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(box_rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * esize};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(map, half_in ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                  const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  const CUtensorMapDataType dt = dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                            : (dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = fn(map, dt, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled failed (%d)", static_cast<int>(r)); return MSDA_ERR_BAD_SHAPE; }
   return 0;
@@ -580,17 +705,17 @@ static int make_map(CUtensorMap* map, const void* base, long long rows, int cols
 // Widest n-block (multiple of `unit`, dividing Nout, <= 256 columns so two accumulators fit TMEM) whose slice of W
 // (block_n x K 16-bit) still fits in shared memory beside the activation ring; the smallest legal block otherwise.
 static int pick_block_n(int Nout, int K, int unit, bool f32_out) {
-  const int AUX_BYTES = f32_out ? AUX_BYTES_32 : AUX_BYTES_16;
+  // tail = everything after the operand buffers; the TMA-store tiles are the largest variant
+  const int tail = (f32_out ? AUX_BYTES_32 : AUX_BYTES_16) > AUX_BYTES_TMA ? (f32_out ? AUX_BYTES_32 : AUX_BYTES_16) : AUX_BYTES_TMA;
   int best = 0, smallest = 0;
   for (int bn = unit; bn <= 256 && bn <= Nout; bn += unit) {
     if (Nout % bn) continue;
     if (!smallest) smallest = bn;
-    if (bn * K * 2 + STAGES * SMEM_A + AUX_BYTES + 1024 <= kMaxSmem) best = bn;
+    if (bn * K * 2 + 3 * SMEM_A + tail + 1024 <= kMaxSmem) best = bn;     // resident W with at least a 3-deep A ring
   }
   if (best) return best;
-  // nothing fits resident: largest block whose streaming stages fit
   for (int bn = 256; bn >= unit; bn -= unit)
-    if (Nout % bn == 0 && bn % unit == 0 && STAGES * (SMEM_A + bn * BLOCK_K * 2) + AUX_BYTES + 1024 <= kMaxSmem) return bn;
+    if (Nout % bn == 0 && bn % unit == 0 && 3 * (SMEM_A + bn * BLOCK_K * 2) + tail + 1024 <= kMaxSmem) return bn;
   return smallest ? smallest : unit;
 }
 
@@ -606,24 +731,47 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
     snprintf(t_err, sizeof(t_err), "operands must be 16-byte aligned");
     return MSDA_ERR_MISALIGNED;
   }
-  CUtensorMap tmA, tmB;
-  int rc = make_map(&tmA, x, R, K, BLOCK_M, half_in);
+  const int in_dt = half_in ? 1 : 0;
+  CUtensorMap tmA, tmB, tmC, tmC2;
+  int rc = make_map(&tmA, x, R, K, BLOCK_M, BLOCK_K, in_dt);
   if (rc) return rc;
-  rc = make_map(&tmB, w, Nout, K, block_n, half_in);
+  rc = make_map(&tmB, w, Nout, K, block_n, BLOCK_K, in_dt);
   if (rc) return rc;
+  tmC = tmA; tmC2 = tmA;   // placeholders when the epilogue does not store through TMA
+  // TMA-store epilogue: plain 16-bit stores in 64-column steps, and the fp32 query outputs in 32-column steps
+  bool tma_out = false;
+  if (g_tma_store) {
+    if (ep.mode == EPI_STORE && !ep.out_f32 && block_n % 64 == 0 && (reinterpret_cast<uintptr_t>(ep.out) & 15u) == 0 &&
+        (ep.out_ld * 2) % 16 == 0) {
+      rc = make_map(&tmC, ep.out, R, ep.out_ld, 32, 64, ep.out_half ? 1 : 0);
+      if (rc) return rc;
+      tma_out = true;
+    } else if (ep.mode == EPI_QUERY) {
+      rc = make_map(&tmC, ep.loc_out, R, ep.n_loc, 32, 32, 2);
+      if (rc) return rc;
+      rc = make_map(&tmC2, ep.aw_out, R, ep.n_aw, 32, 32, 2);
+      if (rc) return rc;
+      tma_out = true;
+    }
+  }
   static int sms = 0;
   if (!sms) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  // resident-W mode whenever the CTA's slice of W fits beside the activation ring
   const int num_n = Nout / block_n;
   const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
   const int bres_bytes = block_n * K * 2;
-  const int AUX_BYTES = (ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16;
-  const bool b_res = g_allow_resident && bres_bytes + STAGES * SMEM_A + AUX_BYTES + 1024 <= kMaxSmem && num_n <= sms;
-  const int smem = (b_res ? STAGES * SMEM_A + bres_bytes : STAGES * (SMEM_A + block_n * BLOCK_K * 2)) + AUX_BYTES + 1024;
+  const int tail = tma_out ? AUX_BYTES_TMA : ((ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16);
+  // resident-W mode whenever the CTA's slice of W fits beside an activation ring of at least 3 stages
+  const bool b_res = g_allow_resident && bres_bytes + 3 * SMEM_A + tail + 1024 <= kMaxSmem && num_n <= sms;
+  const int stage_bytes = b_res ? SMEM_A : SMEM_A + block_n * BLOCK_K * 2;
+  const int fixed = (b_res ? bres_bytes : 0) + tail + 1024;
+  int stages = STAGES;
+  while (stages > 2 && stages * stage_bytes + fixed > kMaxSmem) --stages;
+  if (stages * stage_bytes + fixed > kMaxSmem) { snprintf(t_err, sizeof(t_err), "GEMM tile does not fit shared memory"); return MSDA_ERR_UNSUPPORTED; }
+  const int smem = stages * stage_bytes + fixed;
   int grid;
   if (b_res) {
     long long per_n = sms / num_n;
@@ -636,23 +784,29 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   ++msda::g_launches;
   const int Ri = static_cast<int>(R), br = b_res ? 1 : 0, hi = half_in ? 1 : 0;
   cudaError_t cfg = cudaSuccess;
-#define PG_LAUNCH(MODE, F32, HALF, RELU, GATE)                                                                            \
+#define PG_LAUNCH(MODE, F32, HALF, RELU, GATE, TMA)                                                                        \
   do {                                                                                                                     \
     static bool configured = false;                                                                                        \
     if (!configured) {                                                                                                     \
-      cfg = cudaFuncSetAttribute(linear_tc_kernel<MODE, F32, HALF, RELU, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+      cfg = cudaFuncSetAttribute(linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
       configured = cfg == cudaSuccess;                                                                                     \
     }                                                                                                                      \
     if (cfg == cudaSuccess)                                                                                                \
-      linear_tc_kernel<MODE, F32, HALF, RELU, GATE><<<grid, THREADS, smem, st>>>(tmA, tmB, Ri, Nout, K, block_n, br, hi, ep); \
+      linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, Ri, Nout, K, block_n, br, stages, hi, ep); \
+  } while (0)
+#define PG_STORE16(RELU, GATE)                                                                                             \
+  do {                                                                                                                     \
+    if (tma_out) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, RELU, GATE, true); else PG_LAUNCH(EPI_STORE, false, false, RELU, GATE, true); } \
+    else { if (half_out) PG_LAUNCH(EPI_STORE, false, true, RELU, GATE, false); else PG_LAUNCH(EPI_STORE, false, false, RELU, GATE, false); }       \
   } while (0)
   const bool half_out = ep.out_half != 0;
-  if (ep.mode == EPI_QUERY) PG_LAUNCH(EPI_QUERY, true, false, false, false);
-  else if (ep.mode == EPI_ZIRA) { if (half_out) PG_LAUNCH(EPI_ZIRA, false, true, false, false); else PG_LAUNCH(EPI_ZIRA, false, false, false, false); }
-  else if (ep.out_f32) PG_LAUNCH(EPI_STORE, true, false, false, false);
-  else if (ep.gate) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, false, true); else PG_LAUNCH(EPI_STORE, false, false, false, true); }
-  else if (ep.relu) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, true, false); else PG_LAUNCH(EPI_STORE, false, false, true, false); }
-  else { if (half_out) PG_LAUNCH(EPI_STORE, false, true, false, false); else PG_LAUNCH(EPI_STORE, false, false, false, false); }
+  if (ep.mode == EPI_QUERY) { if (tma_out) PG_LAUNCH(EPI_QUERY, true, false, false, false, true); else PG_LAUNCH(EPI_QUERY, true, false, false, false, false); }
+  else if (ep.mode == EPI_ZIRA) { if (half_out) PG_LAUNCH(EPI_ZIRA, false, true, false, false, false); else PG_LAUNCH(EPI_ZIRA, false, false, false, false, false); }
+  else if (ep.out_f32) PG_LAUNCH(EPI_STORE, true, false, false, false, false);
+  else if (ep.gate) PG_STORE16(false, true);
+  else if (ep.relu) PG_STORE16(true, false);
+  else PG_STORE16(false, false);
+#undef PG_STORE16
 #undef PG_LAUNCH
   if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
   cudaError_t e = cudaGetLastError();
@@ -663,7 +817,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
 }  // namespace pg
 
 extern "C" int msda_b200_gemm_set_resident(int on) { pg::g_allow_resident = on != 0; return 0; }
-extern "C" int msda_b200_gemm_set_staged(int) { return 0; }   // kept for ABI stability: staging was removed
+extern "C" int msda_b200_gemm_set_staged(int on) { pg::g_tma_store = on != 0; return 0; }
 
 extern "C" {
 
