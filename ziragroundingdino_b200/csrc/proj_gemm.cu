@@ -476,10 +476,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (GATE && chunk_par * 64 < block_n) gate_fetch(chunk_par * 64);
         for (int c0 = chunk_par * 64; c0 < block_n; c0 += 128) {
           const int gc = n_idx + c0;
-          if (lane == 0) tma_store_wait_read();      // the previous store of this warp has finished reading the tile
-          __syncwarp();
           uint4 gt[8];
           if (GATE) {
+            if (lane == 0) tma_store_wait_read();    // the gate transposition reuses the tile: previous store must have read it
+            __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(swz(tile, it * 4 + g_rsub, g_j)) = gnext[it];
             __syncwarp();
@@ -515,6 +515,10 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             uint4 pk[4];
             pack_16(v, HALF_OUT, zero, pk);
+            if (!GATE && hf == 0) {   // wait as late as possible: the previous store's smem read overlaps this step's TMEM load + math
+              if (lane == 0) tma_store_wait_read();
+              __syncwarp();
+            }
 #pragma unroll
             for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(tile, lane, 4 * hf + i)) = pk[i];
           }
