@@ -141,6 +141,10 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr instead
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
@@ -347,7 +351,8 @@ def run_ours(args):
         ips, layers, t = cpu_images_per_s(20.0, threads)
         out["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
                                "sample": "1 image x %d of 6 encoder layers fwd+bwd (fp32, torch CPU, grid_sample core), %.1f s" % (layers, t)}
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
