@@ -329,6 +329,11 @@ def run_ours(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same launch
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["msda_bwd_vec_kernel<bf16,32>"]["dram_bytes_per_launch"]
+    except (OSError, KeyError, ValueError):
+        pass
     peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
     images = IMAGES_PER_GPU * world * args.steps
     value = images / (ms / 1e3)
@@ -341,10 +346,15 @@ def run_ours(args):
                                    "fwd_l2_algorithmic_gbps": ab["fwd_l2"] / us_fwd / 1e3,
                                    "bwd_l2_algorithmic_gbps": ab["bwd_l2"] / us_bwd / 1e3},
         "roofline": {"kernel": "msda_bwd_vec_kernel<bf16,32>", "bound": "hbm", "achieved": ab["bwd_hbm"] / us_bwd / 1e3,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": ab["bwd_hbm"] / us_bwd / 1e3 / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": ab["bwd_hbm"] / us_bwd / 1e3 / hbm_peak, "traffic": traffic,
+                     "algorithmic_bytes": ab["bwd_hbm"],
                      "peak_source": peak_src,
-                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by L1TEX/L2 reduction "
-                             "throughput, not HBM -- see DESIGN.md and profiles/"},
+                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by L1TEX->XBAR reduction "
+                             "requests (ncu: l1tex 86 %, lts 69 %, DRAM 6 %), not HBM -- see DESIGN.md 4.2 and profiles/"},
+        "roofline_l2": {"kernels": "msda_fwd_vec_kernel + msda_bwd_vec_kernel", "bound": "l2-gather",
+                        "achieved": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3, "peak": 15900.0, "unit": "GB/s",
+                        "frac": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3 / 15900.0,
+                        "peak_source": "msda_b200_probe_gather, random 64 B segments of an L2-resident buffer (profiles/r1_sweep_core_first.jsonl)"},
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

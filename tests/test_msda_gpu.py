@@ -273,3 +273,28 @@ def test_config1_vs_fp64_truth_and_reference_cuda_op():
         np.abs(r_out.cpu().numpy() - truth).max(), (r_out.cpu() - out).abs().max().item()))
     assert (r_out.cpu() - out).abs().max() < 1e-5
     assert rel_err(gv, r_gv.cpu()) < 1e-4 and rel_err(gl, r_gl.cpu()) < 1e-4 and rel_err(ga, r_ga.cpu()) < 1e-4
+
+
+def test_gradcheck_fp64_tiny():
+    """torch.autograd.gradcheck of the op in fp64 on a tiny problem: samples on, inside and
+    outside the borders; points within 1e-3 of a pixel boundary are nudged away (the op is not differentiable there)."""
+    import ziragroundingdino_b200 as zb
+    dev = _dev()
+    shapes = [(6, 5), (3, 3)]
+    N, M, D, Lq, P, L = 1, 2, 4, 7, 2, 2
+    g = torch.Generator().manual_seed(17)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(N, S, M, D, generator=g, dtype=torch.float64)
+    loc = torch.rand(N, Lq, M, L, P, 2, generator=g, dtype=torch.float64) * 1.2 - 0.1
+    for l, (h, w) in enumerate(shapes):       # keep every sample >= 1e-3 pixels away from integer coordinates
+        for ax, size in ((0, w), (1, h)):
+            pix = loc[:, :, :, l, :, ax] * size - 0.5
+            frac = pix - pix.floor()
+            pix = torch.where(frac < 1e-3, pix + 2e-3, torch.where(frac > 1 - 1e-3, pix - 2e-3, pix))
+            loc[:, :, :, l, :, ax] = (pix + 0.5) / size
+    aw = torch.softmax(torch.randn(N, Lq, M, L * P, generator=g, dtype=torch.float64), -1).view(N, Lq, M, L, P)
+    sh = torch.tensor(shapes, dtype=torch.long, device=dev)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    v, l_, a = (t.to(dev).requires_grad_(True) for t in (value, loc, aw))
+    fn = lambda vv, ll, aa: zb.MultiScaleDeformableAttnFunction.apply(vv, sh, lsi, ll, aa, 64)
+    assert torch.autograd.gradcheck(fn, (v, l_, a), eps=1e-6, atol=1e-6, rtol=1e-4, nondet_tol=1e-12)
