@@ -94,6 +94,16 @@ int msda_backward_f16(const void *value, const int64_t *spatial_shapes, const in
                       int L, int Lq, int P, float *grad_value, float *grad_loc, float *grad_aw,
                       int zero_grad_value, void *stream);
 
+/* Backward with the query-side epilogue backward fused in (16-bit storage, D = 32, L = 4, P = 4): same scatter into
+ * grad_value, but instead of grad_sampling_loc / grad_attn_weight it writes dq [N*Lq, 3*M*L*P] (16-bit) =
+ * [d sampling_offsets | d attention logits], i.e. the backward of ms_deform_attn.py:296 (softmax) and :306-319
+ * (offsets -> locations; ref is [N*Lq, L, ref_dim] fp32) finished in registers -- the operand of the
+ * query-projection dgrad GEMM, with no fp32 round trip through HBM. */
+int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                            const float *loc, const float *aw, const void *grad_out, const float *ref, int ref_dim,
+                            int N, int S, int M, int D, int L, int Lq, int P, float *grad_value, void *dq,
+                            int zero_grad_value, int is_half, void *stream);
+
 /* ---- tuning / introspection (not part of the reference interface) ------------------------------
  * Kernel variant knobs used by bench.py sweeps; defaults are the shipped configuration.
  *   key "fwd_sample_batch"  : samples whose corner loads are issued together (1, 2 or 4)

@@ -10,6 +10,8 @@ template <typename VT>
 cudaError_t forward_f32acc(const VT*, const int64_t*, const int64_t*, const float*, const float*, VT*, int, int, int, int, int, int, int, cudaStream_t);
 template <typename VT>
 cudaError_t backward_f32acc(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template <typename VT>
+cudaError_t backward_fused_q(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 cudaError_t forward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t backward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace msda
@@ -149,6 +151,33 @@ int msda_b200_get_tuning(const char* key) {
 MSDA_DEFINE_F32ACC(f32, float, float)
 MSDA_DEFINE_F32ACC(bf16, void, __nv_bfloat16)
 MSDA_DEFINE_F32ACC(f16, void, __half)
+
+int msda_backward_fusedq_16(const void* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                            const void* grad_out, const float* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
+                            float* gv, void* dq, int zero_gv, int is_half, void* stream) {
+  t_err[0] = 0;
+  int rc = check_common(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, 2);
+  if (rc) return rc;
+  if (!grad_out || !gv || !dq || !ref) return fail(MSDA_ERR_NULL_POINTER, "null pointer");
+  if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 4))
+    return fail(MSDA_ERR_UNSUPPORTED, "fused query backward needs D=32, L=4, P=4 (got D=%d L=%d P=%d)", D, L, P);
+  if (!aligned16(grad_out) || !aligned16(gv) || !aligned16(dq) || !aligned16(ref))
+    return fail(MSDA_ERR_MISALIGNED, "pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (zero_gv && N > 0) {
+    rc = cuda_status(cudaMemsetAsync(gv, 0, sizeof(float) * static_cast<size_t>(N) * S * M * D, st), "grad_value memset");
+    if (rc) return rc;
+  }
+  if (N == 0 || Lq == 0) return MSDA_OK;
+  cudaError_t e;
+  if (is_half)
+    e = msda::backward_fused_q<__half>(static_cast<const __half*>(value), shapes, lstart, loc, aw, static_cast<const __half*>(grad_out),
+                                       gv, ref, ref_dim, dq, 1, N, S, M, Lq, st);
+  else
+    e = msda::backward_fused_q<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(value), shapes, lstart, loc, aw,
+                                              static_cast<const __nv_bfloat16*>(grad_out), gv, ref, ref_dim, dq, 0, N, S, M, Lq, st);
+  return cuda_status(e, "msda_backward_fusedq launch");
+}
 
 int msda_forward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,
                      const double* aw, int N, int S, int M, int D, int L, int Lq, int P, double* out, void* stream) {

@@ -131,14 +131,25 @@ __device__ __forceinline__ void reduce_scatter16(float (&v)[16], int lig) {
   }
 }
 
-template <typename VT, int D, typename V>
+// FUSEQ (L == 4, P == 4, 8 lanes per unit): instead of writing grad_sampling_loc / grad_attn_weight in fp32, finish the
+// backward of the query-side epilogue in registers -- d_offset = grad_loc / (W_l, H_l) (2-d reference points) or
+// grad_loc * ref_wh * 0.5 / P (4-d), d_logit = aw * (grad_aw - sum grad_aw * aw) -- and write the 16-bit operand
+// [d_offsets | d_logits] of the query-projection dgrad GEMM directly (fq.dq, row stride 3*M*L*P).
+struct FuseQ {
+  const float* ref;     // [N*Lq, L, ref_dim]
+  uint16_t* dq;         // [N*Lq, 3*M*L*P]
+  int ref_dim;
+  int is_half;
+};
+
+template <typename VT, int D, typename V, bool FUSEQ>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_aw, int S, int M, int L, int Lq, long long units,
-                    int passes, int q_fast) {
+                    int passes, int q_fast, FuseQ fq) {
   constexpr int CH = V::CH;
   constexpr int LPG = D / CH;
   constexpr int UPW = 32 / LPG;
@@ -204,6 +215,11 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       }
     }
 
+    // FUSEQ: after the reduce-scatter lane `lig` holds, per level, either (grad_x, grad_y) of point lig/2 (even lanes)
+    // or grad_attn of point lig/2 (odd lanes); they are kept until the softmax dot product over all 16 samples is known.
+    float fq_a[4], fq_b[4], fq_aw[4];
+    float fq_dot = 0.f;
+
     for (int l = 0; l < L; ++l) {
       const int H = sH[l], W = sW[l];
       const size_t loff = static_cast<size_t>(sStart[l]) * row;
@@ -256,12 +272,52 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         }
       }
       reduce_scatter16<LPG>(red, lig);
-      if (active) {
+      if constexpr (FUSEQ) {
+        // LPG == 8, R == 2: red[0], red[1] = entries 2*lig, 2*lig+1 of (w, h, a, pad) x 4 points
+        const int p = lig >> 1;
+        const float my_aw = p == 0 ? as[0] : (p == 1 ? as[1] : (p == 2 ? as[2] : as[3]));
+        if (l < 4) { fq_a[l] = red[0]; fq_b[l] = red[1]; fq_aw[l] = my_aw; }
+        if (lig & 1) fq_dot = fmaf(red[0], my_aw, fq_dot);      // odd lanes hold grad_attn of point p
+      } else {
+        if (active) {
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const int idx = lig * R + r, p = idx >> 2, comp = idx & 3;
-          if (comp < 2) glp[(l * P + p) * 2 + comp] = red[r];
-          else if (comp == 2) gap[l * P + p] = red[r];
+          for (int r = 0; r < R; ++r) {
+            const int idx = lig * R + r, p = idx >> 2, comp = idx & 3;
+            if (comp < 2) glp[(l * P + p) * 2 + comp] = red[r];
+            else if (comp == 2) gap[l * P + p] = red[r];
+          }
+        }
+      }
+    }
+    if constexpr (FUSEQ) {
+      // softmax dot product over the unit's 16 samples: the 4 odd lanes hold 4 terms each
+      fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 1);
+      fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 2);
+      fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 4);
+      if (active) {
+        const int p = lig >> 1;
+        const int n_aw = M * 16, ld = 3 * n_aw;
+        uint16_t* orow = fq.dq + static_cast<size_t>(bq) * ld;
+        const float* rp = fq.ref + static_cast<size_t>(bq) * 4 * fq.ref_dim;
+        const bool hf = fq.is_half != 0;
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          if (lig & 1) {
+            const float d = fq_aw[l] * (fq_a[l] - fq_dot);
+            uint16_t w16;
+            if (hf) { __half t = __float2half_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t); }
+            else { __nv_bfloat16 t = __float2bfloat16_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t); }
+            orow[2 * n_aw + m * 16 + l * 4 + p] = w16;
+          } else {
+            float sx, sy;
+            if (fq.ref_dim == 2) { sx = 1.f / static_cast<float>(sW[l]); sy = 1.f / static_cast<float>(sH[l]); }
+            else { sx = rp[l * 4 + 2] * 0.125f; sy = rp[l * 4 + 3] * 0.125f; }     // * 0.5 / P with P == 4
+            const float dx = fq_a[l] * sx, dy = fq_b[l] * sy;
+            uint32_t w32;
+            if (hf) { __half2 t = __floats2half2_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t); }
+            else { __nv_bfloat162 t = __floats2bfloat162_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t); }
+            *reinterpret_cast<uint32_t*>(orow + m * 32 + (l * 4 + p) * 2) = w32;
+          }
         }
       }
     }
@@ -399,18 +455,18 @@ static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const 
   return cudaGetLastError();
 }
 
-template <typename VT, int D, typename V>
+template <typename VT, int D, typename V, bool FUSEQ>
 static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                     const float* loc, const float* aw, const VT* grad_out, float* gv,
-                                    float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
+                                    float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st, FuseQ fq) {
   constexpr int TILE = (32 / (D / V::CH)) * kWarpsPerBlock;
   const long long units = static_cast<long long>(N) * Lq * M;
   const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
   const int passes = g_tuning.bwd_passes;
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   ++g_launches;
-  msda_bwd_vec_kernel<VT, D, V><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
-      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast);
+  msda_bwd_vec_kernel<VT, D, V, FUSEQ><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, fq);
   return cudaGetLastError();
 }
 
@@ -418,13 +474,25 @@ template <typename VT, int D>
 static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                   const float* loc, const float* aw, const VT* grad_out, float* gv,
                                   float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
+  const FuseQ none{nullptr, nullptr, 0, 0};
   // narrow layout needs D/4 <= 16 lanes per unit
   if constexpr (Vec<VT>::CH == 8 && D <= 64) {
     if (g_tuning.bwd_narrow)
-      return launch_bwd_vec_t<VT, D, VecQ<VT>>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+      return launch_bwd_vec_t<VT, D, VecQ<VT>, false>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st, none);
   }
-  return launch_bwd_vec_t<VT, D, Vec<VT>>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st);
+  return launch_bwd_vec_t<VT, D, Vec<VT>, false>(value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, N, S, M, L, Lq, st, none);
 }
+
+// 16-bit storage, D == 32, L == 4, P == 4: backward with the query-side epilogue backward fused in (see FuseQ)
+template <typename VT>
+cudaError_t backward_fused_q(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                             const VT* grad_out, float* gv, const float* ref, int ref_dim, void* dq, int is_half, int N, int S,
+                             int M, int Lq, cudaStream_t st) {
+  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half};
+  return launch_bwd_vec_t<VT, 32, VecQ<VT>, true>(value, shapes, lstart, loc, aw, grad_out, gv, nullptr, nullptr, N, S, M, 4, Lq, st, fq);
+}
+template cudaError_t backward_fused_q<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_fused_q<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 
 // Storage types whose locations / weights / gradients are fp32 (float, bf16, half).
 template <typename VT>

@@ -76,6 +76,24 @@ def cast_mask16(x_f32_2d, row_mask, dtype):
     return out
 
 
+def backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, grad_core, ref, ref_dim):
+    """Scatter backward with the query-side epilogue backward fused in -> (grad_value fp32, dq_cat 16-bit)."""
+    N, S, M, D = value.shape
+    Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
+    dq = torch.empty((N * Lq, 3 * M * L * P), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        rc = _lib.lib().msda_backward_fusedq_16(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                loc.data_ptr(), aw.data_ptr(), grad_core.data_ptr(), ref.data_ptr(), ref_dim, N, S,
+                                                M, D, L, Lq, P, grad_value.data_ptr(), dq.data_ptr(), 1,
+                                                1 if value.dtype == torch.float16 else 0, _stream(value))
+    _lib.check(rc, "msda_backward_fusedq_16")
+    return grad_value, dq
+
+
+fuse_query_backward = True   # A/B switch (tests, benchmarks)
+
+
 def supported(embed_dim, M, L, P, dtype):
     lp = L * P
     return (dtype in (torch.bfloat16, torch.float16) and embed_dim % 64 == 0 and embed_dim <= 1024 and lp <= 32
@@ -133,9 +151,12 @@ class FusedMSDeformAttnFunction(Function):
         dt = value.dtype
         g2d = grad_out.contiguous().view(N * Lq, C)
         d_core = linear16(g2d, prep.w_o_t)
-        grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
-                                                                   d_core.view(N, Lq, C), im2col_step)
-        dq_cat = query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * Lq, M, L, P, dt)
+        if fuse_query_backward and (L, P, C // M) == (4, 4, 32):
+            grad_value, dq_cat = backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim)
+        else:
+            grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
+                                                                       d_core.view(N, Lq, C), im2col_step)
+            dq_cat = query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * Lq, M, L, P, dt)
         d_query = linear16(dq_cat, prep.w_cat_t).view(N, Lq, C) if ctx.needs_input_grad[0] else None
         gv16 = cast_mask16(grad_value.view(N * S, C), row_mask, dt)
         d_value_in = linear16(gv16, prep.w_v_t).view(N, S, C) if ctx.needs_input_grad[1] else None

@@ -58,6 +58,14 @@ class RepZeroLinear(nn.Linear):
             w = base_weight + self.freeze_linear.weight
             b = None if base_bias is None else base_bias + self.freeze_linear.bias
             return F.linear(input, w, b), None
+        if (input.is_cuda and input.dtype in (torch.bfloat16, torch.float16) and self.bias is not None and base_bias is not None
+                and self.in_features % 64 == 0 and self.out_features % 64 == 0 and 3 * self.out_features <= 2048):
+            # one tcgen05 GEMM over [W_0; W_f; W_b] with the fold and the loss reduction in its epilogue (fused.py)
+            from . import fused
+            x2d = input.reshape(-1, self.in_features).contiguous()
+            y, loss = fused.ZiRaLinear16Function.apply(x2d, None, base_weight, base_bias, self.freeze_linear.weight,
+                                                       self.freeze_linear.bias, self.weight, self.bias, self.scaling)
+            return y.view(*input.shape[:-1], self.out_features), loss
         branch = self.scaling * F.linear(input, self.weight, self.bias)
         adapter_out = branch + self.freeze_linear(input)
         loss = (self.zero_inter_loss(branch, torch.zeros_like(branch))
