@@ -20,6 +20,10 @@
  *   value  [N][S][M][D]      loc [N][Lq][M][L][P][2] (x then y, normalised to [0,1])
  *   aw     [N][Lq][M][L][P]  out [N][Lq][M*D]        shapes [L][2] = (H, W) int64, start [L] int64
  *
+ * Coordinate arithmetic: the source line `loc * size - 0.5` (im2col.cuh:285-286, :363-364) is compiled by nvcc into a
+ * single fused multiply-add (FFMA / DFMA with a -0.5 immediate in the SASS of the reference op built under oracle/_ref),
+ * so the restatement uses fmaf()/fma() -- one rounding.  Everything else is compiled with -ffp-contract=off.
+ *
  * The CUDA kernels accumulate grad_value with atomics in an undefined order; here accumulation is
  * sequential in (q, l, p, corner) order inside each (b, m) slice, and slices are independent, so
  * the OpenMP version is deterministic.
@@ -27,6 +31,9 @@
 #include <math.h>
 #include <stdint.h>
 #include <string.h>
+
+#define FMA_f32(a, b, c) fmaf((a), (b), (c))
+#define FMA_f64(a, b, c) fma((a), (b), (c))
 
 #define ORACLE_DEFINE(T, SUFFIX)                                                                   \
   void msda_oracle_forward_##SUFFIX(const T *value, const int64_t *shapes, const int64_t *start,   \
@@ -48,9 +55,8 @@
             for (int p = 0; p < P; ++p) {                                                          \
               const T lw_ = lp[(l * P + p) * 2], lh_ = lp[(l * P + p) * 2 + 1];                    \
               const T a = ap[l * P + p];                                                           \
-              /* im2col.cuh:285-286: product rounded to T, then minus one half */                  \
-              volatile T ph = lh_ * (T)H, pw = lw_ * (T)W;                                         \
-              const T h = ph - (T)0.5, w = pw - (T)0.5;                                            \
+              /* im2col.cuh:285-286 as nvcc compiles it: one fused multiply-add (see header) */    \
+              const T h = FMA_##SUFFIX(lh_, (T)H, (T)-0.5), w = FMA_##SUFFIX(lw_, (T)W, (T)-0.5);  \
               if (!(h > -1 && w > -1 && h < H && w < W)) continue;                                 \
               const int h0 = (int)floor((double)h), w0 = (int)floor((double)w);                    \
               const int h1 = h0 + 1, w1 = w0 + 1;                                                  \
@@ -99,8 +105,7 @@
             for (int p = 0; p < P; ++p) {                                                          \
               const T lw_ = lp[(l * P + p) * 2], lh_ = lp[(l * P + p) * 2 + 1];                    \
               const T a = ap[l * P + p];                                                           \
-              volatile T ph = lh_ * (T)H, pw = lw_ * (T)W;                                         \
-              const T h = ph - (T)0.5, w = pw - (T)0.5;                                            \
+              const T h = FMA_##SUFFIX(lh_, (T)H, (T)-0.5), w = FMA_##SUFFIX(lw_, (T)W, (T)-0.5);  \
               if (!(h > -1 && w > -1 && h < H && w < W)) continue;                                 \
               const int h0 = (int)floor((double)h), w0 = (int)floor((double)w);                    \
               const int h1 = h0 + 1, w1 = w0 + 1;                                                  \

@@ -130,14 +130,12 @@ template <> __device__ __forceinline__ __nv_bfloat16 from_acc<__nv_bfloat16, flo
 template <> __device__ __forceinline__ __half from_acc<__half, float>(float v) { return __float2half_rn(v); }
 
 // ---- the reference's sampling-coordinate arithmetic ----------------------------------------------
-// ms_deform_im2col_cuda.cuh:285-286: `loc * size - 0.5` with the product rounded before the
-// subtraction (the reference's 0.5 is a double literal, so nvcc cannot contract it into an FMA).
-__device__ __forceinline__ float im_coord(float loc, int size) {
-  return __fsub_rn(__fmul_rn(loc, static_cast<float>(size)), 0.5f);
-}
-__device__ __forceinline__ double im_coord(double loc, int size) {
-  return __dsub_rn(__dmul_rn(loc, static_cast<double>(size)), 0.5);
-}
+// ms_deform_im2col_cuda.cuh:285-286 writes `loc * size - 0.5`.  As nvcc compiles the reference op (default -fmad=true)
+// this is ONE fused multiply-add -- `FFMA R, loc, size, -0.5` / `DFMA ...` in the SASS of oracle/_ref, forward and
+// backward kernels alike -- so it is a single rounding here too: with two roundings the result sits 1.3e-5 from the
+// reference op at config 1 (sigma = 1 values), i.e. over the 1e-5 bar; with the FMA it agrees to ~2e-7.
+__device__ __forceinline__ float im_coord(float loc, int size) { return __fmaf_rn(loc, static_cast<float>(size), -0.5f); }
+__device__ __forceinline__ double im_coord(double loc, int size) { return __fma_rn(loc, static_cast<double>(size), -0.5); }
 __device__ __forceinline__ int floor_int(float x) { return __float2int_rd(x); }
 __device__ __forceinline__ int floor_int(double x) { return __double2int_rd(x); }
 

@@ -88,18 +88,18 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           Vec<VT>::load(vl + e1 + row, t.c2, v[s][1]);
           Vec<VT>::load(vl + e3, t.c3, v[s][2]);
           Vec<VT>::load(vl + e3 + row, t.c4, v[s][3]);
-          // attention weight folded into the four bilinear weights: 4 FMAs per channel instead of 5
-          const float a = as[p0 + s], ha = t.hh * a, la = t.lh * a;
-          k[s][0] = ha * t.hw; k[s][1] = ha * t.lw; k[s][2] = la * t.hw; k[s][3] = la * t.lw;
+          k[s][0] = t.hh * t.hw; k[s][1] = t.hh * t.lw; k[s][2] = t.lh * t.hw; k[s][3] = t.lh * t.lw;
         }
 #pragma unroll
         for (int s = 0; s < SB; ++s) {
+          // same association as the reference (im2col.cuh:80-82, :290): bilinear value first, then times the attention
+          // weight.  Folding the weight into the four taps saves one FMA per channel but moves the result ~1e-5 away
+          // from the reference op at sigma = 1 inputs (measured: profiles/r1_parity_table.txt), i.e. onto the parity bar.
+          const float a = as[p0 + s];
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
-            acc[c] = fmaf(k[s][0], v[s][0][c], acc[c]);
-            acc[c] = fmaf(k[s][1], v[s][1][c], acc[c]);
-            acc[c] = fmaf(k[s][2], v[s][2][c], acc[c]);
-            acc[c] = fmaf(k[s][3], v[s][3][c], acc[c]);
+            const float val = k[s][0] * v[s][0][c] + k[s][1] * v[s][1][c] + k[s][2] * v[s][2][c] + k[s][3] * v[s][3][c];
+            acc[c] = fmaf(val, a, acc[c]);
           }
         }
       }

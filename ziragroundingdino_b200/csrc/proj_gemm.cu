@@ -758,12 +758,11 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
       tma_out = true;
     }
   }
-  static int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  static int sms_of[64] = {};
+  if (!sms_of[dev_id & 63]) cudaDeviceGetAttribute(&sms_of[dev_id & 63], cudaDevAttrMultiProcessorCount, dev_id);
+  const int sms = sms_of[dev_id & 63];
   const int num_n = Nout / block_n;
   const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
   const int bres_bytes = block_n * K * 2;
@@ -790,10 +789,10 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   cudaError_t cfg = cudaSuccess;
 #define PG_LAUNCH(MODE, F32, HALF, RELU, GATE, TMA)                                                                        \
   do {                                                                                                                     \
-    static bool configured = false;                                                                                        \
-    if (!configured) {                                                                                                     \
+    static bool configured[64] = {};   /* the attribute is per device */                                                 \
+    if (!configured[dev_id & 63]) {                                                                                        \
       cfg = cudaFuncSetAttribute(linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
-      configured = cfg == cudaSuccess;                                                                                     \
+      configured[dev_id & 63] = cfg == cudaSuccess;                                                                        \
     }                                                                                                                      \
     if (cfg == cudaSuccess)                                                                                                \
       linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, Ri, Nout, K, block_n, br, stages, hi, ep); \
