@@ -271,7 +271,7 @@ def test_config1_vs_fp64_truth_and_reference_cuda_op():
     torch.cuda.synchronize()
     print("config1 fwd: refCUDA-vs-truth=%.3e new-vs-refCUDA=%.3e" % (
         np.abs(r_out.cpu().numpy() - truth).max(), (r_out.cpu() - out).abs().max().item()))
-    assert (r_out.cpu() - out).abs().max() < 1e-5
+    assert (r_out.cpu() - out).abs().max() < 1e-6     # measured 0.0: same coordinate FMA, same blend association
     assert rel_err(gv, r_gv.cpu()) < 1e-4 and rel_err(gl, r_gl.cpu()) < 1e-4 and rel_err(ga, r_ga.cpu()) < 1e-4
 
 
