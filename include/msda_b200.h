@@ -131,7 +131,9 @@ long long msda_b200_launch_count(void);
  *   ONE GEMM against w_cat = [W_offsets; W_attention] ([3*M*L*P, K]); the epilogue turns offsets into
  *   sampling locations (:306-319; ref is [R, L, ref_dim], ref_dim 2 or 4) and logits into softmax
  *   weights (:296), writing loc_out [R, M, L, P, 2] and aw_out [R, M, L, P] in fp32 -- exactly the two
- *   tensors msda_forward_* consumes.  Needs (L*P) | 32 and M*L*P % 32 == 0.
+ *   tensors msda_forward_* consumes.  Needs M*L*P % 32 == 0; when L*P does not divide 32 (L = 5) the logits are stored
+ *   raw and a second small kernel applies the softmax in place.  msda_query_bwd_prep_16 writes rows of ld_out >= 3*M*L*P
+ *   elements (zero padded: the row is the K dimension of the dgrad GEMM, which needs a multiple of 64).
  * msda_query_bwd_prep_16 / msda_cast_mask_16: elementwise backward companions (see proj_elementwise.cu). */
 int msda_linear_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out,
                    int out_ld, int out_f32, const uint8_t *row_mask, int is_half, void *stream);
@@ -144,8 +146,8 @@ int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_c
                        const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
                        float *aw_out, int is_half, void *stream);
 int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const float *aw, const float *ref, int ref_dim,
-                           const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int is_half,
-                           void *stream);
+                           const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int ld_out,
+                           int is_half, void *stream);
 int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, int cols, void *out, int is_half,
                       void *stream);
 /* ZiRa training-mode projection (semantics of RepZeroLinear, groundingdino_dual_zero_rep_branch.py:119-125, beside a

@@ -46,7 +46,7 @@ def test_linear16_16bit_out_and_row_mask(dtype, eps):
 
 
 @pytest.mark.parametrize("ref_dim", [2, 4])
-@pytest.mark.parametrize("M,L,P", [(8, 4, 4), (4, 2, 4), (8, 4, 2), (16, 2, 1)])
+@pytest.mark.parametrize("M,L,P", [(8, 4, 4), (4, 2, 4), (8, 4, 2), (16, 2, 1), (8, 5, 4)])
 def test_query_proj16(ref_dim, M, L, P):
     from ziragroundingdino_b200 import fused
     R, K = 2500, 256
@@ -54,7 +54,7 @@ def test_query_proj16(ref_dim, M, L, P):
     q = _rand((R, K), torch.bfloat16, 7)
     w = _rand((3 * n_aw, K), torch.bfloat16, 8, 0.05)
     b = _rand((3 * n_aw,), torch.float32, 9)
-    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)][:L], device=DEV)
+    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21), (7, 11)][:L], device=DEV)
     g = torch.Generator().manual_seed(10)
     ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
     loc, aw = fused.query_proj16(q, w, b, ref, ref_dim, shapes, M, L, P)
@@ -71,17 +71,20 @@ def test_query_proj16(ref_dim, M, L, P):
     assert (aw.sum((-1, -2)) - 1).abs().max().item() < 1e-5
 
 
-def test_backward_elementwise_kernels():
+@pytest.mark.parametrize("L", [4, 5])
+def test_backward_elementwise_kernels(L):
     from ziragroundingdino_b200 import fused
-    R, M, L, P = 777, 8, 4, 4
-    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)], device=DEV)
+    R, M, P = 777, 8, 4
+    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21), (7, 11)][:L], device=DEV)
     g = torch.Generator().manual_seed(11)
     gl = torch.randn(R, M, L, P, 2, generator=g).to(DEV)
     ga = torch.randn(R, M, L, P, generator=g).to(DEV)
     aw = torch.randn(R, M, L * P, generator=g).softmax(-1).view(R, M, L, P).to(DEV)
+    n_cat = 3 * M * L * P
     for ref_dim in (2, 4):
         ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
         out = fused.query_bwd_prep16(gl, ga, aw, ref, ref_dim, shapes, R, M, L, P, torch.bfloat16)
+        assert out.shape == (R, fused.padded_k(n_cat)) and out[:, n_cat:].abs().max().item() == 0   # zero padding (L = 5: 480 -> 512)
         if ref_dim == 2:
             norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
             d_off = gl / norm[None, None, :, None, :]
@@ -90,7 +93,7 @@ def test_backward_elementwise_kernels():
         a2, g2 = aw.view(R, M, L * P), ga.view(R, M, L * P)
         d_logit = a2 * (g2 - (g2 * a2).sum(-1, keepdim=True))
         want = torch.cat([d_off.reshape(R, -1), d_logit.reshape(R, -1)], 1)
-        assert (out.float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() * 1.01
+        assert (out[:, :n_cat].float() - want).abs().max().item() <= 2 ** -8 * want.abs().max().item() * 1.01
     x = torch.randn(999, 256, generator=g).to(DEV)
     mask = (torch.arange(999, device=DEV) % 3 == 0).to(torch.uint8)
     y = fused.cast_mask16(x, mask, torch.bfloat16)
@@ -391,3 +394,25 @@ def test_fused_query_backward_matches_two_kernel_path(ref_dim, dtype):
     eps16 = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
     assert d.max().item() <= 2 * eps16 * dq0.float().abs().max().item()
     assert (d > 0).float().mean().item() < 0.05                       # identical up to rare 1-ulp rounding differences
+
+
+def test_module_fused_five_levels():
+    """Config 5 shape class (L = 5, P = 4: softmax runs of 20 straddle the 32-column epilogue chunk, stacked K = 480
+    padded to 512): fused bf16 module vs the fp64 oracle restatement, forward and input gradients."""
+    import ziragroundingdino_b200 as zb
+    from oracle import msda_oracle as O
+    shapes = [(16, 29), (8, 15), (4, 8), (2, 4), (1, 2)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(2, shapes, 256, torch.bfloat16)
+    assert m._use_fused(src, refp)
+    q, v = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    y = m(query=q, value=v, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    gy = _rand(tuple(y.shape), torch.bfloat16, 61)
+    y.backward(gy)
+    params = {k: p.detach().double().cpu() for k, p in m.state_dict().items()}
+    tq, tv = query.double().cpu().requires_grad_(True), src.double().cpu().requires_grad_(True)
+    truth = O.module_forward(params, tq, tv, mask.cpu(), refp.double().cpu(), sh.cpu(), 8, 5, 4)
+    truth.backward(gy.double().cpu())
+    assert (y.detach().double().cpu() - truth.detach()).abs().max().item() < 1e-2 * truth.abs().max().item()
+    assert rel_err(v.grad.double().cpu(), tv.grad) < 3e-2
+    d = (q.grad.double().cpu() - tq.grad).abs()
+    assert (d > 3e-2 * tq.grad.abs().max().item()).double().mean().item() < 2e-3

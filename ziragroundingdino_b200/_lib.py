@@ -48,7 +48,7 @@ def lib():
     L.msda_linear_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp]
     L.msda_linear_act_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp]
     L.msda_query_proj_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]
-    L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _vp]
+    L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _i, _vp]
     L.msda_cast_mask_16.argtypes = [_vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_zira_linear_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp]

@@ -31,30 +31,44 @@ __device__ __forceinline__ uint16_t to16(float v, bool is_half) {
 __global__ void __launch_bounds__(256)
 query_bwd_prep_kernel(const float* __restrict__ grad_loc, const float* __restrict__ grad_aw, const float* __restrict__ aw,
                       const float* __restrict__ ref, const int64_t* __restrict__ shapes, long long R, int M, int L, int P,
-                      int ref_dim, int is_half, uint16_t* __restrict__ out) {
+                      int ref_dim, int is_half, uint16_t* __restrict__ out, int ld_out) {
   __shared__ float s_inv[MSDA_MAX_LEVELS * 2];
   if (threadIdx.x < L) {
     s_inv[2 * threadIdx.x] = 1.f / static_cast<float>(shapes[2 * threadIdx.x + 1]);
     s_inv[2 * threadIdx.x + 1] = 1.f / static_cast<float>(shapes[2 * threadIdx.x]);
   }
   __syncthreads();
-  const int lp = L * P, n_aw = M * lp, n_loc = 2 * n_aw, ld = n_loc + n_aw, tpr = ld / 4;   // threads per row
+  // ld_out >= 3*M*L*P: the row may be zero-padded to a multiple of 64 so that it can be the K dimension of the dgrad GEMM
+  const int lp = L * P, n_aw = M * lp, n_loc = 2 * n_aw, ld = ld_out, tpr = ld / 4;   // threads per row
   const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const bool live = idx < R * tpr;
   const long long row = live ? idx / tpr : 0;
   const int col = live ? static_cast<int>(idx % tpr) * 4 : 0;
   float o[4] = {0.f, 0.f, 0.f, 0.f};
-  const bool is_logit = col >= n_loc;
+  const bool is_logit = col >= n_loc && col < n_loc + n_aw;
+  const bool is_pad = col >= n_loc + n_aw;
   float4 a = make_float4(0.f, 0.f, 0.f, 0.f), g = a;
   if (live && is_logit) {
     a = __ldg(reinterpret_cast<const float4*>(aw + row * n_aw + (col - n_loc)));
     g = __ldg(reinterpret_cast<const float4*>(grad_aw + row * n_aw + (col - n_loc)));
   }
-  // softmax backward: runs of lp logits = lp/4 consecutive threads (a run never straddles a warp)
+  // softmax backward: runs of lp logits = lp/4 consecutive threads.  Power-of-two groups reduce with shuffles (a run
+  // never straddles a warp); other run lengths (L*P = 20) re-read the run -- 2*lp cached loads per thread.
   float dot = g.x * a.x + g.y * a.y + g.z * a.z + g.w * a.w;
-  for (int o_ = 1; o_ < lp / 4; o_ <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o_);
+  const int tpg = lp / 4;
+  if ((tpg & (tpg - 1)) == 0) {
+    for (int o_ = 1; o_ < tpg; o_ <<= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o_);
+  } else if (live && is_logit) {
+    const int run0 = ((col - n_loc) / lp) * lp;
+    const float* ga = grad_aw + row * n_aw + run0;
+    const float* aa = aw + row * n_aw + run0;
+    dot = 0.f;
+    for (int j = 0; j < lp; ++j) dot = fmaf(__ldg(ga + j), __ldg(aa + j), dot);
+  }
   if (!live) return;
-  if (is_logit) {
+  if (is_pad) {
+    // zero padding
+  } else if (is_logit) {
     o[0] = a.x * (g.x - dot); o[1] = a.y * (g.y - dot); o[2] = a.z * (g.z - dot); o[3] = a.w * (g.w - dot);
   } else {
     const float4 gl = __ldg(reinterpret_cast<const float4*>(grad_loc + row * n_loc + col));
@@ -165,15 +179,17 @@ int msda_zira_bwd_prep_16(const void* dy, const void* pre, const void* adapter, 
 
 
 int msda_query_bwd_prep_16(const float* grad_loc, const float* grad_aw, const float* aw, const float* ref, int ref_dim,
-                           const int64_t* spatial_shapes, long long R, int M, int L, int P, void* out, int is_half,
+                           const int64_t* spatial_shapes, long long R, int M, int L, int P, void* out, int ld_out, int is_half,
                            void* stream) {
   if (!grad_loc || !grad_aw || !aw || !ref || !spatial_shapes || !out) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || M <= 0 || L <= 0 || L > MSDA_MAX_LEVELS || P <= 0 || (ref_dim != 2 && ref_dim != 4)) return MSDA_ERR_BAD_SHAPE;
-  if ((L * P) % 4 || (L * P) > 128 || ((L * P / 4) & (L * P / 4 - 1))) return MSDA_ERR_UNSUPPORTED;
-  const long long n = R * (3ll * M * L * P / 4);
+  if ((L * P) % 4 || (L * P) > 128 || ld_out < 3 * M * L * P || ld_out % 4) return MSDA_ERR_UNSUPPORTED;
+  const int tpg = L * P / 4;
+  if ((tpg & (tpg - 1)) == 0 && 32 % tpg) return MSDA_ERR_UNSUPPORTED;
+  const long long n = R * (ld_out / 4);
   ++msda::g_launches;
   query_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      grad_loc, grad_aw, aw, ref, spatial_shapes, R, M, L, P, ref_dim, is_half, static_cast<uint16_t*>(out));
+      grad_loc, grad_aw, aw, ref, spatial_shapes, R, M, L, P, ref_dim, is_half, static_cast<uint16_t*>(out), ld_out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

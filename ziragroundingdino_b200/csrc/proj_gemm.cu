@@ -285,6 +285,7 @@ __device__ __forceinline__ void softmax_runs(float (&v)[32]) {
 
 __device__ __forceinline__ void epi_softmax(const EpiParams& ep, float (&v)[32]) {
   const int lp = ep.L * ep.P;
+  if (32 % lp != 0) return;   // runs straddle chunks (e.g. L*P = 20): logits are stored raw, softmax_rows_kernel finishes
   if (lp == 16) softmax_runs<16>(v);
   else if (lp == 32) softmax_runs<32>(v);
   else if (lp == 8) softmax_runs<8>(v);
@@ -674,6 +675,20 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// In-place softmax over runs of `lp` consecutive fp32 values (one thread per run) -- used when L*P does not divide the
+// 32-column epilogue chunk (L = 5, P = 4).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long long runs, int lp) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= runs) return;
+  float* p = x + i * lp;
+  float mx = p[0];
+  for (int j = 1; j < lp; ++j) mx = fmaxf(mx, p[j]);
+  float sum = 0.f;
+  for (int j = 0; j < lp; ++j) sum += __expf(p[j] - mx);
+  const float inv = __fdividef(1.f, sum);
+  for (int j = 0; j < lp; ++j) p[j] = __expf(p[j] - mx) * inv;
+}
+
 // ---- host side ------------------------------------------------------------------------------------
 thread_local char t_err[256] = "";
 
@@ -854,8 +869,8 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   pg::t_err[0] = 0;
   if (!ref || !spatial_shapes || !loc_out || !aw_out) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
   const int n_aw = M * L * P, n_loc = 2 * n_aw, lp = L * P;
-  if ((ref_dim != 2 && ref_dim != 4) || L > MSDA_MAX_LEVELS || lp > 32 || 32 % lp || n_aw % 32) {
-    snprintf(pg::t_err, sizeof(pg::t_err), "fused query projection needs L*P dividing 32 and M*L*P %% 32 == 0 (L=%d P=%d M=%d)", L, P, M);
+  if ((ref_dim != 2 && ref_dim != 4) || L > MSDA_MAX_LEVELS || n_aw % 32 || 3 * n_aw > pg::MAX_N) {
+    snprintf(pg::t_err, sizeof(pg::t_err), "fused query projection needs M*L*P %% 32 == 0 and 3*M*L*P <= %d (L=%d P=%d M=%d)", pg::MAX_N, L, P, M);
     return MSDA_ERR_UNSUPPORTED;
   }
   pg::EpiParams ep;
@@ -863,8 +878,16 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   ep.mode = pg::EPI_QUERY;
   ep.bias = bias_cat; ep.loc_out = loc_out; ep.aw_out = aw_out; ep.ref = ref; ep.shapes = spatial_shapes;
   ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
-  return pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
-                    static_cast<cudaStream_t>(stream));
+  int rc = pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
+                      static_cast<cudaStream_t>(stream));
+  if (rc == 0 && 32 % lp != 0) {   // softmax runs straddle the epilogue chunks: normalise the stored logits in place
+    const long long runs = R * M;
+    ++msda::g_launches;
+    pg::softmax_rows_kernel<<<static_cast<unsigned>((runs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(aw_out, runs, lp);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { snprintf(pg::t_err, sizeof(pg::t_err), "softmax_rows_kernel: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
+  }
+  return rc;
 }
 
 int msda_zira_linear_16(const void* x, const void* w_stack, const float* bias3, const float* scaling, long long R, int K,

@@ -56,11 +56,17 @@ def query_proj16(q2d, w_cat, bias_cat_f32, ref, ref_dim, spatial_shapes, M, L, P
     return loc, aw
 
 
+def padded_k(n):
+    """Row length of the stacked query gradient: 3*M*L*P rounded up to the GEMM's K granularity (64)."""
+    return (n + 63) // 64 * 64
+
+
 def query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, R, M, L, P, dtype):
-    out = torch.empty((R, 3 * M * L * P), dtype=dtype, device=aw.device)
+    ld = padded_k(3 * M * L * P)
+    out = torch.empty((R, ld), dtype=dtype, device=aw.device)
     with torch.cuda.device(aw.device):
         rc = _lib.lib().msda_query_bwd_prep_16(grad_loc.data_ptr(), grad_aw.data_ptr(), aw.data_ptr(), ref.data_ptr(), ref_dim,
-                                               spatial_shapes.data_ptr(), R, M, L, P, out.data_ptr(),
+                                               spatial_shapes.data_ptr(), R, M, L, P, out.data_ptr(), ld,
                                                1 if dtype == torch.float16 else 0, _stream(aw))
     _lib.check(rc, "msda_query_bwd_prep_16")
     return out
@@ -96,8 +102,10 @@ fuse_query_backward = True   # A/B switch (tests, benchmarks)
 
 def supported(embed_dim, M, L, P, dtype):
     lp = L * P
-    return (dtype in (torch.bfloat16, torch.float16) and embed_dim % 64 == 0 and embed_dim <= 1024 and lp <= 32
-            and 32 % lp == 0 and lp % 4 == 0 and (M * lp) % 32 == 0 and 3 * M * lp <= 1024 and (3 * M * lp) % 64 == 0)
+    tpg = lp // 4
+    pow2 = tpg > 0 and (tpg & (tpg - 1)) == 0
+    return (dtype in (torch.bfloat16, torch.float16) and embed_dim % 64 == 0 and embed_dim <= 1024 and lp % 4 == 0
+            and (not pow2 or 32 % tpg == 0) and (M * lp) % 32 == 0 and padded_k(3 * M * lp) <= 2048 and L <= 16)
 
 
 class Prepared:
@@ -112,7 +120,9 @@ class Prepared:
             self.b_v, self.b_o = b_v.detach().float(), b_o.detach().float()
             self.b_cat = torch.cat([b_off.detach(), b_aw.detach()], 0).float()
             self.w_v_t, self.w_o_t = self.w_v.t().contiguous(), self.w_o.t().contiguous()
-            self.w_cat_t = self.w_cat.t().contiguous()
+            n = self.w_cat.shape[0]
+            self.w_cat_t = torch.zeros((self.w_cat.shape[1], padded_k(n)), dtype=self.w_cat.dtype, device=self.w_cat.device)
+            self.w_cat_t[:, :n] = self.w_cat.t()          # zero-padded along K to the GEMM's granularity
 
 
 class FusedMSDeformAttnFunction(Function):
@@ -164,8 +174,9 @@ class FusedMSDeformAttnFunction(Function):
         if ctx.wgrad:  # plain library GEMMs; the module's own linears are frozen in the ZiRa configuration
             n_loc = 2 * M * L * P
             q2d, v2d = query.reshape(N * Lq, C), value_in.reshape(N * S, C)
-            dw_cat = dq_cat.t() @ q2d
-            db_cat = dq_cat.float().sum(0)
+            n_cat = 3 * M * L * P
+            dw_cat = dq_cat[:, :n_cat].t() @ q2d
+            db_cat = dq_cat[:, :n_cat].float().sum(0)
             grads = [gv16.t() @ v2d, gv16.float().sum(0).to(dt), dw_cat[:n_loc], db_cat[:n_loc].to(dt), dw_cat[n_loc:],
                      db_cat[n_loc:].to(dt), g2d.t() @ core.view(N * Lq, C), g2d.float().sum(0).to(dt)]
             grads = [g if ctx.needs_input_grad[11 + i] else None for i, g in enumerate(grads)]
@@ -218,12 +229,17 @@ class QueryProj16Function(Function):
         R = q2d.shape[0]
         dq_cat = query_bwd_prep16(g_loc.contiguous(), g_aw.contiguous(), aw, ref, ref.shape[-1], spatial_shapes, R, M, L, P,
                                   q2d.dtype)
-        gq = linear16(dq_cat, w_cat.t().contiguous()) if ctx.needs_input_grad[0] else None
+        n_cat = 3 * M * L * P
+        gq = None
+        if ctx.needs_input_grad[0]:
+            w_t = torch.zeros((w_cat.shape[1], padded_k(n_cat)), dtype=w_cat.dtype, device=w_cat.device)
+            w_t[:, :n_cat] = w_cat.t()
+            gq = linear16(dq_cat, w_t)
         n_loc = 2 * M * L * P
         gw = gb = None
         if any(ctx.needs_input_grad[1:5]):
-            gw = dq_cat.t() @ q2d
-            gb = dq_cat.float().sum(0).to(q2d.dtype)
+            gw = dq_cat[:, :n_cat].t() @ q2d
+            gb = dq_cat[:, :n_cat].float().sum(0).to(q2d.dtype)
         pick = lambda i, t: t if (t is not None and ctx.needs_input_grad[i]) else None
         return (gq, pick(1, None if gw is None else gw[:n_loc]), pick(2, None if gb is None else gb[:n_loc]),
                 pick(3, None if gw is None else gw[n_loc:]), pick(4, None if gb is None else gb[n_loc:]), None, None, None,
