@@ -84,7 +84,8 @@ def test_backward_elementwise_kernels(L):
     for ref_dim in (2, 4):
         ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
         out = fused.query_bwd_prep16(gl, ga, aw, ref, ref_dim, shapes, R, M, L, P, torch.bfloat16)
-        assert out.shape == (R, fused.padded_k(n_cat)) and out[:, n_cat:].abs().max().item() == 0   # zero padding (L = 5: 480 -> 512)
+        assert out.shape == (R, fused.padded_k(n_cat))
+        assert out[:, n_cat:].numel() == 0 or out[:, n_cat:].abs().max().item() == 0   # zero padding (L = 5: 480 -> 512)
         if ref_dim == 2:
             norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).float()
             d_off = gl / norm[None, None, :, None, :]

@@ -706,6 +706,10 @@ static PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 // row-major [rows, cols] matrix of `esize`-byte elements, box = box_rows x box_cols (box_cols * esize == 128),
 // 128-byte swizzle.  dtype: 0 bf16, 1 f16, 2 f32.
 static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols, int dtype) {
+  // cuTensorMapEncodeTiled is a DRIVER call: it needs the primary context bound to the calling thread.  A thread that
+  // has only ever gone through torch's cudaSetDevice (e.g. an autograd worker) may not have it bound yet -> error 201.
+  thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
   auto fn = encode_fn();
   if (!fn) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled unavailable"); return MSDA_ERR_NO_DEVICE; }
   const int esize = dtype == 2 ? 4 : 2;
