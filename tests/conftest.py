@@ -13,6 +13,11 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # a fresh checkout has no built artefacts (*.so is git-ignored): build the product library once (nvcc, ~20 s)
+    lib = os.path.join(ROOT, "ziragroundingdino_b200", "_lib", "libmsda_b200.so")
+    if not os.path.exists(lib):
+        import subprocess
+        subprocess.check_call(["bash", os.path.join(ROOT, "ziragroundingdino_b200", "csrc", "build.sh")])
 
 
 def load_golden(name):
