@@ -255,9 +255,9 @@ def run_ours(args):
         run()
     ms = timed(run, args.steps)
     launches = launches_per_step * args.steps
-    if sampler is not None and ms < 600.0:   # nvidia-smi needs a few hundred ms to start: keep the same load up (untimed)
-        t_end = time.time() + 0.8
-        while time.time() < t_end:
+    if ms < 600.0:   # nvidia-smi needs a few hundred ms to start: keep the same load up (untimed).  `ms` is the max over
+        # ranks, so every rank runs the same number of extra steps (they contain the all-reduce).
+        for _ in range(int(800.0 / (ms / args.steps)) + 1):
             run()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
