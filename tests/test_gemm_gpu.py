@@ -417,3 +417,22 @@ def test_module_fused_five_levels():
     assert rel_err(v.grad.double().cpu(), tv.grad) < 3e-2
     d = (q.grad.double().cpu() - tq.grad).abs()
     assert (d > 3e-2 * tq.grad.abs().max().item()).double().mean().item() < 2e-3
+
+
+def test_module_fused_sequence_first_layout():
+    """batch_first=False (the reference default): the fused path sees permuted, non-contiguous views."""
+    import ziragroundingdino_b200 as zb
+    shapes = [(12, 16), (6, 8), (3, 4), (2, 2)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(3, shapes, 256, torch.bfloat16)
+    m.batch_first = False
+    q_sf, v_sf = query.transpose(0, 1).contiguous().requires_grad_(True), src.transpose(0, 1).contiguous().requires_grad_(True)
+    kw = dict(key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    y_sf = m(query=q_sf, value=v_sf, **kw)
+    assert y_sf.shape == q_sf.shape
+    y_sf.float().square().mean().backward()
+    m.batch_first = True
+    q_bf, v_bf = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    y_bf = m(query=q_bf, value=v_bf, **kw)
+    y_bf.float().square().mean().backward()
+    assert torch.equal(y_sf.transpose(0, 1), y_bf)
+    assert rel_err(v_sf.grad.transpose(0, 1).float().cpu(), v_bf.grad.float().cpu()) < 1e-3    # atomics order only
