@@ -148,6 +148,12 @@ int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_c
 int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const float *aw, const float *ref, int ref_dim,
                            const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int ld_out,
                            int is_half, void *stream);
+/* fp32 modules (the reference's default precision): the projections stay library fp32 GEMMs (a tf32 tensor-core product
+ * would miss the 1e-5 bar) but the elementwise tail of ms_deform_attn.py:290-319 is two kernels: raw = [offsets | logits]
+ * pre-activations [R, 3*M*L*P] -> loc_out [R, M, L, P, 2], aw_out [R, M, L, P].  Its backward is
+ * msda_query_bwd_prep_16 with is_half = 2 (fp32 output, ld_out = 3*M*L*P). */
+int msda_query_post_f32(const float *raw, const float *ref, int ref_dim, const int64_t *spatial_shapes, long long R, int M,
+                        int L, int P, float *loc_out, float *aw_out, void *stream);
 int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, int cols, void *out, int is_half,
                       void *stream);
 /* ZiRa training-mode projection (semantics of RepZeroLinear, groundingdino_dual_zero_rep_branch.py:119-125, beside a

@@ -55,6 +55,7 @@ def lib():
     L.msda_add_layernorm_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_add_layernorm_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]
+    L.msda_query_post_f32.argtypes = [_vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     _lib = L
     return L

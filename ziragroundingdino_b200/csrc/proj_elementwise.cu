@@ -81,10 +81,62 @@ query_bwd_prep_kernel(const float* __restrict__ grad_loc, const float* __restric
       o[j] = gv[j] * sc;
     }
   }
+  if (is_half == 2) {   // fp32 output (fp32 modules)
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + row * ld + col) = make_float4(o[0], o[1], o[2], o[3]);
+    return;
+  }
   uint2 w;
   w.x = to16(o[0], is_half != 0) | (static_cast<uint32_t>(to16(o[1], is_half != 0)) << 16);
   w.y = to16(o[2], is_half != 0) | (static_cast<uint32_t>(to16(o[3], is_half != 0)) << 16);
   *reinterpret_cast<uint2*>(out + row * ld + col) = w;
+}
+
+// ---- fp32 modules: the elementwise tail of the query projections as two kernels instead of ~10 eager ops -------
+// raw [R, 3*M*L*P] = [sampling_offsets | attention logits] pre-activations (bias included), straight from the GEMM.
+//   loc = ref + raw_off / (W_l, H_l)                    (2-d reference points, ms_deform_attn.py:306-311)
+//   loc = ref_xy + raw_off / P * ref_wh * 0.5           (4-d reference boxes,  :312-319)     -- same operation order
+//   aw  = softmax over each run of L*P logits           (:296)
+__global__ void __launch_bounds__(256)
+query_post_loc_kernel(const float* __restrict__ raw, const float* __restrict__ ref, const int64_t* __restrict__ shapes,
+                      long long R, int M, int L, int P, int ref_dim, float* __restrict__ loc) {
+  __shared__ float s_norm[MSDA_MAX_LEVELS * 2];
+  if (threadIdx.x < L) {
+    s_norm[2 * threadIdx.x] = static_cast<float>(shapes[2 * threadIdx.x + 1]);
+    s_norm[2 * threadIdx.x + 1] = static_cast<float>(shapes[2 * threadIdx.x]);
+  }
+  __syncthreads();
+  const int n_loc = 2 * M * L * P, ld = 3 * M * L * P, tpr = n_loc / 4;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= R * tpr) return;
+  const long long row = idx / tpr;
+  const int col = static_cast<int>(idx % tpr) * 4;
+  const float4 v = __ldg(reinterpret_cast<const float4*>(raw + row * ld + col));
+  const float in[4] = {v.x, v.y, v.z, v.w};
+  const float* rp = ref + row * L * ref_dim;
+  float o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = col + j, xy = c & 1, l = (c / (2 * P)) % L;
+    if (ref_dim == 2) o[j] = rp[l * 2 + xy] + __fdiv_rn(in[j], s_norm[2 * l + xy]);
+    else o[j] = rp[l * 4 + xy] + __fdiv_rn(in[j], static_cast<float>(P)) * rp[l * 4 + 2 + xy] * 0.5f;
+  }
+  *reinterpret_cast<float4*>(loc + row * n_loc + col) = make_float4(o[0], o[1], o[2], o[3]);
+}
+
+// one thread per run of lp logits (adjacent threads own adjacent runs: coalesced across the warp)
+__global__ void __launch_bounds__(256)
+query_post_softmax_kernel(const float* __restrict__ raw, long long R, int M, int lp, float* __restrict__ aw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= R * M) return;
+  const long long row = i / M;
+  const int m = static_cast<int>(i % M);
+  const float* p = raw + row * (3ll * M * lp) + 2 * M * lp + m * lp;
+  float* o = aw + i * lp;
+  float mx = p[0];
+  for (int j = 1; j < lp; ++j) mx = fmaxf(mx, p[j]);
+  float sum = 0.f;
+  for (int j = 0; j < lp; ++j) sum += expf(p[j] - mx);
+  for (int j = 0; j < lp; ++j) o[j] = expf(p[j] - mx) / sum;
 }
 
 // 8 elements per thread; `cols` (row length) must be a multiple of 8
@@ -177,6 +229,20 @@ int msda_zira_bwd_prep_16(const void* dy, const void* pre, const void* adapter, 
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
 
+
+int msda_query_post_f32(const float* raw, const float* ref, int ref_dim, const int64_t* spatial_shapes, long long R, int M, int L,
+                        int P, float* loc_out, float* aw_out, void* stream) {
+  if (!raw || !ref || !spatial_shapes || !loc_out || !aw_out) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || M <= 0 || L <= 0 || L > MSDA_MAX_LEVELS || P <= 0 || (ref_dim != 2 && ref_dim != 4) || (2 * M * L * P) % 4)
+    return MSDA_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n1 = R * (2ll * M * L * P / 4), n2 = R * M;
+  msda::g_launches += 2;
+  query_post_loc_kernel<<<static_cast<unsigned>((n1 + 255) / 256), 256, 0, st>>>(raw, ref, spatial_shapes, R, M, L, P, ref_dim, loc_out);
+  query_post_softmax_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(raw, R, M, L * P, aw_out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
 
 int msda_query_bwd_prep_16(const float* grad_loc, const float* grad_aw, const float* aw, const float* ref, int ref_dim,
                            const int64_t* spatial_shapes, long long R, int M, int L, int P, void* out, int ld_out, int is_half,

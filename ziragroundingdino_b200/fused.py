@@ -310,3 +310,38 @@ class ZiRaLinear16Function(Function):
         gbb = (d_b.float().sum(0) * s32).to(dt) if need[7] else None
         gs = ds.to(dt) if need[8] else None
         return gx, None, gw0, gb0, gwf, gbf, gwb, gbb, gs
+
+
+class QueryPostF32Function(Function):
+    """fp32 modules: raw [R, 3*M*L*P] = [sampling_offsets | attention logits] pre-activations -> (sampling locations,
+    softmax weights) in two kernels (forward) and one (backward) instead of ~10 eager ops (ms_deform_attn.py:290-319)."""
+
+    @staticmethod
+    def forward(ctx, raw, ref, spatial_shapes, M, L, P):
+        R = raw.shape[0]
+        raw = raw.contiguous()
+        ref = ref.to(torch.float32).contiguous()
+        loc = torch.empty((R, M, L, P, 2), dtype=torch.float32, device=raw.device)
+        aw = torch.empty((R, M, L, P), dtype=torch.float32, device=raw.device)
+        with torch.cuda.device(raw.device):
+            rc = _lib.lib().msda_query_post_f32(raw.data_ptr(), ref.data_ptr(), ref.shape[-1], spatial_shapes.data_ptr(), R, M, L, P,
+                                                loc.data_ptr(), aw.data_ptr(), _stream(raw))
+        _lib.check(rc, "msda_query_post_f32")
+        ctx.save_for_backward(ref, spatial_shapes, aw)
+        ctx.dims = (M, L, P)
+        return loc, aw
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_loc, g_aw):
+        ref, spatial_shapes, aw = ctx.saved_tensors
+        M, L, P = ctx.dims
+        R = aw.shape[0]
+        n = 3 * M * L * P
+        d_raw = torch.empty((R, n), dtype=torch.float32, device=aw.device)
+        with torch.cuda.device(aw.device):
+            rc = _lib.lib().msda_query_bwd_prep_16(g_loc.contiguous().data_ptr(), g_aw.contiguous().data_ptr(), aw.data_ptr(),
+                                                   ref.data_ptr(), ref.shape[-1], spatial_shapes.data_ptr(), R, M, L, P,
+                                                   d_raw.data_ptr(), n, 2, _stream(aw))
+        _lib.check(rc, "msda_query_bwd_prep_16(fp32)")
+        return d_raw, None, None, None, None, None

@@ -282,6 +282,25 @@ class MultiScaleDeformableAttention(nn.Module):
         if key_padding_mask is not None:
             value = value.masked_fill(key_padding_mask[..., None], float(0))
         value = value.view(bs, num_value, M, -1)
+        if (value.dtype == torch.float32 and (L * P) % 4 == 0 and not reference_points.requires_grad
+                and reference_points.shape[-1] in (2, 4) and self.fused_enabled):
+            # fp32: library GEMM for [sampling_offsets | attention_weights] (one product, shared input), then the
+            # elementwise tail (locations + softmax) as two kernels instead of ~10 eager ops
+            w_cat = torch.cat([self.sampling_offsets.weight, self.attention_weights.weight], 0)
+            b_cat = torch.cat([self.sampling_offsets.bias, self.attention_weights.bias], 0)
+            raw = F.linear(query.reshape(bs * num_query, -1), w_cat, b_cat)
+            loc, aw = fused.QueryPostF32Function.apply(raw, reference_points.reshape(bs * num_query, L, -1), spatial_shapes,
+                                                       M, L, P)
+            output = MultiScaleDeformableAttnFunction.apply(
+                value.contiguous(), spatial_shapes, level_start_index, loc.view(bs, num_query, M, L, P, 2),
+                aw.view(bs, num_query, M, L, P), self.im2col_step)
+            output, loss_o = self._project(output, self.output_proj, self.output_proj_adapter)
+            self.zero_inter_loss = None
+            if loss_v is not None or loss_o is not None:
+                self.zero_inter_loss = sum(x for x in (loss_v, loss_o) if x is not None)
+            if not self.batch_first:
+                output = output.permute(1, 0, 2)
+            return output
         acc_dtype = torch.float64 if value.dtype == torch.float64 else torch.float32
         # 16-bit activations: offsets -> locations and the softmax are evaluated in fp32
         sampling_offsets = self.sampling_offsets(query).view(bs, num_query, M, L, P, 2).to(acc_dtype)
