@@ -128,3 +128,44 @@ def test_zira_branches_train_eval_merge(dtype):
     assert float(m.value_proj_adapter.scaling) == pytest.approx(0.1)
     assert float(m.value_proj_adapter.weight.abs().max()) == pytest.approx(1e-8)
     assert float(o_loss_v) > 0
+
+
+def test_module_under_autocast():
+    """fp32 module under torch.autocast(bf16) (the reference trainer's AMP switch, train_multidatasets.py:169): the
+    projections autocast to bf16, the op runs its 16-bit kernels with fp32 locations/weights; result close to fp32."""
+    import ziragroundingdino_b200 as zb
+    dev = torch.device("cuda:0")
+    g = load_golden("module_d32")
+    m, (C, M, L, P, bf) = _load_module(g, torch.float32, dev)
+    q, v, refp, sh, lsi, mask = _inputs(g, torch.float32, dev, bf)
+    kw = dict(key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    y32 = m(query=q, value=v, **kw)
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y16 = m(query=q, value=v, **kw)
+    assert y16.dtype == torch.bfloat16
+    assert (y16.float() - y32).abs().max().item() < 3e-2 * y32.abs().max().item()
+    y16.float().square().mean().backward()
+    assert torch.isfinite(q.grad).all() and torch.isfinite(v.grad).all()
+
+
+def test_module_many_images_and_single_query():
+    """Shapes at the edges: a batch larger than im2col_step's default divisor logic cares about, and Lq = 1."""
+    import ziragroundingdino_b200 as zb
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    m = zb.MultiScaleDeformableAttention(256, 8, 4, 4, batch_first=True).to(dev)
+    shapes = [(4, 5), (2, 3), (1, 2), (1, 1)]
+    S = sum(h * w for h, w in shapes)
+    sh = torch.tensor(shapes, device=dev)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    for N, Lq in ((64, 3), (128, 1), (96, 2)):          # 96 % min(96, 64) != 0 -> the reference's observable error
+        x = torch.randn(N, S, 256, device=dev)
+        q = torch.randn(N, Lq, 256, device=dev)
+        refp = torch.rand(N, Lq, 4, 2, device=dev)
+        call = lambda: m(query=q, value=x, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+        if N % min(N, 64):
+            with pytest.raises(RuntimeError, match="must divide im2col_step"):
+                call()
+        else:
+            y = call()
+            assert y.shape == (N, Lq, 256) and torch.isfinite(y).all()
