@@ -178,6 +178,8 @@ int msda_b200_gemm_set_resident(int on);
 /* A/B switch: 1 (default) stores the epilogue through TMA from 128B-swizzled tiles; 0 = shared-memory transposition +
  * coalesced st.global. */
 int msda_b200_gemm_set_staged(int on);
+/* A/B switch: store tiles per epilogue warp (1 or 2) and whether a resident W slice is kept in preference to the second tile. */
+int msda_b200_gemm_set_store_bufs(int bufs, int prefer_resident);
 
 /* ---- the op's immediate caller: residual + LayerNorm ------------------------------
  * `src = norm(src + src2)` of the reference's DeformableTransformerEncoderLayer (transformer_for_adapter.py:901-902 after

@@ -57,10 +57,9 @@ if sys.argv[1:] and sys.argv[1] == "run":
         cases[which]()
     torch.cuda.synchronize()
 else:
-    for staged in (1, 0):
-        for res in (1, 0):
-            L.msda_b200_gemm_set_staged(staged); L.msda_b200_gemm_set_resident(res)
-            for name, fn in cases.items():
-                if "cublas" in name and (staged, res) != (1, 1):
-                    continue
-                print("tma_store=%d resident=%d  %-36s cold %7.1f us   warm %7.1f us" % (staged, res, name, timeit(fn, True), timeit(fn, False)))
+    for bufs, pres in ((2, 0), (2, 1), (1, 1)):
+        L.msda_b200_gemm_set_store_bufs(bufs, pres)
+        for name, fn in cases.items():
+            if "cublas" in name and (bufs, pres) != (2, 0):
+                continue
+            print("store_bufs=%d prefer_resident=%d  %-36s cold %7.1f us   warm %7.1f us" % (bufs, pres, name, timeit(fn, True), timeit(fn, False)))

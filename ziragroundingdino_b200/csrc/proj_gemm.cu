@@ -49,6 +49,8 @@ constexpr int TMA_TILE_BYTES = 32 * 128;                        // one epilogue 
 constexpr int AUX_BYTES_TMA = AUX_BASE + EPI_WARPS * TMA_TILE_BYTES;
 constexpr int kMaxSmem = 227 * 1024;
 bool g_allow_resident = true;
+int g_store_bufs = 1;            // store tiles per epilogue warp; 2 measured slower (profiles/r1_gemm_ab.txt), kept as an A/B knob
+bool g_prefer_resident = true;   // true: never give up a resident W slice for the second store tile
 bool g_tma_store = true;         // msda_b200_gemm_set_staged(0) turns the TMA-store epilogue off (A/B)
 bool g_staged_store = true;      // msda_b200_gemm_set_staged(0|1)   // msda_b200_set_tuning("gemm_resident", 0|1)
 
@@ -118,6 +120,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 // 16-byte chunk j of row r inside a 32 x 128-byte tile laid out for CU_TENSOR_MAP_SWIZZLE_128B
@@ -304,7 +307,7 @@ template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE, bool TMA_
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int R, int Nout,
-                 int K, int block_n, int b_resident, int stages, int half_in, EpiParams ep) {
+                 int K, int block_n, int b_resident, int stages, int store_bufs, int half_in, EpiParams ep) {
   // b_resident: the CTA owns ONE n-block for its whole life and keeps that slice of W (block_n x K) in shared
   // memory, loaded once; only the activation tiles stream through the ring (K = 256, N <= 256: 128 KiB of W).
   // Otherwise A and B tiles stream together (any shape).
@@ -316,7 +319,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int stage_bytes = b_resident ? SMEM_A : SMEM_A + b_tile_bytes;
   uint8_t* smem_bres = smem + stages * stage_bytes;                       // resident W slice: (K/64) tiles
   uint8_t* tma_tiles = smem_bres + (b_resident ? (K / BLOCK_K) * b_tile_bytes : 0);   // 1024-aligned (all sizes above are)
-  uint8_t* aux = tma_tiles + (TMA_OUT ? EPI_WARPS * TMA_TILE_BYTES : 0);
+  uint8_t* aux = tma_tiles + (TMA_OUT ? EPI_WARPS * store_bufs * TMA_TILE_BYTES : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -463,7 +466,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ---- 16-bit output through TMA: 64 columns (128 bytes per row) per step, written into this warp's
         // 128B-swizzled 32 x 128-byte tile (conflict-free STS), then ONE cp.async.bulk.tensor store.  Rows >= R are
         // clipped by the tensor map.  The two warps of a lane quarter alternate 64-column groups.
-        uint8_t* tile = tma_tiles + (warp - 2) * TMA_TILE_BYTES;
+        // one or two store tiles per warp: with two, a step only waits for the store issued two steps ago
+        uint8_t* tile0 = tma_tiles + (warp - 2) * store_bufs * TMA_TILE_BYTES;
+        int buf = 0;
         uint4 gnext[8];
         const int g_j = lane & 7, g_rsub = lane >> 3;           // gate fetch: 8 lanes along a 128-byte row, 4 rows per instr
         auto gate_fetch = [&](int c) {
@@ -477,9 +482,11 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (GATE && chunk_par * 64 < block_n) gate_fetch(chunk_par * 64);
         for (int c0 = chunk_par * 64; c0 < block_n; c0 += 128) {
           const int gc = n_idx + c0;
+          uint8_t* tile = tile0 + buf * TMA_TILE_BYTES;
           uint4 gt[8];
           if (GATE) {
-            if (lane == 0) tma_store_wait_read();    // the gate transposition reuses the tile: previous store must have read it
+            // the gate transposition reuses the tile: the store that last used it must have read it
+            if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
             __syncwarp();
 #pragma unroll
             for (int it = 0; it < 8; ++it) *reinterpret_cast<uint4*>(swz(tile, it * 4 + g_rsub, g_j)) = gnext[it];
@@ -517,7 +524,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint4 pk[4];
             pack_16(v, HALF_OUT, zero, pk);
             if (!GATE && hf == 0) {   // wait as late as possible: the previous store's smem read overlaps this step's TMEM load + math
-              if (lane == 0) tma_store_wait_read();
+              if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
               __syncwarp();
             }
 #pragma unroll
@@ -526,12 +533,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_async_smem();
           __syncwarp();
           if (lane == 0) tma_store_2d(&tmC, tile, gc, static_cast<int>(row0));
+          if (store_bufs == 2) buf ^= 1;
         }
       } else if (TMA_OUT && MODE == EPI_QUERY) {
         // ---- fp32 sampling locations / softmax weights through TMA: 32 columns (128 bytes per row) per step
-        uint8_t* tile = tma_tiles + (warp - 2) * TMA_TILE_BYTES;
+        uint8_t* tile0 = tma_tiles + (warp - 2) * store_bufs * TMA_TILE_BYTES;
+        int buf = 0;
         for (int c0 = chunk_par * 32; c0 < block_n; c0 += 64) {
           const int gc = n_idx + c0;
+          uint8_t* tile = tile0 + buf * TMA_TILE_BYTES;
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           float v[32], o32[32];
@@ -556,7 +566,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 32; ++j) o32[j] = v[j];
           }
-          if (lane == 0) tma_store_wait_read();
+          if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
           __syncwarp();
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -567,6 +577,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (is_loc) tma_store_2d(&tmC, tile, gc, static_cast<int>(row0));
             else tma_store_2d(&tmC2, tile, gc - ep.n_loc, static_cast<int>(row0));
           }
+          if (store_bufs == 2) buf ^= 1;
         }
       } else {
         // GATE: the gate rows of a chunk are fetched one chunk AHEAD with coalesced loads (lanes along the row: 8 rows x 64
@@ -785,10 +796,17 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   const int num_n = Nout / block_n;
   const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
   const int bres_bytes = block_n * K * 2;
-  const int tail = tma_out ? AUX_BYTES_TMA : ((ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16);
-  // resident-W mode whenever the CTA's slice of W fits beside an activation ring of at least 3 stages
-  const bool b_res = g_allow_resident && bres_bytes + 3 * SMEM_A + tail + 1024 <= kMaxSmem && num_n <= sms;
-  const int stage_bytes = b_res ? SMEM_A : SMEM_A + block_n * BLOCK_K * 2;
+  const int tail1 = tma_out ? AUX_BYTES_TMA : ((ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16);
+  const int tail2 = tail1 + EPI_WARPS * TMA_TILE_BYTES;                    // second store tile per epilogue warp
+  const int stream_stage = SMEM_A + block_n * BLOCK_K * 2;
+  auto fits_res = [&](int tail) { return g_allow_resident && num_n <= sms && bres_bytes + 3 * SMEM_A + tail + 1024 <= kMaxSmem; };
+  auto fits_str = [&](int tail) { return 3 * stream_stage + tail + 1024 <= kMaxSmem; };
+  bool b_res;
+  int store_bufs = 1, tail = tail1;
+  if (tma_out && g_store_bufs == 2 && fits_res(tail2)) { b_res = true; store_bufs = 2; tail = tail2; }
+  else if (tma_out && g_store_bufs == 2 && !g_prefer_resident && fits_str(tail2)) { b_res = false; store_bufs = 2; tail = tail2; }
+  else b_res = fits_res(tail1);
+  const int stage_bytes = b_res ? SMEM_A : stream_stage;
   const int fixed = (b_res ? bres_bytes : 0) + tail + 1024;
   int stages = STAGES;
   while (stages > 2 && stages * stage_bytes + fixed > kMaxSmem) --stages;
@@ -814,7 +832,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
       configured[dev_id & 63] = cfg == cudaSuccess;                                                                        \
     }                                                                                                                      \
     if (cfg == cudaSuccess)                                                                                                \
-      linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, Ri, Nout, K, block_n, br, stages, hi, ep); \
+      linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, Ri, Nout, K, block_n, br, stages, store_bufs, hi, ep); \
   } while (0)
 #define PG_STORE16(RELU, GATE)                                                                                             \
   do {                                                                                                                     \
@@ -840,6 +858,11 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
 
 extern "C" int msda_b200_gemm_set_resident(int on) { pg::g_allow_resident = on != 0; return 0; }
 extern "C" int msda_b200_gemm_set_staged(int on) { pg::g_tma_store = on != 0; return 0; }
+extern "C" int msda_b200_gemm_set_store_bufs(int bufs, int prefer_resident) {
+  pg::g_store_bufs = bufs == 2 ? 2 : 1;
+  pg::g_prefer_resident = prefer_resident != 0;
+  return 0;
+}
 
 extern "C" {
 
