@@ -165,13 +165,14 @@ int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, 
  * (x W_b^T + b_b) and adapter_out, both [R, F] 16-bit, are what the backward needs; either may be NULL.
  * msda_zira_bwd_prep_16 builds the K-stacked operand [dY_eff | dO | dB] ([R, 3F]) of the dgrad GEMM
  * (msda_linear_16 against [W_0^T | W_f^T | s W_b^T]) and adds d(loss)/d(scaling) = sum dB * pre to *ds_out
- * (pre-zeroed fp32 scalar, may be NULL). */
+ * (pre-zeroed fp32 scalar, may be NULL).  colsum_out (pre-zeroed fp32 [3F], may be NULL; needs 256 % (F/8) == 0)
+ * receives the column sums of the three blocks before rounding = the bias gradients of W_0 | W_f | W_b / s. */
 int msda_zira_linear_16(const void *x, const void *w_stack, const float *bias3, const float *scaling, long long R, int K,
                         int F, void *out, const uint8_t *row_mask, void *pre_out, void *adapter_out, float *loss_sums,
                         int is_half, void *stream);
 int msda_zira_bwd_prep_16(const void *dy, const void *pre, const void *adapter, const uint8_t *row_mask,
                           const float *scaling, const float *dloss, long long R, int F, void *out, float *ds_out,
-                          int is_half, void *stream);
+                          float *colsum_out, int is_half, void *stream);
 const char *msda_b200_gemm_last_error(void);
 /* A/B switch for benchmarks: 1 (default) keeps each CTA's slice of W resident in shared memory when it fits. */
 int msda_b200_gemm_set_resident(int on);

@@ -51,7 +51,7 @@ def lib():
     L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _i, _vp]
     L.msda_cast_mask_16.argtypes = [_vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_zira_linear_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
-    L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp]
+    L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _i, _vp]
     L.msda_add_layernorm_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_add_layernorm_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]

@@ -168,36 +168,55 @@ __device__ __forceinline__ float from16(uint16_t v, bool is_half) {
 __global__ void __launch_bounds__(256)
 zira_bwd_prep_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict__ pre, const uint16_t* __restrict__ adapter,
                      const uint8_t* __restrict__ row_mask, const float* __restrict__ scaling, const float* __restrict__ dloss,
-                     long long R, int F, int is_half, uint16_t* __restrict__ out, float* __restrict__ ds_out) {
-  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+                     long long R, int F, int is_half, uint16_t* __restrict__ out, float* __restrict__ ds_out,
+                     float* __restrict__ colsum_out) {
+  // Grid-stride over (row, 8-feature group).  The host only asks for column sums when 256 % (F/8) == 0, so a thread
+  // keeps the same feature group on every trip and its 3 x 8 partial column sums stay in registers.
   const int f8 = F / 8;
-  float ds = 0.f;   // this thread's share of d(loss)/d(scaling) = sum dB * pre, taken before dB is rounded to 16 bit
-  if (i < R * f8) {
-  const long long row = i / f8;
-  const int col = static_cast<int>(i % f8) * 8;
   const bool h = is_half != 0;
   const float s = __ldg(scaling);
   const float gl = __ldg(dloss) / (static_cast<float>(R) * static_cast<float>(F));
-  const bool masked = row_mask != nullptr && row_mask[row] != 0;
-  const uint4 a = __ldg(reinterpret_cast<const uint4*>(dy + row * F + col));
-  const uint4 b = __ldg(reinterpret_cast<const uint4*>(pre + row * F + col));
-  const uint4 c = __ldg(reinterpret_cast<const uint4*>(adapter + row * F + col));
-  const uint16_t* pa = reinterpret_cast<const uint16_t*>(&a);
-  const uint16_t* pb = reinterpret_cast<const uint16_t*>(&b);
-  const uint16_t* pc = reinterpret_cast<const uint16_t*>(&c);
-  uint16_t o0[8], o1[8], o2[8];
+  float ds = 0.f;   // this thread's share of d(loss)/d(scaling) = sum dB * pre, taken before dB is rounded to 16 bit
+  float cs[3][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float dye = masked ? 0.f : from16(pa[j], h);
-    const float d_o = dye + gl * fminf(fmaxf(from16(pc[j], h), -1.f), 1.f);
-    const float d_b = d_o + gl * fminf(fmaxf(s * from16(pb[j], h), -1.f), 1.f);
-    o0[j] = to16(dye, h); o1[j] = to16(d_o, h); o2[j] = to16(d_b, h);
-    ds = fmaf(d_b, from16(pb[j], h), ds);
+  for (int j = 0; j < 8; ++j) cs[0][j] = cs[1][j] = cs[2][j] = 0.f;
+  const long long total = R * f8, stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / f8;
+    const int col = static_cast<int>(i % f8) * 8;
+    const bool masked = row_mask != nullptr && row_mask[row] != 0;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(dy + row * F + col));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(pre + row * F + col));
+    const uint4 c = __ldg(reinterpret_cast<const uint4*>(adapter + row * F + col));
+    const uint16_t* pa = reinterpret_cast<const uint16_t*>(&a);
+    const uint16_t* pb = reinterpret_cast<const uint16_t*>(&b);
+    const uint16_t* pc = reinterpret_cast<const uint16_t*>(&c);
+    uint16_t o0[8], o1[8], o2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float dye = masked ? 0.f : from16(pa[j], h);
+      const float d_o = dye + gl * fminf(fmaxf(from16(pc[j], h), -1.f), 1.f);
+      const float d_b = d_o + gl * fminf(fmaxf(s * from16(pb[j], h), -1.f), 1.f);
+      o0[j] = to16(dye, h); o1[j] = to16(d_o, h); o2[j] = to16(d_b, h);
+      ds = fmaf(d_b, from16(pb[j], h), ds);
+      cs[0][j] += dye; cs[1][j] += d_o; cs[2][j] += d_b;
+    }
+    uint16_t* orow = out + row * 3 * F + col;
+    *reinterpret_cast<uint4*>(orow) = *reinterpret_cast<const uint4*>(o0);
+    *reinterpret_cast<uint4*>(orow + F) = *reinterpret_cast<const uint4*>(o1);
+    *reinterpret_cast<uint4*>(orow + 2 * F) = *reinterpret_cast<const uint4*>(o2);
   }
-  uint16_t* orow = out + row * 3 * F + col;
-  *reinterpret_cast<uint4*>(orow) = *reinterpret_cast<const uint4*>(o0);
-  *reinterpret_cast<uint4*>(orow + F) = *reinterpret_cast<const uint4*>(o1);
-  *reinterpret_cast<uint4*>(orow + 2 * F) = *reinterpret_cast<const uint4*>(o2);
+  if (colsum_out != nullptr) {   // bias gradients: column sums of dY_eff | dO | dB, combined per CTA in shared memory
+    extern __shared__ float s_cols[];   // 3 * F floats
+    for (int k = threadIdx.x; k < 3 * F; k += blockDim.x) s_cols[k] = 0.f;
+    __syncthreads();
+    const int col = static_cast<int>((static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) % f8) * 8;
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&s_cols[q * F + col + j], cs[q][j]);
+    __syncthreads();
+    for (int k = threadIdx.x; k < 3 * F; k += blockDim.x) atomicAdd(colsum_out + k, s_cols[k]);
   }
   if (ds_out != nullptr) {   // block reduction, one atomic per CTA
     __shared__ float s_part[8];
@@ -217,14 +236,19 @@ zira_bwd_prep_kernel(const uint16_t* __restrict__ dy, const uint16_t* __restrict
 extern "C" {
 
 int msda_zira_bwd_prep_16(const void* dy, const void* pre, const void* adapter, const uint8_t* row_mask, const float* scaling,
-                          const float* dloss, long long R, int F, void* out, float* ds_out, int is_half, void* stream) {
+                          const float* dloss, long long R, int F, void* out, float* ds_out, float* colsum_out, int is_half,
+                          void* stream) {
   if (!dy || !pre || !adapter || !scaling || !dloss || !out) return MSDA_ERR_NULL_POINTER;
   if (R <= 0 || F <= 0 || F % 8) return MSDA_ERR_BAD_SHAPE;
+  if (colsum_out != nullptr && (256 % (F / 8) != 0 || 3 * F * sizeof(float) > 48 * 1024)) return MSDA_ERR_UNSUPPORTED;
   const long long n = R * (F / 8);
+  const long long want = (n + 255) / 256;
+  // with column sums: a few CTAs per SM so the per-CTA flush (3F atomics) stays negligible
+  const unsigned blocks = static_cast<unsigned>(colsum_out != nullptr ? (want < 148 * 8 ? want : 148 * 8) : want);
   ++msda::g_launches;
-  zira_bwd_prep_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  zira_bwd_prep_kernel<<<blocks, 256, colsum_out != nullptr ? 3 * F * sizeof(float) : 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const uint16_t*>(dy), static_cast<const uint16_t*>(pre), static_cast<const uint16_t*>(adapter), row_mask,
-      scaling, dloss, R, F, is_half, static_cast<uint16_t*>(out), ds_out);
+      scaling, dloss, R, F, is_half, static_cast<uint16_t*>(out), ds_out, colsum_out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }

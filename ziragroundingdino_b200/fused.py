@@ -288,11 +288,15 @@ class ZiRaLinear16Function(Function):
         dt = x2d.dtype
         gl32 = gloss.detach().float().reshape(1).contiguous()
         stacked = torch.empty((R, 3 * F), dtype=dt, device=x2d.device)
-        ds = torch.zeros(1, dtype=torch.float32, device=x2d.device)
+        need = ctx.needs_input_grad
+        scal = torch.zeros(1 + 3 * F, dtype=torch.float32, device=x2d.device)   # [d scaling | column sums of dY, dO, dB]
+        ds, colsum = scal[:1], scal[1:]
+        fused_colsum = (need[3] or need[5] or need[7]) and 256 % (F // 8) == 0 and 3 * F * 4 <= 48 * 1024
         with torch.cuda.device(x2d.device):
             rc = _lib.lib().msda_zira_bwd_prep_16(gy.contiguous().data_ptr(), pre.data_ptr(), adapter.data_ptr(),
                                                   0 if row_mask is None else row_mask.data_ptr(), s32.data_ptr(), gl32.data_ptr(),
-                                                  R, F, stacked.data_ptr(), ds.data_ptr(), 1 if dt == torch.float16 else 0,
+                                                  R, F, stacked.data_ptr(), ds.data_ptr(),
+                                                  colsum.data_ptr() if fused_colsum else 0, 1 if dt == torch.float16 else 0,
                                                   _stream(x2d))
         _lib.check(rc, "msda_zira_bwd_prep_16")
         s = s32.to(dt)
@@ -301,13 +305,16 @@ class ZiRaLinear16Function(Function):
             w_t = torch.cat([w0.t(), wf.t(), (wb * s).t()], 1).contiguous()
             gx = linear16(stacked, w_t)
         d_y, d_o, d_b = stacked[:, :F], stacked[:, F:2 * F], stacked[:, 2 * F:]
-        need = ctx.needs_input_grad
+        if fused_colsum:
+            bias_sum = lambda k, blk: colsum[k * F:(k + 1) * F]
+        else:
+            bias_sum = lambda k, blk: blk.float().sum(0)
         gw0 = d_y.t() @ x2d if need[2] else None
-        gb0 = d_y.float().sum(0).to(dt) if need[3] else None
+        gb0 = bias_sum(0, d_y).to(dt) if need[3] else None
         gwf = d_o.t() @ x2d if need[4] else None
-        gbf = d_o.float().sum(0).to(dt) if need[5] else None
+        gbf = bias_sum(1, d_o).to(dt) if need[5] else None
         gwb = (d_b.t() @ x2d) * s if need[6] else None
-        gbb = (d_b.float().sum(0) * s32).to(dt) if need[7] else None
+        gbb = (bias_sum(2, d_b) * s32).to(dt) if need[7] else None
         gs = ds.to(dt) if need[8] else None
         return gx, None, gw0, gb0, gwf, gbf, gwb, gbb, gs
 
