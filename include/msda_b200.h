@@ -192,6 +192,20 @@ int msda_add_layernorm_fwd_16(const void *x, const void *r, const float *gamma, 
 int msda_add_layernorm_bwd_16(const void *dy, const void *z, const float *gamma, const float *mean, const float *rstd,
                               long long R, int C, void *dz, int is_half, void *stream);
 
+/* ---- the step in front of the encoder: GroupNorm of the input projection ----------
+ * `GroupNorm(32, hidden_dim)` that closes each level of the reference's input_proj (groundingdino_dual_zero_rep_branch.py:
+ * 258-277; with the ZiRa conv adapter :492-493) on channels-last rows: image n's HW rows of C 16-bit channels start at
+ * x + n * x_image_stride (elements), so x / y / dy / dx may be level slices of a flattened [N, S, C] tensor (the layout
+ * the projection GEMM writes and the encoder reads).  gamma / beta fp32 [C].  scratch = N*C*2 doubles, zeroed by the
+ * caller.  fwd writes y and mean_rstd [N, G, 2] fp32.  bwd writes dx; on return scratch[n][c] = (sum dy*xhat, sum dy),
+ * whose sums over n are d gamma / d beta.  C % 8 == 0, C % G == 0, C/8 a power of two <= 256. */
+int msda_group_norm_fwd_16(const void *x, long long x_image_stride, const float *gamma, const float *beta, int N,
+                           long long HW, int C, int G, float eps, void *y, long long y_image_stride, float *mean_rstd,
+                           double *scratch, int is_half, void *stream);
+int msda_group_norm_bwd_16(const void *dy, long long dy_image_stride, const void *x, long long x_image_stride,
+                           const float *gamma, const float *mean_rstd, int N, long long HW, int C, int G, void *dx,
+                           long long dx_image_stride, double *scratch, int is_half, void *stream);
+
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
  * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =
  * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */

@@ -10,6 +10,7 @@ Sources exercised (relative to /root/reference/groundingdino/models/GroundingDIN
   ms_deform_attn.py:90-130   multi_scale_deformable_attn_pytorch  (+ torch autograd for the grads)
   ms_deform_attn.py:133-355  MultiScaleDeformableAttention (CPU branch, :345-348)
   groundingdino_dual_zero_rep_branch.py:62-64, :105-135  RepZeroLinear (train / eval / __rep__)
+  groundingdino_dual_zero_rep_branch.py:64-103, :492-493 RepZeroConv2d and its use beside input_proj
 """
 import ast
 import importlib.util
@@ -36,20 +37,21 @@ def load_reference_msda():
     return mod
 
 
-def load_reference_rep_zero_linear():
+def load_reference_rep_zero_linear(name="RepZeroLinear"):
     path = os.path.join(REF_DIR, "groundingdino_dual_zero_rep_branch.py")
     tree = ast.parse(open(path).read())
     keep = []
     for node in tree.body:
-        if isinstance(node, ast.ClassDef) and node.name == "RepZeroLinear":
+        if isinstance(node, ast.ClassDef) and node.name == name:
             keep.append(node)
         if isinstance(node, ast.Assign) and any(
             isinstance(t, ast.Name) and t.id in ("zero_value", "lan_scale", "vis_scale") for t in node.targets
         ):
             keep.append(node)
-    ns = {"torch": torch, "nn": torch.nn, "Tensor": torch.Tensor}
+    from torch.nn.common_types import _size_2_t
+    ns = {"torch": torch, "nn": torch.nn, "Tensor": torch.Tensor, "_size_2_t": _size_2_t}
     exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
-    return ns["RepZeroLinear"]
+    return ns[name]
 
 
 def core_case(ref, seed, N, shapes, M, D, Lq, P, dtype, lo=-0.1, hi=1.1, special=False):
@@ -166,6 +168,52 @@ def zira_case(RepZeroLinear, seed):
     return res
 
 
+def zira_conv_case(RepZeroConv2d, seed, cin, cout, groups, ksize, stride, padding, hw):
+    """RepZeroConv2d (groundingdino_dual_zero_rep_branch.py:64-103) alone, and inside the input projection of one
+    level exactly as the reference composes it (:492-493): GroupNorm(conv_0(x) + adapter(x))."""
+    torch.manual_seed(seed)
+    m = RepZeroConv2d(cin, cout, kernel_size=ksize, stride=stride, padding=padding).double()
+    base = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, kernel_size=ksize, stride=stride, padding=padding),
+                               torch.nn.GroupNorm(groups, cout)).double()
+    with torch.no_grad():
+        m.weight.normal_(0, 0.05)
+        m.bias.normal_(0, 0.05)
+        m.freeze_conv.weight.normal_(0, 0.1)
+        m.freeze_conv.bias.normal_(0, 0.1)
+        m.scaling.fill_(0.3)
+        base[1].weight.normal_(1, 0.2)
+        base[1].bias.normal_(0, 0.2)
+    x = torch.randn(2, cin, *hw, dtype=torch.float64)
+    res = {"x": x.numpy(), "meta": np.array([cin, cout, groups, ksize, stride, padding])}
+    for k, v in m.state_dict().items():
+        res["pre." + k] = v.numpy().copy()
+    for k, v in base.state_dict().items():
+        res["base." + k] = v.numpy().copy()
+    m.train()
+    xi = x.clone().requires_grad_(True)
+    out, loss = m(xi)
+    src = base[1](base[0](xi) + out)                       # :493
+    gsrc = torch.randn_like(src)
+    (src * gsrc).sum().add(loss * 0.1).backward()
+    res.update(train_out=out.detach().numpy(), train_loss=loss.detach().numpy().reshape(1), train_src=src.detach().numpy(),
+               grad_src=gsrc.numpy(), grad_x=xi.grad.numpy())
+    for k, p in m.named_parameters():
+        res["pgrad." + k] = p.grad.numpy().copy()
+    m.eval()
+    eo, el = m(x)
+    res.update(eval_out=eo.detach().numpy(), eval_loss=el.detach().numpy().reshape(1),
+               eval_src=base[1](base[0](x) + eo).detach().numpy())
+    m.__rep__()
+    for k, v in m.state_dict().items():
+        res["post." + k] = v.detach().numpy().copy()
+    m.eval()
+    res["merged_eval_out"] = m(x)[0].detach().numpy()
+    m.train()
+    mo, ml = m(x)
+    res.update(merged_train_out=mo.detach().numpy(), merged_train_loss=ml.detach().numpy().reshape(1))
+    return res
+
+
 def main():
     ref = load_reference_msda()
     cases = {
@@ -182,6 +230,9 @@ def main():
         "module_d32": module_case(ref, 24, 64, 2, 4, 4, [(6, 8), (3, 4), (2, 2), (1, 1)], 1, 0, 2, True, False, True),
     }
     cases["zira_rep_linear"] = zira_case(load_reference_rep_zero_linear(), 31)
+    conv = load_reference_rep_zero_linear("RepZeroConv2d")
+    cases["zira_rep_conv1x1"] = zira_conv_case(conv, 32, 24, 16, 4, 1, 1, 0, (5, 6))
+    cases["zira_rep_conv3x3s2"] = zira_conv_case(conv, 33, 12, 16, 4, 3, 2, 1, (7, 6))
     total = 0
     for name, arrs in cases.items():
         p = os.path.join(OUT, name + ".npz")

@@ -122,3 +122,78 @@ def test_zira_rep_zero_linear_matches_reference_fixture():
     m.eval()
     y, l2 = m.forward_folded(t["x"], base.weight, base.bias)
     assert l2 is None and (y - (base(t["x"]) + m(t["x"])[0])).abs().max() < 1e-13
+
+
+@pytest.mark.parametrize("name", ["zira_rep_conv1x1", "zira_rep_conv3x3s2"])
+def test_zira_rep_zero_conv2d_matches_reference_fixture(name):
+    """Host logic of row N3 on CPU/fp64: the drop-in RepZeroConv2d and its rows (channels-last, im2col) fold."""
+    g = load_golden(name)
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    cin, cout, groups, ksize, stride, padding = (int(v) for v in g["meta"])
+    m = zb.RepZeroConv2d(cin, cout, kernel_size=ksize, stride=stride, padding=padding).double()
+    m.load_state_dict({k[4:]: v for k, v in t.items() if k.startswith("pre.")})
+    base = torch.nn.Sequential(torch.nn.Conv2d(cin, cout, ksize, stride, padding), torch.nn.GroupNorm(groups, cout)).double()
+    base.load_state_dict({k[5:]: v for k, v in t.items() if k.startswith("base.")})
+    m.train()
+    x = t["x"].clone().requires_grad_(True)
+    out, loss = m(x)
+    assert (out - t["train_out"]).abs().max() < 1e-13 and abs(float(loss.detach()) - float(t["train_loss"])) < 1e-13
+    # the rows fold: GroupNorm(conv_0(x) + adapter(x)) on [N, HW, C] rows, reference lines :492-493
+    from ziragroundingdino_b200.layer_ops import group_norm_rows
+    assert m.rows_foldable(base[0])
+    N, _, H, W = x.shape
+    rows = x.flatten(2).transpose(1, 2)
+    y, (ho, wo), loss2 = m.forward_folded_rows(rows, (H, W), base[0])
+    src = group_norm_rows(y, base[1]).transpose(1, 2).reshape(N, cout, ho, wo)
+    assert (src - t["train_src"]).abs().max() < 1e-11 and abs(float(loss2.detach()) - float(t["train_loss"])) < 1e-13
+    ((src * t["grad_src"]).sum() + loss2 * 0.1).backward()
+    assert (x.grad - t["grad_x"]).abs().max() < 1e-10
+    for k, p in m.named_parameters():
+        assert (p.grad - t["pgrad." + k]).abs().max() < 1e-10, k
+    m.eval()
+    eo, el = m(t["x"])
+    assert (eo - t["eval_out"]).abs().max() < 1e-13 and float(el) == 0
+    y, (ho, wo), l3 = m.forward_folded_rows(t["x"].flatten(2).transpose(1, 2), (H, W), base[0])
+    src = group_norm_rows(y, base[1]).transpose(1, 2).reshape(N, cout, ho, wo)
+    assert l3 is None and (src - t["eval_src"]).abs().max() < 1e-11
+    m.__rep__()
+    for k, v in m.state_dict().items():
+        assert (v - t["post." + k]).abs().max() < 1e-15, k
+    assert (m(t["x"])[0] - t["merged_eval_out"]).abs().max() < 1e-13
+    m.train()
+    mo, ml = m(t["x"])
+    assert (mo - t["merged_train_out"]).abs().max() < 1e-13 and abs(float(ml) - float(t["merged_train_loss"])) < 1e-13
+
+
+def test_zira_input_proj_keys_and_level_wiring():
+    """ZiRaInputProj: the reference's parameter names (groundingdino_dual_zero_rep_branch.py:258-305) and level wiring
+    (:483-523), checked against a literal transcription of that loop built from nn modules."""
+    torch.manual_seed(0)
+    m = zb.ZiRaInputProj(num_channels=(8, 12, 16), hidden_dim=32, num_feature_levels=5, norm_groups=4).double()
+    keys = set(m.state_dict())
+    for l in range(5):
+        for k in ("input_proj.%d.0.weight", "input_proj.%d.0.bias", "input_proj.%d.1.weight", "input_proj.%d.1.bias",
+                  "input_proj_conv_adapter.%d.weight", "input_proj_conv_adapter.%d.bias", "input_proj_conv_adapter.%d.scaling",
+                  "input_proj_conv_adapter.%d.freeze_conv.weight", "input_proj_conv_adapter.%d.freeze_conv.bias"):
+            assert k % l in keys
+    assert len(keys) == 5 * 9
+    assert m.input_proj[3][0].kernel_size == (3, 3) and m.input_proj[3][0].in_channels == 16
+    assert m.input_proj[4][0].in_channels == 32 and m.input_proj_conv_adapter[4].stride == (2, 2)
+    with torch.no_grad():
+        for a in m.input_proj_conv_adapter:
+            a.weight.normal_(0, 0.05); a.freeze_conv.weight.normal_(0, 0.05); a.freeze_conv.bias.normal_(0, 0.05)
+    feats = [torch.randn(2, 8, 12, 10, dtype=torch.float64), torch.randn(2, 12, 6, 5, dtype=torch.float64),
+             torch.randn(2, 16, 3, 3, dtype=torch.float64)]
+    for training in (True, False):
+        m.train(training)
+        outs, loss = m(feats)
+        want, wl = [], 0.0
+        for l in range(5):
+            x = feats[l] if l < 3 else (feats[-1] if l == 3 else want[-1])
+            a, zl = m.input_proj_conv_adapter[l](x)
+            want.append(m.input_proj[l][1](m.input_proj[l][0](x) + a))
+            wl = wl + zl
+        assert [tuple(o.shape) for o in outs] == [tuple(w.shape) for w in want]
+        for o, w in zip(outs, want):
+            assert (o - w).abs().max() < 1e-12
+        assert abs(float(loss) - float(wl)) < 1e-12

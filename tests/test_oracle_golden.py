@@ -87,3 +87,28 @@ def test_rep_zero_linear_restatement_matches_reference():
     # merged eval == unmerged train up to the 1e-8 re-initialised branch
     assert np.abs(g["merged_eval_out"] - g["train_out"]).max() < 1e-12
     assert np.abs(g["merged_train_out"] - g["train_out"]).max() < 1e-6
+
+
+@pytest.mark.parametrize("name", ["zira_rep_conv1x1", "zira_rep_conv3x3s2"])
+def test_rep_zero_conv2d_restatement_matches_reference(name):
+    g = load_golden(name)
+    t = {k: torch.from_numpy(v) for k, v in g.items()}
+    cin, cout, groups, ksize, stride, padding = (int(v) for v in g["meta"])
+    pre = (t["pre.weight"], t["pre.bias"], t["pre.scaling"], t["pre.freeze_conv.weight"], t["pre.freeze_conv.bias"])
+    out, loss = O.rep_zero_conv2d(t["x"], *pre, training=True, stride=stride, padding=padding)
+    assert np.abs(out.numpy() - g["train_out"]).max() < 1e-13
+    assert abs(float(loss) - float(g["train_loss"][0])) < 1e-13
+    out_e, loss_e = O.rep_zero_conv2d(t["x"], *pre, training=False, stride=stride, padding=padding)
+    assert np.abs(out_e.numpy() - g["eval_out"]).max() < 1e-13 and float(loss_e) == 0.0
+    base = (t["base.0.weight"], t["base.0.bias"], t["base.1.weight"], t["base.1.bias"], groups)
+    src, _ = O.input_proj_level(t["x"], *base, pre, training=True, stride=stride, padding=padding)
+    assert np.abs(src.numpy() - g["train_src"]).max() < 1e-12
+    src_e, _ = O.input_proj_level(t["x"], *base, pre, training=False, stride=stride, padding=padding)
+    assert np.abs(src_e.numpy() - g["eval_src"]).max() < 1e-12
+    post = O.rep_merge(*pre, init_scale=0.1)      # vis_scale == lan_scale == 0.1 (:62-63)
+    names = ["post.weight", "post.bias", "post.scaling", "post.freeze_conv.weight", "post.freeze_conv.bias"]
+    for got, n in zip(post, names):
+        assert np.abs(got.numpy() - g[n]).max() < 1e-15, n
+    out_m, _ = O.rep_zero_conv2d(t["x"], *post, training=False, stride=stride, padding=padding)
+    assert np.abs(out_m.numpy() - g["merged_eval_out"]).max() < 1e-13
+    assert np.abs(g["merged_eval_out"] - g["train_out"]).max() < 1e-12

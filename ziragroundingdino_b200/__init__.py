@@ -3,6 +3,8 @@
 from . import _C  # noqa: F401
 from .ms_deform_attn import (MultiScaleDeformableAttention, MultiScaleDeformableAttnFunction,  # noqa: F401
                              multi_scale_deformable_attn_pytorch)
-from .zira import RepZeroLinear, merge_all  # noqa: F401
+from .zira import RepZeroConv2d, RepZeroLinear, merge_all  # noqa: F401
+from .input_proj import ZiRaInputProj  # noqa: F401
 
-__all__ = ["MultiScaleDeformableAttention", "MultiScaleDeformableAttnFunction", "RepZeroLinear", "merge_all", "_C"]
+__all__ = ["MultiScaleDeformableAttention", "MultiScaleDeformableAttnFunction", "RepZeroLinear", "RepZeroConv2d",
+           "ZiRaInputProj", "merge_all", "_C"]

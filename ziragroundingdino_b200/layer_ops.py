@@ -64,6 +64,58 @@ def add_layer_norm(x, r, norm, dropout_p=0.0, training=False):
     return norm(x + r)
 
 
+class GroupNormRowsFunction(Function):
+    """``GroupNorm(G, C)`` over channels-last rows: x [N, HW, C] 16-bit -> y [N, HW, C] -- SURVEY.md 8(f) row N3, the
+    reference's ``nn.GroupNorm(32, hidden_dim)`` of input_proj (groundingdino_dual_zero_rep_branch.py:258-277) on the
+    layout the projection GEMM writes.  The incoming gradient may be a level slice of the flattened [N, S, C] gradient
+    (image stride S*C): it is read in place."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, G, eps):
+        N, HW, C = x.shape
+        x = x.contiguous()
+        g32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty_like(x)
+        mean_rstd = torch.empty((N, G, 2), dtype=torch.float32, device=x.device)
+        scratch = torch.zeros((N, C, 2), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().msda_group_norm_fwd_16(x.data_ptr(), HW * C, g32.data_ptr(), b32.data_ptr(), N, HW, C, G, float(eps),
+                                                   y.data_ptr(), HW * C, mean_rstd.data_ptr(), scratch.data_ptr(),
+                                                   1 if x.dtype == torch.float16 else 0, _stream(x))
+        _lib.check(rc, "msda_group_norm_fwd_16")
+        ctx.save_for_backward(x, g32, mean_rstd)
+        ctx.G = G
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        x, g32, mean_rstd = ctx.saved_tensors
+        N, HW, C = x.shape
+        if not (dy.stride(2) == 1 and dy.stride(1) == C and dy.stride(0) % 8 == 0 and dy.data_ptr() % 16 == 0):
+            dy = dy.contiguous()
+        dx = torch.empty_like(x)
+        scratch = torch.zeros((N, C, 2), dtype=torch.float64, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = _lib.lib().msda_group_norm_bwd_16(dy.data_ptr(), dy.stride(0), x.data_ptr(), HW * C, g32.data_ptr(),
+                                                   mean_rstd.data_ptr(), N, HW, C, ctx.G, dx.data_ptr(), HW * C,
+                                                   scratch.data_ptr(), 1 if x.dtype == torch.float16 else 0, _stream(x))
+        _lib.check(rc, "msda_group_norm_bwd_16")
+        dw = scratch[:, :, 0].sum(0).to(dy.dtype) if ctx.needs_input_grad[1] else None
+        db = scratch[:, :, 1].sum(0).to(dy.dtype) if ctx.needs_input_grad[2] else None
+        return dx, dw, db, None, None
+
+
+def group_norm_rows(x, norm):
+    """GroupNorm over channels-last rows x [N, HW, C].  Fused on CUDA 16-bit; otherwise the library GroupNorm on the
+    channels-first view (the reference's own call)."""
+    C = x.shape[-1]
+    if (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and norm.affine and C % 8 == 0 and C % norm.num_groups == 0
+            and C // 8 <= 256 and 256 % (C // 8) == 0):
+        return GroupNormRowsFunction.apply(x, norm.weight, norm.bias, norm.num_groups, norm.eps)
+    return norm(x.transpose(1, 2)).transpose(1, 2)
+
+
 def _linear_act16(x2d, w, bias_f32, relu=False, gate=None):
     R, K = x2d.shape
     Nout = w.shape[0]

@@ -24,6 +24,93 @@ import torch.nn.functional as F
 
 zero_value = 1e-8
 lan_scale = 0.1
+vis_scale = 0.1
+
+
+def _folded_rows(x_rows, training, w0, b0, wf, bf, wb, bb, scaling):
+    """Rows [.., K] -> (base + adapter, loss) for weight matrices [F, K]: the shared body of the linear and the
+    im2col'd convolution fold.  Training on CUDA 16-bit = ONE tcgen05 GEMM over [W_0; W_f; W_b] (fused.py)."""
+    Fo, K = w0.shape
+    if not training:
+        return F.linear(x_rows, w0 + wf, b0 + bf), None
+    if (x_rows.is_cuda and x_rows.dtype in (torch.bfloat16, torch.float16) and K % 64 == 0 and Fo % 64 == 0 and 3 * Fo <= 2048):
+        from . import fused
+        x2d = x_rows.reshape(-1, K).contiguous()
+        y, loss = fused.ZiRaLinear16Function.apply(x2d, None, w0, b0, wf, bf, wb, bb, scaling)
+        return y.view(*x_rows.shape[:-1], Fo), loss
+    branch = scaling * F.linear(x_rows, wb, bb)
+    adapter_out = branch + F.linear(x_rows, wf, bf)
+    loss = (F.smooth_l1_loss(branch, torch.zeros_like(branch)) + F.smooth_l1_loss(adapter_out, torch.zeros_like(adapter_out)))
+    return F.linear(x_rows, w0, b0) + adapter_out, loss
+
+
+class RepZeroConv2d(nn.Conv2d):
+    """The reference's convolutional ZiRa branch (groundingdino_dual_zero_rep_branch.py:64-103): same constructor,
+    parameter names (``weight``, ``bias``, ``scaling``, ``freeze_conv.weight``, ``freeze_conv.bias``), train / eval
+    outputs and ``__rep__`` merge as there.  It sits beside ``input_proj[l][0]`` (:292-302, :492-493)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias=True,
+                 padding_mode="zeros", device=None, dtype=None, zero_value=zero_value):
+        super().__init__(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias, padding_mode, device, dtype)
+        self.scaling = nn.parameter.Parameter(torch.ones(1, device=device, dtype=dtype) * vis_scale)
+        nn.init.constant_(self.weight, val=zero_value)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, val=zero_value)
+        self.freeze_conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias,
+                                     padding_mode, device, dtype)
+        nn.init.constant_(self.freeze_conv.weight, val=0.0)
+        if self.bias is not None:
+            nn.init.constant_(self.freeze_conv.bias, val=0.0)
+        self.zero_inter_loss = torch.nn.SmoothL1Loss(reduction="mean")
+
+    def forward(self, input):
+        """Stand-alone use, exactly the reference contract: NCHW in, ``(output, zero_inter_loss)`` out."""
+        if self.training:
+            branch_output = self.scaling * super().forward(input)
+            output = branch_output + self.freeze_conv(input)
+            loss = (self.zero_inter_loss(branch_output, torch.zeros_like(branch_output))
+                    + self.zero_inter_loss(output, torch.zeros_like(output)))
+            return output, loss
+        return self.freeze_conv(input), torch.zeros(1).to(input)
+
+    def rows_foldable(self, base_conv):
+        """True when conv == GEMM over channels-last rows (possibly after im2col): what forward_folded_rows needs."""
+        return (self.groups == 1 and self.dilation == (1, 1) and self.padding_mode == "zeros" and self.bias is not None
+                and isinstance(base_conv, nn.Conv2d) and base_conv.bias is not None
+                and base_conv.weight.shape == self.weight.shape and base_conv.stride == self.stride
+                and base_conv.padding == self.padding and base_conv.dilation == self.dilation and base_conv.groups == 1)
+
+    def forward_folded_rows(self, x_rows, hw, base_conv):
+        """``base_conv(x) + self(x)[0]`` and the zero-inter loss on channels-last rows.
+
+        x_rows [N, H*W, C_in] (hw = (H, W)); returns (rows [N, H_out*W_out, C_out], (H_out, W_out), loss or None).
+        A 1x1 convolution is a GEMM over the rows as they are; a k x k one is im2col'd first (the only such level of the
+        reference is the 13x21 extra level, :269-276).  Both then run as one fused GEMM in training (see _folded_rows)."""
+        N, HW, Cin = x_rows.shape
+        H, W = hw
+        kh, kw = self.kernel_size
+        Fo = self.out_channels
+        if (kh, kw) == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0):
+            rows, out_hw = x_rows, (H, W)
+        else:
+            x = x_rows.reshape(N, H, W, Cin).permute(0, 3, 1, 2)
+            cols = F.unfold(x, (kh, kw), padding=self.padding, stride=self.stride)          # [N, Cin*kh*kw, L]
+            rows = cols.transpose(1, 2).contiguous()
+            out_hw = ((H + 2 * self.padding[0] - kh) // self.stride[0] + 1, (W + 2 * self.padding[1] - kw) // self.stride[1] + 1)
+        y, loss = _folded_rows(rows, self.training, base_conv.weight.reshape(Fo, -1), base_conv.bias,
+                               self.freeze_conv.weight.reshape(Fo, -1), self.freeze_conv.bias, self.weight.reshape(Fo, -1),
+                               self.bias, self.scaling)
+        return y, out_hw, loss
+
+    def __rep__(self):
+        with torch.no_grad():
+            self.freeze_conv.weight.data = self.weight.data * self.scaling + self.freeze_conv.weight.data
+            if self.bias is not None:
+                self.freeze_conv.bias.data = self.bias.data * self.scaling + self.freeze_conv.bias.data
+        self.scaling = nn.parameter.Parameter(torch.ones(1).to(self.weight.data) * vis_scale)
+        nn.init.constant_(self.weight, val=zero_value)
+        if self.bias is not None:
+            nn.init.constant_(self.bias, val=zero_value)
 
 
 class RepZeroLinear(nn.Linear):
