@@ -46,7 +46,7 @@ def parse():
 
 def workload_config(n_gpus):
     return {"workload": "config2: GroundingDINO Swin-T 6-layer deformable encoder (MSDeformAttn + residual/LN + FFN 256-2048-256) "
-                        "fwd+bwd, frozen layers, trainable ZiRa input branch",
+                        "fwd+bwd, frozen layers; trainable ZiRa conv adapters on input_proj (192/384/768->256 1x1 + 3x3/s2 level, GroupNorm)",
             "images_per_gpu": IMAGES_PER_GPU, "global_batch": IMAGES_PER_GPU * n_gpus, "image": "800x1333",
             "levels": [[100, 167], [50, 84], [25, 42], [13, 21]], "tokens_per_image": 22223, "d_model": 256, "heads": 8,
             "points": 4, "layers": NUM_LAYERS, "padding": "per-image valid fraction 0.6-1.0 of the canvas",
@@ -64,8 +64,10 @@ def cpu_images_per_s(budget_s, threads):
     t1 = cpu_encoder.timed_step(syn.SWIN_T_800x1333, 1, threads)       # also the warm-up
     layers = max(1, min(NUM_LAYERS, int(budget_s / max(t1, 1e-3))))
     t = cpu_encoder.timed_step(syn.SWIN_T_800x1333, layers, threads)
-    per_image = t * NUM_LAYERS / layers
-    return 1.0 / per_image, layers, t
+    cpu_encoder.timed_front(syn.SWIN_T_800x1333, threads)                # warm-up
+    t_front = cpu_encoder.timed_front(syn.SWIN_T_800x1333, threads)
+    per_image = t * NUM_LAYERS / layers + t_front
+    return 1.0 / per_image, layers, t + t_front
 
 
 def run_reference(args):
@@ -78,7 +80,7 @@ def run_reference(args):
     budget = min(30.0, 150.0 / (total + args.warmup))
     for i in range(args.warmup + total):
         ips, layers, t = cpu_images_per_s(budget, threads)
-        sample = "1 image x %d of 6 encoder layers fwd+bwd per step (fp32, torch CPU, grid_sample core)" % layers
+        sample = "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers) fwd+bwd per step (fp32, torch CPU, grid_sample core)" % layers
         if i >= args.warmup:
             vals.append(ips)
     v = sum(vals) / len(vals)
@@ -165,26 +167,44 @@ def run_ours(args):
     enc = enc.to(dt)
     for p in enc.parameters():
         p.requires_grad_(False)
-    base_in = torch.nn.Linear(C, C).to(dev).to(dt)
-    for p in base_in.parameters():
-        p.requires_grad_(False)
-    branch = zb.RepZeroLinear(C, C).to(dev).to(dt)
-    branch.train()
-    params = [p for p in branch.parameters()]
+    # front of the encoder = the reference's trainable part: frozen input_proj (1x1 convs over the Swin-T
+    # maps 192/384/768 -> 256, 3x3/s2 extra level, GroupNorm(32)) with a trainable RepZeroConv2d adapter beside each conv
+    front = zb.ZiRaInputProj((192, 384, 768), C, len(shapes)).to(dev)
+    with torch.no_grad():
+        for a in front.input_proj_conv_adapter:   # a branch mid-training: non-trivial soft-frozen and fresh weights
+            sc = a.weight[0].numel() ** -0.5
+            a.weight.normal_(0, 0.1 * sc); a.freeze_conv.weight.normal_(0, 0.1 * sc)
+    front = front.to(dt)
+    front.train()
+    params = []
+    for n_, p in front.named_parameters():
+        p.requires_grad_("adapter" in n_)          # the reference's before_train rule (:733-734)
+        if p.requires_grad:
+            params.append(p)
     bucket = FlatGradBucket(params, world)
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4, capturable=True)
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4, capturable=True, fused=True)
 
     sh, lsi = syn.level_tensors(shapes, dev)
     g = torch.Generator().manual_seed(99 + rank)
     mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g)
-    host_feat = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
+    feat_hw = list(shapes[:3])
+    feat_rows = [h * w for h, w in feat_hw]
+    feat_off = [0]
+    for c_, r_ in zip((192, 384, 768), feat_rows):
+        feat_off.append(feat_off[-1] + r_ * c_)
+    # the three backbone maps of the batch, channels-last rows, packed level after level: ONE pinned buffer / ONE copy per step
+    host_feat = torch.randn(N * feat_off[-1], generator=g).to(dt).pin_memory()
     host_pos = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
     host_mask = mask.cpu().pin_memory()
     feat, pos = host_feat.to(dev), host_pos.to(dev)
+
+    def level_maps(packed):
+        return [packed[N * feat_off[i]:N * feat_off[i + 1]].view(N, feat_rows[i], c_) for i, c_ in enumerate((192, 384, 768))]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
     def fwd_bwd(feat_, pos_, mask_):
-        src, zloss = branch.forward_folded(feat_, base_in.weight, base_in.bias)
+        src, proj_shapes, zloss = front.forward_rows(level_maps(feat_), feat_hw)
+        assert proj_shapes == [tuple(x) for x in shapes]
         out = enc(src, pos_, shapes, sh, lsi, valid, mask_)
         # mean(out^2) with fp32 accumulation and no fp32 copy of the 91 MB activation
         loss = torch.linalg.vector_norm(out, 2, dtype=torch.float32).square() / out.numel() + 0.1 * zloss.float()
@@ -366,7 +386,7 @@ def run_ours(args):
         threads = os.cpu_count() or 1
         ips, layers, t = cpu_images_per_s(20.0, threads)
         out["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                               "sample": "1 image x %d of 6 encoder layers fwd+bwd (fp32, torch CPU, grid_sample core), %.1f s" % (layers, t)}
+                               "sample": "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers) fwd+bwd (fp32, torch CPU, grid_sample core), %.1f s" % (layers, t)}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

@@ -56,3 +56,31 @@ def timed_step(shapes, layers, threads, d_model=256, M=8, P=4, seed=0):
         x = encoder_layer(p, x, pos, refp, sh, None, M, L, P)
     x.square().mean().backward()
     return time.perf_counter() - t0
+
+
+def timed_front(shapes, threads, channels=(192, 384, 768), d_model=256, seed=0):
+    """Seconds for one image through the ZiRa-augmented input projection (oracle.input_proj_level per level:
+    groundingdino_dual_zero_rep_branch.py:483-523) forward + backward w.r.t. the adapter parameters, fp32."""
+    torch.set_num_threads(threads)
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    nb = len(channels)
+    feats = [torch.randn(1, c, h, w, generator=g) for c, (h, w) in zip(channels, shapes[:nb])]
+    levels = []
+    cin = channels[-1]
+    for l in range(len(shapes)):
+        c, k = (channels[l], 1) if l < nb else (cin, 3)
+        base = (r(d_model, c, k, k), torch.zeros(d_model), torch.ones(d_model), torch.zeros(d_model))
+        adapter = [t.requires_grad_(True) for t in (r(d_model, c, k, k), r(d_model), torch.full((1,), 0.1), r(d_model, c, k, k), r(d_model))]
+        levels.append((base, adapter, k))
+        if l >= nb:
+            cin = d_model
+    t0 = time.perf_counter()
+    srcs, total = [], 0.0
+    for l, (base, adapter, k) in enumerate(levels):
+        x = feats[l] if l < nb else (feats[-1] if l == nb else srcs[-1])
+        src, loss = O.input_proj_level(x, *base, 32, adapter, True, stride=1 if k == 1 else 2, padding=0 if k == 1 else 1)
+        srcs.append(src)
+        total = total + loss
+    (sum(s.square().mean() for s in srcs) + 0.1 * total).backward()
+    return time.perf_counter() - t0

@@ -47,18 +47,32 @@ gn_channel_sums_kernel(const uint16_t* __restrict__ a, long long a_image_stride,
   }
   const uint16_t* ap = a + n * a_image_stride + cg * 8;
   const uint16_t* xp = MODE == 1 ? x + n * x_image_stride + cg * 8 : nullptr;
-  for (long long r = static_cast<long long>(blockIdx.x) * rows_per_trip + rslot; r < HW;
-       r += static_cast<long long>(gridDim.x) * rows_per_trip) {
-    float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(ap + r * C)), h, v);
-    if (MODE == 0) {
+  // four independent row loads in flight per thread (the loop is latency-bound otherwise)
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_trip;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * rows_per_trip + rslot; r0 < HW; r0 += 4 * step) {
+    uint4 raw[4], rawx[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { p[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
-    } else {
-      float xv[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(xp + r * C)), h, xv);
+    for (int u = 0; u < 4; ++u) {
+      const long long r = r0 + u * step;
+      if (r < HW) {
+        raw[u] = __ldg(reinterpret_cast<const uint4*>(ap + r * C));
+        if (MODE == 1) rawx[u] = __ldg(reinterpret_cast<const uint4*>(xp + r * C));
+      }
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { p[j] = fmaf(v[j], (xv[j] - mu[j]) * rs[j], p[j]); q[j] += v[j]; }
+    for (int u = 0; u < 4; ++u) {
+      if (r0 + u * step >= HW) break;
+      float v[8];
+      unpack8(raw[u], h, v);
+      if (MODE == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { p[j] += v[j]; q[j] = fmaf(v[j], v[j], q[j]); }
+      } else {
+        float xv[8];
+        unpack8(rawx[u], h, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { p[j] = fmaf(v[j], (xv[j] - mu[j]) * rs[j], p[j]); q[j] += v[j]; }
+      }
     }
   }
   for (int k = threadIdx.x; k < 2 * C; k += blockDim.x) s_acc[k] = 0.f;
@@ -100,23 +114,35 @@ gn_fwd_apply_kernel(const uint16_t* __restrict__ x, long long x_image_stride, co
     }
   }
   __syncthreads();
-  const long long total = HW * c8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / c8;
-    const int c0 = static_cast<int>(i % c8) * 8;
-    float v[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_image_stride + r * C + c0)), h, v);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c0)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c0 + 4));
-    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  // blockDim.x (256) is a multiple of C/8, so a thread keeps its 8 channels on every trip: constants hoisted
+  const int c0 = static_cast<int>(threadIdx.x % c8) * 8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      v[j] = fmaf((v[j] - s_mr[2 * g]) * s_mr[2 * g + 1], ga[j], be[j]);
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    sc[j] = s_mr[2 * g + 1] * __ldg(gamma + c0 + j);
+    sh[j] = fmaf(-s_mr[2 * g], sc[j], __ldg(beta + c0 + j));
+  }
+  const int rows_per_trip = 256 / c8;
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_trip;
+  const uint16_t* xp = x + n * x_image_stride + c0;
+  uint16_t* yp = y + n * y_image_stride + c0;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * rows_per_trip + threadIdx.x / c8; r0 < HW; r0 += 2 * step) {
+    const long long r1 = r0 + step;
+    const uint4 a0 = __ldg(reinterpret_cast<const uint4*>(xp + r0 * C));
+    uint4 a1 = a0;
+    if (r1 < HW) a1 = __ldg(reinterpret_cast<const uint4*>(xp + r1 * C));
+    float v[8];
+    unpack8(a0, h, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+    *reinterpret_cast<uint4*>(yp + r0 * C) = pack8(v, h);
+    if (r1 < HW) {
+      unpack8(a1, h, v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], sc[j], sh[j]);
+      *reinterpret_cast<uint4*>(yp + r1 * C) = pack8(v, h);
     }
-    *reinterpret_cast<uint4*>(y + n * y_image_stride + r * C + c0) = pack8(v, h);
   }
 }
 
@@ -143,24 +169,42 @@ gn_bwd_apply_kernel(const uint16_t* __restrict__ dy, long long dy_image_stride, 
     s_g[4 * g + 3] = static_cast<float>(B / cnt);
   }
   __syncthreads();
-  const long long total = HW * c8;
-  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const long long r = i / c8;
-    const int c0 = static_cast<int>(i % c8) * 8;
-    float d[8], xv[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(dy + n * dy_image_stride + r * C + c0)), h, d);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(x + n * x_image_stride + r * C + c0)), h, xv);
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c0)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c0 + 4));
-    const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  // dx = dy * a - x * b - c with per-channel constants a = rstd*gamma, b = rstd^2*A, c = rstd*(B - mean*rstd*A)
+  const int c0 = static_cast<int>(threadIdx.x % c8) * 8;
+  float ka[8], kb[8], kc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c0 + j) / cpg;
-      const float rstd = s_g[4 * g + 1];
-      const float xhat = (xv[j] - s_g[4 * g]) * rstd;
-      d[j] = rstd * (d[j] * ga[j] - xhat * s_g[4 * g + 2] - s_g[4 * g + 3]);
+  for (int j = 0; j < 8; ++j) {
+    const int g = (c0 + j) / cpg;
+    const float mean = s_g[4 * g], rstd = s_g[4 * g + 1], A = s_g[4 * g + 2], B = s_g[4 * g + 3];
+    ka[j] = rstd * __ldg(gamma + c0 + j);
+    kb[j] = rstd * rstd * A;
+    kc[j] = rstd * (B - mean * rstd * A);
+  }
+  const int rows_per_trip = 256 / c8;
+  const long long step = static_cast<long long>(gridDim.x) * rows_per_trip;
+  const uint16_t* dyp = dy + n * dy_image_stride + c0;
+  const uint16_t* xp = x + n * x_image_stride + c0;
+  uint16_t* dxp = dx + n * dx_image_stride + c0;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * rows_per_trip + threadIdx.x / c8; r0 < HW; r0 += 2 * step) {
+    const long long r1 = r0 + step;
+    const uint4 d0 = __ldg(reinterpret_cast<const uint4*>(dyp + r0 * C));
+    const uint4 x0 = __ldg(reinterpret_cast<const uint4*>(xp + r0 * C));
+    uint4 d1 = d0, x1 = x0;
+    if (r1 < HW) {
+      d1 = __ldg(reinterpret_cast<const uint4*>(dyp + r1 * C));
+      x1 = __ldg(reinterpret_cast<const uint4*>(xp + r1 * C));
     }
-    *reinterpret_cast<uint4*>(dx + n * dx_image_stride + r * C + c0) = pack8(d, h);
+    float d[8], xv[8];
+    unpack8(d0, h, d); unpack8(x0, h, xv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], ka[j], -fmaf(xv[j], kb[j], kc[j]));
+    *reinterpret_cast<uint4*>(dxp + r0 * C) = pack8(d, h);
+    if (r1 < HW) {
+      unpack8(d1, h, d); unpack8(x1, h, xv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) d[j] = fmaf(d[j], ka[j], -fmaf(xv[j], kb[j], kc[j]));
+      *reinterpret_cast<uint4*>(dxp + r1 * C) = pack8(d, h);
+    }
   }
 }
 
@@ -181,7 +225,8 @@ dim3 sums_grid(int N, long long HW, int C) {
 }
 
 dim3 apply_grid(int N, long long HW, int C) {
-  long long bx = (HW * (C / 8) + 255) / 256;
+  const int rows_per_trip = 256 / (C / 8);
+  long long bx = (HW + 2 * rows_per_trip - 1) / (2 * rows_per_trip);   // two rows per thread per trip
   const long long cap = (148 * 16 + N - 1) / N;
   if (bx > cap) bx = cap;
   return dim3(static_cast<unsigned>(bx), static_cast<unsigned>(N));

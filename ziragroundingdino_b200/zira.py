@@ -90,16 +90,24 @@ class RepZeroConv2d(nn.Conv2d):
         H, W = hw
         kh, kw = self.kernel_size
         Fo = self.out_channels
+        as_rows = lambda w: w.reshape(Fo, -1)
         if (kh, kw) == (1, 1) and self.stride == (1, 1) and self.padding == (0, 0):
             rows, out_hw = x_rows, (H, W)
         else:
-            x = x_rows.reshape(N, H, W, Cin).permute(0, 3, 1, 2)
-            cols = F.unfold(x, (kh, kw), padding=self.padding, stride=self.stride)          # [N, Cin*kh*kw, L]
-            rows = cols.transpose(1, 2).contiguous()
-            out_hw = ((H + 2 * self.padding[0] - kh) // self.stride[0] + 1, (W + 2 * self.padding[1] - kw) // self.stride[1] + 1)
-        y, loss = _folded_rows(rows, self.training, base_conv.weight.reshape(Fo, -1), base_conv.bias,
-                               self.freeze_conv.weight.reshape(Fo, -1), self.freeze_conv.bias, self.weight.reshape(Fo, -1),
-                               self.bias, self.scaling)
+            # im2col straight from the channels-last map: pad, then a strided window view [N, Ho, Wo, kh, kw, C] copied
+            # once; K runs (ky, kx, c), so the weights are permuted to match instead of transposing the activation
+            ph, pw = self.padding
+            sh_, sw_ = self.stride
+            Ho, Wo = (H + 2 * ph - kh) // sh_ + 1, (W + 2 * pw - kw) // sw_ + 1
+            xp = F.pad(x_rows.reshape(N, H, W, Cin), (0, 0, pw, pw, ph, ph))
+            Hp, Wp = H + 2 * ph, W + 2 * pw
+            win = xp.as_strided((N, Ho, Wo, kh, kw, Cin), (Hp * Wp * Cin, sh_ * Wp * Cin, sw_ * Cin, Wp * Cin, Cin, 1))
+            rows, out_hw = win.reshape(N, Ho * Wo, kh * kw * Cin), (Ho, Wo)
+            as_rows = lambda w: w.permute(0, 2, 3, 1).reshape(Fo, -1)
+        cast = (lambda t: t) if self.weight.dtype == x_rows.dtype else (lambda t: t.to(x_rows.dtype))
+        y, loss = _folded_rows(rows, self.training, as_rows(base_conv.weight), base_conv.bias,
+                               cast(as_rows(self.freeze_conv.weight)), cast(self.freeze_conv.bias), cast(as_rows(self.weight)),
+                               cast(self.bias), cast(self.scaling))
         return y, out_hw, loss
 
     def __rep__(self):
