@@ -84,3 +84,39 @@ def timed_front(shapes, threads, channels=(192, 384, 768), d_model=256, seed=0):
         total = total + loss
     (sum(s.square().mean() for s in srcs) + 0.1 * total).backward()
     return time.perf_counter() - t0
+
+
+def multihead_attention(p, prefix, query, key, value, n_heads, key_padding_mask=None, attn_mask=None):
+    """nn.MultiheadAttention (seq-first, dropout 0) restated from its published definition -- PyTorch is third-party
+    arithmetic on this path (the reference pins torch==2.4.0, requirements.txt:1): softmax(Q K^T / sqrt(d)) V with the
+    packed in_proj and out_proj.  query [Lq, B, C], key/value [Lk, B, C]; key_padding_mask [B, Lk] bool (True = ignore)."""
+    Lq, B, C = query.shape
+    d = C // n_heads
+    w, b = p[prefix + "in_proj_weight"], p[prefix + "in_proj_bias"]
+    q = F.linear(query, w[:C], b[:C]).reshape(Lq, B * n_heads, d).transpose(0, 1)
+    k = F.linear(key, w[C:2 * C], b[C:2 * C]).reshape(-1, B * n_heads, d).transpose(0, 1)
+    v = F.linear(value, w[2 * C:], b[2 * C:]).reshape(-1, B * n_heads, d).transpose(0, 1)
+    att = q @ k.transpose(1, 2) / (d ** 0.5)
+    if attn_mask is not None:
+        att = att.masked_fill(attn_mask, float("-inf")) if attn_mask.dtype == torch.bool else att + attn_mask
+    if key_padding_mask is not None:
+        att = att.view(B, n_heads, Lq, -1).masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(B * n_heads, Lq, -1)
+    out = (att.softmax(-1) @ v).transpose(0, 1).reshape(Lq, B, C)
+    return F.linear(out, p[prefix + "out_proj.weight"], p[prefix + "out_proj.bias"])
+
+
+def decoder_layer(p, tgt, query_pos, ref4, memory, memory_text, text_mask, shapes, mask, M, L, P):
+    """transformer_for_adapter.py:1024-1073 with use_adapter=False, use_text_cross_attention=True, dropout 0.
+    ``p`` uses the reference's state_dict keys.  tgt/query_pos [nq, B, C], ref4 [nq, B, L, 4], memory [S, B, C]."""
+    C = tgt.shape[-1]
+    ln = lambda x, n: F.layer_norm(x, (C,), p[n + ".weight"], p[n + ".bias"])
+    q = tgt + query_pos
+    tgt = ln(tgt + multihead_attention(p, "self_attn.", q, q, tgt, M), "norm2")
+    text = memory_text.transpose(0, 1)
+    tgt = ln(tgt + multihead_attention(p, "ca_text.", tgt + query_pos, text, text, M, key_padding_mask=text_mask), "catext_norm")
+    attn_p = {k[len("cross_attn."):]: v for k, v in p.items() if k.startswith("cross_attn.")}
+    tgt2 = O.module_forward(attn_p, (tgt + query_pos).transpose(0, 1), memory.transpose(0, 1), mask,
+                            ref4.transpose(0, 1), shapes, M, L, P).transpose(0, 1)
+    tgt = ln(tgt + tgt2, "norm1")
+    ffn = F.linear(F.relu(F.linear(tgt, p["linear1.weight"], p["linear1.bias"])), p["linear2.weight"], p["linear2.bias"])
+    return ln(tgt + ffn, "norm3")

@@ -11,6 +11,7 @@ Sources exercised (relative to /root/reference/groundingdino/models/GroundingDIN
   ms_deform_attn.py:133-355  MultiScaleDeformableAttention (CPU branch, :345-348)
   groundingdino_dual_zero_rep_branch.py:62-64, :105-135  RepZeroLinear (train / eval / __rep__)
   groundingdino_dual_zero_rep_branch.py:64-103, :492-493 RepZeroConv2d and its use beside input_proj
+  transformer_for_adapter.py:809-907, :910-1073  DeformableTransformerEncoderLayer / DecoderLayer (use_adapter=False)
 """
 import ast
 import importlib.util
@@ -214,6 +215,88 @@ def zira_conv_case(RepZeroConv2d, seed, cin, cout, groups, ksize, stride, paddin
     return res
 
 
+def load_reference_layers(ref):
+    """DeformableTransformerEncoderLayer / DecoderLayer (transformer_for_adapter.py:809-907, :910-1073) executed from
+    their AST (the file imports detectron2-dependent modules at the top), with MSDeformAttn bound to the reference's own
+    MultiScaleDeformableAttention (CPU branch) and _get_activation_fn taken from the reference's utils.py:188-201."""
+    ns = {"torch": torch, "nn": torch.nn, "F": torch.nn.functional, "Tensor": torch.Tensor,
+          "Optional": __import__("typing").Optional, "MSDeformAttn": ref.MultiScaleDeformableAttention}
+    tree = ast.parse(open(os.path.join(REF_DIR, "utils.py")).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "_get_activation_fn"]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "utils.py", "exec"), ns)
+    tree = ast.parse(open(os.path.join(REF_DIR, "transformer_for_adapter.py")).read())
+    keep = [n for n in tree.body if isinstance(n, ast.ClassDef)
+            and n.name in ("DeformableTransformerEncoderLayer", "DeformableTransformerDecoderLayer")]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "transformer_for_adapter.py", "exec"), ns)
+    return ns["DeformableTransformerEncoderLayer"], ns["DeformableTransformerDecoderLayer"]
+
+
+def _randomise(layer, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, p in layer.named_parameters():
+            if "sampling_offsets.bias" in n:
+                continue                                   # keep the directional grid init
+            if p.dim() > 1:
+                p.copy_(torch.randn(p.shape, generator=g, dtype=p.dtype) * (0.05 if "sampling_offsets" in n else 0.2))
+            elif "norm" in n and n.endswith("weight"):
+                p.copy_(1 + 0.2 * torch.randn(p.shape, generator=g, dtype=p.dtype))
+            else:
+                p.copy_(0.1 * torch.randn(p.shape, generator=g, dtype=p.dtype))
+
+
+def layer_cases(ref, seed):
+    Enc, Dec = load_reference_layers(ref)
+    C, FF, M, L, P = 32, 64, 4, 3, 2
+    shapes = [(5, 6), (3, 3), (2, 2)]
+    S = sum(h * w for h, w in shapes)
+    N, nq, ntext = 2, 7, 5
+    torch.manual_seed(seed)
+    sh = torch.tensor(shapes, dtype=torch.long)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    mask = torch.zeros(N, S, dtype=torch.bool)
+    mask[1, S - 9:] = True
+    out = {}
+    # ---- encoder layer (use_adapter=False as in GroundingDINO_SwinT_OGC_rep.py:56) ----
+    enc = Enc(C, FF, 0.0, "relu", L, M, P, use_adapter=False).double()
+    _randomise(enc, seed + 1)
+    src = torch.randn(N, S, C, dtype=torch.float64, requires_grad=True)
+    pos = torch.randn(N, S, C, dtype=torch.float64)
+    refp = torch.rand(N, S, L, 2, dtype=torch.float64)
+    y, aloss = enc(src, pos, refp, sh, lsi, mask)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    res = {"src": src.detach().numpy(), "pos": pos.numpy(), "reference_points": refp.numpy(), "shapes": sh.numpy(),
+           "mask": mask.numpy(), "out": y.detach().numpy(), "adapter_loss": aloss.detach().numpy(), "grad_out": gy.numpy(),
+           "grad_src": src.grad.numpy(), "cfg": np.asarray([C, FF, M, L, P], dtype=np.int64)}
+    for k, v in enc.state_dict().items():
+        res["param." + k] = v.numpy()
+    out["layer_encoder"] = res
+    # ---- decoder layer (text cross-attention on, as in the GroundingDINO config; seq-first tensors) ----
+    dec = Dec(C, FF, 0.0, "relu", L, M, P, use_text_cross_attention=True, use_adapter=False).double()
+    _randomise(dec, seed + 2)
+    tgt = torch.randn(nq, N, C, dtype=torch.float64, requires_grad=True)
+    qpos = torch.randn(nq, N, C, dtype=torch.float64)
+    ref4 = torch.cat([torch.rand(nq, N, L, 2, dtype=torch.float64) * 0.8 + 0.1,
+                      torch.rand(nq, N, L, 2, dtype=torch.float64) * 0.45 + 0.05], -1)
+    memory = torch.randn(S, N, C, dtype=torch.float64, requires_grad=True)
+    text = torch.randn(N, ntext, C, dtype=torch.float64)
+    tmask = torch.zeros(N, ntext, dtype=torch.bool)
+    tmask[0, -2:] = True
+    y, aloss = dec(tgt=tgt, tgt_query_pos=qpos, tgt_reference_points=ref4, memory_text=text, text_attention_mask=tmask,
+                   memory=memory, memory_key_padding_mask=mask, memory_level_start_index=lsi, memory_spatial_shapes=sh)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    res = {"tgt": tgt.detach().numpy(), "query_pos": qpos.numpy(), "reference_points": ref4.numpy(), "memory": memory.detach().numpy(),
+           "memory_text": text.numpy(), "text_mask": tmask.numpy(), "shapes": sh.numpy(), "mask": mask.numpy(),
+           "out": y.detach().numpy(), "adapter_loss": aloss.detach().numpy(), "grad_out": gy.numpy(),
+           "grad_tgt": tgt.grad.numpy(), "grad_memory": memory.grad.numpy(), "cfg": np.asarray([C, FF, M, L, P], dtype=np.int64)}
+    for k, v in dec.state_dict().items():
+        res["param." + k] = v.numpy()
+    out["layer_decoder"] = res
+    return out
+
+
 def main():
     ref = load_reference_msda()
     cases = {
@@ -233,6 +316,7 @@ def main():
     conv = load_reference_rep_zero_linear("RepZeroConv2d")
     cases["zira_rep_conv1x1"] = zira_conv_case(conv, 32, 24, 16, 4, 1, 1, 0, (5, 6))
     cases["zira_rep_conv3x3s2"] = zira_conv_case(conv, 33, 12, 16, 4, 3, 2, 1, (7, 6))
+    cases.update(layer_cases(ref, 41))
     total = 0
     for name, arrs in cases.items():
         p = os.path.join(OUT, name + ".npz")

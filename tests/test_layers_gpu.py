@@ -1,0 +1,102 @@
+"""GPU: row N1 of SURVEY.md 8(f) -- the encoder / decoder layers around MultiScaleDeformableAttention -- against
+fixtures generated from the REFERENCE's own layer classes (tests/golden/make_golden.py: layer_cases, fp64, CPU).
+fp64 on the GPU runs the generic kernels + library linears: bar 1e-9 (same arithmetic, different summation order).
+bf16 runs the fused path (tcgen05 GEMMs, fused add+LayerNorm / FFN): outputs are LayerNorm-normalised O(1) values, bar
+5e-2 absolute on outputs (a few bf16 roundings through 3-4 normalisations), 8e-2 relative (Frobenius) on input gradients."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _load(layer, g, dtype):
+    sd = {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")}
+    layer = layer.double()
+    layer.load_state_dict(sd)          # strict: the reference's key names must match ours exactly
+    return layer.to(DEV).to(dtype).eval()
+
+
+def _t(g, k, dtype=None):
+    t = torch.from_numpy(g[k]).to(DEV)
+    return t.to(dtype) if dtype is not None and t.is_floating_point() else t
+
+
+@pytest.mark.parametrize("dtype,out_tol,grad_tol", [(torch.float64, 1e-9, 1e-8), (torch.float32, 2e-4, 2e-3)])
+def test_encoder_layer_vs_reference_fixture(dtype, out_tol, grad_tol):
+    import ziragroundingdino_b200 as zb
+    g = load_golden("layer_encoder")
+    C, FF, M, L, P = (int(v) for v in g["cfg"])
+    layer = _load(zb.DeformableTransformerEncoderLayer(C, FF, 0.0, "relu", L, M, P, use_adapter=False), g, dtype)
+    sh = _t(g, "shapes")
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    src = _t(g, "src", dtype).requires_grad_(True)
+    y, aloss = layer(src, _t(g, "pos", dtype), _t(g, "reference_points", dtype), sh, lsi, _t(g, "mask"))
+    y.backward(_t(g, "grad_out", dtype))
+    assert float(aloss) == 0.0
+    assert np.abs(y.detach().double().cpu().numpy() - g["out"]).max() < out_tol
+    assert rel_err(src.grad.double().cpu(), torch.from_numpy(g["grad_src"])) < grad_tol
+
+
+@pytest.mark.parametrize("dtype,out_tol,grad_tol", [(torch.float64, 1e-9, 1e-8), (torch.float32, 2e-4, 2e-3)])
+def test_decoder_layer_vs_reference_fixture(dtype, out_tol, grad_tol):
+    import ziragroundingdino_b200 as zb
+    g = load_golden("layer_decoder")
+    C, FF, M, L, P = (int(v) for v in g["cfg"])
+    layer = _load(zb.DeformableTransformerDecoderLayer(C, FF, 0.0, "relu", L, M, P, use_text_cross_attention=True,
+                                                       use_adapter=False), g, dtype)
+    sh = _t(g, "shapes")
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    tgt = _t(g, "tgt", dtype).requires_grad_(True)
+    mem = _t(g, "memory", dtype).requires_grad_(True)
+    y, aloss = layer(tgt=tgt, tgt_query_pos=_t(g, "query_pos", dtype), tgt_reference_points=_t(g, "reference_points", dtype),
+                     memory_text=_t(g, "memory_text", dtype), text_attention_mask=_t(g, "text_mask"), memory=mem,
+                     memory_key_padding_mask=_t(g, "mask"), memory_level_start_index=lsi, memory_spatial_shapes=sh)
+    y.backward(_t(g, "grad_out", dtype))
+    assert float(aloss) == 0.0
+    assert np.abs(y.detach().double().cpu().numpy() - g["out"]).max() < out_tol
+    assert rel_err(tgt.grad.double().cpu(), torch.from_numpy(g["grad_tgt"])) < grad_tol
+    assert rel_err(mem.grad.double().cpu(), torch.from_numpy(g["grad_memory"])) < grad_tol
+
+
+def test_layers_reject_the_bottleneck_adapter():
+    import ziragroundingdino_b200 as zb
+    with pytest.raises(NotImplementedError):
+        zb.DeformableTransformerEncoderLayer(use_adapter=True)
+    with pytest.raises(NotImplementedError):
+        zb.DeformableTransformerDecoderLayer(use_adapter=True)
+
+
+def test_decoder_layer_bf16_fused_vs_oracle():
+    """Model-sized decoder layer (C=256, 900 queries, Swin-T memory) in bf16 on the fused path against the oracle
+    restatement (oracle/cpu_encoder.decoder_layer, pinned to the reference fixture) in fp64 on the same parameters."""
+    import ziragroundingdino_b200 as zb
+    from oracle import cpu_encoder
+    torch.manual_seed(3)
+    C, FF, M, L, P, N, nq, nt = 256, 2048, 8, 4, 4, 2, 300, 16
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    layer = zb.DeformableTransformerDecoderLayer(C, FF, 0.0, "relu", L, M, P, use_text_cross_attention=True)
+    with torch.no_grad():
+        layer.cross_attn.sampling_offsets.weight.normal_(0, 0.01)
+        layer.cross_attn.attention_weights.weight.normal_(0, 0.05)
+    layer = layer.to(DEV).to(torch.bfloat16).eval()
+    sh = torch.tensor(shapes, device=DEV)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    bf = lambda *s: torch.randn(*s, device=DEV).to(torch.bfloat16)
+    tgt, qpos, mem, text = bf(nq, N, C), bf(nq, N, C), bf(S, N, C), bf(N, nt, C)
+    ref4 = torch.cat([torch.rand(nq, N, L, 2, device=DEV) * 0.8 + 0.1, torch.rand(nq, N, L, 2, device=DEV) * 0.4 + 0.05], -1).to(torch.bfloat16)
+    mask = torch.zeros(N, S, dtype=torch.bool, device=DEV)
+    mask[1, S - 100:] = True
+    tmask = torch.zeros(N, nt, dtype=torch.bool, device=DEV)
+    tmask[0, -3:] = True
+    y, _ = layer(tgt=tgt, tgt_query_pos=qpos, tgt_reference_points=ref4, memory_text=text, text_attention_mask=tmask,
+                 memory=mem, memory_key_padding_mask=mask, memory_level_start_index=lsi, memory_spatial_shapes=sh)
+    d = lambda t: t.detach().double().cpu()
+    p = {k: d(v) for k, v in layer.state_dict().items()}
+    ref = cpu_encoder.decoder_layer(p, d(tgt), d(qpos), d(ref4), d(mem), d(text), tmask.cpu(), sh.cpu(), mask.cpu(), M, L, P)
+    assert (d(y) - ref).abs().max().item() < 5e-2
+    assert rel_err(d(y), ref) < 1e-2

@@ -112,3 +112,31 @@ def test_rep_zero_conv2d_restatement_matches_reference(name):
     out_m, _ = O.rep_zero_conv2d(t["x"], *post, training=False, stride=stride, padding=padding)
     assert np.abs(out_m.numpy() - g["merged_eval_out"]).max() < 1e-13
     assert np.abs(g["merged_eval_out"] - g["train_out"]).max() < 1e-12
+
+
+def _layer_params(g):
+    return {k[6:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")}
+
+
+def test_encoder_layer_restatement_matches_reference():
+    """oracle.cpu_encoder.encoder_layer (the CPU arm of bench.py) against the reference's own
+    DeformableTransformerEncoderLayer (fixture generated from transformer_for_adapter.py:809-907)."""
+    from oracle import cpu_encoder
+    g = load_golden("layer_encoder")
+    C, FF, M, L, P = (int(v) for v in g["cfg"])
+    p = _layer_params(g)
+    p = {(k[len("self_attn."):] if k.startswith("self_attn.") else k): v for k, v in p.items()}
+    t = lambda k: torch.from_numpy(g[k])
+    out = cpu_encoder.encoder_layer(p, t("src"), t("pos"), t("reference_points"), t("shapes"), t("mask"), M, L, P)
+    assert np.abs(out.numpy() - g["out"]).max() < 1e-11
+    assert float(g["adapter_loss"][0]) == 0.0
+
+
+def test_decoder_layer_restatement_matches_reference():
+    from oracle import cpu_encoder
+    g = load_golden("layer_decoder")
+    C, FF, M, L, P = (int(v) for v in g["cfg"])
+    t = lambda k: torch.from_numpy(g[k])
+    out = cpu_encoder.decoder_layer(_layer_params(g), t("tgt"), t("query_pos"), t("reference_points"), t("memory"),
+                                    t("memory_text"), t("text_mask"), t("shapes"), t("mask"), M, L, P)
+    assert np.abs(out.numpy() - g["out"]).max() < 1e-11

@@ -5,6 +5,9 @@ from .ms_deform_attn import (MultiScaleDeformableAttention, MultiScaleDeformable
                              multi_scale_deformable_attn_pytorch)
 from .zira import RepZeroConv2d, RepZeroLinear, merge_all  # noqa: F401
 from .input_proj import ZiRaInputProj  # noqa: F401
+from .encoder import DeformableEncoder, DeformableTransformerEncoderLayer  # noqa: F401
+from .decoder import DeformableTransformerDecoderLayer  # noqa: F401
 
 __all__ = ["MultiScaleDeformableAttention", "MultiScaleDeformableAttnFunction", "RepZeroLinear", "RepZeroConv2d",
-           "ZiRaInputProj", "merge_all", "_C"]
+           "ZiRaInputProj", "DeformableTransformerEncoderLayer", "DeformableTransformerDecoderLayer", "DeformableEncoder",
+           "merge_all", "_C"]

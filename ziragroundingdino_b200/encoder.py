@@ -18,9 +18,13 @@ from .ms_deform_attn import MultiScaleDeformableAttention
 
 
 class DeformableTransformerEncoderLayer(nn.Module):
-    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4):
+    def __init__(self, d_model=256, d_ffn=1024, dropout=0.1, activation="relu", n_levels=4, n_heads=8, n_points=4,
+                 use_adapter=False, **unused):
         super().__init__()
         assert activation == "relu"
+        if use_adapter:
+            raise NotImplementedError("the bottleneck Adapter of the reference's encoder FFN is outside this path "
+                                      "(the ZiRa configuration sets use_adapter=False)")
         self.self_attn = MultiScaleDeformableAttention(embed_dim=d_model, num_levels=n_levels, num_heads=n_heads,
                                                        num_points=n_points, batch_first=True)
         self.dropout1 = nn.Dropout(dropout)
