@@ -28,9 +28,20 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IMAGES_PER_GPU = 4
+IMAGES_PER_GPU = 4          # config 2 (default); --config 4 switches to 8 (set_config)
 NUM_LAYERS = 6
+NUM_QUERIES = 900
 METRIC = "encoder6_msdeformattn_fwd_bwd_images_per_s"
+CONFIG = 2
+
+
+def set_config(cfg):
+    """--config 2 (default, BASELINE.json configs[1]) or --config 4 (configs[3]: the ZiRa fine-tuning step proxy of
+    SURVEY.md 8(d): input_proj + adapters -> 6 encoder layers -> 900 fixed queries -> 6 decoder layers -> L1 loss)."""
+    global IMAGES_PER_GPU, METRIC, CONFIG
+    CONFIG = cfg
+    if cfg == 4:
+        IMAGES_PER_GPU, METRIC = 8, "zira_step_images_per_s"
 
 
 def parse():
@@ -41,10 +52,25 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
-    return ap.parse_args()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json workload: 2 = configs[1] (default), "
+                    "4 = configs[3], the ZiRa step proxy with the decoder")
+    a = ap.parse_args()
+    set_config(a.config)
+    return a
 
 
 def workload_config(n_gpus):
+    if CONFIG == 4:
+        return {"workload": "config4: ZiRa fine-tuning step proxy -- synthetic Swin-T maps (192/384/768 ch) -> input_proj + trainable "
+                            "RepZeroConv2d adapters + GroupNorm -> 6 frozen deformable encoder layers -> 900 fixed-index queries -> 6 "
+                            "frozen decoder layers (MHA self-attn, MSDeformAttn cross-attn, FFN) -> L1 loss + 0.1 x zero-inter loss; "
+                            "AdamW lr 1e-3 wd 1e-4, grad-clip 0.1, one all-reduce of the adapter gradients",
+                "images_per_gpu": IMAGES_PER_GPU, "global_batch": IMAGES_PER_GPU * n_gpus, "image": "800x1333",
+                "levels": [[100, 167], [50, 84], [25, 42], [13, 21]], "tokens_per_image": 22223, "queries": NUM_QUERIES,
+                "d_model": 256, "heads": 8, "points": 4, "layers": "6 enc + 6 dec",
+                "padding": "per-image valid fraction 0.6-1.0 of the canvas", "parallelism": "dp%d" % n_gpus,
+                "omitted": "Swin backbone, BERT, text fusion / text cross-attention, two-stage query selection, Hungarian criterion",
+                "l2": "working set per step > 126 MB L2; no explicit flush"}
     return {"workload": "config2: GroundingDINO Swin-T 6-layer deformable encoder (MSDeformAttn + residual/LN + FFN 256-2048-256) "
                         "fwd+bwd, frozen layers; trainable ZiRa conv adapters on input_proj (192/384/768->256 1x1 + 3x3/s2 level, GroupNorm)",
             "images_per_gpu": IMAGES_PER_GPU, "global_batch": IMAGES_PER_GPU * n_gpus, "image": "800x1333",
@@ -67,7 +93,12 @@ def cpu_images_per_s(budget_s, threads):
     cpu_encoder.timed_front(syn.SWIN_T_800x1333, threads)                # warm-up
     t_front = cpu_encoder.timed_front(syn.SWIN_T_800x1333, threads)
     per_image = t * NUM_LAYERS / layers + t_front
-    return 1.0 / per_image, layers, t + t_front
+    t_dec = 0.0
+    if CONFIG == 4:
+        cpu_encoder.timed_decoder(syn.SWIN_T_800x1333, 1, threads)       # warm-up
+        t_dec = cpu_encoder.timed_decoder(syn.SWIN_T_800x1333, NUM_LAYERS, threads)
+        per_image += t_dec
+    return 1.0 / per_image, layers, t + t_front + t_dec
 
 
 def run_reference(args):
@@ -80,7 +111,8 @@ def run_reference(args):
     budget = min(30.0, 150.0 / (total + args.warmup))
     for i in range(args.warmup + total):
         ips, layers, t = cpu_images_per_s(budget, threads)
-        sample = "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers) fwd+bwd per step (fp32, torch CPU, grid_sample core)" % layers
+        sample = "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers%s) fwd+bwd per step (fp32, torch CPU, grid_sample core)" % (
+            layers, ", 6 decoder layers" if CONFIG == 4 else "")
         if i >= args.warmup:
             vals.append(ips)
     v = sum(vals) / len(vals)
@@ -167,6 +199,18 @@ def run_ours(args):
     enc = enc.to(dt)
     for p in enc.parameters():
         p.requires_grad_(False)
+    dec_layers = None
+    if CONFIG == 4:
+        from ziragroundingdino_b200.decoder import DeformableTransformerDecoderLayer
+        dec_layers = torch.nn.ModuleList([DeformableTransformerDecoderLayer(C, 2048, 0.0, "relu", len(shapes), 8, 4)
+                                          for _ in range(NUM_LAYERS)]).to(dev)
+        with torch.no_grad():
+            for layer in dec_layers:
+                layer.cross_attn.sampling_offsets.weight.normal_(0, 0.01)
+                layer.cross_attn.attention_weights.weight.normal_(0, 0.02)
+        dec_layers = dec_layers.to(dt)
+        for p in dec_layers.parameters():
+            p.requires_grad_(False)
     # front of the encoder = the reference's trainable part: frozen input_proj (1x1 convs over the Swin-T
     # maps 192/384/768 -> 256, 3x3/s2 extra level, GroupNorm(32)) with a trainable RepZeroConv2d adapter beside each conv
     front = zb.ZiRaInputProj((192, 384, 768), C, len(shapes)).to(dev)
@@ -202,12 +246,28 @@ def run_ours(args):
         return [packed[N * feat_off[i]:N * feat_off[i + 1]].view(N, feat_rows[i], c_) for i, c_ in enumerate((192, 384, 768))]
     loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
 
+    if CONFIG == 4:   # fixed random stand-ins for the two-stage query selection and the matched targets
+        q_idx = torch.randint(0, S, (N, NUM_QUERIES), generator=g).to(dev)
+        q_pos = torch.randn(NUM_QUERIES, N, C, generator=g).to(dt).to(dev)
+        boxes = torch.cat([torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.8 + 0.1,
+                           torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.45 + 0.05], -1).to(dev)
+        targets = torch.randn(NUM_QUERIES, N, C, generator=g).to(dev)
+        ref4 = (boxes[:, :, None, :] * torch.cat([valid, valid], -1)[None]).to(dt)       # transformer_for_adapter.py:720-724
+
     def fwd_bwd(feat_, pos_, mask_):
         src, proj_shapes, zloss = front.forward_rows(level_maps(feat_), feat_hw)
         assert proj_shapes == [tuple(x) for x in shapes]
         out = enc(src, pos_, shapes, sh, lsi, valid, mask_)
-        # mean(out^2) with fp32 accumulation and no fp32 copy of the 91 MB activation
-        loss = torch.linalg.vector_norm(out, 2, dtype=torch.float32).square() / out.numel() + 0.1 * zloss.float()
+        if CONFIG == 4:
+            tgt = torch.gather(out, 1, q_idx[:, :, None].expand(N, NUM_QUERIES, C)).transpose(0, 1)
+            memory = out.transpose(0, 1)
+            for layer in dec_layers:
+                tgt, _ = layer(tgt=tgt, tgt_query_pos=q_pos, tgt_reference_points=ref4, memory=memory,
+                               memory_key_padding_mask=mask_, memory_level_start_index=lsi, memory_spatial_shapes=sh)
+            loss = torch.nn.functional.l1_loss(tgt.float(), targets) + 0.1 * zloss.float()
+        else:
+            # mean(out^2) with fp32 accumulation and no fp32 copy of the 91 MB activation
+            loss = torch.linalg.vector_norm(out, 2, dtype=torch.float32).square() / out.numel() + 0.1 * zloss.float()
         loss.backward()
         return loss
 

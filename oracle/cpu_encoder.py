@@ -112,11 +112,41 @@ def decoder_layer(p, tgt, query_pos, ref4, memory, memory_text, text_mask, shape
     ln = lambda x, n: F.layer_norm(x, (C,), p[n + ".weight"], p[n + ".bias"])
     q = tgt + query_pos
     tgt = ln(tgt + multihead_attention(p, "self_attn.", q, q, tgt, M), "norm2")
-    text = memory_text.transpose(0, 1)
-    tgt = ln(tgt + multihead_attention(p, "ca_text.", tgt + query_pos, text, text, M, key_padding_mask=text_mask), "catext_norm")
+    if memory_text is not None:      # use_text_cross_attention
+        text = memory_text.transpose(0, 1)
+        tgt = ln(tgt + multihead_attention(p, "ca_text.", tgt + query_pos, text, text, M, key_padding_mask=text_mask), "catext_norm")
     attn_p = {k[len("cross_attn."):]: v for k, v in p.items() if k.startswith("cross_attn.")}
     tgt2 = O.module_forward(attn_p, (tgt + query_pos).transpose(0, 1), memory.transpose(0, 1), mask,
                             ref4.transpose(0, 1), shapes, M, L, P).transpose(0, 1)
     tgt = ln(tgt + tgt2, "norm1")
     ffn = F.linear(F.relu(F.linear(tgt, p["linear1.weight"], p["linear1.bias"])), p["linear2.weight"], p["linear2.bias"])
     return ln(tgt + ffn, "norm3")
+
+
+def timed_decoder(shapes, layers, threads, nq=900, d_model=256, M=8, P=4, seed=0):
+    """Seconds for one image's 900 queries through `layers` decoder layers (no text cross-attention) fwd+bwd, fp32;
+    gradients flow to the queries and to the encoder memory as in the training step."""
+    torch.set_num_threads(threads)
+    L = len(shapes)
+    S = sum(h * w for h, w in shapes)
+    g = torch.Generator().manual_seed(seed)
+    sh = torch.tensor(shapes, dtype=torch.long)
+    r = lambda *s, std=0.02: torch.randn(*s, generator=g) * std
+    params = []
+    for i in range(layers):
+        p = {("cross_attn." + k if k.split(".")[0] in ("value_proj", "sampling_offsets", "attention_weights", "output_proj") else k): v
+             for k, v in make_layer_params(d_model, 2048, M, L, P, seed + i).items()}
+        p.update({"self_attn.in_proj_weight": r(3 * d_model, d_model, std=0.06), "self_attn.in_proj_bias": torch.zeros(3 * d_model),
+                  "self_attn.out_proj.weight": r(d_model, d_model, std=0.06), "self_attn.out_proj.bias": torch.zeros(d_model),
+                  "norm3.weight": torch.ones(d_model), "norm3.bias": torch.zeros(d_model)})
+        params.append(p)
+    memory = torch.randn(S, 1, d_model, generator=g).requires_grad_(True)
+    tgt = torch.randn(nq, 1, d_model, generator=g).requires_grad_(True)
+    qpos = torch.randn(nq, 1, d_model, generator=g)
+    ref4 = torch.cat([torch.rand(nq, 1, L, 2, generator=g) * 0.8 + 0.1, torch.rand(nq, 1, L, 2, generator=g) * 0.45 + 0.05], -1)
+    t0 = time.perf_counter()
+    x = tgt
+    for p in params:
+        x = decoder_layer(p, x, qpos, ref4, memory, None, None, sh, None, M, L, P)
+    x.abs().mean().backward()
+    return time.perf_counter() - t0
