@@ -404,6 +404,21 @@ def run_ours(args):
     us_fwd = kernel_us(lambda: zb._C.ms_deform_attn_forward(*cargs, 64))
     us_bwd = kernel_us(lambda: zb._C.ms_deform_attn_backward(*cargs, inp["grad_out"], 64))
 
+    # live probes of the two memory-system limits these kernels run against (nothing but the access shape):
+    #   gather : random 64-byte rows (one bf16 head row) read from an L2-resident 22 MB buffer
+    #   scatter: random 128-byte fp32 rows sent with red.global.add.v4.f32 into an L2-resident 91 MB buffer
+    Lc = _lib.lib()
+    pbuf = torch.zeros(91 << 18, dtype=torch.float32, device=dev)
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    cs = torch.cuda.current_stream().cuda_stream
+    g_blocks, g_iters, s_blocks, s_iters = 148 * 16, 512, 148 * 16, 256
+    us_pg = kernel_us(lambda: Lc.msda_b200_probe_gather(pbuf.data_ptr(), 22 << 20, 64, g_iters, g_blocks, sink.data_ptr(), cs), 5)
+    us_ps = kernel_us(lambda: Lc.msda_b200_probe_scatter(pbuf.data_ptr(), pbuf.numel() * 4, 0, s_iters, s_blocks, cs), 5)
+    gather_peak = g_blocks * 256 * 16 * g_iters / us_pg / 1e3           # GB/s
+    scatter_peak = s_blocks * 256 * 16 * s_iters / us_ps / 1e3          # GB/s of reduction payload
+    red_bytes = N * inp["dims"][5] * inp["dims"][2] * inp["dims"][4] * inp["dims"][6] * 4 * 128   # one 128 B fp32 row per corner
+    del pbuf
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -435,12 +450,19 @@ def run_ours(args):
                      "peak": hbm_peak, "unit": "GB/s", "frac": ab["bwd_hbm"] / us_bwd / 1e3 / hbm_peak, "traffic": traffic,
                      "algorithmic_bytes": ab["bwd_hbm"],
                      "peak_source": peak_src,
-                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by L1TEX->XBAR reduction "
-                             "requests (ncu: l1tex 86 %, lts 69 %, DRAM 6 %), not HBM -- see DESIGN.md 4.2 and profiles/"},
+                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by the L2 reduction rate "
+                             "(roofline_l2_scatter; ncu: l1tex 86 %, lts 69 %, DRAM 6 %), not HBM -- see DESIGN.md 4.2 and profiles/"},
         "roofline_l2": {"kernels": "msda_fwd_vec_kernel + msda_bwd_vec_kernel", "bound": "l2-gather",
-                        "achieved": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3, "peak": 15900.0, "unit": "GB/s",
-                        "frac": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3 / 15900.0,
-                        "peak_source": "msda_b200_probe_gather, random 64 B segments of an L2-resident buffer (profiles/r1_sweep_core_first.jsonl)"},
+                        "achieved": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3, "peak": gather_peak, "unit": "GB/s",
+                        "frac": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3 / gather_peak,
+                        "peak_source": "msda_b200_probe_gather run in this process: random 64 B rows of an L2-resident 22 MB buffer"},
+        "roofline_l2_scatter": {"kernel": "msda_bwd_vec_kernel<bf16,32>", "bound": "l2-reduction",
+                                "achieved": red_bytes / us_bwd / 1e3, "peak": scatter_peak, "unit": "GB/s",
+                                "frac": red_bytes / us_bwd / 1e3 / scatter_peak, "reduction_bytes": red_bytes,
+                                "peak_source": "msda_b200_probe_scatter run in this process: red.global.add.v4.f32 of random 128 B "
+                                               "rows into an L2-resident 91 MB buffer, nothing else in flight",
+                                "note": "grad_value leaves the SM as one 128-byte fp32 reduction per bilinear corner "
+                                        "(N*Lq*M*L*P*4 rows); the kernel also re-gathers value and writes grad_loc / grad_aw"},
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1

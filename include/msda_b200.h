@@ -142,6 +142,12 @@ int msda_linear_16(const void *x, const void *w, const float *bias, long long R,
  * the dgrad GEMM of linear2.  16-bit output, leading dimension Nout; Nout <= 2048. */
 int msda_linear_act_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out, int relu,
                        const void *gate, int is_half, void *stream);
+/* The same two fusions with the ReLU mask kept as ONE BIT per activation instead of re-reading the 16-bit activation in
+ * the backward: a forward launch (relu_bits_out != NULL) applies bias + ReLU and also writes bits[(c/32) * R + row]
+ * (bit j = out[row, c + j] > 0; [Nout/32, R] uint32, word-major); the backward launch (gate_bits != NULL) keeps acc where
+ * the bit is set.  Exactly one of the two pointers must be non-NULL.  Nout % 32 == 0. */
+int msda_linear_act_bits_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out,
+                            uint32_t *relu_bits_out, const uint32_t *gate_bits, int is_half, void *stream);
 int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_cat, const float *ref, int ref_dim,
                        const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
                        float *aw_out, int is_half, void *stream);
@@ -211,6 +217,10 @@ int msda_group_norm_bwd_16(const void *dy, long long dy_image_stride, const void
  * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */
 int msda_b200_probe_gather(const void *buf, long long bytes, int seg_bytes, int iters, int blocks, void *sink,
                            void *stream);
+/* Scatter twin: groups of lanes send 128-byte fp32 rows to random 128 B-aligned rows of `buf` (bytes long, fp32,
+ * contents are modified).  mode 0 = red.global.add.v4.f32 x 8 lanes (the backward kernel's instruction), 1 = st.global.v4
+ * x 8 lanes, 2 = scalar red.global.add.f32 x 32 lanes.  Row payload moved = blocks * 256 * iters * (mode == 2 ? 4 : 16) bytes. */
+int msda_b200_probe_scatter(void *buf, long long bytes, int mode, int iters, int blocks, void *stream);
 
 #ifdef __cplusplus
 }

@@ -350,6 +350,42 @@ def test_ffn_fused(dtype, eps16, gate_fused, monkeypatch):
         assert rel_err(a.grad.double().cpu(), b.grad.cpu()) < 6 * eps16, n
 
 
+@pytest.mark.parametrize("staged", [False, True])
+@pytest.mark.parametrize("dtype,eps16", [(torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)])
+@pytest.mark.parametrize("R", [1111, 128, 77])
+def test_ffn_frozen_weights_bit_gate(dtype, eps16, R, staged):
+    """Frozen FFN weights: the forward keeps one bit per hidden activation and the backward's gated dgrad reads the bits
+    (msda_linear_act_bits_16).  The result must equal the 16-bit-gate path exactly (same arithmetic, same mask) and match
+    torch fp64; also through the non-TMA store path."""
+    from ziragroundingdino_b200 import _lib
+    from ziragroundingdino_b200.layer_ops import FFN16Function
+    C, Fh = 256, 2048
+    x = _rand((R, C), dtype, 61)
+    w1, b1 = _rand((Fh, C), dtype, 62, 0.06), _rand((Fh,), dtype, 63, 0.1)
+    w2, b2 = _rand((C, Fh), dtype, 64, 0.03), _rand((C,), dtype, 65, 0.1)
+    gy = _rand((R, C), dtype, 66)
+    _lib.lib().msda_b200_gemm_set_staged(0 if staged else 1)
+    try:
+        res = []
+        for bits in (True, False):
+            FFN16Function.bit_gate_when_frozen = bits
+            xi = x.clone().requires_grad_(True)
+            y = FFN16Function.apply(xi, w1, b1, w2, b2)
+            y.backward(gy)
+            res.append((y.detach(), xi.grad))
+    finally:
+        FFN16Function.bit_gate_when_frozen = True
+        _lib.lib().msda_b200_gemm_set_staged(1)
+    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
+    xd = x.double().requires_grad_(True)
+    h = torch.relu(torch.nn.functional.linear(xd, w1.double(), b1.double()))
+    h16 = h.detach().to(dtype).double()
+    yd = torch.nn.functional.linear(h + (h16 - h.detach()), w2.double(), b2.double())
+    yd.backward(gy.double())
+    assert (res[0][0].double() - yd.detach()).abs().max().item() <= 3 * eps16 * yd.abs().max().item()
+    assert rel_err(res[0][1].double().cpu(), xd.grad.cpu()) < 6 * eps16
+
+
 def test_encoder_layer_fused_vs_library_ops():
     """Encoder layer with the fused residual+LayerNorm / FFN pieces vs the same layer on library ops (bf16)."""
     import ziragroundingdino_b200 as zb

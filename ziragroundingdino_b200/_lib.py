@@ -47,6 +47,7 @@ def lib():
     L.msda_b200_gemm_last_error.restype = ctypes.c_char_p
     L.msda_linear_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp]
     L.msda_linear_act_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp]
+    L.msda_linear_act_bits_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _vp]
     L.msda_query_proj_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]
     L.msda_query_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _i, _i, _vp]
     L.msda_cast_mask_16.argtypes = [_vp, _vp, _ll, _i, _vp, _i, _vp]
@@ -59,6 +60,7 @@ def lib():
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]
     L.msda_query_post_f32.argtypes = [_vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
+    L.msda_b200_probe_scatter.argtypes = [_vp, _ll, _i, _i, _i, _vp]
     _lib = L
     return L
 

@@ -34,7 +34,41 @@ __global__ void __launch_bounds__(256) gather_probe_kernel(const uint4* __restri
   }
   if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) sink[0] = tid;  // keep the loads alive
 }
+
+// Scatter twin of the probe above: groups of 8 lanes send one 128-byte fp32 row (red.global.add.v4.f32 per lane, the
+// instruction the backward kernel uses for grad_value) to random 128 B-aligned rows of an L2-sized buffer, nothing else
+// in the way.  MODE 0 = red.v4.f32, 1 = st.global.v4 (plain store, same shape), 2 = scalar red.f32 (32 lanes per row).
+template <int MODE>
+__global__ void __launch_bounds__(256) scatter_probe_kernel(float* __restrict__ buf, uint32_t nrow, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  constexpr int LPG = MODE == 2 ? 32 : 8;
+  const uint32_t group = tid / LPG, lig = tid % LPG;
+  const float v = 1e-6f * static_cast<float>(lig);
+  for (int i = 0; i < iters; ++i) {
+    const uint32_t row = mix(group * 2654435761u + static_cast<uint32_t>(i) * 40503u) % nrow;
+    float* p = buf + static_cast<size_t>(row) * 32;
+    if (MODE == 0)
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p + lig * 4), "f"(v), "f"(v), "f"(v), "f"(v) : "memory");
+    else if (MODE == 1)
+      asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p + lig * 4), "f"(v), "f"(v), "f"(v), "f"(v) : "memory");
+    else
+      asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p + lig), "f"(v) : "memory");
+  }
+}
 }  // namespace
+
+extern "C" int msda_b200_probe_scatter(void* buf, long long bytes, int mode, int iters, int blocks, void* stream) {
+  if (!buf || bytes < 128 || iters <= 0 || blocks <= 0) return MSDA_ERR_BAD_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const uint32_t nrow = static_cast<uint32_t>(bytes / 128);
+  float* b = static_cast<float*>(buf);
+  if (mode == 0) scatter_probe_kernel<0><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 1) scatter_probe_kernel<1><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 2) scatter_probe_kernel<2><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else return MSDA_ERR_UNSUPPORTED;
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
 
 extern "C" int msda_b200_probe_gather(const void* buf, long long bytes, int seg_bytes, int iters, int blocks,
                                       void* sink, void* stream) {

@@ -67,6 +67,10 @@ struct EpiParams {
   const uint8_t* row_mask; // [R] or null
   int relu;                // max(., 0) after the bias
   const void* gate;        // optional 16-bit [R, out_ld]: out = acc where gate > 0 else 0 (ReLU backward fused in a dgrad)
+  // 1-bit form of the same gate: word (c / 32) * R + row holds bits (column c + j > 0), j = 0..31 -- [Nout/32, R]
+  // uint32, word-major so that the 32 lanes (rows) of a warp read / write 128 contiguous bytes.
+  uint32_t* relu_bits;       // written by a RELU launch (may be null)
+  const uint32_t* gate_bits; // read by a GATE launch instead of `gate` (may be null)
   // EPI_QUERY: columns [0, n_loc) are sampling offsets laid out (m, l, p, xy); columns [n_loc, n_loc + n_aw)
   // are attention logits laid out (m, l*p).
   float* loc_out;          // [R, n_loc]
@@ -479,12 +483,23 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             gnext[it] = (rr < rows_valid) ? __ldg(reinterpret_cast<const uint4*>(g + rr * 2ll * ep.out_ld + g_j * 16)) : make_uint4(0u, 0u, 0u, 0u);
           }
         };
-        if (GATE && chunk_par * 64 < block_n) gate_fetch(chunk_par * 64);
+        const bool bit_gate = GATE && ep.gate_bits != nullptr;
+        uint32_t gb_next[2] = {0u, 0u};
+        auto bits_fetch = [&](int c) {   // this row's two gate words of a 64-column step, one step ahead
+          if (live) {
+            gb_next[0] = __ldg(ep.gate_bits + static_cast<size_t>((n_idx + c) >> 5) * R + row);
+            gb_next[1] = __ldg(ep.gate_bits + static_cast<size_t>(((n_idx + c) >> 5) + 1) * R + row);
+          }
+        };
+        if (GATE && chunk_par * 64 < block_n) { if (bit_gate) bits_fetch(chunk_par * 64); else gate_fetch(chunk_par * 64); }
         for (int c0 = chunk_par * 64; c0 < block_n; c0 += 128) {
           const int gc = n_idx + c0;
           uint8_t* tile = tile0 + buf * TMA_TILE_BYTES;
           uint4 gt[8];
-          if (GATE) {
+          uint32_t gb[2] = {gb_next[0], gb_next[1]};
+          if (GATE && bit_gate) {
+            if (c0 + 128 < block_n) bits_fetch(c0 + 128);
+          } else if (GATE) {
             // the gate transposition reuses the tile: the store that last used it must have read it
             if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
             __syncwarp();
@@ -512,7 +527,17 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (GATE) {
+            if (RELU && ep.relu_bits != nullptr) {   // 1 bit per activation for the backward's gate (word-major: coalesced)
+              uint32_t m = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+              if (live) ep.relu_bits[static_cast<size_t>((gc >> 5) + hf) * R + row] = m;
+            }
+            if (GATE && bit_gate) {
+              const uint32_t m = gb[hf];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (m >> j) & 1u ? v[j] : 0.f;
+            } else if (GATE) {
               const uint32_t* gw = reinterpret_cast<const uint32_t*>(gt) + 16 * hf;
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -523,7 +548,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             uint4 pk[4];
             pack_16(v, HALF_OUT, zero, pk);
-            if (!GATE && hf == 0) {   // wait as late as possible: the previous store's smem read overlaps this step's TMEM load + math
+            if ((!GATE || bit_gate) && hf == 0) {   // wait as late as possible: the previous store's smem read overlaps this step's TMEM load + math
               if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
               __syncwarp();
             }
@@ -592,11 +617,15 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             gnext[it] = (rr < rows_valid) ? __ldg(reinterpret_cast<const uint4*>(g + rr * 2ll * ep.out_ld + g_c16 * 16)) : make_uint4(0u, 0u, 0u, 0u);
           }
         };
-        if (GATE && chunk_par * 32 < block_n) gate_fetch(chunk_par * 32);
+        const bool bit_gate = GATE && ep.gate_bits != nullptr;
+        if (GATE && !bit_gate && chunk_par * 32 < block_n) gate_fetch(chunk_par * 32);
         for (int c0 = chunk_par * 32; c0 < block_n; c0 += 64) {
           const int gc = n_idx + c0;
           uint4 gt[4];
-          if (GATE) {
+          uint32_t gbw = 0u;
+          if (GATE && bit_gate) {
+            if (live) gbw = __ldg(ep.gate_bits + static_cast<size_t>(gc >> 5) * R + row);
+          } else if (GATE) {
 #pragma unroll
             for (int it = 0; it < 4; ++it) *reinterpret_cast<uint4*>(stage + (it * 8 + g_rsub) * 80 + g_c16 * 16) = gnext[it];
             __syncwarp();
@@ -620,7 +649,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
             }
-            if (GATE) {   // keep where the gate activation is positive: ReLU backward fused into the dgrad
+            if (RELU && ep.relu_bits != nullptr) {
+              uint32_t m = 0u;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m |= (v[j] > 0.f ? 1u : 0u) << j;
+              if (live) ep.relu_bits[static_cast<size_t>(gc >> 5) * R + row] = m;
+            }
+            if (GATE && bit_gate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = (gbw >> j) & 1u ? v[j] : 0.f;
+            } else if (GATE) {   // keep where the gate activation is positive: ReLU backward fused into the dgrad
               const uint32_t* gw = reinterpret_cast<const uint32_t*>(gt);
 #pragma unroll
               for (int j = 0; j < 16; ++j) {
@@ -843,7 +881,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   if (ep.mode == EPI_QUERY) { if (tma_out) PG_LAUNCH(EPI_QUERY, true, false, false, false, true); else PG_LAUNCH(EPI_QUERY, true, false, false, false, false); }
   else if (ep.mode == EPI_ZIRA) { if (half_out) PG_LAUNCH(EPI_ZIRA, false, true, false, false, false); else PG_LAUNCH(EPI_ZIRA, false, false, false, false, false); }
   else if (ep.out_f32) PG_LAUNCH(EPI_STORE, true, false, false, false, false);
-  else if (ep.gate) PG_STORE16(false, true);
+  else if (ep.gate || ep.gate_bits) PG_STORE16(false, true);
   else if (ep.relu) PG_STORE16(true, false);
   else PG_STORE16(false, false);
 #undef PG_STORE16
@@ -887,6 +925,23 @@ int msda_linear_act_16(const void* x, const void* w, const float* bias, long lon
   memset(&ep, 0, sizeof(ep));
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.relu = relu; ep.gate = gate;
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+int msda_linear_act_bits_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out,
+                            uint32_t* relu_bits_out, const uint32_t* gate_bits, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out) { snprintf(pg::t_err, sizeof(pg::t_err), "null output"); return MSDA_ERR_NULL_POINTER; }
+  if ((relu_bits_out != nullptr) == (gate_bits != nullptr)) {
+    snprintf(pg::t_err, sizeof(pg::t_err), "exactly one of relu_bits_out / gate_bits must be given");
+    return MSDA_ERR_BAD_SHAPE;
+  }
+  if (Nout % 32) { snprintf(pg::t_err, sizeof(pg::t_err), "bit gates need Nout %% 32 == 0"); return MSDA_ERR_UNSUPPORTED; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias;
+  ep.relu = relu_bits_out != nullptr; ep.relu_bits = relu_bits_out; ep.gate_bits = gate_bits;
   return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 

@@ -128,6 +128,20 @@ def _linear_act16(x2d, w, bias_f32, relu=False, gate=None):
     return out
 
 
+def _linear_act_bits16(x2d, w, bias_f32, relu_bits=None, gate_bits=None):
+    """msda_linear_act_bits_16: bias + ReLU writing the 1-bit mask (relu_bits given, filled) or a gated store (gate_bits)."""
+    R, K = x2d.shape
+    Nout = w.shape[0]
+    out = torch.empty((R, Nout), dtype=x2d.dtype, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_act_bits_16(x2d.data_ptr(), w.data_ptr(), 0 if bias_f32 is None else bias_f32.data_ptr(), R, K,
+                                                Nout, out.data_ptr(), 0 if relu_bits is None else relu_bits.data_ptr(),
+                                                0 if gate_bits is None else gate_bits.data_ptr(),
+                                                1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_linear_act_bits_16")
+    return out
+
+
 class FFN16Function(Function):
     """``linear2(relu(linear1(x)))`` on 16-bit activations (reference transformer_for_adapter.py:880-881).
 
@@ -139,22 +153,39 @@ class FFN16Function(Function):
     # Measured on B200 (profiles/r1_gemm_ab.txt, R = 88 892): fused bias+ReLU forward 115 us vs cuBLAS + ReLU kernel 230 us;
     # gated dgrad 227 us vs cuBLAS + threshold kernel 250 us.  The switch exists for A/B runs.
     fuse_relu_backward = True
+    # Frozen FFN weights (the ZiRa configuration): the backward needs relu'(h) only, so the forward keeps ONE BIT per hidden
+    # activation ([d_ffn/32, R] words written by the same epilogue) and frees the 2048-wide activation: the gated dgrad then
+    # streams its 364 MB output without reading 364 MB of h back (HBM moves ~3.9 TB/s per direction on this part).
+    bit_gate_when_frozen = True
 
     @staticmethod
     def forward(ctx, x, w1, b1, w2, b2):
         shape = x.shape
         x2d = x.reshape(-1, shape[-1]).contiguous()
+        ctx.shape = shape
+        ctx.bits = (FFN16Function.bit_gate_when_frozen and FFN16Function.fuse_relu_backward and not any(ctx.needs_input_grad[1:])
+                    and w1.shape[0] % 32 == 0)
+        if ctx.bits:
+            bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
+            h = _linear_act_bits16(x2d, w1.contiguous(), b1.float(), relu_bits=bits)
+            y = torch.nn.functional.linear(h, w2, b2)
+            ctx.save_for_backward(bits, w1, w2)
+            return y.view(*shape[:-1], w2.shape[0])
         h = _linear_act16(x2d, w1.contiguous(), b1.float(), relu=True)
         y = torch.nn.functional.linear(h, w2, b2)
         ctx.save_for_backward(x2d, h, w1, w2)
-        ctx.shape = shape
         return y.view(*shape[:-1], w2.shape[0])
 
     @staticmethod
     @once_differentiable
     def backward(ctx, dy):
-        x2d, h, w1, w2 = ctx.saved_tensors
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        if ctx.bits:
+            bits, w1, w2 = ctx.saved_tensors
+            dh = _linear_act_bits16(dy2, w2.t().contiguous(), None, gate_bits=bits)
+            dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
+            return dx, None, None, None, None
+        x2d, h, w1, w2 = ctx.saved_tensors
         if FFN16Function.fuse_relu_backward:
             dh = _linear_act16(dy2, w2.t().contiguous(), None, gate=h)    # (dy W2) gated by relu'(.) in the GEMM epilogue
         else:
