@@ -1,4 +1,6 @@
 """Fused pieces of the encoder layer around MultiScaleDeformableAttention."""
+import weakref
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -8,6 +10,28 @@ from . import _lib
 
 def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+_DERIVED = {}
+
+
+def derived(p, kind):
+    """Kernel-ready form of a parameter -- ``"f32"`` (fp32 contiguous copy: LayerNorm / GroupNorm affine, biases) or
+    ``"t"`` (contiguous transpose: the dgrad operand) -- built once per parameter version instead of once per call
+    (the layers around the path are frozen in the ZiRa configuration; each rebuild is a ~3 us kernel, ~60 per step).
+    Nothing is cached while a CUDA graph is being captured (the copy would live in the graph's private pool)."""
+    key = (id(p), kind)
+    ent = _DERIVED.get(key)
+    if ent is not None and ent[0]() is p and ent[1] == (p._version, p.data_ptr(), p.dtype, p.device):
+        return ent[2]
+    with torch.no_grad():
+        v = p.detach().float().contiguous() if kind == "f32" else p.detach().t().contiguous()
+    if not (p.is_cuda and torch.cuda.is_current_stream_capturing()):
+        if len(_DERIVED) > 1024:                      # entries of parameters that no longer exist
+            for k in [k for k, e in _DERIVED.items() if e[0]() is None]:
+                del _DERIVED[k]
+        _DERIVED[key] = (weakref.ref(p), (p._version, p.data_ptr(), p.dtype, p.device), v)
+    return v
 
 
 class AddLayerNormFunction(Function):
@@ -23,7 +47,7 @@ class AddLayerNormFunction(Function):
         z, y = torch.empty_like(x2), torch.empty_like(x2)
         mean = torch.empty(R, dtype=torch.float32, device=x.device)
         rstd = torch.empty(R, dtype=torch.float32, device=x.device)
-        g32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        g32, b32 = derived(weight, "f32"), derived(bias, "f32")
         with torch.cuda.device(x.device):
             rc = _lib.lib().msda_add_layernorm_fwd_16(x2.data_ptr(), r2.data_ptr(), g32.data_ptr(), b32.data_ptr(), R, C, float(eps),
                                                       z.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
@@ -74,7 +98,7 @@ class GroupNormRowsFunction(Function):
     def forward(ctx, x, weight, bias, G, eps):
         N, HW, C = x.shape
         x = x.contiguous()
-        g32, b32 = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        g32, b32 = derived(weight, "f32"), derived(bias, "f32")
         y = torch.empty_like(x)
         mean_rstd = torch.empty((N, G, 2), dtype=torch.float32, device=x.device)
         scratch = torch.zeros((N, C, 2), dtype=torch.float64, device=x.device)
@@ -167,11 +191,11 @@ class FFN16Function(Function):
                     and w1.shape[0] % 32 == 0)
         if ctx.bits:
             bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
-            h = _linear_act_bits16(x2d, w1.contiguous(), b1.float(), relu_bits=bits)
+            h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
             y = torch.nn.functional.linear(h, w2, b2)
             ctx.save_for_backward(bits, w1, w2)
             return y.view(*shape[:-1], w2.shape[0])
-        h = _linear_act16(x2d, w1.contiguous(), b1.float(), relu=True)
+        h = _linear_act16(x2d, w1.contiguous(), derived(b1, "f32"), relu=True)
         y = torch.nn.functional.linear(h, w2, b2)
         ctx.save_for_backward(x2d, h, w1, w2)
         return y.view(*shape[:-1], w2.shape[0])
@@ -182,12 +206,12 @@ class FFN16Function(Function):
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         if ctx.bits:
             bits, w1, w2 = ctx.saved_tensors
-            dh = _linear_act_bits16(dy2, w2.t().contiguous(), None, gate_bits=bits)
+            dh = _linear_act_bits16(dy2, derived(w2, "t"), None, gate_bits=bits)
             dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
             return dx, None, None, None, None
         x2d, h, w1, w2 = ctx.saved_tensors
         if FFN16Function.fuse_relu_backward:
-            dh = _linear_act16(dy2, w2.t().contiguous(), None, gate=h)    # (dy W2) gated by relu'(.) in the GEMM epilogue
+            dh = _linear_act16(dy2, derived(w2, "t"), None, gate=h)    # (dy W2) gated by relu'(.) in the GEMM epilogue
         else:
             dh = torch.ops.aten.threshold_backward(dy2 @ w2, h, 0)
         dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
