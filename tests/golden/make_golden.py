@@ -12,6 +12,7 @@ Sources exercised (relative to /root/reference/groundingdino/models/GroundingDIN
   groundingdino_dual_zero_rep_branch.py:62-64, :105-135  RepZeroLinear (train / eval / __rep__)
   groundingdino_dual_zero_rep_branch.py:64-103, :492-493 RepZeroConv2d and its use beside input_proj
   transformer_for_adapter.py:809-907, :910-1073  DeformableTransformerEncoderLayer / DecoderLayer (use_adapter=False)
+  utils.py:56-116, transformer_for_adapter.py:216-262, :311-329  proposals, valid ratios, flatten, top-k selection
 """
 import ast
 import importlib.util
@@ -297,6 +298,64 @@ def layer_cases(ref, seed):
     return out
 
 
+def transformer_io_case(seed):
+    """gen_encoder_output_proposals (utils.py:56-116) and Transformer.get_valid_ratio (transformer_for_adapter.py:216-223)
+    executed from their AST, plus the inline flatten / top-k code of Transformer.forward (:238-262, :311-329) run on the
+    same inputs as literal statements (they are not separate functions in the reference)."""
+    ns = {"torch": torch, "Tensor": torch.Tensor}
+    tree = ast.parse(open(os.path.join(REF_DIR, "utils.py")).read())
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "gen_encoder_output_proposals"]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "utils.py", "exec"), ns)
+    tree = ast.parse(open(os.path.join(REF_DIR, "transformer_for_adapter.py")).read())
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == "Transformer":
+            keep = [n for n in node.body if isinstance(n, ast.FunctionDef) and n.name == "get_valid_ratio"]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "transformer_for_adapter.py", "exec"), ns)
+    torch.manual_seed(seed)
+    N, C, nq = 2, 8, 5
+    shapes = [(6, 8), (3, 4), (2, 2)]
+    masks = []
+    for (h, w), (vh, vw) in zip(shapes, [(6, 8), (3, 4), (2, 2)]):
+        m = torch.zeros(N, h, w, dtype=torch.bool)
+        m[1, max(1, int(h * 0.7)):, :] = True
+        m[1, :, max(1, int(w * 0.6)):] = True
+        masks.append(m)
+    srcs = [torch.randn(N, C, h, w, dtype=torch.float64) for h, w in shapes]
+    poss = [torch.randn(N, C, h, w, dtype=torch.float64) for h, w in shapes]
+    level_embed = torch.randn(len(shapes), C, dtype=torch.float64)
+    # :238-262
+    src_flatten, mask_flatten, lvl_pos = [], [], []
+    for lvl, (src, mask, pos_embed) in enumerate(zip(srcs, masks, poss)):
+        src_flatten.append(src.flatten(2).transpose(1, 2))
+        mask_flatten.append(mask.flatten(1))
+        lvl_pos.append(pos_embed.flatten(2).transpose(1, 2) + level_embed[lvl].view(1, 1, -1))
+    src_flatten, mask_flatten, lvl_pos = torch.cat(src_flatten, 1), torch.cat(mask_flatten, 1), torch.cat(lvl_pos, 1)
+    spatial_shapes = torch.as_tensor(shapes, dtype=torch.long)
+    level_start_index = torch.cat((spatial_shapes.new_zeros((1,)), spatial_shapes.prod(1).cumsum(0)[:-1]))
+    valid_ratios = torch.stack([ns["get_valid_ratio"](None, m) for m in masks], 1)
+    res = {"shapes": spatial_shapes.numpy(), "level_embed": level_embed.numpy(), "src_flatten": src_flatten.numpy(),
+           "mask_flatten": mask_flatten.numpy(), "lvl_pos_embed_flatten": lvl_pos.numpy(),
+           "level_start_index": level_start_index.numpy(), "valid_ratios": valid_ratios.numpy()}
+    for i, (s_, m_, p_) in enumerate(zip(srcs, masks, poss)):
+        res["src%d" % i], res["mask%d" % i], res["pos%d" % i] = s_.numpy(), m_.numpy(), p_.numpy()
+    memory = torch.randn(N, src_flatten.shape[1], C, dtype=torch.float64)
+    for name, lw in (("", None), ("_learnedwh", torch.tensor([0.3, -0.2], dtype=torch.float64))):
+        om, op = ns["gen_encoder_output_proposals"](memory, mask_flatten, spatial_shapes, lw)
+        res["output_memory" + name], res["output_proposals" + name] = om.numpy(), op.numpy()
+    res["memory"], res["learnedwh"] = memory.numpy(), np.array([0.3, -0.2])
+    # :311-329
+    om, op = ns["gen_encoder_output_proposals"](memory, mask_flatten, spatial_shapes)
+    logits = torch.randn(N, src_flatten.shape[1], 6, dtype=torch.float64)
+    coord = torch.randn(N, src_flatten.shape[1], 4, dtype=torch.float64) + op.masked_fill(op.isinf(), 0.0)
+    topk_logits = logits.max(-1)[0]
+    topk_proposals = torch.topk(topk_logits, nq, dim=1)[1]
+    res.update(class_logits=logits.numpy(), coord_unselected=coord.numpy(), topk_proposals=topk_proposals.numpy(),
+               refpoint_embed_undetach=torch.gather(coord, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).numpy(),
+               init_box_proposal=torch.gather(op, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, 4)).sigmoid().numpy(),
+               tgt_undetach=torch.gather(om, 1, topk_proposals.unsqueeze(-1).repeat(1, 1, C)).numpy())
+    return res
+
+
 def main():
     ref = load_reference_msda()
     cases = {
@@ -317,6 +376,7 @@ def main():
     cases["zira_rep_conv1x1"] = zira_conv_case(conv, 32, 24, 16, 4, 1, 1, 0, (5, 6))
     cases["zira_rep_conv3x3s2"] = zira_conv_case(conv, 33, 12, 16, 4, 3, 2, 1, (7, 6))
     cases.update(layer_cases(ref, 41))
+    cases["transformer_io"] = transformer_io_case(51)
     total = 0
     for name, arrs in cases.items():
         p = os.path.join(OUT, name + ".npz")
