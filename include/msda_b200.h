@@ -137,6 +137,11 @@ long long msda_b200_launch_count(void);
  * msda_query_bwd_prep_16 / msda_cast_mask_16: elementwise backward companions (see proj_elementwise.cu). */
 int msda_linear_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, void *out,
                    int out_ld, int out_f32, const uint8_t *row_mask, int is_half, void *stream);
+/* out = accum + x W^T + bias, all 16-bit [R, Nout]: the dgrad of a projection added straight onto the gradient that is
+ * already there (residual path, other consumers of the same activation) instead of a separate elementwise add pass.
+ * `out` may alias `accum`.  Nout % 8 == 0. */
+int msda_linear_accum_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, const void *accum,
+                         void *out, int is_half, void *stream);
 /* FFN companions (row N1; reference transformer_for_adapter.py:876-885): out = relu(x W^T + bias) when relu != 0, and
  * out = (x W^T + bias) where gate > 0 else 0 when gate != NULL (gate: 16-bit [R, Nout]) -- the ReLU backward fused into
  * the dgrad GEMM of linear2.  16-bit output, leading dimension Nout; Nout <= 2048. */

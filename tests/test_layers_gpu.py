@@ -100,3 +100,80 @@ def test_decoder_layer_bf16_fused_vs_oracle():
     ref = cpu_encoder.decoder_layer(p, d(tgt), d(qpos), d(ref4), d(mem), d(text), tmask.cpu(), sh.cpu(), mask.cpu(), M, L, P)
     assert (d(y) - ref).abs().max().item() < 5e-2
     assert rel_err(d(y), ref) < 1e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("with_mask", [True, False])
+def test_encoder_layer_block_functions_vs_stagewise(dtype, with_mask):
+    """Frozen encoder layer (the ZiRa configuration): each half as ONE autograd Function whose dgrad GEMMs accumulate onto
+    the residual gradient (blocks.py, msda_linear_accum_16) vs the stage-wise Functions + autograd's elementwise adds.
+    Forward runs the same kernels (bit-equal); the input gradient differs only by where the 16-bit roundings fall, and
+    both are checked against an fp64 evaluation of the layer (oracle.cpu_encoder.encoder_layer) on the same parameters."""
+    import ziragroundingdino_b200 as zb
+    from oracle import cpu_encoder
+    torch.manual_seed(5)
+    C, FF, M, L, P, N = 256, 2048, 8, 4, 4, 2
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    layer = zb.DeformableTransformerEncoderLayer(C, FF, 0.0, "relu", L, M, P)
+    with torch.no_grad():
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+        layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+        layer.norm1.weight.normal_(1, 0.1); layer.norm2.bias.normal_(0, 0.1)
+    layer = layer.to(DEV).to(dtype)
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    sh = torch.tensor(shapes, device=DEV)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    src0 = torch.randn(N, S, C, device=DEV).to(dtype)
+    pos = torch.randn(N, S, C, device=DEV).to(dtype)
+    refp = torch.rand(N, S, L, 2, device=DEV)
+    mask = None
+    if with_mask:
+        mask = torch.zeros(N, S, dtype=torch.bool, device=DEV)
+        mask[1, S - 150:] = True
+    gy = torch.randn(N, S, C, device=DEV).to(dtype)
+    res = {}
+    for blocks_on in (True, False):
+        zb.DeformableTransformerEncoderLayer.block_functions = blocks_on
+        try:
+            x = src0.clone().requires_grad_(True)
+            y, _ = layer(x, pos, refp, sh, lsi, mask)
+            y.backward(gy)
+            res[blocks_on] = (y.detach(), x.grad)
+        finally:
+            zb.DeformableTransformerEncoderLayer.block_functions = True
+    assert torch.equal(res[True][0], res[False][0])
+    assert rel_err(res[True][1].float().cpu(), res[False][1].float().cpu()) < 2e-2
+    # fp64 truth of the same layer
+    d = lambda t: t.detach().double().cpu()
+    p = {(k[len("self_attn."):] if k.startswith("self_attn.") else k): d(v) for k, v in layer.state_dict().items()}
+    xd = d(src0).requires_grad_(True)
+    ref = cpu_encoder.encoder_layer(p, xd, d(pos), d(refp), sh.cpu(), None if mask is None else mask.cpu(), M, L, P)
+    ref.backward(d(gy))
+    assert (d(res[True][0]) - ref.detach()).abs().max().item() < 6e-2
+    e_block, e_stage = rel_err(d(res[True][1]), xd.grad), rel_err(d(res[False][1]), xd.grad)
+    # bf16 carries 8 mantissa bits through ~10 rounded intermediates; the bar is the stage-wise path's own distance
+    assert e_block < (6e-2 if dtype == torch.bfloat16 else 3e-2) and e_block <= e_stage * 1.2 + 1e-3
+
+
+def test_linear_accum16_in_place_and_out_of_place():
+    from ziragroundingdino_b200 import blocks, _lib
+    for dtype, eps in ((torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)):
+        for R, K, Nout in ((1000, 256, 256), (4 * 22223 + 3, 384, 256), (77, 512, 64)):
+            g = torch.Generator().manual_seed(R)
+            x = torch.randn(R, K, generator=g).to(dtype).to(DEV)
+            w = (torch.randn(Nout, K, generator=g) * 0.06).to(dtype).to(DEV)
+            acc = torch.randn(R, Nout, generator=g).to(dtype).to(DEV)
+            want = acc.double() + x.double() @ w.double().t()
+            out = torch.empty_like(acc)
+            for staged in (1, 0):
+                _lib.lib().msda_b200_gemm_set_staged(staged)
+                try:
+                    blocks.linear_accum16(x, w, acc, out)
+                    a2 = acc.clone()
+                    blocks.linear_accum16(x, w, a2)
+                finally:
+                    _lib.lib().msda_b200_gemm_set_staged(1)
+                assert (out.double() - want).abs().max().item() <= eps * want.abs().max().item() * 1.05
+                assert torch.equal(out, a2)

@@ -46,6 +46,7 @@ def lib():
         getattr(L, "msda_backward_" + sfx).argtypes = _BWD
     L.msda_b200_gemm_last_error.restype = ctypes.c_char_p
     L.msda_linear_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp]
+    L.msda_linear_accum_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]
     L.msda_linear_act_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp]
     L.msda_linear_act_bits_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _vp]
     L.msda_query_proj_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]

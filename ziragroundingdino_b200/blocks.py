@@ -1,0 +1,163 @@
+"""Encoder-layer sub-blocks as single autograd Functions.
+
+The reference's layer (transformer_for_adapter.py:890-907) uses ``src`` three times in the attention half -- residual,
+``value``, and ``query = src + pos`` -- and twice in the FFN half, so plain autograd sums the incoming gradients with
+separate elementwise add passes (3 per layer, 45 MB read twice + written once each).  Here each half is ONE Function
+whose backward lets the dgrad GEMMs accumulate onto the gradient that is already there (``msda_linear_accum_16`` /
+cuBLAS beta = 1), so no add pass remains.  Used only when everything inside the block is frozen (the ZiRa
+configuration: gradients flow *through* the layers to the input-projection adapters); otherwise the layer composes the
+stage-wise Functions as before.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _C, _lib, fused
+from .layer_ops import _linear_act_bits16, _stream, derived
+
+
+def _add_ln_fwd(x2, r2, g32, b32, eps):
+    R, C = x2.shape
+    z, y = torch.empty_like(x2), torch.empty_like(x2)
+    mean = torch.empty(R, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(R, dtype=torch.float32, device=x2.device)
+    with torch.cuda.device(x2.device):
+        rc = _lib.lib().msda_add_layernorm_fwd_16(x2.data_ptr(), r2.data_ptr(), g32.data_ptr(), b32.data_ptr(), R, C, float(eps),
+                                                  z.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                  1 if x2.dtype == torch.float16 else 0, _stream(x2))
+    _lib.check(rc, "msda_add_layernorm_fwd_16")
+    return z, y, mean, rstd
+
+
+def _add_ln_bwd(dy2, z, g32, mean, rstd):
+    R, C = z.shape
+    dz = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        rc = _lib.lib().msda_add_layernorm_bwd_16(dy2.data_ptr(), z.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                  R, C, dz.data_ptr(), 1 if z.dtype == torch.float16 else 0, _stream(z))
+    _lib.check(rc, "msda_add_layernorm_bwd_16")
+    return dz
+
+
+def linear_accum16(x2d, w, accum, out=None):
+    """out = accum + x2d @ w^T (16-bit); ``out`` defaults to accumulating in place."""
+    R, K = x2d.shape
+    Nout = w.shape[0]
+    out = accum if out is None else out
+    assert x2d.is_contiguous() and w.is_contiguous() and accum.is_contiguous() and accum.shape == (R, Nout) and accum.dtype == x2d.dtype
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_accum_16(x2d.data_ptr(), w.data_ptr(), 0, R, K, Nout, accum.data_ptr(), out.data_ptr(),
+                                             1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_linear_accum_16")
+    return out
+
+
+class SelfAttnBlockFunction(Function):
+    """``norm1(src + MSDeformAttn(query = src + pos, value = src))`` with every parameter frozen: returns the block
+    output; backward returns d(src) only, with the value-projection and query-projection dgrads accumulated onto the
+    residual gradient inside the GEMM epilogues."""
+
+    @staticmethod
+    def forward(ctx, src, pos, row_mask, reference_points, spatial_shapes, level_start_index, prep, M, L, P, im2col_step,
+                g32, b32, eps):
+        N, S, C = src.shape
+        src2d = src.reshape(N * S, C).contiguous()
+        q2d = src2d if pos is None else (src + pos).reshape(N * S, C)
+        ref = reference_points.to(torch.float32).contiguous()
+        ref_dim = ref.shape[-1]
+        value = fused.linear16(src2d, prep.w_v, prep.b_v, row_mask).view(N, S, M, C // M)
+        loc, aw = fused.query_proj16(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
+        loc, aw = loc.view(N, S, M, L, P, 2), aw.view(N, S, M, L, P)
+        core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
+        attn = fused.linear16(core.view(N * S, C), prep.w_o, prep.b_o)
+        z, y, mean, rstd = _add_ln_fwd(src2d, attn, g32, b32, eps)
+        ctx.dims = (N, S, C, M, L, P, ref_dim, im2col_step)
+        ctx.prep = prep
+        ctx.save_for_backward(row_mask, ref, spatial_shapes, level_start_index, value, loc, aw, z, g32, mean, rstd)
+        return y.view(N, S, C)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        row_mask, ref, spatial_shapes, level_start_index, value, loc, aw, z, g32, mean, rstd = ctx.saved_tensors
+        N, S, C, M, L, P, ref_dim, im2col_step = ctx.dims
+        prep = ctx.prep
+        dt = value.dtype
+        dz = _add_ln_bwd(dy.reshape(N * S, C).contiguous(), z, g32, mean, rstd)     # d(src) via the residual AND d(attn out)
+        d_core = fused.linear16(dz, prep.w_o_t)
+        if fused.fuse_query_backward and (L, P, C // M) == (4, 4, 32):
+            grad_value, dq_cat = fused.backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim)
+        else:
+            grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
+                                                                       d_core.view(N, S, C), im2col_step)
+            dq_cat = fused.query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * S, M, L, P, dt)
+        gv16 = fused.cast_mask16(grad_value.view(N * S, C), row_mask, dt)
+        d_src = linear_accum16(gv16, prep.w_v_t, dz)            # dz += d(value_proj input)
+        d_src = linear_accum16(dq_cat, prep.w_cat_t, d_src)     # dz += d(query) (= d(src) through query = src + pos)
+        return (d_src.view(N, S, C),) + (None,) * 13
+
+
+class FFNBlockFunction(Function):
+    """``norm2(x + linear2(relu(linear1(x))))`` with frozen weights: 1-bit ReLU mask, and the linear1 dgrad accumulates
+    onto the residual gradient (cuBLAS beta = 1) instead of a separate add."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, g32, b32, eps):
+        shape = x.shape
+        x2d = x.reshape(-1, shape[-1]).contiguous()
+        bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
+        h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
+        y2 = torch.nn.functional.linear(h, w2, b2)
+        z, y, mean, rstd = _add_ln_fwd(x2d, y2, g32, b32, eps)
+        ctx.save_for_backward(bits, w1, w2, z, g32, mean, rstd)
+        ctx.shape = shape
+        return y.view(shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        bits, w1, w2, z, g32, mean, rstd = ctx.saved_tensors
+        dz = _add_ln_bwd(dy.reshape(z.shape).contiguous(), z, g32, mean, rstd)
+        dh = _linear_act_bits16(dz, derived(w2, "t"), None, gate_bits=bits)
+        dx = torch.addmm(dz, dh, w1)
+        return (dx.view(ctx.shape),) + (None,) * 7
+
+
+def _frozen(*mods):
+    return not any(p.requires_grad for m in mods for p in m.parameters())
+
+
+def _ln_ok(norm, C):
+    return norm.elementwise_affine and norm.bias is not None and C % 8 == 0 and C <= 1024
+
+
+def self_attn_block(layer, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask):
+    """The attention half of an encoder layer as one Function, or None when the block form does not apply."""
+    attn, norm = layer.self_attn, layer.norm1
+    C = src.shape[-1]
+    if not (src.is_cuda and src.dtype in (torch.bfloat16, torch.float16) and attn.batch_first and _ln_ok(norm, C)
+            and _frozen(attn, norm) and torch.is_grad_enabled() and src.requires_grad
+            and (pos is None or (not pos.requires_grad and pos.dtype == src.dtype))
+            and not (layer.training and getattr(layer.dropout1, "p", 0.0) > 0)
+            and attn.value_proj_adapter is None and attn.output_proj_adapter is None
+            and attn._use_fused(src, reference_points)):
+        return None
+    prep = attn._prepared()
+    row_mask = None if key_padding_mask is None else key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
+    attn.zero_inter_loss = None
+    return SelfAttnBlockFunction.apply(src, pos, row_mask, reference_points, spatial_shapes, level_start_index, prep,
+                                       attn.num_heads, attn.num_levels, attn.num_points, attn.im2col_step,
+                                       derived(norm.weight, "f32"), derived(norm.bias, "f32"), norm.eps)
+
+
+def ffn_block(layer, x):
+    """The FFN half of an encoder layer as one Function, or None when the block form does not apply."""
+    l1, l2, norm = layer.linear1, layer.linear2, layer.norm2
+    C = x.shape[-1]
+    if not (x.is_cuda and x.dtype in (torch.bfloat16, torch.float16) and _ln_ok(norm, C) and _frozen(l1, l2, norm)
+            and torch.is_grad_enabled() and x.requires_grad and l1.bias is not None and l2.bias is not None
+            and C % 64 == 0 and l1.out_features % 32 == 0 and l1.out_features <= 2048
+            and not (layer.training and (getattr(layer.dropout2, "p", 0.0) > 0 or getattr(layer.dropout3, "p", 0.0) > 0))):
+        return None
+    return FFNBlockFunction.apply(x, l1.weight, l1.bias, l2.weight, l2.bias, derived(norm.weight, "f32"),
+                                  derived(norm.bias, "f32"), norm.eps)

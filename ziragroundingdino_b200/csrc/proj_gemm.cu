@@ -69,6 +69,8 @@ struct EpiParams {
   const void* gate;        // optional 16-bit [R, out_ld]: out = acc where gate > 0 else 0 (ReLU backward fused in a dgrad)
   // 1-bit form of the same gate: word (c / 32) * R + row holds bits (column c + j > 0), j = 0..31 -- [Nout/32, R]
   // uint32, word-major so that the 32 lanes (rows) of a warp read / write 128 contiguous bytes.
+  const void* accum;         // optional 16-bit [R, out_ld] added to the product before the store (may alias `out`: a tile is
+                             // read and then written by the same warp) -- gradient accumulation without a separate add pass
   uint32_t* relu_bits;       // written by a RELU launch (may be null)
   const uint32_t* gate_bits; // read by a GATE launch instead of `gate` (may be null)
   // EPI_QUERY: columns [0, n_loc) are sampling offsets laid out (m, l, p, xy); columns [n_loc, n_loc + n_aw)
@@ -232,6 +234,19 @@ __device__ __forceinline__ void pack_16(const float (&v)[32], bool half_out, boo
     o[i].y = zero ? 0u : pack16(v[8 * i + 2], v[8 * i + 3], half_out);
     o[i].z = zero ? 0u : pack16(v[8 * i + 4], v[8 * i + 5], half_out);
     o[i].w = zero ? 0u : pack16(v[8 * i + 6], v[8 * i + 7], half_out);
+  }
+}
+
+// v[0..31] += 32 16-bit values packed in 16 words (bf16 or IEEE half)
+__device__ __forceinline__ void add_packed16(float (&v)[32], const uint32_t* w, bool half_in) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    if (half_in) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+      v[2 * j] += t.x; v[2 * j + 1] += t.y;
+    } else {
+      v[2 * j] += __uint_as_float(w[j] << 16); v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+    }
   }
 }
 
@@ -497,6 +512,12 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* tile = tile0 + buf * TMA_TILE_BYTES;
           uint4 gt[8];
           uint32_t gb[2] = {gb_next[0], gb_next[1]};
+          uint4 ain[8];
+          if (!RELU && !GATE && ep.accum != nullptr) {   // this row's 64 columns of the tensor to accumulate onto
+            const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.accum) + row * ep.out_ld + gc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ain[i] = live ? ap[i] : make_uint4(0u, 0u, 0u, 0u);
+          }
           if (GATE && bit_gate) {
             if (c0 + 128 < block_n) bits_fetch(c0 + 128);
           } else if (GATE) {
@@ -523,6 +544,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
               v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
             }
+            if (!RELU && !GATE && ep.accum != nullptr) add_packed16(v, reinterpret_cast<const uint32_t*>(ain) + 16 * hf, HALF_OUT);
             if (RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -634,6 +656,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             __syncwarp();
             if (c0 + 64 < block_n) gate_fetch(c0 + 64);
           }
+          uint4 ain[4];
+          const bool do_acc = MODE == EPI_STORE && !OUT_F32 && !RELU && !GATE && ep.accum != nullptr;
+          if (do_acc) {
+            const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.accum) + row * ep.out_ld + gc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) ain[i] = live ? ap[i] : make_uint4(0u, 0u, 0u, 0u);
+          }
           uint32_t r[32];
           tmem_ld32(taddr + c0, r);
           float v[32];
@@ -645,6 +674,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
           }
           if (MODE == EPI_STORE) {
+            if (do_acc) add_packed16(v, reinterpret_cast<const uint32_t*>(ain), HALF_OUT);
             if (RELU) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
@@ -915,6 +945,18 @@ int msda_linear_16(const void* x, const void* w, const float* bias, long long R,
   ep.mode = pg::EPI_STORE;
   ep.out = out; ep.out_ld = out_ld; ep.out_f32 = out_f32; ep.out_half = is_half; ep.bias = bias; ep.row_mask = row_mask;
   return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, out_f32 != 0), is_half != 0, ep, static_cast<cudaStream_t>(stream));
+}
+
+int msda_linear_accum_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, const void* accum,
+                         void* out, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out || !accum) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  if (Nout % 8) { snprintf(pg::t_err, sizeof(pg::t_err), "accumulating store needs Nout %% 8 == 0"); return MSDA_ERR_UNSUPPORTED; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.accum = accum;
+  return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 int msda_linear_act_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out, int relu,

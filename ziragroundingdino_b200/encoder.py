@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import blocks
 from .layer_ops import add_layer_norm, ffn
 from .ms_deform_attn import MultiScaleDeformableAttention
 
@@ -41,13 +42,24 @@ class DeformableTransformerEncoderLayer(nn.Module):
     def with_pos_embed(tensor, pos):
         return tensor if pos is None else tensor + pos
 
+    # one autograd Function per half when everything inside is frozen (blocks.py): no elementwise gradient adds
+    block_functions = True
+
     def forward_ffn(self, src):
         adapter_loss = src.new_zeros(1)
+        out = blocks.ffn_block(self, src) if self.block_functions else None
+        if out is not None:
+            return out, adapter_loss
         src2 = ffn(src, self.linear1, self.linear2, self.dropout2.p, self.training)
         src = add_layer_norm(src, src2, self.norm2, self.dropout3.p, self.training)
         return src, adapter_loss
 
     def forward(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask=None):
+        out = None
+        if self.block_functions:
+            out = blocks.self_attn_block(self, src, pos, reference_points, spatial_shapes, level_start_index, key_padding_mask)
+        if out is not None:
+            return self.forward_ffn(out)
         src2 = self.self_attn(query=self.with_pos_embed(src, pos), reference_points=reference_points, value=src,
                               spatial_shapes=spatial_shapes, level_start_index=level_start_index,
                               key_padding_mask=key_padding_mask)

@@ -231,19 +231,26 @@ class MultiScaleDeformableAttention(nn.Module):
         self.zero_inter_loss = sum(losses) if losses else None
         return out.view(N, Lq, C)
 
+    def _raw_weights(self):
+        w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
+        w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
+        return (w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
+                self.attention_weights.bias, w_o, b_o)
+
+    def _prepared(self, raw=None):
+        """Kernel-ready weights (fused.Prepared), rebuilt only when a parameter changed."""
+        key = tuple((t.data_ptr(), t._version, t.dtype) for t in self.parameters())
+        if getattr(self, "_prep_key", None) != key:
+            self._prep, self._prep_key = fused.Prepared(*(raw if raw is not None else self._raw_weights())), key
+        return self._prep
+
     def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
         has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None
         if has_branch and self.training:
             return self._forward_fused_zira_train(query, value, key_padding_mask, reference_points, spatial_shapes,
                                                   level_start_index)
-        w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
-        w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
-        raw = (w_v, b_v, self.sampling_offsets.weight, self.sampling_offsets.bias, self.attention_weights.weight,
-               self.attention_weights.bias, w_o, b_o)
-        srcs = [p for p in self.parameters()]
-        key = tuple((t.data_ptr(), t._version, t.dtype) for t in srcs)
-        if getattr(self, "_prep_key", None) != key:      # rebuilt only when a parameter changed
-            self._prep, self._prep_key = fused.Prepared(*raw), key
+        raw = self._raw_weights()
+        self._prepared(raw)
         row_mask = None
         if key_padding_mask is not None:
             row_mask = key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
