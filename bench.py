@@ -52,6 +52,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--profile-step", action="store_true", help="run one warm-up and ONE eager step, then exit (for an ncu "
+                    "launch list: nothing is timed, nothing is printed)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json workload: 2 = configs[1] (default), "
                     "4 = configs[3], the ZiRa step proxy with the decoder")
     a = ap.parse_args()
@@ -315,6 +317,17 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = t.item()
         return ms
+
+    if args.profile_step:
+        step(feat, pos, mask)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(feat, pos, mask)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ---- device-resident timing ---------------------------------------------------------------------
     # The step (forward, backward, all-reduce, clip, AdamW) is captured once in a CUDA graph: ~250 launches of

@@ -22,6 +22,8 @@ b1 = torch.randn(2048, device=dev)
 ref = torch.rand(R, 4, 2, device=dev)
 shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)], device=dev)
 h = torch.randn(R, 2048, device=dev).bfloat16()
+bits = torch.empty(2048 // 32, R, dtype=torch.int32, device=dev)
+acc = torch.randn(R, 256, device=dev).bfloat16()
 flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 L = _lib.lib()
 
@@ -31,6 +33,9 @@ cases = {
     "dgrad K=384 ->256": lambda: fused.linear16(x384, w384, None),
     "ffn1 256->2048 relu": lambda: layer_ops._linear_act16(x, w1, b1, relu=True),
     "ffn2 dgrad 256->2048 gated": lambda: layer_ops._linear_act16(x, w1, None, gate=h),
+    "ffn1 256->2048 relu + bits": lambda: layer_ops._linear_act_bits16(x, w1, b1, relu_bits=bits),
+    "ffn2 dgrad 256->2048 bit-gated": lambda: layer_ops._linear_act_bits16(x, w1, None, gate_bits=bits),
+    "dgrad 256->256 accumulate": lambda: __import__("ziragroundingdino_b200.blocks", fromlist=["x"]).linear_accum16(x, w, acc),
     "cublas 256->2048 + relu": lambda: torch.relu(torch.nn.functional.linear(x, w1, b1.bfloat16())),
     "cublas 256->256": lambda: torch.nn.functional.linear(x, w, b.bfloat16()),
 }
@@ -57,9 +62,7 @@ if sys.argv[1:] and sys.argv[1] == "run":
         cases[which]()
     torch.cuda.synchronize()
 else:
-    for bufs, pres in ((2, 0), (2, 1), (1, 1)):
+    for bufs, pres in ((1, 1),):
         L.msda_b200_gemm_set_store_bufs(bufs, pres)
         for name, fn in cases.items():
-            if "cublas" in name and (bufs, pres) != (2, 0):
-                continue
             print("store_bufs=%d prefer_resident=%d  %-36s cold %7.1f us   warm %7.1f us" % (bufs, pres, name, timeit(fn, True), timeit(fn, False)))
