@@ -63,6 +63,11 @@ def lib():
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     L.msda_b200_probe_scatter.argtypes = [_vp, _ll, _i, _i, _i, _vp]
     _lib = L
+    # A/B knobs for measurement runs: MSDA_B200_TUNING="bwd_merge=1,fwd_passes=4"
+    for item in filter(None, os.environ.get("MSDA_B200_TUNING", "").split(",")):
+        k, _, v = item.partition("=")
+        if L.msda_b200_set_tuning(k.strip().encode(), int(v)) != 0:
+            raise RuntimeError("MSDA_B200_TUNING: unknown key %r" % k)
     return L
 
 
