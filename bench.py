@@ -3,19 +3,21 @@
 
 Workload (configs[1], "config 2"): GroundingDINO Swin-T 6-layer deformable encoder, forward + backward,
 4 images per GPU padded to 800x1333 (levels 100x167, 50x84, 25x42, 13x21; S = 22 223 tokens/image), bf16,
-as it runs inside a ZiRa incremental fine-tuning step: the twelve... here six encoder MSDeformAttn layers and
-their FFNs are FROZEN (groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:50), the only trainable
-parameters are a ZiRa RepZeroLinear branch at the transformer input (stand-in for the reference's
-input_proj adapters, groundingdino_dual_zero_rep_branch.py:487-523), so backward carries activation
-gradients through every layer (grad_value / grad_sampling_loc / grad_attn_weight + dgrad GEMMs) and weight
-gradients only for the branch.  With N > 1 GPUs each rank runs its own 4 images (weak scaling) and the
-branch gradients are all-reduced in ONE flat NCCL bucket per step.
+as it runs inside a ZiRa incremental fine-tuning step: the six encoder MSDeformAttn layers and their FFNs are FROZEN
+(groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:50); the trainable parameters are the reference's own --
+the RepZeroConv2d adapters beside input_proj (groundingdino_dual_zero_rep_branch.py:292-302, :483-523), fed with
+synthetic Swin-T maps (192/384/768 channels) -- so backward carries activation gradients through every layer
+(grad_value / grad_sampling_loc / grad_attn_weight + dgrad GEMMs) down to the adapters, then clip + AdamW.
+With N > 1 GPUs each rank runs its own 4 images (weak scaling) and the adapter gradients are all-reduced in ONE flat
+NCCL bucket per step.  `--config 4` = configs[3]: 8 images/GPU and the 6-layer decoder (900 queries) on top.
 
 One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step
 with pinned-host inputs copied in and the loss read back every step.  `roofline` is for the dominant
-kernel (the backward scatter); `cpu_baseline` is the reference's CPU path (oracle port) on a bounded sample.
+kernel (the backward scatter) against HBM as the contract asks; `roofline_l2` / `roofline_l2_scatter` are the two
+memory-system limits that actually bind it, probed live; `cpu_baseline` is the reference's CPU path (oracle port)
+on a bounded sample.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|4] [--impl reference]
 """
 import argparse
 import json

@@ -133,3 +133,33 @@ def test_zira_input_proj_module_vs_eager(training):
         merged, _ = m(feats)
         for o, w in zip(merged, want):
             assert (o.float() - w.float()).abs().max().item() < 6 * 2 ** -8 * w.float().abs().max().item()
+
+
+def test_input_proj_fp32_master_adapters_with_bf16_activations():
+    """Mixed precision the way a trainer would run it: frozen input_proj in bf16, trainable adapter parameters kept in
+    fp32 (cast to bf16 on the way into the fused GEMM, gradients arrive back in fp32)."""
+    import ziragroundingdino_b200 as zb
+    torch.manual_seed(13)
+    m = zb.ZiRaInputProj().to(DEV)
+    m.input_proj.to(torch.bfloat16)
+    with torch.no_grad():
+        for a in m.input_proj_conv_adapter:
+            sc = (a.weight[0].numel()) ** -0.5
+            a.weight.normal_(0, 0.3 * sc); a.freeze_conv.weight.normal_(0, 0.3 * sc)
+    for n, p in m.named_parameters():
+        p.requires_grad_("adapter" in n)
+    m.train()
+    hw = [(25, 42), (13, 21), (7, 11)]
+    rows = [_rand((2, h * w, c), torch.bfloat16, 30 + i) for i, (c, (h, w)) in enumerate(zip((192, 384, 768), hw))]
+    src, shapes, loss = m.forward_rows(rows, hw)
+    assert src.dtype == torch.bfloat16 and shapes == [(25, 42), (13, 21), (7, 11), (4, 6)]
+    (src.float().square().mean() + 0.1 * loss.float()).backward()
+    for n, p in m.named_parameters():
+        if "adapter" in n:
+            assert p.grad is not None and p.grad.dtype == torch.float32 and torch.isfinite(p.grad).all(), n
+    # same module with bf16 adapters: the fp32-master run must agree to bf16 rounding of the parameters
+    m2 = zb.ZiRaInputProj().to(DEV)
+    m2.load_state_dict(m.state_dict())
+    m2 = m2.to(torch.bfloat16).train()
+    src2, _, loss2 = m2.forward_rows(rows, hw)
+    assert (src.float() - src2.float()).abs().max().item() < 0.1 and abs(float(loss) - float(loss2)) < 2e-2 * float(loss2)
