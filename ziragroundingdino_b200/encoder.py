@@ -4,8 +4,10 @@ Mirrors the reference's ``DeformableTransformerEncoderLayer`` (transformer_for_a
 sub-module names, so checkpoint keys ``transformer.encoder.layers.{i}.self_attn.*`` / ``norm1`` /
 ``linear1`` ... load unchanged) with ``use_adapter=False`` as in the ZiRa configuration
 (groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:56).  The MSDeformAttn module inside is the
-B200-native one; residual + LayerNorm are one fused kernel per direction (layer_ops.py); the FFN GEMMs are
-still library ops.  ``DeformableEncoder`` is the 6-layer stack used by bench.py (BASELINE.json
+B200-native one; residual + LayerNorm are one fused kernel per direction and the FFN's two K = d_model products run on
+the tcgen05 GEMM with ReLU / 1-bit-gate epilogues (layer_ops.py; the two K = d_ffn products stay library GEMMs); with
+frozen parameters each half of the layer is ONE autograd Function whose dgrads accumulate in the GEMM epilogue
+(blocks.py) -- SURVEY.md section 8(f) row N1.  ``DeformableEncoder`` is the 6-layer stack used by bench.py (BASELINE.json
 config 2); the text-fusion and text-encoder sub-layers of the reference encoder loop
 (transformer_for_adapter.py:563-612) are out of scope and omitted.
 """
