@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--all-valid", action="store_true", help="no padding: every image fills the 800x1333 canvas (SURVEY.md 8(d) "
+                    "asks for this case next to the padded one)")
     ap.add_argument("--profile-step", action="store_true", help="run one warm-up and ONE eager step, then exit (for an ncu "
                     "launch list: nothing is timed, nothing is printed)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json workload: 2 = configs[1] (default), "
@@ -234,7 +236,7 @@ def run_ours(args):
 
     sh, lsi = syn.level_tensors(shapes, dev)
     g = torch.Generator().manual_seed(99 + rank)
-    mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g)
+    mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g, all_valid=args.all_valid)
     feat_hw = list(shapes[:3])
     feat_rows = [h * w for h, w in feat_hw]
     feat_off = [0]
@@ -470,7 +472,8 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=graph is not None), "clocks": clocks, "gpu_launches": launches,
+        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=graph is not None,
+                                            **({"padding": "none (all-valid case)"} if args.all_valid else {})), "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "images": N,
                                    "fwd_l2_algorithmic_gbps": ab["fwd_l2"] / us_fwd / 1e3,
