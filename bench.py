@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--all-valid", action="store_true", help="no padding: every image fills the 800x1333 canvas (SURVEY.md 8(d) "
                     "asks for this case next to the padded one)")
+    ap.add_argument("--gaps", action="store_true", help="after warm-up, trace 3 steps with torch.profiler (CUPTI) and print to "
+                    "stderr how much of a step is kernel time vs idle gaps between kernels; nothing is timed for the JSON line")
     ap.add_argument("--profile-step", action="store_true", help="run one warm-up and ONE eager step, then exit (for an ncu "
                     "launch list: nothing is timed, nothing is printed)")
     ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json workload: 2 = configs[1] (default), "
@@ -362,6 +364,36 @@ def run_ours(args):
             graph_upd.replay()
     else:
         run = lambda: step(feat, pos, mask)
+    if args.gaps:
+        from torch.profiler import ProfilerActivity, profile
+        for _ in range(5):
+            run()
+        torch.cuda.synchronize()
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+        ev = sorted((e for e in prof.events() if e.device_type.name == "CUDA" and e.time_range.end > e.time_range.start),
+                    key=lambda e: e.time_range.start)
+        busy = sum(e.time_range.end - e.time_range.start for e in ev)
+        span = ev[-1].time_range.end - ev[0].time_range.start
+        gaps = [b.time_range.start - a.time_range.end for a, b in zip(ev, ev[1:])]
+        pos_gaps = [g_ for g_ in gaps if g_ > 0]
+        print("gaps: %d kernels over 3 steps, span %.1f us, kernel time %.1f us (%.1f %%), idle %.1f us; median gap %.2f us, "
+              "gaps > 5 us: %d (%.1f us)" % (len(ev), span, busy, 100.0 * busy / span, span - busy,
+                                             sorted(pos_gaps)[len(pos_gaps) // 2] if pos_gaps else 0.0,
+                                             sum(1 for g_ in pos_gaps if g_ > 5), sum(g_ for g_ in pos_gaps if g_ > 5)), file=sys.stderr)
+        agg = {}
+        for e in ev:
+            a_ = agg.setdefault(e.name[:90], [0, 0.0])
+            a_[0] += 1
+            a_[1] += e.time_range.end - e.time_range.start
+        print("%10s %6s %5s %9s  kernel (in-graph, warm, per step)" % ("total_us", "share", "n", "avg_us"), file=sys.stderr)
+        for k_, (c_, t_) in sorted(agg.items(), key=lambda x: -x[1][1])[:24]:
+            print("%10.1f %5.1f%% %5d %9.1f  %s" % (t_ / 3, 100.0 * t_ / busy, c_ // 3, t_ / c_, k_), file=sys.stderr)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     sampler = ClockSampler(local) if rank == 0 else None      # samples through warm-up and the timed region (same load)
     for _ in range(max(args.warmup, 3)):
         run()
