@@ -385,11 +385,11 @@ def run_ours(args):
                                              sum(1 for g_ in pos_gaps if g_ > 5), sum(g_ for g_ in pos_gaps if g_ > 5)), file=sys.stderr)
         agg = {}
         for e in ev:
-            a_ = agg.setdefault(e.name[:90], [0, 0.0])
+            a_ = agg.setdefault(e.name[:int(os.environ.get("BENCH_GAPS_NAME", "90"))], [0, 0.0])
             a_[0] += 1
             a_[1] += e.time_range.end - e.time_range.start
         print("%10s %6s %5s %9s  kernel (in-graph, warm, per step)" % ("total_us", "share", "n", "avg_us"), file=sys.stderr)
-        for k_, (c_, t_) in sorted(agg.items(), key=lambda x: -x[1][1])[:24]:
+        for k_, (c_, t_) in sorted(agg.items(), key=lambda x: -x[1][1])[:int(os.environ.get("BENCH_GAPS_TOP", "24"))]:
             print("%10.1f %5.1f%% %5d %9.1f  %s" % (t_ / 3, 100.0 * t_ / busy, c_ // 3, t_ / c_, k_), file=sys.stderr)
         if world > 1:
             dist.destroy_process_group()
