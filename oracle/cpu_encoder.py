@@ -150,3 +150,31 @@ def timed_decoder(shapes, layers, threads, nq=900, d_model=256, M=8, P=4, seed=0
         x = decoder_layer(p, x, qpos, ref4, memory, None, None, sh, None, M, L, P)
     x.abs().mean().backward()
     return time.perf_counter() - t0
+
+
+def bi_attention_block(p, v, l, mask_v, mask_l, num_heads):
+    """The reference's BiAttentionBlock (fuse_modules.py:258-307 around BiMultiHeadAttention :154-254), dropout 0, restated
+    with the attention matrix materialised exactly as the reference does: logits -> minus global max (:174) -> clamp
+    +-50000 (:177-183) -> image<-text softmax over text (:207-213); transposed logits -> minus row max (:186-187) -> clamp
+    (:188-195) -> mask -> text<-image softmax over image tokens (:198-205).  ``p`` uses the reference's state_dict keys."""
+    C = v.shape[-1]
+    v = F.layer_norm(v, (C,), p["layer_norm_v.weight"], p["layer_norm_v.bias"])
+    l = F.layer_norm(l, (l.shape[-1],), p["layer_norm_l.weight"], p["layer_norm_l.bias"])
+    lin = lambda x, n: F.linear(x, p["attn." + n + ".weight"], p["attn." + n + ".bias"])
+    B, n_img, _ = v.shape
+    E = p["attn.v_proj.weight"].shape[0]
+    d = E // num_heads
+    split = lambda t: t.view(B, -1, num_heads, d).transpose(1, 2).reshape(B * num_heads, -1, d)
+    q, k = split(lin(v, "v_proj") * d ** -0.5), split(lin(l, "l_proj"))
+    vv, vl = split(lin(v, "values_v_proj")), split(lin(l, "values_l_proj"))
+    w = torch.bmm(q, k.transpose(1, 2))
+    w = (w - w.max()).clamp(min=-50000, max=50000)
+    wl = w.transpose(1, 2)
+    wl = (wl - wl.max(dim=-1, keepdim=True)[0]).clamp(min=-50000, max=50000)
+    if mask_v is not None:
+        wl = wl.masked_fill(mask_v[:, None, None, :].repeat(1, num_heads, 1, 1).flatten(0, 1), float("-inf"))
+    if mask_l is not None:
+        w = w.masked_fill(mask_l[:, None, None, :].repeat(1, num_heads, 1, 1).flatten(0, 1), float("-inf"))
+    out_v = torch.bmm(w.softmax(-1), vl).view(B, num_heads, n_img, d).transpose(1, 2).reshape(B, n_img, E)
+    out_l = torch.bmm(wl.softmax(-1), vv).view(B, num_heads, -1, d).transpose(1, 2).reshape(B, -1, E)
+    return v + p["gamma_v"] * lin(out_v, "out_v_proj"), l + p["gamma_l"] * lin(out_l, "out_l_proj")

@@ -13,6 +13,7 @@ Sources exercised (relative to /root/reference/groundingdino/models/GroundingDIN
   groundingdino_dual_zero_rep_branch.py:64-103, :492-493 RepZeroConv2d and its use beside input_proj
   transformer_for_adapter.py:809-907, :910-1073  DeformableTransformerEncoderLayer / DecoderLayer (use_adapter=False)
   utils.py:56-116, transformer_for_adapter.py:216-262, :311-329  proposals, valid ratios, flatten, top-k selection
+  fuse_modules.py:99-307  BiMultiHeadAttention / BiAttentionBlock (image <-> text fusion)
 """
 import ast
 import importlib.util
@@ -356,6 +357,43 @@ def transformer_io_case(seed):
     return res
 
 
+def bi_attention_case(seed):
+    """BiAttentionBlock / BiMultiHeadAttention (fuse_modules.py:99-307) executed from their AST (the file imports timm,
+    which is absent; DropPath is only instantiated for drop_path > 0)."""
+    ns = {"torch": torch, "nn": torch.nn, "F": torch.nn.functional, "DropPath": None}
+    tree = ast.parse(open(os.path.join(REF_DIR, "fuse_modules.py")).read())
+    keep = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name in ("BiMultiHeadAttention", "BiAttentionBlock")]
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "fuse_modules.py", "exec"), ns)
+    torch.manual_seed(seed)
+    C, E, H, B, n_img, n_text = 32, 64, 4, 2, 41, 7
+    blk = ns["BiAttentionBlock"](v_dim=C, l_dim=C, embed_dim=E, num_heads=H, dropout=0.0, drop_path=0.0).double()
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            if n.startswith("gamma"):
+                p.copy_(0.5 + 0.1 * torch.randn_like(p))          # layer scale large enough to matter
+            elif n.endswith("bias"):
+                p.copy_(0.1 * torch.randn_like(p))
+            elif "layer_norm" in n:
+                p.copy_(1 + 0.1 * torch.randn_like(p))
+    v = torch.randn(B, n_img, C, dtype=torch.float64, requires_grad=True)
+    l = torch.randn(B, n_text, C, dtype=torch.float64, requires_grad=True)
+    mask_v = torch.zeros(B, n_img, dtype=torch.bool)
+    mask_v[1, -9:] = True
+    mask_l = torch.zeros(B, n_text, dtype=torch.bool)
+    mask_l[0, -2:] = True
+    ov, ol = blk(v, l, attention_mask_v=mask_v.clone(), attention_mask_l=mask_l.clone())
+    gv, gl = torch.randn_like(ov), torch.randn_like(ol)
+    ((ov * gv).sum() + (ol * gl).sum()).backward()
+    res = {"v": v.detach().numpy(), "l": l.detach().numpy(), "mask_v": mask_v.numpy(), "mask_l": mask_l.numpy(),
+           "out_v": ov.detach().numpy(), "out_l": ol.detach().numpy(), "grad_out_v": gv.numpy(), "grad_out_l": gl.numpy(),
+           "grad_v": v.grad.numpy(), "grad_l": l.grad.numpy(), "cfg": np.asarray([C, E, H], dtype=np.int64)}
+    for k, t in blk.state_dict().items():
+        res["param." + k] = t.numpy()
+    ov2, ol2 = blk(v.detach(), l.detach())                       # no masks
+    res["out_v_nomask"], res["out_l_nomask"] = ov2.detach().numpy(), ol2.detach().numpy()
+    return res
+
+
 def main():
     ref = load_reference_msda()
     cases = {
@@ -377,6 +415,7 @@ def main():
     cases["zira_rep_conv3x3s2"] = zira_conv_case(conv, 33, 12, 16, 4, 3, 2, 1, (7, 6))
     cases.update(layer_cases(ref, 41))
     cases["transformer_io"] = transformer_io_case(51)
+    cases["bi_attention"] = bi_attention_case(61)
     total = 0
     for name, arrs in cases.items():
         p = os.path.join(OUT, name + ".npz")

@@ -7,7 +7,8 @@ from .zira import RepZeroConv2d, RepZeroLinear, merge_all  # noqa: F401
 from .input_proj import ZiRaInputProj  # noqa: F401
 from .encoder import DeformableEncoder, DeformableTransformerEncoderLayer  # noqa: F401
 from .decoder import DeformableTransformerDecoderLayer  # noqa: F401
+from .fuse_modules import BiAttentionBlock, BiMultiHeadAttention  # noqa: F401
 
 __all__ = ["MultiScaleDeformableAttention", "MultiScaleDeformableAttnFunction", "RepZeroLinear", "RepZeroConv2d",
-           "ZiRaInputProj", "DeformableTransformerEncoderLayer", "DeformableTransformerDecoderLayer", "DeformableEncoder",
+           "ZiRaInputProj", "BiAttentionBlock", "BiMultiHeadAttention", "DeformableTransformerEncoderLayer", "DeformableTransformerDecoderLayer", "DeformableEncoder",
            "merge_all", "_C"]

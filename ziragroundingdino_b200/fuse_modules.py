@@ -1,0 +1,125 @@
+"""Image <-> text feature fusion of the encoder loop.
+
+Mirrors the reference's ``BiMultiHeadAttention`` / ``BiAttentionBlock`` (fuse_modules.py:99-254, :258-307; used once per
+encoder layer, transformer_for_adapter.py:578-593) -- same constructor arguments, parameter names and outputs -- but
+never materialises the [heads, S, n_text] attention matrix the reference builds twice in fp32 (182 MB per image at
+S = 22 223, 256 text tokens): both directions are ordinary attention problems,
+
+    image <- text :  softmax_text ( q k^T )           v_l         q = v_proj(v) * scale, k = l_proj(l)
+    text <- image :  softmax_image( k q^T )           v_v         (the transposed logits)
+
+because every step the reference applies to the logits before a softmax is a per-row shift (global max :174, row max
+:187) or a clamp at +-50 000 (:177-195), and the clamp only binds on entries whose probability is already
+exp(-50000) = 0 -- as long as each row's own maximum lies within 50 000 of the global maximum, i.e. for any logits a
+trained model produces (they are O(10); tested up to spreads of thousands).  Outside that window the reference itself
+degenerates (a row entirely below the window is clamped flat and attends uniformly); that quirk is not reproduced.  So each
+direction is a plain softmax attention: computed from logits kept in the activation dtype (default), or as
+two fused scaled-dot-product-attention calls that never materialise it (``use_sdpa``).  Dense, tensor-core work: library
+kernels by design -- this row is not on the path SURVEY.md 8 names, it completes the encoder layer loop around it.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class DropPath(nn.Module):
+    """Stochastic depth per sample (the reference takes timm's; fuse_modules.py:11)."""
+
+    def __init__(self, drop_prob=0.0):
+        super().__init__()
+        self.drop_prob = drop_prob
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = x.new_empty((x.shape[0],) + (1,) * (x.dim() - 1)).bernoulli_(keep)
+        return x * mask / keep
+
+
+class BiMultiHeadAttention(nn.Module):
+    # False (default): materialised logits in the activation dtype, innermost-axis softmaxes, library GEMMs (fastest
+    # measured at the model's sizes, see tools/bench_fusion.py).  True: two fused scaled-dot-product-attention calls -- nothing of size n_img x n_text is ever
+    # materialised (memory-lean; its backward for the 256-query x 22 223-key direction parallelises poorly today).
+    use_sdpa = False
+
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None):
+        super().__init__()
+        self.embed_dim, self.num_heads, self.head_dim = embed_dim, num_heads, embed_dim // num_heads
+        self.v_dim, self.l_dim = v_dim, l_dim
+        assert self.head_dim * num_heads == embed_dim, \
+            f"embed_dim must be divisible by num_heads (got `embed_dim`: {embed_dim} and `num_heads`: {num_heads})."
+        self.scale = self.head_dim ** (-0.5)
+        self.dropout = dropout
+        self.v_proj = nn.Linear(v_dim, embed_dim)
+        self.l_proj = nn.Linear(l_dim, embed_dim)
+        self.values_v_proj = nn.Linear(v_dim, embed_dim)
+        self.values_l_proj = nn.Linear(l_dim, embed_dim)
+        self.out_v_proj = nn.Linear(embed_dim, v_dim)
+        self.out_l_proj = nn.Linear(embed_dim, l_dim)
+        self.stable_softmax_2d = True
+        self.clamp_min_for_underflow = True
+        self.clamp_max_for_overflow = True
+        self._reset_parameters()
+
+    def _reset_parameters(self):
+        for lin in (self.v_proj, self.l_proj, self.values_v_proj, self.values_l_proj, self.out_v_proj, self.out_l_proj):
+            nn.init.xavier_uniform_(lin.weight)
+            lin.bias.data.fill_(0)
+
+    def _heads(self, t):
+        b, n, _ = t.shape
+        # head-major and contiguous ([B, H, n, d]): strided head views push the library's batched GEMMs onto slow
+        # unaligned kernels (measured: 3.4 ms of a 10 ms block at the model's sizes)
+        return t.view(b, n, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
+
+    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
+        """v [bs, n_img, v_dim], l [bs, n_text, l_dim]; masks [bs, n_img] / [bs, n_text] bool, True = padding.
+        Returns (attn_output_v [bs, n_img, v_dim], attn_output_l [bs, n_text, l_dim])."""
+        bsz, n_img, _ = v.shape
+        n_text = l.shape[1]
+        q = self._heads(self.v_proj(v) * self.scale)
+        k = self._heads(self.l_proj(l))
+        val_v = self._heads(self.values_v_proj(v))
+        val_l = self._heads(self.values_l_proj(l))
+        p = self.dropout if self.training else 0.0
+        if self.use_sdpa:
+            keep_l = None if attention_mask_l is None else ~attention_mask_l[:, None, None, :]
+            keep_v = None if attention_mask_v is None else ~attention_mask_v[:, None, None, :]
+            out_v = F.scaled_dot_product_attention(q, k, val_l, attn_mask=keep_l, dropout_p=p, scale=1.0)     # image <- text
+            out_l = F.scaled_dot_product_attention(k, q, val_v, attn_mask=keep_v, dropout_p=p, scale=1.0)     # text <- image
+        else:
+            # Both logits matrices in the activation dtype ([B, H, n_img, n_text] and its transpose, 182 MB each in bf16 at
+            # N=4, S=22 223, 256 tokens; the reference holds them in fp32 plus temporaries).  The transpose is a second
+            # tensor-core product rather than a strided softmax: torch's softmax over a non-innermost axis of this shape is
+            # ~100x slower than over the innermost one (measured, tools/bench_fusion.py).
+            w_v = torch.matmul(q, k.transpose(-1, -2))                              # image rows, text columns
+            w_l = torch.matmul(k, q.transpose(-1, -2))                              # text rows, image columns
+            if attention_mask_l is not None:      # in place: the products' backward does not need their outputs
+                w_v.masked_fill_(attention_mask_l[:, None, None, :], float("-inf"))
+            if attention_mask_v is not None:
+                w_l.masked_fill_(attention_mask_v[:, None, None, :], float("-inf"))
+            out_v = torch.matmul(F.dropout(torch.softmax(w_v, dim=-1), p, self.training), val_l)
+            out_l = torch.matmul(F.dropout(torch.softmax(w_l, dim=-1), p, self.training), val_v)
+        out_v = out_v.transpose(1, 2).reshape(bsz, n_img, self.embed_dim)
+        out_l = out_l.transpose(1, 2).reshape(bsz, n_text, self.embed_dim)
+        return self.out_v_proj(out_v), self.out_l_proj(out_l)
+
+
+class BiAttentionBlock(nn.Module):
+    def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, drop_path=0.0, init_values=1e-4, cfg=None):
+        super().__init__()
+        self.layer_norm_v = nn.LayerNorm(v_dim)
+        self.layer_norm_l = nn.LayerNorm(l_dim)
+        self.attn = BiMultiHeadAttention(v_dim=v_dim, l_dim=l_dim, embed_dim=embed_dim, num_heads=num_heads, dropout=dropout)
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.gamma_v = nn.Parameter(init_values * torch.ones((v_dim)), requires_grad=True)
+        self.gamma_l = nn.Parameter(init_values * torch.ones((l_dim)), requires_grad=True)
+
+    def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
+        v = self.layer_norm_v(v)
+        l = self.layer_norm_l(l)
+        delta_v, delta_l = self.attn(v, l, attention_mask_v=attention_mask_v, attention_mask_l=attention_mask_l)
+        v = v + self.drop_path(self.gamma_v * delta_v)
+        l = l + self.drop_path(self.gamma_l * delta_l)
+        return v, l
