@@ -78,6 +78,16 @@ class BiMultiHeadAttention(nn.Module):
         Returns (attn_output_v [bs, n_img, v_dim], attn_output_l [bs, n_text, l_dim])."""
         bsz, n_img, _ = v.shape
         n_text = l.shape[1]
+        n_img_in = n_img
+        if not self.use_sdpa and n_img % 8 and v.is_cuda:
+            # S = 22 223 is odd: a [.., n_text, S] logits matrix then has rows that are not 16-byte aligned and the library
+            # falls back to its unaligned GEMM / softmax kernels.  Pad the image tokens to a multiple of 8 with masked rows.
+            pad = 8 - n_img % 8
+            v = F.pad(v, (0, 0, 0, pad))
+            if attention_mask_v is None:
+                attention_mask_v = v.new_zeros((bsz, n_img), dtype=torch.bool)
+            attention_mask_v = F.pad(attention_mask_v, (0, pad), value=True)
+            n_img += pad
         q = self._heads(self.v_proj(v) * self.scale)
         k = self._heads(self.l_proj(l))
         val_v = self._heads(self.values_v_proj(v))
@@ -103,7 +113,7 @@ class BiMultiHeadAttention(nn.Module):
             out_l = torch.matmul(F.dropout(torch.softmax(w_l, dim=-1), p, self.training), val_v)
         out_v = out_v.transpose(1, 2).reshape(bsz, n_img, self.embed_dim)
         out_l = out_l.transpose(1, 2).reshape(bsz, n_text, self.embed_dim)
-        return self.out_v_proj(out_v), self.out_l_proj(out_l)
+        return self.out_v_proj(out_v[:, :n_img_in]), self.out_l_proj(out_l)
 
 
 class BiAttentionBlock(nn.Module):
