@@ -198,7 +198,7 @@ def run_ours(args):
     shapes = syn.SWIN_T_800x1333
     S = sum(h * w for h, w in shapes)
     N, C, dt = IMAGES_PER_GPU, 256, torch.bfloat16
-    torch.manual_seed(1234 + rank)
+    torch.manual_seed(1234)          # replicas: every rank builds the same weights; only the data differs per rank (seed 99 + rank)
     enc = encoder.DeformableEncoder(NUM_LAYERS).to(dev)
     with torch.no_grad():
         for layer in enc.layers:   # query-dependent offsets / weights, as in a trained model
