@@ -472,3 +472,52 @@ def test_module_fused_sequence_first_layout():
     y_bf.float().square().mean().backward()
     assert torch.equal(y_sf.transpose(0, 1), y_bf)
     assert rel_err(v_sf.grad.transpose(0, 1).float().cpu(), v_bf.grad.float().cpu()) < 1e-3    # atomics order only
+
+
+def test_side_stream_and_cuda_graph_replay_match_eager():
+    """The reference op's threading contract: kernels go to the CURRENT stream of the current device, no
+    internal synchronisation, no global state.  The bf16 module (fused path, forward + backward) must give the same result
+    on a side stream and when replayed from a captured CUDA graph with new input data as on the default stream."""
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(2, shapes, 256, torch.bfloat16, seed=3)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    kw = dict(key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    gy = torch.randn_like(query)
+
+    def run(q, v):
+        y = m(query=q, value=v, **kw)
+        y.backward(gy)
+        return y
+
+    q0, v0 = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    y0 = run(q0, v0)
+    torch.cuda.synchronize()
+    # side stream
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    q1, v1 = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    with torch.cuda.stream(s):
+        y1 = run(q1, v1)
+    s.synchronize()
+    assert torch.equal(y0, y1) and torch.equal(q0.grad, q1.grad)
+    # grad_value is summed with atomics (order differs run to run), rounded to bf16, then multiplied by W_v: ~1 bf16 ulp flips
+    assert rel_err(v1.grad.float().cpu(), v0.grad.float().cpu()) < 1e-2
+    # CUDA graph: capture with one set of data, replay with another
+    qs, vs = torch.zeros_like(query).requires_grad_(True), torch.zeros_like(src).requires_grad_(True)
+    with torch.cuda.stream(s):
+        for _ in range(3):
+            qs.grad = vs.grad = None
+            run(qs, vs)
+    torch.cuda.current_stream().wait_stream(s)
+    qs.grad, vs.grad = torch.zeros_like(qs), torch.zeros_like(vs)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        qs.grad.zero_(); vs.grad.zero_()
+        ys = run(qs, vs)
+    with torch.no_grad():
+        qs.copy_(query); vs.copy_(src)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(ys, y0) and torch.equal(qs.grad, q0.grad)
+    assert rel_err(vs.grad.float().cpu(), v0.grad.float().cpu()) < 1e-2
