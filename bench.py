@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py -- BASELINE.json's metric on BASELINE.json's config.
+"""bench.py -- BASELINE.json's metric ("MSDeformAttn fwd+bwd us/layer & GB/s; ZiRa train images/s at 1/2/4/8 B200").
 
-Workload (configs[1], "config 2"): GroundingDINO Swin-T 6-layer deformable encoder, forward + backward,
-4 images per GPU padded to 800x1333 (levels 100x167, 50x84, 25x42, 13x21; S = 22 223 tokens/image), bf16,
-as it runs inside a ZiRa incremental fine-tuning step: the six encoder MSDeformAttn layers and their FFNs are FROZEN
-(groundingdino/config/GroundingDINO_SwinT_OGC_rep.py:50); the trainable parameters are the reference's own --
-the RepZeroConv2d adapters beside input_proj (groundingdino_dual_zero_rep_branch.py:292-302, :483-523), fed with
-synthetic Swin-T maps (192/384/768 channels) -- so backward carries activation gradients through every layer
-(grad_value / grad_sampling_loc / grad_attn_weight + dgrad GEMMs) down to the adapters, then clip + AdamW.
-With N > 1 GPUs each rank runs its own 4 images (weak scaling) and the adapter gradients are all-reduced in ONE flat
-NCCL bucket per step.  `--config 4` = configs[3]: 8 images/GPU and the 6-layer decoder (900 queries) on top.
+The JSON line's `value` is the ZiRa fine-tuning step (BASELINE.json configs[3], "config 4"): 8 images per GPU padded to
+800x1333 (levels 100x167, 50x84, 25x42, 13x21; S = 22 223 tokens/image), bf16 -- synthetic Swin-T maps (192/384/768
+channels) -> frozen input_proj + the reference's TRAINABLE RepZeroConv2d adapters (groundingdino_dual_zero_rep_branch.py
+:292-302, :483-523) + GroupNorm -> six FROZEN deformable encoder layers (GroundingDINO_SwinT_OGC_rep.py:50) -> 900 queries
+-> six frozen decoder layers (self-attention, MSDeformAttn cross-attention, FFN) -> loss; backward carries activation
+gradients through every layer (grad_value / grad_sampling_loc / grad_attn_weight + dgrad GEMMs) down to the adapters, then
+clip + AdamW.  With N > 1 GPUs each rank runs its own images (weak scaling) and the adapter gradients are all-reduced in
+ONE flat NCCL bucket per step.  The same line carries, under `other_workload`, configs[1] ("config 2": the 6-layer encoder
+fwd+bwd at 4 images/GPU, same front and update) measured in the same process, and under `msda_core_us_per_layer` the
+gather / scatter kernels of one layer timed alone -- the "us/layer & GB/s" half of the metric.  `--config 2|4` measures
+one workload only.
 
 One JSON line on stdout (rank 0).  `value` = images/s with inputs resident in HBM; `e2e` = the same step
 with pinned-host inputs copied in and the loss read back every step.  `roofline` is for the dominant
-kernel (the backward scatter) against HBM as the contract asks; `roofline_l2` / `roofline_l2_scatter` are the two
-memory-system limits that actually bind it, probed live; `cpu_baseline` is the reference's CPU path (oracle port)
-on a bounded sample.
+kernel (the backward scatter the step launches) against HBM as the contract asks; `roofline_l2` / `roofline_l2_scatter`
+are the two memory-system limits that actually bind it, probed live; `config5_stride4` is the one HBM-bound case;
+`ref_cuda_us_per_layer` is the reference's own CUDA op on the same launch; `cpu_baseline` is the reference's CPU path
+(oracle port) on a bounded sample.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--config 2|4] [--impl reference]
 """
@@ -30,20 +33,23 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-IMAGES_PER_GPU = 4          # config 2 (default); --config 4 switches to 8 (set_config)
+IMAGES = {2: 4, 4: 8}        # images per GPU of the two workloads
+METRICS = {2: "encoder6_msdeformattn_fwd_bwd_images_per_s", 4: "zira_train_images_per_s"}
 NUM_LAYERS = 6
 NUM_QUERIES = 900
-METRIC = "encoder6_msdeformattn_fwd_bwd_images_per_s"
-CONFIG = 2
+CONFIG = 4                   # primary workload of the JSON line: BASELINE.json's "ZiRa train images/s at 1/2/4/8 B200"
+IMAGES_PER_GPU = IMAGES[CONFIG]
+METRIC = METRICS[CONFIG]
 
 
 def set_config(cfg):
-    """--config 2 (default, BASELINE.json configs[1]) or --config 4 (configs[3]: the ZiRa fine-tuning step proxy of
-    SURVEY.md 8(d): input_proj + adapters -> 6 encoder layers -> 900 fixed queries -> 6 decoder layers -> L1 loss)."""
+    """Primary workload: 4 (default) = BASELINE.json configs[3], the ZiRa fine-tuning step the metric's images/s is
+    quoted on (input_proj + adapters -> 6 encoder layers -> 900 fixed queries -> 6 decoder layers -> L1
+    loss, 8 images/GPU); 2 = configs[1], the 6-layer encoder fwd+bwd at 4 images/GPU.  Without --config the line carries
+    BOTH: the primary as value/e2e and the other under "other_workload"."""
     global IMAGES_PER_GPU, METRIC, CONFIG
     CONFIG = cfg
-    if cfg == 4:
-        IMAGES_PER_GPU, METRIC = 8, "zira_step_images_per_s"
+    IMAGES_PER_GPU, METRIC = IMAGES[cfg], METRICS[cfg]
 
 
 def parse():
@@ -60,15 +66,19 @@ def parse():
                     "stderr how much of a step is kernel time vs idle gaps between kernels; nothing is timed for the JSON line")
     ap.add_argument("--profile-step", action="store_true", help="run one warm-up and ONE eager step, then exit (for an ncu "
                     "launch list: nothing is timed, nothing is printed)")
-    ap.add_argument("--config", type=int, default=2, choices=[2, 4], help="BASELINE.json workload: 2 = configs[1] (default), "
-                    "4 = configs[3], the ZiRa step proxy with the decoder")
+    ap.add_argument("--config", type=int, default=None, choices=[2, 4], help="measure ONE workload only: 4 = configs[3], the ZiRa "
+                    "step with the decoder, 2 = configs[1], the encoder; default: config 4 as the line's value AND config 2 "
+                    "under other_workload")
+    ap.add_argument("--no-config5", action="store_true", help="skip the Swin-B stride-4 (HBM-bound) core-op timing")
     a = ap.parse_args()
-    set_config(a.config)
+    set_config(a.config if a.config is not None else 4)
     return a
 
 
-def workload_config(n_gpus):
-    if CONFIG == 4:
+def workload_config(n_gpus, cfg=None):
+    cfg = CONFIG if cfg is None else cfg
+    IMAGES_PER_GPU = IMAGES[cfg]
+    if cfg == 4:
         return {"workload": "config4: ZiRa fine-tuning step proxy -- synthetic Swin-T maps (192/384/768 ch) -> input_proj + trainable "
                             "RepZeroConv2d adapters + GroupNorm -> 6 frozen deformable encoder layers -> 900 fixed-index queries -> 6 "
                             "frozen decoder layers (MHA self-attn, MSDeformAttn cross-attn, FFN) -> L1 loss + 0.1 x zero-inter loss; "
@@ -172,13 +182,222 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+class ZiraStep:
+    """One workload (config 2 or config 4) resident on one GPU: models, synthetic inputs, the captured step and its
+    end-to-end (pinned host in, loss out) variant."""
+
+    def __init__(self, cfg, world, rank, dev, args):
+        import torch
+        import torch.distributed as dist
+
+        import ziragroundingdino_b200 as zb
+        from ziragroundingdino_b200 import _lib, encoder, synthetic as syn
+        from ziragroundingdino_b200.dp import FlatGradBucket
+
+        self.torch, self.dist, self.cfg, self.world, self.dev = torch, dist, cfg, world, dev
+        nvtx = torch.cuda.nvtx
+        shapes = syn.SWIN_T_800x1333
+        S = sum(h * w for h, w in shapes)
+        N, C, dt = IMAGES[cfg], 256, torch.bfloat16
+        self.N = N
+        torch.manual_seed(1234)          # replicas: every rank builds the same weights; only the data differs per rank (seed 99 + rank)
+        enc = encoder.DeformableEncoder(NUM_LAYERS).to(dev)
+        with torch.no_grad():
+            for layer in enc.layers:   # query-dependent offsets / weights, as in a trained model
+                layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+                layer.self_attn.attention_weights.weight.normal_(0, 0.02)
+        enc = enc.to(dt)
+        for p in enc.parameters():
+            p.requires_grad_(False)
+        dec_layers = None
+        if cfg == 4:
+            from ziragroundingdino_b200.decoder import DeformableTransformerDecoderLayer
+            dec_layers = torch.nn.ModuleList([DeformableTransformerDecoderLayer(C, 2048, 0.0, "relu", len(shapes), 8, 4)
+                                              for _ in range(NUM_LAYERS)]).to(dev)
+            with torch.no_grad():
+                for layer in dec_layers:
+                    layer.cross_attn.sampling_offsets.weight.normal_(0, 0.01)
+                    layer.cross_attn.attention_weights.weight.normal_(0, 0.02)
+            dec_layers = dec_layers.to(dt)
+            for p in dec_layers.parameters():
+                p.requires_grad_(False)
+        # front of the encoder = the reference's trainable part (SURVEY.md 8(f) N3): frozen input_proj (1x1 convs over the Swin-T
+        # maps 192/384/768 -> 256, 3x3/s2 extra level, GroupNorm(32)) with a trainable RepZeroConv2d adapter beside each conv
+        front = zb.ZiRaInputProj((192, 384, 768), C, len(shapes)).to(dev)
+        with torch.no_grad():
+            for a in front.input_proj_conv_adapter:   # a branch mid-training: non-trivial soft-frozen and fresh weights
+                sc = a.weight[0].numel() ** -0.5
+                a.weight.normal_(0, 0.1 * sc); a.freeze_conv.weight.normal_(0, 0.1 * sc)
+        front = front.to(dt)
+        front.train()
+        params = []
+        for n_, p in front.named_parameters():
+            p.requires_grad_("adapter" in n_)          # the reference's before_train rule (:733-734)
+            if p.requires_grad:
+                params.append(p)
+        bucket = FlatGradBucket(params, world)
+        opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4, capturable=True, fused=True)
+        self.bucket = bucket
+
+        sh, lsi = syn.level_tensors(shapes, dev)
+        g = torch.Generator().manual_seed(99 + rank)
+        mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g, all_valid=args.all_valid)
+        feat_hw = list(shapes[:3])
+        feat_rows = [h * w for h, w in feat_hw]
+        feat_off = [0]
+        for c_, r_ in zip((192, 384, 768), feat_rows):
+            feat_off.append(feat_off[-1] + r_ * c_)
+        # the three backbone maps of the batch, channels-last rows, packed level after level: ONE pinned buffer / ONE copy per step
+        self.host_feat = torch.randn(N * feat_off[-1], generator=g).to(dt).pin_memory()
+        self.host_pos = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
+        self.host_mask = mask.cpu().pin_memory()
+        self.feat, self.pos, self.mask = self.host_feat.to(dev), self.host_pos.to(dev), mask
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+        def level_maps(packed):
+            return [packed[N * feat_off[i]:N * feat_off[i + 1]].view(N, feat_rows[i], c_) for i, c_ in enumerate((192, 384, 768))]
+
+        if cfg == 4:   # fixed random stand-ins for the two-stage query selection and the matched targets
+            q_idx = torch.randint(0, S, (N, NUM_QUERIES), generator=g).to(dev)
+            q_pos = torch.randn(NUM_QUERIES, N, C, generator=g).to(dt).to(dev)
+            boxes = torch.cat([torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.8 + 0.1,
+                               torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.45 + 0.05], -1).to(dev)
+            targets = torch.randn(NUM_QUERIES, N, C, generator=g).to(dev)
+            ref4 = (boxes[:, :, None, :] * torch.cat([valid, valid], -1)[None]).to(dt)       # transformer_for_adapter.py:720-724
+
+        class MeanSquare(torch.autograd.Function):
+            """mean(x^2) with fp32 accumulation: one reduction forward, ONE elementwise kernel backward (autograd through
+            vector_norm().square() spends three full passes on div / masked_fill / mul)."""
+
+            @staticmethod
+            def forward(ctx, x):
+                ctx.save_for_backward(x)
+                return torch.linalg.vector_norm(x, 2, dtype=torch.float32).square() / x.numel()
+
+            @staticmethod
+            def backward(ctx, g_):
+                (x,) = ctx.saved_tensors
+                return x * (g_ * (2.0 / x.numel())).to(x.dtype)
+
+        def fwd_bwd(feat_, pos_, mask_):
+            # NVTX ranges (SURVEY.md section 5): front / encoder / decoder / backward show up in an nsys / ncu --nvtx timeline
+            nvtx.range_push("zira.front")
+            src, proj_shapes, zloss = front.forward_rows(level_maps(feat_), feat_hw)
+            nvtx.range_pop()
+            assert proj_shapes == [tuple(x) for x in shapes]
+            nvtx.range_push("zira.encoder")
+            out = enc(src, pos_, shapes, sh, lsi, valid, mask_)
+            nvtx.range_pop()
+            if cfg == 4:
+                nvtx.range_push("zira.decoder")
+                tgt = torch.gather(out, 1, q_idx[:, :, None].expand(N, NUM_QUERIES, C)).transpose(0, 1)
+                memory = out.transpose(0, 1)
+                for layer in dec_layers:
+                    tgt, _ = layer(tgt=tgt, tgt_query_pos=q_pos, tgt_reference_points=ref4, memory=memory,
+                                   memory_key_padding_mask=mask_, memory_level_start_index=lsi, memory_spatial_shapes=sh)
+                loss = torch.nn.functional.l1_loss(tgt.float(), targets) + 0.1 * zloss.float()
+                nvtx.range_pop()
+            else:
+                # mean(out^2) with fp32 accumulation and no fp32 copy of the 91 MB activation
+                loss = MeanSquare.apply(out) + 0.1 * zloss.float()
+            nvtx.range_push("zira.backward")
+            loss.backward()
+            nvtx.range_pop()
+            return loss
+
+        def update():
+            nvtx.range_push("zira.update")
+            torch.nn.utils.clip_grad_norm_(params, 0.1)
+            opt.step()
+            bucket.zero_grad()
+            nvtx.range_pop()
+
+        def step(feat_, pos_, mask_):
+            loss = fwd_bwd(feat_, pos_, mask_)
+            bucket.all_reduce()          # the path's only collective; a no-op for one rank
+            update()
+            return loss
+
+        self.step_eager = lambda: step(self.feat, self.pos, self.mask)
+        self._fwd_bwd, self._update = fwd_bwd, update
+        self.graph = None
+        self.static_loss = None
+        self._lib = _lib
+
+    def warm_and_capture(self, use_graph):
+        """3 eager steps on a side stream, count launches of one step, then capture: one graph for forward+backward, one for
+        clip+AdamW; the NCCL all-reduce between them stays an eager call on the same stream (nothing for a single rank)."""
+        torch = self.torch
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(3):
+                self.step_eager()
+        torch.cuda.current_stream().wait_stream(s)
+        n0 = self._lib.launch_count()
+        self.step_eager()
+        self.launches_per_step = self._lib.launch_count() - n0
+        if use_graph:
+            self.graph, self.graph_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._fwd_bwd(self.feat, self.pos, self.mask)
+            self.bucket.all_reduce()
+            with torch.cuda.graph(self.graph_upd):
+                self._update()
+
+    def run(self):
+        if self.graph is None:
+            return self.step_eager()
+        self.graph.replay()
+        self.bucket.all_reduce()
+        self.graph_upd.replay()
+        return self.static_loss
+
+    # ---- end to end: pinned host inputs in, loss out, every step --------------------------------------
+    # A two-deep input pipeline, as a data loader would run it: step i's host->device copies are issued on a copy
+    # stream into a staging set while step i-1 computes; at the start of step i a device-to-device copy moves the
+    # staged inputs into the buffers the captured graph reads.  Every step still copies its own inputs from pinned
+    # host memory and reads its loss back; the host waits for the loss of step i before it returns.
+    def e2e_setup(self):
+        torch = self.torch
+        self.copy_stream = torch.cuda.Stream()
+        self.stage = [torch.empty_like(self.feat), torch.empty_like(self.pos), torch.empty_like(self.mask)]
+        self.staged_ready, self.staged_free = torch.cuda.Event(), torch.cuda.Event()
+        self.staged_free.record(torch.cuda.current_stream())
+        self._prefetch()
+
+    def _prefetch(self):
+        torch = self.torch
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(self.staged_free)           # previous contents consumed
+            self.stage[0].copy_(self.host_feat, non_blocking=True)
+            self.stage[1].copy_(self.host_pos, non_blocking=True)
+            self.stage[2].copy_(self.host_mask, non_blocking=True)
+            self.staged_ready.record(self.copy_stream)
+
+    def e2e_step(self):
+        cur = self.torch.cuda.current_stream()
+        cur.wait_event(self.staged_ready)
+        self.feat.copy_(self.stage[0], non_blocking=True)
+        self.pos.copy_(self.stage[1], non_blocking=True)
+        self.mask.copy_(self.stage[2], non_blocking=True)
+        self.staged_free.record(cur)
+        self._prefetch()                                        # next step's inputs travel while this step computes
+        loss = self.run()
+        self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        cur.synchronize()
+
+    @property
+    def h2d_bytes(self):
+        return self.host_feat.numel() * 2 + self.host_pos.numel() * 2 + self.host_mask.numel()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import ziragroundingdino_b200 as zb
-    from ziragroundingdino_b200 import _lib, encoder, synthetic as syn
-    from ziragroundingdino_b200.dp import FlatGradBucket
+    from ziragroundingdino_b200 import _lib, synthetic as syn
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -194,115 +413,6 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert _lib.lib().msda_b200_device_arch() >= 100
-
-    shapes = syn.SWIN_T_800x1333
-    S = sum(h * w for h, w in shapes)
-    N, C, dt = IMAGES_PER_GPU, 256, torch.bfloat16
-    torch.manual_seed(1234)          # replicas: every rank builds the same weights; only the data differs per rank (seed 99 + rank)
-    enc = encoder.DeformableEncoder(NUM_LAYERS).to(dev)
-    with torch.no_grad():
-        for layer in enc.layers:   # query-dependent offsets / weights, as in a trained model
-            layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
-            layer.self_attn.attention_weights.weight.normal_(0, 0.02)
-    enc = enc.to(dt)
-    for p in enc.parameters():
-        p.requires_grad_(False)
-    dec_layers = None
-    if CONFIG == 4:
-        from ziragroundingdino_b200.decoder import DeformableTransformerDecoderLayer
-        dec_layers = torch.nn.ModuleList([DeformableTransformerDecoderLayer(C, 2048, 0.0, "relu", len(shapes), 8, 4)
-                                          for _ in range(NUM_LAYERS)]).to(dev)
-        with torch.no_grad():
-            for layer in dec_layers:
-                layer.cross_attn.sampling_offsets.weight.normal_(0, 0.01)
-                layer.cross_attn.attention_weights.weight.normal_(0, 0.02)
-        dec_layers = dec_layers.to(dt)
-        for p in dec_layers.parameters():
-            p.requires_grad_(False)
-    # front of the encoder = the reference's trainable part: frozen input_proj (1x1 convs over the Swin-T
-    # maps 192/384/768 -> 256, 3x3/s2 extra level, GroupNorm(32)) with a trainable RepZeroConv2d adapter beside each conv
-    front = zb.ZiRaInputProj((192, 384, 768), C, len(shapes)).to(dev)
-    with torch.no_grad():
-        for a in front.input_proj_conv_adapter:   # a branch mid-training: non-trivial soft-frozen and fresh weights
-            sc = a.weight[0].numel() ** -0.5
-            a.weight.normal_(0, 0.1 * sc); a.freeze_conv.weight.normal_(0, 0.1 * sc)
-    front = front.to(dt)
-    front.train()
-    params = []
-    for n_, p in front.named_parameters():
-        p.requires_grad_("adapter" in n_)          # the reference's before_train rule (:733-734)
-        if p.requires_grad:
-            params.append(p)
-    bucket = FlatGradBucket(params, world)
-    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4, capturable=True, fused=True)
-
-    sh, lsi = syn.level_tensors(shapes, dev)
-    g = torch.Generator().manual_seed(99 + rank)
-    mask, valid = encoder.padded_batch_masks(shapes, N, dev, generator=g, all_valid=args.all_valid)
-    feat_hw = list(shapes[:3])
-    feat_rows = [h * w for h, w in feat_hw]
-    feat_off = [0]
-    for c_, r_ in zip((192, 384, 768), feat_rows):
-        feat_off.append(feat_off[-1] + r_ * c_)
-    # the three backbone maps of the batch, channels-last rows, packed level after level: ONE pinned buffer / ONE copy per step
-    host_feat = torch.randn(N * feat_off[-1], generator=g).to(dt).pin_memory()
-    host_pos = torch.randn(N, S, C, generator=g).to(dt).pin_memory()
-    host_mask = mask.cpu().pin_memory()
-    feat, pos = host_feat.to(dev), host_pos.to(dev)
-
-    def level_maps(packed):
-        return [packed[N * feat_off[i]:N * feat_off[i + 1]].view(N, feat_rows[i], c_) for i, c_ in enumerate((192, 384, 768))]
-    loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
-
-    if CONFIG == 4:   # fixed random stand-ins for the two-stage query selection and the matched targets
-        q_idx = torch.randint(0, S, (N, NUM_QUERIES), generator=g).to(dev)
-        q_pos = torch.randn(NUM_QUERIES, N, C, generator=g).to(dt).to(dev)
-        boxes = torch.cat([torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.8 + 0.1,
-                           torch.rand(NUM_QUERIES, N, 2, generator=g) * 0.45 + 0.05], -1).to(dev)
-        targets = torch.randn(NUM_QUERIES, N, C, generator=g).to(dev)
-        ref4 = (boxes[:, :, None, :] * torch.cat([valid, valid], -1)[None]).to(dt)       # transformer_for_adapter.py:720-724
-
-    class MeanSquare(torch.autograd.Function):
-        """mean(x^2) with fp32 accumulation: one reduction forward, ONE elementwise kernel backward (autograd through
-        vector_norm().square() spends three full passes on div / masked_fill / mul)."""
-
-        @staticmethod
-        def forward(ctx, x):
-            ctx.save_for_backward(x)
-            return torch.linalg.vector_norm(x, 2, dtype=torch.float32).square() / x.numel()
-
-        @staticmethod
-        def backward(ctx, g):
-            (x,) = ctx.saved_tensors
-            return x * (g * (2.0 / x.numel())).to(x.dtype)
-
-    def fwd_bwd(feat_, pos_, mask_):
-        src, proj_shapes, zloss = front.forward_rows(level_maps(feat_), feat_hw)
-        assert proj_shapes == [tuple(x) for x in shapes]
-        out = enc(src, pos_, shapes, sh, lsi, valid, mask_)
-        if CONFIG == 4:
-            tgt = torch.gather(out, 1, q_idx[:, :, None].expand(N, NUM_QUERIES, C)).transpose(0, 1)
-            memory = out.transpose(0, 1)
-            for layer in dec_layers:
-                tgt, _ = layer(tgt=tgt, tgt_query_pos=q_pos, tgt_reference_points=ref4, memory=memory,
-                               memory_key_padding_mask=mask_, memory_level_start_index=lsi, memory_spatial_shapes=sh)
-            loss = torch.nn.functional.l1_loss(tgt.float(), targets) + 0.1 * zloss.float()
-        else:
-            # mean(out^2) with fp32 accumulation and no fp32 copy of the 91 MB activation
-            loss = MeanSquare.apply(out) + 0.1 * zloss.float()
-        loss.backward()
-        return loss
-
-    def update():
-        torch.nn.utils.clip_grad_norm_(params, 0.1)
-        opt.step()
-        opt.zero_grad(set_to_none=False)
-
-    def step(feat_, pos_, mask_):
-        loss = fwd_bwd(feat_, pos_, mask_)
-        bucket.all_reduce()          # the path's only collective; a no-op for one rank
-        update()
-        return loss
 
     def barrier():
         if world > 1:
@@ -324,11 +434,12 @@ def run_ours(args):
             ms = t.item()
         return ms
 
+    wl = ZiraStep(CONFIG, world, rank, dev, args)
     if args.profile_step:
-        step(feat, pos, mask)
+        wl.step_eager()
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step(feat, pos, mask)
+        wl.step_eager()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         if world > 1:
@@ -336,34 +447,10 @@ def run_ours(args):
         return
 
     # ---- device-resident timing ---------------------------------------------------------------------
-    # The step (forward, backward, all-reduce, clip, AdamW) is captured once in a CUDA graph: ~250 launches of
-    # 20-1000 us each would otherwise leave the GPU waiting on the Python launch path.
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        for _ in range(3):
-            step(feat, pos, mask)
-    torch.cuda.current_stream().wait_stream(s)
-    n0 = _lib.launch_count()
-    step(feat, pos, mask)
-    launches_per_step = _lib.launch_count() - n0
-    graph = None
-    if not args.no_graph:
-        # one graph for forward+backward, one for clip+AdamW; the NCCL all-reduce between them stays an eager
-        # call on the same stream (for a single rank there is nothing between the two replays)
-        graph, graph_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            static_loss = fwd_bwd(feat, pos, mask)
-        bucket.all_reduce()
-        with torch.cuda.graph(graph_upd):
-            update()
-
-        def run():
-            graph.replay()
-            bucket.all_reduce()
-            graph_upd.replay()
-    else:
-        run = lambda: step(feat, pos, mask)
+    # The step (forward, backward, all-reduce, clip, AdamW) is captured once in CUDA graphs: ~250-400 launches of
+    # 5-1000 us each would otherwise leave the GPU waiting on the Python launch path.
+    wl.warm_and_capture(not args.no_graph)
+    run = wl.run
     if args.gaps:
         from torch.profiler import ProfilerActivity, profile
         for _ in range(5):
@@ -398,74 +485,74 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         run()
     ms = timed(run, args.steps)
-    launches = launches_per_step * args.steps
+    launches = wl.launches_per_step * args.steps
     if ms < 600.0:   # nvidia-smi needs a few hundred ms to start: keep the same load up (untimed).  `ms` is the max over
         # ranks, so every rank runs the same number of extra steps (they contain the all-reduce).
         for _ in range(int(800.0 / (ms / args.steps)) + 1):
             run()
         torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-
-    # ---- end to end: pinned host inputs in, loss out, every step --------------------------------------
-    # A two-deep input pipeline, as a data loader would run it: step i's host->device copies are issued on a copy
-    # stream into a staging set while step i-1 computes; at the start of step i a device-to-device copy moves the
-    # staged inputs into the buffers the captured graph reads.  Every step still copies its own 91 MB from pinned
-    # host memory and reads its loss back; the host waits for the loss of step i before it returns.
-    copy_stream = torch.cuda.Stream()
-    stage_feat, stage_pos, stage_mask = torch.empty_like(feat), torch.empty_like(pos), torch.empty_like(mask)
-    staged_ready, staged_free = torch.cuda.Event(), torch.cuda.Event()
-
-    def prefetch():
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(staged_free)           # previous contents consumed
-            stage_feat.copy_(host_feat, non_blocking=True)
-            stage_pos.copy_(host_pos, non_blocking=True)
-            stage_mask.copy_(host_mask, non_blocking=True)
-            staged_ready.record(copy_stream)
-
-    staged_free.record(torch.cuda.current_stream())
-    prefetch()
-
-    def e2e_step():
-        cur = torch.cuda.current_stream()
-        cur.wait_event(staged_ready)
-        feat.copy_(stage_feat, non_blocking=True)
-        pos.copy_(stage_pos, non_blocking=True)
-        mask.copy_(stage_mask, non_blocking=True)
-        staged_free.record(cur)
-        prefetch()                                        # next step's inputs travel while this step computes
-        if graph is not None:
-            run()
-            loss = static_loss
-        else:
-            loss = step(feat, pos, mask)
-        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        cur.synchronize()
-
+    wl.e2e_setup()
     for _ in range(2):
-        e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
-    h2d = host_feat.numel() * 2 + host_pos.numel() * 2 + host_mask.numel()
+        wl.e2e_step()
+    ms_e2e = timed(wl.e2e_step, args.steps)
+    h2d = wl.h2d_bytes
+    N = wl.N
+    use_graph = wl.graph is not None
+    del wl, run
+    torch.cuda.empty_cache()
 
-    # ---- the dominant kernel alone: backward scatter of one layer (CUDA events on the launching stream) ----
-    inp = syn.core_inputs(shapes, N, dtype=dt, regime="local", device=dev, seed=5)
-    cargs = (inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"])
-    ab = syn.algorithmic_bytes(*inp["dims"], 2)
+    # ---- the other workload of BASELINE.json's metric, same process, same protocol (config 2 <-> config 4) --------
+    other = None
+    if args.config is None:
+        oc = 2 if CONFIG == 4 else 4
+        w2 = ZiraStep(oc, world, rank, dev, args)
+        w2.warm_and_capture(not args.no_graph)
+        for _ in range(max(args.warmup, 3)):
+            w2.run()
+        ms2 = timed(w2.run, args.steps)
+        w2.e2e_setup()
+        for _ in range(2):
+            w2.e2e_step()
+        ms2_e2e = timed(w2.e2e_step, args.steps)
+        img2 = IMAGES[oc] * world * args.steps
+        other = {"metric": METRICS[oc], "value": img2 / (ms2 / 1e3), "unit": "images/s", "ms_per_step": ms2 / args.steps,
+                 "images_per_gpu": IMAGES[oc], "gpu_launches": w2.launches_per_step * args.steps,
+                 "e2e": {"value": img2 / (ms2_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": w2.h2d_bytes, "d2h_bytes_per_step": 4},
+                 "workload": workload_config(world, oc)["workload"]}
+        del w2
+        torch.cuda.empty_cache()
 
-    def kernel_us(fn, reps=10):
-        for _ in range(3):
-            fn()
+    # ---- the dominant kernels alone (CUDA events on the launching stream) -----------------------------------------
+    # One encoder layer's gather and scatter at config 2's launch (4 images, bf16).  The scatter timed is the kernel the
+    # step runs -- msda_backward_fusedq_16 (query-side backward fused in) -- with its inputs ROTATED over 3 input sets
+    # (3 x ~460 MB > the 126 MB L2), so every launch starts as cold as it does inside the step.
+    KN = 4
+    sets = [syn.core_inputs(syn.SWIN_T_800x1333, KN, dtype=torch.bfloat16, regime="local", device=dev, seed=5 + i) for i in range(3)]
+    dims = sets[0]["dims"]
+    ab = syn.algorithmic_bytes(*dims, 2)
+    refs = [syn.encoder_reference_points(syn.SWIN_T_800x1333, torch.ones(KN, 4, 2, device=dev), dev).contiguous() for _ in sets]
+    from ziragroundingdino_b200 import fused
+
+    def kernel_us(fns, reps=12):
+        for f in fns:
+            f()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         a.record()
-        for _ in range(reps):
-            fn()
+        for i in range(reps):
+            fns[i % len(fns)]()
         b.record()
         torch.cuda.synchronize()
         return a.elapsed_time(b) * 1e3 / reps
 
-    us_fwd = kernel_us(lambda: zb._C.ms_deform_attn_forward(*cargs, 64))
-    us_bwd = kernel_us(lambda: zb._C.ms_deform_attn_backward(*cargs, inp["grad_out"], 64))
+    cargs = [(i_["value"], i_["shapes"], i_["level_start"], i_["loc"], i_["aw"]) for i_ in sets]
+    us_fwd = kernel_us([(lambda c=c: zb._C.ms_deform_attn_forward(*c, 64)) for c in cargs])
+    n0 = _lib.launch_count()
+    fused.backward_fusedq16(*cargs[0], sets[0]["grad_out"], refs[0], 2)
+    bwd_launches = _lib.launch_count() - n0
+    us_bwd = kernel_us([(lambda c=c, i_=i_, r=r: fused.backward_fusedq16(*c, i_["grad_out"], r, 2)) for c, i_, r in zip(cargs, sets, refs)])
+    us_bwd_plain = kernel_us([(lambda c=c, i_=i_: zb._C.ms_deform_attn_backward(*c, i_["grad_out"], 64)) for c, i_ in zip(cargs, sets)])
 
     # live probes of the two memory-system limits these kernels run against (nothing but the access shape):
     #   gather : random 64-byte rows (one bf16 head row) read from an L2-resident 22 MB buffer
@@ -475,12 +562,47 @@ def run_ours(args):
     sink = torch.zeros(4, dtype=torch.int32, device=dev)
     cs = torch.cuda.current_stream().cuda_stream
     g_blocks, g_iters, s_blocks, s_iters = 148 * 16, 512, 148 * 16, 256
-    us_pg = kernel_us(lambda: Lc.msda_b200_probe_gather(pbuf.data_ptr(), 22 << 20, 64, g_iters, g_blocks, sink.data_ptr(), cs), 5)
-    us_ps = kernel_us(lambda: Lc.msda_b200_probe_scatter(pbuf.data_ptr(), pbuf.numel() * 4, 0, s_iters, s_blocks, cs), 5)
+    us_pg = kernel_us([lambda: Lc.msda_b200_probe_gather(pbuf.data_ptr(), 22 << 20, 64, g_iters, g_blocks, sink.data_ptr(), cs)], 5)
+    us_ps = kernel_us([lambda: Lc.msda_b200_probe_scatter(pbuf.data_ptr(), pbuf.numel() * 4, 0, s_iters, s_blocks, cs)], 5)
     gather_peak = g_blocks * 256 * 16 * g_iters / us_pg / 1e3           # GB/s
     scatter_peak = s_blocks * 256 * 16 * s_iters / us_ps / 1e3          # GB/s of reduction payload
-    red_bytes = N * inp["dims"][5] * inp["dims"][2] * inp["dims"][4] * inp["dims"][6] * 4 * 128   # one 128 B fp32 row per corner
+    red_rows = KN * dims[5] * dims[2] * dims[4] * dims[6] * 4           # one 128 B fp32 row per bilinear corner
     del pbuf
+
+    # config 5, stride-4 reading (Swin-B 1024x1800, 5 levels, S = 153 520, 2 images, bf16): the 157 MB value map is NOT
+    # L2-resident -- the one configuration where HBM binds; reported against the HBM-compulsory bytes.
+    c5 = None
+    if rank == 0 and not args.no_config5:
+        i5 = syn.core_inputs(syn.SWIN_B_1024x1800_S4, 2, dtype=torch.bfloat16, regime="local", device=dev, seed=9)
+        a5 = (i5["value"], i5["shapes"], i5["level_start"], i5["loc"], i5["aw"])
+        ab5 = syn.algorithmic_bytes(*i5["dims"], 2)
+        us5f = kernel_us([lambda: zb._C.ms_deform_attn_forward(*a5, 64)], 5)
+        us5b = kernel_us([lambda: zb._C.ms_deform_attn_backward(*a5, i5["grad_out"], 64)], 5)
+        c5 = {"workload": "Swin-B 1024x1800, 5 levels (256x450 ... 16x29), S=153520, 2 images, bf16, encoder self-attention",
+              "fwd_us": us5f, "bwd_us": us5b, "fwd_hbm_compulsory_bytes": ab5["fwd_hbm"], "bwd_hbm_compulsory_bytes": ab5["bwd_hbm"],
+              "fwd_hbm_gbps": ab5["fwd_hbm"] / us5f / 1e3, "bwd_hbm_gbps": ab5["bwd_hbm"] / us5b / 1e3}
+        del i5, a5
+
+    # the reference's own CUDA op (oracle/_ref/ref_C.so, built in place from the unmodified sources) on the same box and
+    # the same launch, fp32 (it has no bf16): a BASELINE leg like cpu_baseline -- reported beside ours, never on the path
+    ref_ab = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import build_ref
+            ref = build_ref.load()
+        except Exception:
+            ref = None
+        if ref is not None:
+            i32 = syn.core_inputs(syn.SWIN_T_800x1333, KN, dtype=torch.float32, regime="local", device=dev, seed=5)
+            a32 = (i32["value"], i32["shapes"], i32["level_start"], i32["loc"], i32["aw"])
+            ref_ab = {"images": KN, "dtype": "f32",
+                      "ref_fwd_us": kernel_us([lambda: ref.ms_deform_attn_forward(*a32, 64)], 5),
+                      "ref_bwd_us": kernel_us([lambda: ref.ms_deform_attn_backward(*a32, i32["grad_out"], 64)], 5),
+                      "ours_f32_fwd_us": kernel_us([lambda: zb._C.ms_deform_attn_forward(*a32, 64)], 5),
+                      "ours_f32_bwd_us": kernel_us([lambda: zb._C.ms_deform_attn_backward(*a32, i32["grad_out"], 64)], 5),
+                      "ours_bf16_fwd_us": us_fwd, "ours_bf16_bwd_us": us_bwd_plain,
+                      "source": "oracle/_ref/ref_C.so = unmodified reference csrc/MsDeformAttn compiled for sm_100a"}
+            del i32, a32
 
     if rank != 0:
         if world > 1:
@@ -493,46 +615,57 @@ def run_ours(args):
     except OSError:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    traffic = None
+    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    bwd_kernel = "msda_bwd_vec_kernel<bf16,32,FUSEQ>"
+    traffic, traffic_src = None, None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same launch
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["msda_bwd_vec_kernel<bf16,32>"]["dram_bytes_per_launch"]
+        ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[bwd_kernel]
+        traffic, traffic_src = ent["dram_bytes_per_launch"], ent["source"]
     except (OSError, KeyError, ValueError):
         pass
-    peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    images = IMAGES_PER_GPU * world * args.steps
+    if c5 is not None:
+        c5["fwd_hbm_frac"] = c5["fwd_hbm_gbps"] / hbm_peak
+        c5["bwd_hbm_frac"] = c5["bwd_hbm_gbps"] / hbm_peak
+    images = N * world * args.steps
     value = images / (ms / 1e3)
+    red_bytes = red_rows * 128
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=graph is not None,
+        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=use_graph,
                                             **({"padding": "none (all-valid case)"} if args.all_valid else {})), "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "images": N,
+        "other_workload": other,
+        "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "bwd_unfused_q": us_bwd_plain, "bwd_launches": bwd_launches,
+                                   "images": KN, "cold_l2": "inputs rotated over 3 sets (> L2)",
                                    "fwd_l2_algorithmic_gbps": ab["fwd_l2"] / us_fwd / 1e3,
                                    "bwd_l2_algorithmic_gbps": ab["bwd_l2"] / us_bwd / 1e3},
-        "roofline": {"kernel": "msda_bwd_vec_kernel<bf16,32>", "bound": "hbm", "achieved": ab["bwd_hbm"] / us_bwd / 1e3,
+        "roofline": {"kernel": bwd_kernel, "bound": "hbm", "achieved": ab["bwd_hbm"] / us_bwd / 1e3,
                      "peak": hbm_peak, "unit": "GB/s", "frac": ab["bwd_hbm"] / us_bwd / 1e3 / hbm_peak, "traffic": traffic,
-                     "algorithmic_bytes": ab["bwd_hbm"],
-                     "peak_source": peak_src,
-                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d); the kernel is bound by the L2 reduction rate "
-                             "(roofline_l2_scatter; ncu: l1tex 86 %, lts 69 %, DRAM 6 %), not HBM -- see DESIGN.md 4.2 and profiles/"},
-        "roofline_l2": {"kernels": "msda_fwd_vec_kernel + msda_bwd_vec_kernel", "bound": "l2-gather",
+                     "traffic_source": traffic_src, "algorithmic_bytes": ab["bwd_hbm"], "peak_source": peak_src,
+                     "note": "HBM-compulsory bytes (2Bv+2Bl+2Ba+Bo, SURVEY 8d) over the duration of msda_backward_fusedq_16, the "
+                             "scatter the step launches; the kernel is bound by the SM->L2 reduction path (roofline_l2_scatter), "
+                             "not HBM -- see DESIGN.md 4.2 and profiles/"},
+        "roofline_l2": {"kernels": "msda_fwd_vec_kernel + " + bwd_kernel, "bound": "l2-gather",
                         "achieved": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3, "peak": gather_peak, "unit": "GB/s",
                         "frac": (ab["fwd_l2"] + ab["bwd_l2"]) / (us_fwd + us_bwd) / 1e3 / gather_peak,
                         "peak_source": "msda_b200_probe_gather run in this process: random 64 B rows of an L2-resident 22 MB buffer"},
-        "roofline_l2_scatter": {"kernel": "msda_bwd_vec_kernel<bf16,32>", "bound": "l2-reduction",
+        "roofline_l2_scatter": {"kernel": bwd_kernel, "bound": "l2-reduction",
                                 "achieved": red_bytes / us_bwd / 1e3, "peak": scatter_peak, "unit": "GB/s",
                                 "frac": red_bytes / us_bwd / 1e3 / scatter_peak, "reduction_bytes": red_bytes,
                                 "peak_source": "msda_b200_probe_scatter run in this process: red.global.add.v4.f32 of random 128 B "
                                                "rows into an L2-resident 91 MB buffer, nothing else in flight",
-                                "note": "grad_value leaves the SM as one 128-byte fp32 reduction per bilinear corner "
-                                        "(N*Lq*M*L*P*4 rows); the kernel also re-gathers value and writes grad_loc / grad_aw"},
+                                "note": "reduction_bytes = one 128-byte fp32 row per bilinear corner (N*Lq*M*L*P*4 rows), the "
+                                        "ALGORITHMIC scatter; a kernel that combines rows on the SM before they leave sends fewer "
+                                        "and can exceed 1.0 of this instruction-shape probe"},
+        "config5_stride4": c5, "ref_cuda_us_per_layer": ref_ab,
     }
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         ips, layers, t = cpu_images_per_s(20.0, threads)
         out["cpu_baseline"] = {"value": ips, "unit": "images/s", "cores": threads, "kind": "port",
-                               "sample": "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers) fwd+bwd (fp32, torch CPU, grid_sample core), %.1f s" % (layers, t)}
+                               "sample": "1 image x (input_proj + ZiRa adapters, %d of 6 encoder layers%s) fwd+bwd (fp32, torch CPU, "
+                                         "grid_sample core), %.1f s" % (layers, ", 6 decoder layers" if CONFIG == 4 else "", t)}
     sys.stdout.flush()
     os.write(json_fd, (json.dumps(out) + "\n").encode())
     if world > 1:

@@ -20,6 +20,17 @@ def pytest_configure(config):
         subprocess.check_call(["bash", os.path.join(ROOT, "ziragroundingdino_b200", "csrc", "build.sh")])
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests need a CUDA device: skip them (instead of failing 180 times) on a CPU-only host."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def load_golden(name):
     with np.load(os.path.join(GOLDEN, name + ".npz")) as z:
         return {k: z[k] for k in z.files}

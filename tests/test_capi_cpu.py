@@ -197,3 +197,30 @@ def test_zira_input_proj_keys_and_level_wiring():
         for o, w in zip(outs, want):
             assert (o - w).abs().max() < 1e-12
         assert abs(float(loss) - float(wl)) < 1e-12
+
+
+def test_host_shapes_under_inference_mode():
+    """inference tensors have no version counter; the shape cache must not touch ``_version`` for them."""
+    import torch
+    from ziragroundingdino_b200 import ms_deform_attn as M
+    with torch.inference_mode():
+        sh = torch.tensor([[4, 5], [2, 3]])
+        assert sh.is_inference()
+        assert M._host_shapes(sh) == ((4, 5), (2, 3))
+        p = torch.nn.Parameter(torch.zeros(2))
+    assert M._version_of(torch.zeros(2)) == 0
+    with torch.inference_mode():
+        t = torch.zeros(2)
+        assert M._version_of(t) != M._version_of(t)       # never equal: no stale cache hit
+    from ziragroundingdino_b200 import layer_ops
+    with torch.inference_mode():
+        w = torch.ones(3, 2)
+        assert layer_ops.derived(w, "t").shape == (2, 3)
+
+
+def test_fusedq_gate_needs_k_multiple_of_64():
+    """3*M*L*P must be a multiple of the dgrad GEMM's K granularity for the fused-query backward."""
+    from ziragroundingdino_b200 import fused
+    assert fused.fusedq_ok(8, 4, 4, 32)
+    assert not fused.fusedq_ok(6, 4, 4, 32)       # 288 columns: un-fused pair with the padded row
+    assert not fused.fusedq_ok(8, 4, 4, 64)

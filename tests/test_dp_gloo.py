@@ -69,3 +69,26 @@ def test_flat_bucket_single_process():
     b = FlatGradBucket(br.parameters(), 1)
     assert b.all_reduce() is None and b.nbytes == (2 * (16 + 4) + 1) * 4
     b.zero()
+
+
+def test_flat_bucket_detects_detached_grads():
+    """optimizer.zero_grad(set_to_none=True) or a re-created Parameter detaches a grad from the bucket; the
+    all-reduce must refuse instead of averaging stale zeros."""
+    import pytest
+    from ziragroundingdino_b200.dp import FlatGradBucket
+    lin = torch.nn.Linear(4, 3)
+    params = list(lin.parameters())
+    bucket = FlatGradBucket(params, 1)
+    bucket.all_reduce()                                   # attached: fine
+    torch.optim.SGD(params, lr=0.1).zero_grad()           # default set_to_none=True
+    with pytest.raises(RuntimeError, match="not a view of the bucket"):
+        bucket.all_reduce()
+    bucket.attach()
+    lin(torch.randn(2, 4)).sum().backward()
+    assert bucket.flat.abs().sum() > 0
+    bucket.zero_grad()
+    assert bucket.flat.abs().sum() == 0
+    bucket.all_reduce()
+    lin.weight.grad = torch.zeros_like(lin.weight)        # a foreign gradient tensor
+    with pytest.raises(RuntimeError):
+        bucket.check_attached()

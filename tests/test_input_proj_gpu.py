@@ -163,3 +163,43 @@ def test_input_proj_fp32_master_adapters_with_bf16_activations():
     m2 = m2.to(torch.bfloat16).train()
     src2, _, loss2 = m2.forward_rows(rows, hw)
     assert (src.float() - src2.float()).abs().max().item() < 0.1 and abs(float(loss) - float(loss2)) < 2e-2 * float(loss2)
+
+
+def test_five_level_training_backward_through_im2col_level():
+    """with num_feature_levels = backbone levels + 2 the last level reads the previous PROJECTED level, which
+    depends on trainable adapters, so the im2col'd 3x3 level (K = 9*256 = 2304 > the tcgen05 GEMM's 2048-column limit)
+    needs d(input) in backward: it must run (library product for that one dgrad), not raise."""
+    import ziragroundingdino_b200 as zb
+    torch.manual_seed(17)
+    m = zb.ZiRaInputProj((192, 384, 768), 256, 5).to(DEV, torch.bfloat16)
+    with torch.no_grad():
+        for a in m.input_proj_conv_adapter:
+            sc = (a.weight[0].numel()) ** -0.5
+            a.weight.normal_(0, 0.3 * sc); a.freeze_conv.weight.normal_(0, 0.3 * sc)
+    for n, p in m.named_parameters():
+        p.requires_grad_("adapter" in n)
+    m.train()
+    hw = [(25, 42), (13, 21), (7, 11)]
+    rows = [_rand((2, h * w, c), torch.bfloat16, 40 + i) for i, (c, (h, w)) in enumerate(zip((192, 384, 768), hw))]
+    src, shapes, loss = m.forward_rows(rows, hw)
+    assert shapes == [(25, 42), (13, 21), (7, 11), (4, 6), (2, 3)]
+    # a loss on the LAST level only: its gradient reaches level 3's adapter solely through the K = 2304 dgrad
+    last = src[:, -6:]
+    last.float().square().mean().backward()
+    g3 = m.input_proj_conv_adapter[3].weight.grad
+    assert g3 is not None and torch.isfinite(g3).all() and g3.abs().max() > 0
+    # eager NCHW reference of the same two levels in fp64 for the gradient of level 3's branch weight
+    d = lambda t: t.detach().double()
+    a3, a4 = m.input_proj_conv_adapter[3], m.input_proj_conv_adapter[4]
+    w3 = d(a3.weight).requires_grad_(True)
+    x = d(rows[2]).transpose(1, 2).reshape(2, 768, 7, 11)
+    F_ = torch.nn.functional
+    y3 = F_.conv2d(x, d(m.input_proj[3][0].weight), d(m.input_proj[3][0].bias), stride=2, padding=1) \
+        + d(a3.scaling) * F_.conv2d(x, w3, d(a3.bias), stride=2, padding=1) + F_.conv2d(x, d(a3.freeze_conv.weight), d(a3.freeze_conv.bias), stride=2, padding=1)
+    s3 = F_.group_norm(y3, 32, d(m.input_proj[3][1].weight), d(m.input_proj[3][1].bias), 1e-5)
+    s3 = s3.to(torch.bfloat16).double() + (s3 - s3.detach())          # the bf16 rounding of the stored level
+    y4 = F_.conv2d(s3, d(m.input_proj[4][0].weight), d(m.input_proj[4][0].bias), stride=2, padding=1) \
+        + d(a4.scaling) * F_.conv2d(s3, d(a4.weight), d(a4.bias), stride=2, padding=1) + F_.conv2d(s3, d(a4.freeze_conv.weight), d(a4.freeze_conv.bias), stride=2, padding=1)
+    s4 = F_.group_norm(y4, 32, d(m.input_proj[4][1].weight), d(m.input_proj[4][1].bias), 1e-5)
+    s4.flatten(2).transpose(1, 2).square().mean().backward()
+    assert rel_err(g3.double().cpu(), w3.grad.cpu()) < 5e-2

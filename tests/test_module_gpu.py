@@ -62,7 +62,7 @@ def test_module_bf16_within_1e2():
     truth = O.module_forward(params, q.detach().double().cpu(), v.detach().double().cpu(), None, refp.double().cpu(),
                              sh.cpu(), M, L, P)
     scale = truth.abs().max().item()
-    assert (out.detach().double().cpu() - truth).abs().max().item() < 2e-2 * max(scale, 1.0)
+    assert (out.detach().double().cpu() - truth).abs().max().item() < 1e-2 * scale      # north_star: bf16 within 1e-2
 
 
 def test_module_errors():

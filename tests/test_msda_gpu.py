@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 
 SWIN_T = [(100, 167), (50, 84), (25, 42), (13, 21)]
 SWIN_B5 = [(128, 225), (64, 113), (32, 57), (16, 29), (8, 15)]
+SWIN_B5_S4 = [(256, 450), (128, 225), (64, 113), (32, 57), (16, 29)]   # stride-4 reading: S = 153 520, value map NOT L2-resident
 
 
 def _dev():
@@ -182,7 +183,8 @@ def test_all_samples_outside_gives_zero():
     assert out.abs().max() == 0 and gv.abs().max() == 0 and gl.abs().max() == 0 and ga.abs().max() == 0
 
 
-@pytest.mark.parametrize("shapes,N,tag", [(SWIN_T, 4, "config2_encoder_N4"), (SWIN_B5, 2, "config5_swinB_N2")])
+@pytest.mark.parametrize("shapes,N,tag", [(SWIN_T, 4, "config2_encoder_N4"), (SWIN_B5, 2, "config5_swinB_N2"),
+                                          (SWIN_B5_S4, 2, "config5_swinB_stride4_N2")])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_full_size_properties(shapes, N, tag, dtype):
     """BASELINE.json full sizes (encoder self-attention, Lq = S): size-independent properties.

@@ -85,7 +85,7 @@ class SelfAttnBlockFunction(Function):
         dt = value.dtype
         dz = _add_ln_bwd(dy.reshape(N * S, C).contiguous(), z, g32, mean, rstd)     # d(src) via the residual AND d(attn out)
         d_core = fused.linear16(dz, prep.w_o_t)
-        if fused.fuse_query_backward and (L, P, C // M) == (4, 4, 32):
+        if fused.fusedq_ok(M, L, P, C // M):
             grad_value, dq_cat = fused.backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim)
         else:
             grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,

@@ -55,6 +55,53 @@ __global__ void __launch_bounds__(256) scatter_probe_kernel(float* __restrict__ 
       asm volatile("red.relaxed.gpu.global.add.f32 [%0], %1;" :: "l"(p + lig), "f"(v) : "memory");
   }
 }
+
+// Round-2 shapes (is the scatter bound by REQUESTS or by BYTES on the SM->L2 path?)
+//   MODE 3: 64-byte fp32 rows (4 lanes x red.v4.f32)            -- half the bytes per row, same row count
+//   MODE 4: 64-byte bf16 rows (4 lanes x red.v4.bf16x2 = 32 ch) -- packed 16-bit reduction, half the bytes of a 128 B fp32 row
+//   MODE 5: 256-byte contiguous fp32 (16 lanes x red.v4.f32)    -- two neighbouring rows as one warp-contiguous request
+//   MODE 6: 128-byte rows staged in shared memory, sent by cp.reduce.async.bulk.global.shared::cta.add.f32 (TMA path,
+//           one elected lane per 4-row warp tile) -- moves the reduction off the LSU -> XBAR request path
+template <int MODE>
+__global__ void __launch_bounds__(256) scatter_probe2_kernel(float* __restrict__ buf, uint32_t nrow128, int iters) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (MODE == 6) {
+    __shared__ __align__(128) float stage[8][2][4 * 32];    // per warp: 2 buffers x 4 rows x 128 B
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t wg = tid >> 5;
+    for (int i = 0; i < iters; ++i) {
+      float* sb = stage[warp][i & 1];
+      if (i >= 2 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
+      *reinterpret_cast<float4*>(sb + lane * 4) = make_float4(1e-6f, 1e-6f, 1e-6f, 1e-6f);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane < 4) {
+        const uint32_t row = mix((wg * 4 + lane) * 2654435761u + static_cast<uint32_t>(i) * 40503u) % nrow128;
+        float* dst = buf + static_cast<size_t>(row) * 32;
+        const uint32_t src = static_cast<uint32_t>(__cvta_generic_to_shared(sb + lane * 32));
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], 128;" :: "l"(dst), "r"(src) : "memory");
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    return;
+  }
+  constexpr int LPG = MODE == 5 ? 16 : 4;
+  const uint32_t group = tid / LPG, lig = tid % LPG;
+  const float v = 1e-6f * static_cast<float>(lig);
+  const uint32_t nseg = MODE == 5 ? nrow128 / 2 : nrow128 * 2;     // 256 B / 64 B segments
+  for (int i = 0; i < iters; ++i) {
+    const uint32_t seg = mix(group * 2654435761u + static_cast<uint32_t>(i) * 40503u) % nseg;
+    float* p = buf + static_cast<size_t>(seg) * (MODE == 5 ? 64 : 16) + lig * 4;
+    if (MODE == 4) {
+      const uint32_t w = 0x3c003c00u;
+      asm volatile("red.relaxed.gpu.global.add.noftz.v4.bf16x2 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(w), "r"(w), "r"(w), "r"(w) : "memory");
+    } else {
+      asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v), "f"(v), "f"(v), "f"(v) : "memory");
+    }
+  }
+}
 }  // namespace
 
 extern "C" int msda_b200_probe_scatter(void* buf, long long bytes, int mode, int iters, int blocks, void* stream) {
@@ -65,6 +112,10 @@ extern "C" int msda_b200_probe_scatter(void* buf, long long bytes, int mode, int
   if (mode == 0) scatter_probe_kernel<0><<<blocks, 256, 0, st>>>(b, nrow, iters);
   else if (mode == 1) scatter_probe_kernel<1><<<blocks, 256, 0, st>>>(b, nrow, iters);
   else if (mode == 2) scatter_probe_kernel<2><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 3) scatter_probe2_kernel<3><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 4) scatter_probe2_kernel<4><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 5) scatter_probe2_kernel<5><<<blocks, 256, 0, st>>>(b, nrow, iters);
+  else if (mode == 6) scatter_probe2_kernel<6><<<blocks, 256, 0, st>>>(b, nrow, iters);
   else return MSDA_ERR_UNSUPPORTED;
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);

@@ -20,6 +20,9 @@ from torch.autograd.function import once_differentiable
 from . import _C, _lib
 
 
+GEMM_MAX_N = 2048   # pg::MAX_N of csrc/proj_gemm.cu: widest output one launch of the tcgen05 GEMM covers
+
+
 def _stream(t):
     return torch.cuda.current_stream(t.device).cuda_stream
 
@@ -100,6 +103,13 @@ def backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, grad_co
 fuse_query_backward = True   # A/B switch (tests, benchmarks)
 
 
+def fusedq_ok(M, L, P, D):
+    """The scatter kernel with the query-side backward fused in writes dq rows of exactly 3*M*L*P columns (L = P = 4,
+    D = 32); the dgrad GEMM that reads them needs K % 64 == 0, so M % 4 != 0 (e.g. 192 / 6 heads) takes the un-fused
+    pair msda_backward + msda_query_bwd_prep_16, whose output row IS padded."""
+    return fuse_query_backward and (L, P, D) == (4, 4, 32) and (3 * M * L * P) % 64 == 0
+
+
 def supported(embed_dim, M, L, P, dtype):
     lp = L * P
     tpg = lp // 4
@@ -161,7 +171,7 @@ class FusedMSDeformAttnFunction(Function):
         dt = value.dtype
         g2d = grad_out.contiguous().view(N * Lq, C)
         d_core = linear16(g2d, prep.w_o_t)
-        if fuse_query_backward and (L, P, C // M) == (4, 4, 32):
+        if fusedq_ok(M, L, P, C // M):
             grad_value, dq_cat = backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim)
         else:
             grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
@@ -262,6 +272,10 @@ class ZiRaLinear16Function(Function):
         R, K = x2d.shape
         F = w0.shape[0]
         dt = x2d.dtype
+        for name, t in (("w0", w0), ("b0", b0), ("wf", wf), ("bf", bf), ("wb", wb), ("bb", bb), ("scaling", s)):
+            if t.dtype != dt:   # the GEMM reads raw 16-bit words: a promoted (fp32) stack would be read as garbage
+                raise TypeError("ZiRaLinear16Function: %s is %s but the activation is %s -- cast the adapter weights with an "
+                                "autograd-visible .to() at the call site" % (name, t.dtype, dt))
         w_stack = _interleave32(w0, wf, wb)
         bias3 = torch.cat([b0, bf, bb]).float()
         s32 = s.detach().float().reshape(1).contiguous()
@@ -303,7 +317,8 @@ class ZiRaLinear16Function(Function):
         gx = None
         if ctx.needs_input_grad[0]:   # dX = dY W_0 + dO W_f + dB (s W_b): one GEMM with K = 3F
             w_t = torch.cat([w0.t(), wf.t(), (wb * s).t()], 1).contiguous()
-            gx = linear16(stacked, w_t)
+            # the tcgen05 GEMM holds Nout <= 2048; the im2col'd 3x3 level has K = 9*C_in (2304 / 6912): library product there
+            gx = linear16(stacked, w_t) if K <= GEMM_MAX_N else stacked @ w_t.t()
         d_y, d_o, d_b = stacked[:, :F], stacked[:, F:2 * F], stacked[:, 2 * F:]
         if fused_colsum:
             bias_sum = lambda k, blk: colsum[k * F:(k + 1) * F]

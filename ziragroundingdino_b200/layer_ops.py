@@ -19,19 +19,25 @@ def derived(p, kind):
     """Kernel-ready form of a parameter -- ``"f32"`` (fp32 contiguous copy: LayerNorm / GroupNorm affine, biases) or
     ``"t"`` (contiguous transpose: the dgrad operand) -- built once per parameter version instead of once per call
     (the layers around the path are frozen in the ZiRa configuration; each rebuild is a ~3 us kernel, ~60 per step).
-    Nothing is cached while a CUDA graph is being captured (the copy would live in the graph's private pool)."""
+    Nothing is cached while a CUDA graph is being captured (the copy would live in the graph's private pool).
+    Like every version-keyed cache, a write through ``p.data`` is not seen: call ``clear_derived()`` after one."""
     key = (id(p), kind)
     ent = _DERIVED.get(key)
-    if ent is not None and ent[0]() is p and ent[1] == (p._version, p.data_ptr(), p.dtype, p.device):
+    inference = p.is_inference()          # no version counter: never cached
+    if ent is not None and not inference and ent[0]() is p and ent[1] == (p._version, p.data_ptr(), p.dtype, p.device):
         return ent[2]
     with torch.no_grad():
         v = p.detach().float().contiguous() if kind == "f32" else p.detach().t().contiguous()
-    if not (p.is_cuda and torch.cuda.is_current_stream_capturing()):
+    if not inference and not (p.is_cuda and torch.cuda.is_current_stream_capturing()):
         if len(_DERIVED) > 1024:                      # entries of parameters that no longer exist
             for k in [k for k, e in _DERIVED.items() if e[0]() is None]:
                 del _DERIVED[k]
         _DERIVED[key] = (weakref.ref(p), (p._version, p.data_ptr(), p.dtype, p.device), v)
     return v
+
+
+def clear_derived():
+    _DERIVED.clear()
 
 
 class AddLayerNormFunction(Function):

@@ -72,11 +72,17 @@ def multi_scale_deformable_attn_pytorch(*args, **kwargs):
 _SHAPE_CACHE = {}
 
 
+def _version_of(t):
+    """Version counter of a tensor, or a fresh object for inference tensors (which have none): never equal, so no caching."""
+    return object() if t.is_inference() else t._version
+
+
 def _host_shapes(spatial_shapes):
     """Host copy of ``spatial_shapes`` as a tuple of (H, W).  Cached per tensor *object* (weak reference) and
     version counter, so a call costs one device->host sync the first time a given tensor is seen and none
     afterwards (the reference syncs on every call, ms_deform_attn.py:284)."""
-    if not spatial_shapes.is_cuda:
+    if not spatial_shapes.is_cuda or spatial_shapes.is_inference():
+        # inference tensors carry no version counter (reading ``_version`` raises): no cache, one sync, as the reference
         return tuple((int(h), int(w)) for h, w in spatial_shapes.tolist())
     key = id(spatial_shapes)
     hit = _SHAPE_CACHE.get(key)
@@ -192,7 +198,8 @@ class MultiScaleDeformableAttention(nn.Module):
             return False
         if reference_points.shape[-1] not in (2, 4) or reference_points.requires_grad:
             return False
-        return True
+        # the 16-bit GEMMs read raw parameter words: fp32 parameters beside 16-bit activations take the generic path
+        return all(p.dtype == value.dtype for p in self.parameters())
 
     def _effective(self, base, adapter):
         """Eval-mode weights of a projection: pretrained + accumulated soft-frozen ZiRa weights
@@ -239,10 +246,16 @@ class MultiScaleDeformableAttention(nn.Module):
 
     def _prepared(self, raw=None):
         """Kernel-ready weights (fused.Prepared), rebuilt only when a parameter changed."""
-        key = tuple((t.data_ptr(), t._version, t.dtype) for t in self.parameters())
+        # keyed on (storage, version, dtype): an in-place update through the parameter (optimizer step, load_state_dict,
+        # __rep__) bumps the version; writing through ``.data`` does NOT -- call ``invalidate_prepared()`` after that
+        key = tuple((t.data_ptr(), _version_of(t), t.dtype) for t in self.parameters())
         if getattr(self, "_prep_key", None) != key:
             self._prep, self._prep_key = fused.Prepared(*(raw if raw is not None else self._raw_weights())), key
         return self._prep
+
+    def invalidate_prepared(self):
+        """Drop the cached kernel-ready weights (needed only after mutating a parameter through ``.data``)."""
+        self._prep_key = None
 
     def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
         has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None

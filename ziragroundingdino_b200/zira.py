@@ -36,7 +36,8 @@ def _folded_rows(x_rows, training, w0, b0, wf, bf, wb, bb, scaling):
     if (x_rows.is_cuda and x_rows.dtype in (torch.bfloat16, torch.float16) and K % 64 == 0 and Fo % 64 == 0 and 3 * Fo <= 2048):
         from . import fused
         x2d = x_rows.reshape(-1, K).contiguous()
-        y, loss = fused.ZiRaLinear16Function.apply(x2d, None, w0, b0, wf, bf, wb, bb, scaling)
+        cast = lambda t: t if t.dtype == x2d.dtype else t.to(x2d.dtype)
+        y, loss = fused.ZiRaLinear16Function.apply(x2d, None, *(cast(t) for t in (w0, b0, wf, bf, wb, bb, scaling)))
         return y.view(*x_rows.shape[:-1], Fo), loss
     branch = scaling * F.linear(x_rows, wb, bb)
     adapter_out = branch + F.linear(x_rows, wf, bf)
@@ -158,8 +159,10 @@ class RepZeroLinear(nn.Linear):
             # one tcgen05 GEMM over [W_0; W_f; W_b] with the fold and the loss reduction in its epilogue (fused.py)
             from . import fused
             x2d = input.reshape(-1, self.in_features).contiguous()
-            y, loss = fused.ZiRaLinear16Function.apply(x2d, None, base_weight, base_bias, self.freeze_linear.weight,
-                                                       self.freeze_linear.bias, self.weight, self.bias, self.scaling)
+            cast = (lambda t: t) if self.weight.dtype == x2d.dtype else (lambda t: t.to(x2d.dtype))   # fp32 master adapters
+            y, loss = fused.ZiRaLinear16Function.apply(x2d, None, cast(base_weight), cast(base_bias), cast(self.freeze_linear.weight),
+                                                       cast(self.freeze_linear.bias), cast(self.weight), cast(self.bias),
+                                                       cast(self.scaling))
             return y.view(*input.shape[:-1], self.out_features), loss
         branch = self.scaling * F.linear(input, self.weight, self.bias)
         adapter_out = branch + self.freeze_linear(input)
