@@ -112,6 +112,10 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
  *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64)
  *   key "bwd_narrow"        : 16-bit storage, 1 = 4 channels per lane in the backward kernel (one full-line
  *                             reduction per corner), 0 = 8 channels per lane
+ *   key "bwd_mma"           : 16-bit storage, D = 32, P = 4: 1 = the coarse tail of the level list (<= 1536 pixels, <= 4
+ *                             levels) accumulates grad_value in tensor memory (tcgen05) and leaves the SM once per
+ *                             (image, head) instead of once per bilinear corner; 0 = every corner is a reduction
+ *   key "bwd_mma_min_units" : smallest N*Lq*M for which bwd_mma applies (default 131072; 0 = always)
  * Returns 0, or MSDA_ERR_UNSUPPORTED for an unknown key / value. */
 int msda_b200_set_tuning(const char *key, int value);
 int msda_b200_get_tuning(const char *key);

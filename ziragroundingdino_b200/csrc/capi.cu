@@ -107,6 +107,8 @@ static int* tuning_slot(const char* key) {
   if (!strcmp(key, "bwd_q_fast")) return &msda::g_tuning.bwd_q_fast;
   if (!strcmp(key, "bwd_passes")) return &msda::g_tuning.bwd_passes;
   if (!strcmp(key, "bwd_narrow")) return &msda::g_tuning.bwd_narrow;
+  if (!strcmp(key, "bwd_mma")) return &msda::g_tuning.bwd_mma;
+  if (!strcmp(key, "bwd_mma_min_units")) return &msda::g_tuning.bwd_mma_min_units;
   return nullptr;
 }
 
@@ -115,6 +117,11 @@ int msda_b200_set_tuning(const char* key, int value) {
   if (!slot) return fail(MSDA_ERR_UNSUPPORTED, "unknown tuning key '%s'", key ? key : "(null)");
   const bool is_batch = slot == &msda::g_tuning.fwd_sample_batch;
   const bool is_pass = slot == &msda::g_tuning.fwd_passes || slot == &msda::g_tuning.bwd_passes;
+  if (slot == &msda::g_tuning.bwd_mma_min_units) {
+    if (value < 0) return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);
+    *slot = value;
+    return MSDA_OK;
+  }
   if ((is_batch && value != 1 && value != 2 && value != 4) || (is_pass && (value < 1 || value > 64)) ||
       (!is_batch && !is_pass && value != 0 && value != 1))
     return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);

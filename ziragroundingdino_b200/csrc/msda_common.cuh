@@ -20,6 +20,8 @@ struct Tuning {
   int bwd_q_fast = 1;
   int bwd_passes = 1;
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
+  int bwd_mma = 1;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu)
+  int bwd_mma_min_units = 131072;   // ... when N*Lq*M is at least this (below it the reductions it saves do not pay for a launch)
 };
 extern Tuning g_tuning;
 extern long long g_launches;
@@ -166,6 +168,24 @@ __device__ __forceinline__ Tap<A> make_tap(A loc_x, A loc_y, int H, int W) {
   t.o3 = t.o1 + W;
   t.o4 = t.o3 + 1;
   return t;
+}
+
+// ---- levels owned by the tensor-memory scatter (msda_scatter_mma.cu) ------------------------------
+constexpr int kMmaBlocks = 12;                 // 128-pixel fp32 accumulator blocks (32 TMEM columns each)
+constexpr int kMmaMaxPixels = kMmaBlocks * 128;
+constexpr int kMmaMaxLevels = 4;               // two levels per builder thread
+// First level of the tail [first, L) whose pixels form the contiguous end [level_start[first], S) of the flattened value
+// map and fit the accumulators; L when none does (or level_start is not the cumulative layout the reference builds,
+// transformer_for_adapter.py:254-256).  Evaluated identically by msda_bwd_vec_kernel (which skips those reductions) and
+// msda_scatter_mma_kernel (which owns them).
+__device__ __forceinline__ int coarse_first_level(const int* sH, const int* sW, const int* sStart, int L, int S) {
+  int first = L, end = S;
+  for (int l = L - 1; l >= 0 && L - l <= kMmaMaxLevels; --l) {
+    if (sStart[l] + sH[l] * sW[l] != end || S - sStart[l] > kMmaMaxPixels) break;
+    first = l;
+    end = sStart[l];
+  }
+  return first;
 }
 
 // Unit (b, q, m) handled by lane-group `j` of pass `pass`.  A pass covers `tile` consecutive units in

@@ -149,7 +149,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_aw, int S, int M, int L, int Lq, long long units,
-                    int passes, int q_fast, FuseQ fq) {
+                    int passes, int q_fast, int mma_tail, FuseQ fq) {
   constexpr int CH = V::CH;
   constexpr int LPG = D / CH;
   constexpr int UPW = 32 / LPG;
@@ -159,12 +159,17 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   static_assert(LPG >= 1 && LPG <= 16 && (LPG & (LPG - 1)) == 0, "D / CH must be a power of two <= 16");
 
   __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
+  __shared__ int sRedLevels;
   if (threadIdx.x < L) {
     sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
     sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
   }
   __syncthreads();
+  // mma_tail: the grad_value contributions of levels >= red_levels are accumulated by msda_scatter_mma_kernel
+  if (threadIdx.x == 0) sRedLevels = mma_tail ? coarse_first_level(sH, sW, sStart, L, S) : L;
+  __syncthreads();
+  const int red_levels = sRedLevels;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lig = lane % LPG;
@@ -229,6 +234,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
       const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
       const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+      const bool do_red = l < red_levels;
       float red[16];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
@@ -265,10 +271,10 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           // element offset of this 4-channel slice relative to the lane's load slice (see `gr` above)
           const int ro = (CH == 4) ? 0 : ((c0 == 0 ? 4 * lig : 4 * LPG + 4 * lig) - CH * lig);
           const float r0 = gr[c0] * a, r1 = gr[c0 + 1] * a, r2 = gr[c0 + 2] * a, r3 = gr[c0 + 3] * a;
-          if (t.c1) red_add_v4(gvl + e1 + ro, k1 * r0, k1 * r1, k1 * r2, k1 * r3);
-          if (t.c2) red_add_v4(gvl + e2 + ro, k2 * r0, k2 * r1, k2 * r2, k2 * r3);
-          if (t.c3) red_add_v4(gvl + e3 + ro, k3 * r0, k3 * r1, k3 * r2, k3 * r3);
-          if (t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
+          if (do_red && t.c1) red_add_v4(gvl + e1 + ro, k1 * r0, k1 * r1, k1 * r2, k1 * r3);
+          if (do_red && t.c2) red_add_v4(gvl + e2 + ro, k2 * r0, k2 * r1, k2 * r2, k2 * r3);
+          if (do_red && t.c3) red_add_v4(gvl + e3 + ro, k3 * r0, k3 * r1, k3 * r2, k3 * r3);
+          if (do_red && t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
         }
       }
       reduce_scatter16<LPG>(red, lig);
@@ -455,6 +461,10 @@ static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const 
   return cudaGetLastError();
 }
 
+template <typename VT>
+cudaError_t launch_scatter_mma(const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                               const VT* grad_out, float* gv, int N, int S, int M, int L, int Lq, cudaStream_t st);
+
 template <typename VT, int D, typename V, bool FUSEQ>
 static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                     const float* loc, const float* aw, const VT* grad_out, float* gv,
@@ -464,10 +474,18 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
   const int passes = g_tuning.bwd_passes;
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
+  // 16-bit storage, D = 32: the coarse tail of the level list accumulates in tensor memory (msda_scatter_mma.cu); this
+  // kernel then skips those reductions.  Both kernels derive the same split from the device-side shapes.
+  int mma_tail = 0;
+  if constexpr (sizeof(VT) == 2 && D == 32) mma_tail = (g_tuning.bwd_mma && units >= g_tuning.bwd_mma_min_units) ? 1 : 0;
   ++g_launches;
   msda_bwd_vec_kernel<VT, D, V, FUSEQ><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
-      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, fq);
-  return cudaGetLastError();
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_tail, fq);
+  cudaError_t e = cudaGetLastError();
+  if constexpr (sizeof(VT) == 2 && D == 32) {
+    if (e == cudaSuccess && mma_tail) e = launch_scatter_mma<VT>(shapes, lstart, loc, aw, grad_out, gv, N, S, M, L, Lq, st);
+  }
+  return e;
 }
 
 template <typename VT, int D>

@@ -7,15 +7,17 @@
 // ridge, i.e. bound by reading X and writing Y, so the design goal is ONE pass over the activation
 // with everything else folded into the epilogue, not peak MMA rate.
 //
-// Structure (one persistent CTA per SM, 192 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 320 threads, warp-specialised):
 //   warp 0     TMA producer: cp.async.bulk.tensor 128x64 (A) and block_n x 64 (B) bf16 boxes, 128B swizzle,
 //              into a 4-stage shared-memory ring; completion on mbarriers (expect_tx).
 //   warp 1     MMA issuer: one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=block_n,
 //              K=16) four times per stage; tcgen05.commit releases the stage and, after the last K
 //              block, publishes the accumulator.  Also owns the TMEM allocation (2 x block_n columns).
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns -> registers (thread = one output row, 32
-//              consecutive columns), bias + {mask | sampling-location | softmax} math, direct 16-byte
-//              stores.  Double-buffered accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
+//   warps 2-9  epilogue (EIGHT warps: two per TMEM lane quarter, alternating column chunks): tcgen05.ld 32 lanes x 32
+//              columns -> registers (thread = one output row, 32 consecutive columns), bias + {mask | sampling-location |
+//              softmax | ReLU / gate | ZiRa fold} math, then a per-warp 128B-swizzled shared-memory tile written back with
+//              ONE TMA store (cp.async.bulk.tensor) per 32 x 128-byte tile, or staged 16-byte stores for the fp32 /
+//              ZiRa outputs.  Double-buffered accumulators let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_bf16.h>
@@ -27,6 +29,7 @@
 #include <cstring>
 
 #include "../../include/msda_b200.h"
+#include "tc_common.cuh"
 
 namespace msda {
 extern long long g_launches;
@@ -91,99 +94,6 @@ struct EpiParams {
   float* loss_sums;        // 2 floats, pre-zeroed by the caller
   int F;
 };
-
-// ---- PTX wrappers ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra WAIT_DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "WAIT_DONE:\n\t"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
-               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
-__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-// 16-byte chunk j of row r inside a 32 x 128-byte tile laid out for CU_TENSOR_MAP_SWIZZLE_128B
-__device__ __forceinline__ uint8_t* swz(uint8_t* tile, int r, int j) { return tile + r * 128 + ((j ^ (r & 7)) << 4); }
-
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t"
-      ".reg .pred P1;\n\t"
-      "elect.sync _|P1, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P1;\n\t"
-      "}" : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile with 128-byte swizzle: rows are 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem_tile, int k_byte_offset) {
-  const uint32_t addr = smem_u32(smem_tile) + k_byte_offset;
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr >> 4) & 0x3fff);        // start address, bits [0,14)
-  d |= static_cast<uint64_t>(0) << 16;                      // leading byte offset: unused for swizzled K-major
-  d |= static_cast<uint64_t>((1024 >> 4) & 0x3fff) << 32;   // stride byte offset, bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                      // descriptor version (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                      // layout: SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: fp32 accumulate, A/B both K-major, 16-bit inputs (bf16 or half)
-__host__ __device__ inline uint32_t umma_idesc(int m, int n, bool half_in) {
-  const uint32_t fmt = half_in ? 0u : 1u;
-  return (1u << 4) | (fmt << 7) | (fmt << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-      "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, bool half_out) {
   if (half_out) {
