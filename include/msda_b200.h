@@ -163,10 +163,24 @@ int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_c
 int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const float *aw, const float *ref, int ref_dim,
                            const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int ld_out,
                            int is_half, void *stream);
-/* fp32 modules (the reference's default precision): the projections stay library fp32 GEMMs (a tf32 tensor-core product
- * would miss the 1e-5 bar) but the elementwise tail of ms_deform_attn.py:290-319 is two kernels: raw = [offsets | logits]
- * pre-activations [R, 3*M*L*P] -> loc_out [R, M, L, P, 2], aw_out [R, M, L, P].  Its backward is
- * msda_query_bwd_prep_16 with is_half = 2 (fp32 output, ld_out = 3*M*L*P). */
+/* ---- fp32 modules (the reference's default precision: AMP off, groundingdino/config/configs/common/train.py:11) -----
+ * The same projections for fp32 activations, on tcgen05 as THREE kind::tf32 products per tile (x_hi w_hi + x_lo w_hi +
+ * x_hi w_lo, fp32 accumulation in tensor memory; hi = upper 19 bits of the fp32 pattern, lo = the exact remainder):
+ * ~1e-6 relative, inside north_star's 1e-5 / 1e-4 bars where a single TF32 product is not.  X [R, K] fp32; the weight is
+ * passed pre-split as w_split = [w_hi; w_lo] ([2*Nout, K] fp32: w_hi = W with the 13 low mantissa bits cleared,
+ * w_lo = W - w_hi).  K % 32 == 0, Nout % 64 == 0, Nout <= 768.  The activation split happens in shared memory.
+ * msda_linear_f32: out[r, :] = (accum ? accum[r, :] : 0) + X[r, :] W^T + bias; rows with row_mask[r] != 0 are written as
+ *   zero.  out / accum fp32 with leading dimension out_ld (out may alias accum).
+ * msda_query_proj_f32: the fused [sampling_offsets; attention_weights] projection with the sampling-location + softmax
+ *   epilogue of msda_query_proj_16 (needs 3*M*L*P % 64 == 0).  Non-finite inputs give NaN where the reference gives Inf. */
+int msda_linear_f32(const float *x, const float *w_split, const float *bias, long long R, int K, int Nout, const float *accum,
+                    float *out, int out_ld, const uint8_t *row_mask, void *stream);
+int msda_query_proj_f32(const float *query, const float *w_cat_split, const float *bias_cat, const float *ref, int ref_dim,
+                        const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
+                        float *aw_out, void *stream);
+/* Elementwise tail of ms_deform_attn.py:290-319 on its own, for fp32 shapes the fused projection does not take: raw =
+ * [offsets | logits] pre-activations [R, 3*M*L*P] -> loc_out [R, M, L, P, 2], aw_out [R, M, L, P].  Its backward is
+ * msda_query_bwd_prep_16 with is_half = 2 (fp32 output, ld_out >= 3*M*L*P). */
 int msda_query_post_f32(const float *raw, const float *ref, int ref_dim, const int64_t *spatial_shapes, long long R, int M,
                         int L, int P, float *loc_out, float *aw_out, void *stream);
 int msda_cast_mask_16(const float *in, const uint8_t *row_mask, long long rows, int cols, void *out, int is_half,

@@ -677,3 +677,79 @@ def test_zira_fused_rejects_mixed_dtypes_and_casts_master_weights():
     assert (y.double() - want).abs().max().item() < 1e-2 * want.abs().max().item()
     (y.float().sum() + loss.float()).backward()
     assert ad.weight.grad is not None and ad.weight.grad.dtype == torch.float32 and torch.isfinite(ad.weight.grad).all()
+
+
+# ---- fp32 projections on tcgen05: three TF32 products per tile (csrc/proj_gemm_f32.cu) --------------------------------
+@pytest.mark.parametrize("R", [1, 127, 129, 1000, 22223])
+@pytest.mark.parametrize("K,Nout", [(256, 256), (256, 128), (384, 256), (64, 64), (32, 192)])
+def test_linear32_tf32x3_vs_fp64(R, K, Nout):
+    """3 x TF32 must land at fp32-GEMM accuracy: <= 3e-6 of max|y| against the fp64 product of the same fp32 operands
+    (a single TF32 product sits at ~5e-4) -- with bias, with a row mask, and accumulating onto an existing tensor."""
+    from ziragroundingdino_b200 import fused
+    x, w, b = _rand((R, K), torch.float32, 1), _rand((Nout, K), torch.float32, 2, 0.06), _rand((Nout,), torch.float32, 3)
+    ws = fused.split_tf32(w)
+    assert torch.equal(ws[:Nout] + ws[Nout:], w)          # the split is exact
+    ref = x.double() @ w.double().t() + b.double()
+    y = fused.linear32(x, ws, b)
+    assert y.shape == (R, Nout) and y.dtype == torch.float32
+    assert rel_err(y.cpu(), ref.cpu()) < 3e-6
+    mask = (torch.arange(R, device=DEV) % 3 == 0).to(torch.uint8)
+    ym = fused.linear32(x, ws, b, row_mask=mask)
+    assert rel_err(ym.cpu(), (ref * (1 - mask.double())[:, None]).cpu()) < 3e-6 and ym[mask.bool()].abs().max().item() == 0
+    acc = _rand((R, Nout), torch.float32, 4)
+    want = acc.double() + x.double() @ w.double().t()
+    ya = fused.linear32(x, ws, None, accum=acc)
+    assert ya.data_ptr() == acc.data_ptr() and rel_err(ya.cpu(), want.cpu()) < 3e-6
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("M,L,P", [(8, 4, 4), (4, 4, 4), (8, 4, 2), (16, 4, 1)])
+def test_query_proj32(ref_dim, M, L, P):
+    from ziragroundingdino_b200 import fused
+    R, K = 2500, 256
+    n_aw = M * L * P
+    q = _rand((R, K), torch.float32, 7)
+    w = _rand((3 * n_aw, K), torch.float32, 8, 0.05)
+    b = _rand((3 * n_aw,), torch.float32, 9)
+    shapes = torch.tensor([(100, 167), (50, 84), (25, 42), (13, 21)][:L], device=DEV)
+    g = torch.Generator().manual_seed(10)
+    ref = torch.rand(R, L, ref_dim, generator=g).to(DEV)
+    assert fused.supported32(K, M, L, P)
+    loc, aw = fused.query_proj32(q, fused.split_tf32(w), b, ref, ref_dim, shapes, M, L, P)
+    pre = q.double() @ w.double().t() + b.double()
+    off = pre[:, :2 * n_aw].view(R, M, L, P, 2)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).double()
+        want_loc = ref.double()[:, None, :, None, :] + off / norm[None, None, :, None, :]
+    else:
+        want_loc = ref.double()[:, None, :, None, :2] + off / P * ref.double()[:, None, :, None, 2:] * 0.5
+    want_aw = pre[:, 2 * n_aw:].view(R, M, L * P).softmax(-1).view(R, M, L, P)
+    assert (loc.double() - want_loc).abs().max().item() < 2e-6
+    assert (aw.double() - want_aw).abs().max().item() < 2e-6
+
+
+def test_module_fp32_fused_launches_and_parity():
+    """fp32 module with frozen linears: 4 forward + 5 backward launches of this library and nothing else on the path
+    (no library GEMM); output within 1e-5 and input gradients within 1e-4 of the fp64 oracle."""
+    import ziragroundingdino_b200 as zb
+    from oracle import msda_oracle as O
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    m, query, src, refp, sh, lsi, mask = _module_inputs(2, shapes, 256, torch.float32, seed=21)
+    for p in m.parameters():
+        p.requires_grad_(False)
+    q, v = query.clone().requires_grad_(True), src.clone().requires_grad_(True)
+    n0 = zb._lib.launch_count()
+    y = m(query=q, value=v, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+    gy = torch.randn(y.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+    y.backward(gy)
+    assert zb._lib.launch_count() - n0 == 9
+    params = {k: p.detach().double().cpu() for k, p in m.state_dict().items()}
+    tq, tv = query.double().cpu().requires_grad_(True), src.double().cpu().requires_grad_(True)
+    truth = O.module_forward(params, tq, tv, mask.cpu(), refp.double().cpu(), sh.cpu(), 8, 4, 4)
+    truth.backward(gy.double().cpu())
+    e_out = (y.detach().double().cpu() - truth.detach()).abs().max().item()
+    print("fp32 fused module: out max-abs %.2e (|out| max %.2f), grad_value_in rel %.2e, grad_query rel %.2e" % (
+        e_out, truth.abs().max().item(), rel_err(v.grad.cpu(), tv.grad), rel_err(q.grad.cpu(), tq.grad)))
+    assert e_out < 1e-5 * max(1.0, truth.abs().max().item())
+    assert rel_err(v.grad.cpu(), tv.grad) < 1e-4
+    assert _frac_over(q.grad, tq.grad, 1e-4) < 1e-4

@@ -367,3 +367,121 @@ class QueryPostF32Function(Function):
                                                    d_raw.data_ptr(), n, 2, _stream(aw))
         _lib.check(rc, "msda_query_bwd_prep_16(fp32)")
         return d_raw, None, None, None, None, None
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32 modules (the reference's default precision): the same fused structure on 3 x TF32 tcgen05 GEMMs
+# (csrc/proj_gemm_f32.cu) -- fp32-GEMM accuracy (~1e-6 relative), so north_star's 1e-5 / 1e-4 bars hold.
+# ---------------------------------------------------------------------------------------------------
+def split_tf32(w):
+    """nn.Linear weight [Nout, K] fp32 -> [2*Nout, K]: rows [0, Nout) = W with the 13 low mantissa bits cleared (what a
+    TF32 operand keeps), rows [Nout, 2*Nout) = the exact remainder.  Done once per parameter version."""
+    w = w.detach().float().contiguous()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return torch.cat([hi, w - hi], 0).contiguous()
+
+
+def linear32(x2d, w_split, bias=None, row_mask=None, accum=None):
+    """x2d [R, K] fp32 @ W^T (+ bias) (+ accum, in place) -> [R, Nout] fp32; rows with row_mask != 0 are zero."""
+    R, K = x2d.shape
+    Nout = w_split.shape[0] // 2
+    assert x2d.is_contiguous() and x2d.dtype == torch.float32 and w_split.dtype == torch.float32 and w_split.shape[1] == K
+    out = accum if accum is not None else torch.empty((R, Nout), dtype=torch.float32, device=x2d.device)
+    if R == 0:
+        return out
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_f32(x2d.data_ptr(), w_split.data_ptr(), 0 if bias is None else bias.data_ptr(), R, K, Nout,
+                                        0 if accum is None else accum.data_ptr(), out.data_ptr(), Nout,
+                                        0 if row_mask is None else row_mask.data_ptr(), _stream(x2d))
+    _lib.check(rc, "msda_linear_f32")
+    return out
+
+
+def query_proj32(q2d, w_cat_split, bias_cat, ref, ref_dim, spatial_shapes, M, L, P):
+    R, K = q2d.shape
+    loc = torch.empty((R, M, L, P, 2), dtype=torch.float32, device=q2d.device)
+    aw = torch.empty((R, M, L, P), dtype=torch.float32, device=q2d.device)
+    if R == 0:
+        return loc, aw
+    with torch.cuda.device(q2d.device):
+        rc = _lib.lib().msda_query_proj_f32(q2d.data_ptr(), w_cat_split.data_ptr(), bias_cat.data_ptr(), ref.data_ptr(), ref_dim,
+                                            spatial_shapes.data_ptr(), R, K, M, L, P, loc.data_ptr(), aw.data_ptr(), _stream(q2d))
+    _lib.check(rc, "msda_query_proj_f32")
+    return loc, aw
+
+
+def supported32(embed_dim, M, L, P):
+    lp = L * P
+    return (embed_dim % 64 == 0 and embed_dim <= 768 and lp % 4 == 0 and 32 % lp == 0 and (3 * M * lp) % 64 == 0
+            and 3 * M * lp <= 768 and L <= 16)
+
+
+class Prepared32:
+    """fp32 weights of one module, TF32-split ([w_hi; w_lo]) in the forward and transposed (dgrad) orientations."""
+
+    def __init__(self, w_v, b_v, w_off, b_off, w_aw, b_aw, w_o, b_o):
+        with torch.no_grad():
+            w_cat = torch.cat([w_off.detach(), w_aw.detach()], 0)
+            self.w_v, self.w_o, self.w_cat = split_tf32(w_v), split_tf32(w_o), split_tf32(w_cat)
+            self.w_v_t, self.w_o_t, self.w_cat_t = split_tf32(w_v.detach().t()), split_tf32(w_o.detach().t()), split_tf32(w_cat.t())
+            self.b_v, self.b_o = b_v.detach().float().contiguous(), b_o.detach().float().contiguous()
+            self.b_cat = torch.cat([b_off.detach(), b_aw.detach()], 0).float().contiguous()
+
+
+class FusedMSDeformAttnFunction32(Function):
+    """Whole-module forward/backward on fp32 activations (batch-first, contiguous): 3 x TF32 GEMMs with the mask /
+    sampling-location / softmax epilogues, the fp32 gather and scatter kernels, no library GEMM unless the module's own
+    linears are trainable (their weight gradients)."""
+
+    @staticmethod
+    def forward(ctx, query, value_in, row_mask, reference_points, spatial_shapes, level_start_index, prep, M, L, P,
+                im2col_step, w_v, b_v, w_off, b_off, w_aw, b_aw, w_o, b_o):
+        N, Lq, C = query.shape
+        S = value_in.shape[1]
+        q2d, v2d = query.reshape(N * Lq, C), value_in.reshape(N * S, C)
+        ref = reference_points.to(torch.float32).contiguous()
+        ref_dim = ref.shape[-1]
+        value = linear32(v2d, prep.w_v, prep.b_v, row_mask).view(N, S, M, C // M)
+        loc, aw = query_proj32(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
+        loc, aw = loc.view(N, Lq, M, L, P, 2), aw.view(N, Lq, M, L, P)
+        core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
+        out = linear32(core.view(N * Lq, C), prep.w_o, prep.b_o).view(N, Lq, C)
+        ctx.dims = (N, Lq, S, C, M, L, P, ref_dim, im2col_step)
+        ctx.prep = prep
+        ctx.wgrad = any(ctx.needs_input_grad[11:19])
+        ctx.save_for_backward(query if ctx.wgrad else None, value_in if ctx.wgrad else None, row_mask, ref, spatial_shapes,
+                              level_start_index, value, loc, aw, core if ctx.wgrad else None)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_out):
+        query, value_in, row_mask, ref, spatial_shapes, level_start_index, value, loc, aw, core = ctx.saved_tensors
+        N, Lq, S, C, M, L, P, ref_dim, im2col_step = ctx.dims
+        prep = ctx.prep
+        g2d = grad_out.contiguous().view(N * Lq, C)
+        d_core = linear32(g2d, prep.w_o_t)
+        grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
+                                                                   d_core.view(N, Lq, C), im2col_step)
+        n_cat = 3 * M * L * P
+        dq_cat = torch.empty((N * Lq, n_cat), dtype=torch.float32, device=value.device)
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().msda_query_bwd_prep_16(grad_loc.data_ptr(), grad_aw.data_ptr(), aw.data_ptr(), ref.data_ptr(), ref_dim,
+                                                   spatial_shapes.data_ptr(), N * Lq, M, L, P, dq_cat.data_ptr(), n_cat, 2,
+                                                   _stream(value))
+        _lib.check(rc, "msda_query_bwd_prep_16(fp32)")
+        d_query = linear32(dq_cat, prep.w_cat_t).view(N, Lq, C) if ctx.needs_input_grad[0] else None
+        gv2d = grad_value.view(N * S, C)
+        # zeroing OUTPUT rows of this bias-free product == zeroing the masked rows of grad_value (backward of :287-288)
+        d_value_in = linear32(gv2d, prep.w_v_t, None, row_mask).view(N, S, C) if ctx.needs_input_grad[1] else None
+        grads = [None] * 8
+        if ctx.wgrad:  # plain library GEMMs; the module's own linears are frozen in the ZiRa configuration
+            n_loc = 2 * M * L * P
+            q2d, v2d = query.reshape(N * Lq, C), value_in.reshape(N * S, C)
+            gvm = gv2d if row_mask is None else gv2d.masked_fill(row_mask.bool()[:, None], 0.0)
+            dw_cat = dq_cat.t() @ q2d
+            db_cat = dq_cat.sum(0)
+            grads = [gvm.t() @ v2d, gvm.sum(0), dw_cat[:n_loc], db_cat[:n_loc], dw_cat[n_loc:], db_cat[n_loc:],
+                     g2d.t() @ core.view(N * Lq, C), g2d.sum(0)]
+            grads = [g if ctx.needs_input_grad[11 + i] else None for i, g in enumerate(grads)]
+        return (d_query, d_value_in, None, None, None, None, None, None, None, None, None, *grads)

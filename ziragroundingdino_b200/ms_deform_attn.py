@@ -238,6 +238,24 @@ class MultiScaleDeformableAttention(nn.Module):
         self.zero_inter_loss = sum(losses) if losses else None
         return out.view(N, Lq, C)
 
+    def _use_fused32(self, value, reference_points):
+        """fp32 activations and parameters: 3 x TF32 tcgen05 projections (fused.FusedMSDeformAttnFunction32).  Un-merged
+        ZiRa branches in training mode keep the stage-wise fp32 path (their loss needs the branch activations)."""
+        if not (self.fused_enabled and value.is_cuda and value.dtype == torch.float32 and not torch.is_autocast_enabled()
+                and fused.supported32(self.embed_dim, self.num_heads, self.num_levels, self.num_points)):
+            return False
+        if reference_points.shape[-1] not in (2, 4) or reference_points.requires_grad:
+            return False
+        if self.training and (self.value_proj_adapter is not None or self.output_proj_adapter is not None):
+            return False
+        return all(p.dtype == torch.float32 for p in self.parameters())
+
+    def _prepared32(self, raw):
+        key = tuple((t.data_ptr(), _version_of(t), t.dtype) for t in self.parameters())
+        if getattr(self, "_prep32_key", None) != key:
+            self._prep32, self._prep32_key = fused.Prepared32(*raw), key
+        return self._prep32
+
     def _raw_weights(self):
         w_v, b_v = self._effective(self.value_proj, self.value_proj_adapter)
         w_o, b_o = self._effective(self.output_proj, self.output_proj_adapter)
@@ -255,7 +273,7 @@ class MultiScaleDeformableAttention(nn.Module):
 
     def invalidate_prepared(self):
         """Drop the cached kernel-ready weights (needed only after mutating a parameter through ``.data``)."""
-        self._prep_key = None
+        self._prep_key = self._prep32_key = None
 
     def _forward_fused(self, query, value, key_padding_mask, reference_points, spatial_shapes, level_start_index):
         has_branch = self.value_proj_adapter is not None or self.output_proj_adapter is not None
@@ -295,6 +313,17 @@ class MultiScaleDeformableAttention(nn.Module):
         if self._use_fused(value, reference_points):
             output = self._forward_fused(query, value, key_padding_mask, reference_points, spatial_shapes,
                                          level_start_index)
+            if not self.batch_first:
+                output = output.permute(1, 0, 2)
+            return output
+        if self._use_fused32(value, reference_points):
+            raw = self._raw_weights()
+            prep = self._prepared32(raw)
+            row_mask = None if key_padding_mask is None else key_padding_mask.reshape(-1).to(torch.uint8).contiguous()
+            self.zero_inter_loss = None
+            output = fused.FusedMSDeformAttnFunction32.apply(
+                query.contiguous(), value.contiguous(), row_mask, reference_points, spatial_shapes, level_start_index, prep,
+                M, L, P, self.im2col_step, *raw)
             if not self.batch_first:
                 output = output.permute(1, 0, 2)
             return output
