@@ -69,6 +69,9 @@ def parse():
     ap.add_argument("--config", type=int, default=None, choices=[2, 4], help="measure ONE workload only: 4 = configs[3], the ZiRa "
                     "step with the decoder, 2 = configs[1], the encoder; default: config 4 as the line's value AND config 2 "
                     "under other_workload")
+    ap.add_argument("--graph-allreduce", action="store_true", help="N > 1: capture the NCCL all-reduce inside ONE CUDA graph with "
+                    "forward+backward and the update (capture_error_mode=thread_local, so the NCCL watchdog thread's event "
+                    "queries do not invalidate the capture -- the round-1 hang) instead of an eager call between two graphs")
     ap.add_argument("--no-config5", action="store_true", help="skip the Swin-B stride-4 (HBM-bound) core-op timing")
     a = ap.parse_args()
     set_config(a.config if a.config is not None else 4)
@@ -324,7 +327,7 @@ class ZiraStep:
         self.static_loss = None
         self._lib = _lib
 
-    def warm_and_capture(self, use_graph):
+    def warm_and_capture(self, use_graph, graph_allreduce=False):
         """3 eager steps on a side stream, count launches of one step, then capture: one graph for forward+backward, one for
         clip+AdamW; the NCCL all-reduce between them stays an eager call on the same stream (nothing for a single rank)."""
         torch = self.torch
@@ -337,7 +340,16 @@ class ZiraStep:
         n0 = self._lib.launch_count()
         self.step_eager()
         self.launches_per_step = self._lib.launch_count() - n0
-        if use_graph:
+        self.one_graph = bool(use_graph and graph_allreduce and self.world > 1)
+        if self.one_graph:
+            # the collective is captured too: thread-local capture mode keeps CUDA calls made by OTHER threads (the NCCL
+            # watchdog polling its events) legal while this thread captures
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_loss = self._fwd_bwd(self.feat, self.pos, self.mask)
+                self.bucket.all_reduce()
+                self._update()
+        elif use_graph:
             self.graph, self.graph_upd = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
                 self.static_loss = self._fwd_bwd(self.feat, self.pos, self.mask)
@@ -349,8 +361,9 @@ class ZiraStep:
         if self.graph is None:
             return self.step_eager()
         self.graph.replay()
-        self.bucket.all_reduce()
-        self.graph_upd.replay()
+        if not self.one_graph:
+            self.bucket.all_reduce()
+            self.graph_upd.replay()
         return self.static_loss
 
     # ---- end to end: pinned host inputs in, loss out, every step --------------------------------------
@@ -449,7 +462,7 @@ def run_ours(args):
     # ---- device-resident timing ---------------------------------------------------------------------
     # The step (forward, backward, all-reduce, clip, AdamW) is captured once in CUDA graphs: ~250-400 launches of
     # 5-1000 us each would otherwise leave the GPU waiting on the Python launch path.
-    wl.warm_and_capture(not args.no_graph)
+    wl.warm_and_capture(not args.no_graph, args.graph_allreduce)
     run = wl.run
     if args.gaps:
         from torch.profiler import ProfilerActivity, profile
@@ -507,7 +520,7 @@ def run_ours(args):
     if args.config is None:
         oc = 2 if CONFIG == 4 else 4
         w2 = ZiraStep(oc, world, rank, dev, args)
-        w2.warm_and_capture(not args.no_graph)
+        w2.warm_and_capture(not args.no_graph, args.graph_allreduce)
         for _ in range(max(args.warmup, 3)):
             w2.run()
         ms2 = timed(w2.run, args.steps)
@@ -632,7 +645,7 @@ def run_ours(args):
     out = {
         "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=use_graph,
+        "data": "synthetic", "config": dict(workload_config(world), cuda_graph=use_graph, allreduce_in_graph=bool(args.graph_allreduce and world > 1),
                                             **({"padding": "none (all-valid case)"} if args.all_valid else {})), "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "other_workload": other,
