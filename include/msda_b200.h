@@ -104,6 +104,18 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
                             int N, int S, int M, int D, int L, int Lq, int P, float *grad_value, void *dq,
                             int zero_grad_value, int is_half, void *stream);
 
+/* The 16-bit backward with a caller-provided scratch buffer.  Same results as msda_backward_{bf16,f16} (dq == NULL:
+ * grad_loc / grad_aw written, ref ignored) or msda_backward_fusedq_16 (dq != NULL: grad_loc / grad_aw ignored); the
+ * scratch lets the tensor-memory scatter own fine levels as well (tuning key "bwd_mma_levels"): the scatter kernel marks
+ * there, per (image, head, 64-query chunk), which pixel ranges of the value map the chunk's samples touch, and the
+ * accumulation kernel skips every (chunk, range) pair that is empty.  `workspace` = msda_backward_workspace_bytes(N, M, Lq)
+ * bytes of device memory, 8-byte aligned, contents ignored and clobbered; NULL = behave as the entry points above. */
+long long msda_backward_workspace_bytes(int N, int M, int Lq);
+int msda_backward_16_ws(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index, const float *loc,
+                        const float *aw, const void *grad_out, const float *ref, int ref_dim, int N, int S, int M, int D,
+                        int L, int Lq, int P, float *grad_value, float *grad_loc, float *grad_aw, void *dq,
+                        int zero_grad_value, int is_half, void *workspace, long long workspace_bytes, void *stream);
+
 /* ---- tuning / introspection (not part of the reference interface) ------------------------------
  * Kernel variant knobs used by bench.py sweeps; defaults are the shipped configuration.
  *   key "fwd_sample_batch"  : samples whose corner loads are issued together (1, 2 or 4)
@@ -116,6 +128,8 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
  *                             levels) accumulates grad_value in tensor memory (tcgen05) and leaves the SM once per
  *                             (image, head) instead of once per bilinear corner; 0 = every corner is a reduction
  *   key "bwd_mma_min_units" : smallest N*Lq*M for which bwd_mma applies (default 131072; 0 = always)
+ *   key "bwd_mma_levels"    : with a workspace (msda_backward_16_ws): how many levels, counted from the coarse end, the
+ *                             range-planned tensor-memory scatter owns (0 = only the coarse tail, first-generation kernel)
  * Returns 0, or MSDA_ERR_UNSUPPORTED for an unknown key / value. */
 int msda_b200_set_tuning(const char *key, int value);
 int msda_b200_get_tuning(const char *key);

@@ -66,6 +66,15 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+def backward_workspace(value, N, M, D, Lq, P):
+    """Scratch tensor for msda_backward_16_ws, or None when the range-planned scatter does not apply (fp32 / fp64 storage,
+    other head sizes, tuning key ``bwd_mma_levels`` == 0)."""
+    if value.dtype not in (torch.bfloat16, torch.float16) or D != 32 or P != 4 or _lib.get_tuning("bwd_mma_levels") <= 0:
+        return None
+    n = _lib.lib().msda_backward_workspace_bytes(N, M, Lq) // 8
+    return torch.empty(max(n, 1), dtype=torch.int64, device=value.device)
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
                             im2col_step):
     """-> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:84-154).
@@ -81,6 +90,16 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     grad_aw = torch.empty(attn_weight.shape, dtype=gdt, device=value.device)
     if N == 0 or Lq == 0:
         return [grad_value.zero_(), grad_loc, grad_aw]
+    ws = backward_workspace(value, N, M, D, Lq, P)
+    if ws is not None:   # 16-bit storage with the range-planned tensor-memory scatter enabled: scratch for its hit masks
+        with torch.cuda.device(value.device):
+            rc = _lib.lib().msda_backward_16_ws(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                sampling_loc.data_ptr(), attn_weight.data_ptr(), grad_output.data_ptr(), 0, 0,
+                                                N, S, M, D, L, Lq, P, grad_value.data_ptr(), grad_loc.data_ptr(),
+                                                grad_aw.data_ptr(), 0, 1, 1 if value.dtype == torch.float16 else 0,
+                                                ws.data_ptr(), ws.numel() * 8, _stream(value.device))
+        _lib.check(rc, "ms_deform_attn_backward")
+        return [grad_value, grad_loc, grad_aw]
     fn = getattr(_lib.lib(), "msda_backward_" + _SUFFIX[value.dtype])
     with torch.cuda.device(value.device):
         rc = fn(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), sampling_loc.data_ptr(),

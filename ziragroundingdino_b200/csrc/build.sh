@@ -7,7 +7,7 @@ mkdir -p "$OUT"
 NVCC=${NVCC:-nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC --expt-relaxed-constexpr ${MSDA_NVCC_EXTRA}"
 pids=()
-for f in msda_core msda_scatter_mma capi probe $(ls "$HERE" | grep -E '^(proj_|zira_|layer_).*\.cu$' | sed 's/\.cu$//'); do
+for f in msda_core msda_scatter_mma msda_scatter_mma2 capi probe $(ls "$HERE" | grep -E '^(proj_|zira_|layer_).*\.cu$' | sed 's/\.cu$//'); do
   $NVCC $FLAGS -c "$HERE/$f.cu" -o "$OUT/$f.o" &
   pids+=($!)
 done

@@ -109,6 +109,7 @@ static int* tuning_slot(const char* key) {
   if (!strcmp(key, "bwd_narrow")) return &msda::g_tuning.bwd_narrow;
   if (!strcmp(key, "bwd_mma")) return &msda::g_tuning.bwd_mma;
   if (!strcmp(key, "bwd_mma_min_units")) return &msda::g_tuning.bwd_mma_min_units;
+  if (!strcmp(key, "bwd_mma_levels")) return &msda::g_tuning.bwd_mma_levels;
   return nullptr;
 }
 
@@ -117,6 +118,11 @@ int msda_b200_set_tuning(const char* key, int value) {
   if (!slot) return fail(MSDA_ERR_UNSUPPORTED, "unknown tuning key '%s'", key ? key : "(null)");
   const bool is_batch = slot == &msda::g_tuning.fwd_sample_batch;
   const bool is_pass = slot == &msda::g_tuning.fwd_passes || slot == &msda::g_tuning.bwd_passes;
+  if (slot == &msda::g_tuning.bwd_mma_levels) {
+    if (value < 0 || value > MSDA_MAX_LEVELS) return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);
+    *slot = value;
+    return MSDA_OK;
+  }
   if (slot == &msda::g_tuning.bwd_mma_min_units) {
     if (value < 0) return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);
     *slot = value;
@@ -184,6 +190,29 @@ int msda_backward_fusedq_16(const void* value, const int64_t* shapes, const int6
     e = msda::backward_fused_q<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(value), shapes, lstart, loc, aw,
                                               static_cast<const __nv_bfloat16*>(grad_out), gv, ref, ref_dim, dq, 0, N, S, M, Lq, st);
   return cuda_status(e, "msda_backward_fusedq launch");
+}
+
+long long msda_backward_workspace_bytes(int N, int M, int Lq) {
+  if (N <= 0 || M <= 0 || Lq <= 0) return 0;
+  return msda::backward_workspace_bytes(N, M, Lq);
+}
+
+int msda_backward_16_ws(const void* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                        const void* grad_out, const float* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
+                        float* gv, float* gl, float* ga, void* dq, int zero_gv, int is_half, void* workspace,
+                        long long workspace_bytes, void* stream) {
+  msda::t_workspace = workspace;
+  msda::t_workspace_bytes = workspace ? workspace_bytes : 0;
+  int rc;
+  if (dq != nullptr)
+    rc = msda_backward_fusedq_16(value, shapes, lstart, loc, aw, grad_out, ref, ref_dim, N, S, M, D, L, Lq, P, gv, dq, zero_gv, is_half, stream);
+  else if (is_half)
+    rc = msda_backward_f16(value, shapes, lstart, loc, aw, grad_out, N, S, M, D, L, Lq, P, gv, gl, ga, zero_gv, stream);
+  else
+    rc = msda_backward_bf16(value, shapes, lstart, loc, aw, grad_out, N, S, M, D, L, Lq, P, gv, gl, ga, zero_gv, stream);
+  msda::t_workspace = nullptr;
+  msda::t_workspace_bytes = 0;
+  return rc;
 }
 
 int msda_forward_f64(const double* value, const int64_t* shapes, const int64_t* lstart, const double* loc,

@@ -21,10 +21,16 @@ struct Tuning {
   int bwd_passes = 1;
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
   int bwd_mma = 1;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu)
+  int bwd_mma_levels = 0;    // > 0 and a workspace given: the last `bwd_mma_levels` levels go through the range-planned
+                             // second-generation kernel (msda_scatter_mma2.cu) instead; 0 = first-generation tail only
   int bwd_mma_min_units = 131072;   // ... when N*Lq*M is at least this (below it the reductions it saves do not pay for a launch)
 };
 extern Tuning g_tuning;
 extern long long g_launches;
+// scratch of the backward call in flight on this thread (set by msda_backward_16_ws around the launch; msda_core.cu)
+extern thread_local void* t_workspace;
+extern thread_local long long t_workspace_bytes;
+long long backward_workspace_bytes(int N, int M, int Lq);
 
 // ---- storage-type traits: one lane always moves 16 bytes of channels -----------------------------
 template <typename VT> struct Vec;
@@ -186,6 +192,66 @@ __device__ __forceinline__ int coarse_first_level(const int* sH, const int* sW, 
     end = sStart[l];
   }
   return first;
+}
+
+// ---- range plan of the second-generation tensor-memory scatter (msda_scatter_mma2.cu) ---------------
+// The levels [first_level, L) are cut into RANGES: contiguous pixel intervals of the flattened value map of at most
+// kR2Px pixels (kR2Blocks accumulator blocks) -- a level larger than that is split into ceil(px / kR2Px) ranges of kR2Px
+// pixels, consecutive small levels at the coarse end are merged into one range.  Range ids count up from the coarse end.
+// msda_bwd_vec_kernel marks, per (image, head, 64-query chunk), which ranges the chunk's samples touch (one bit each);
+// msda_scatter_mma2_kernel walks (image, head, range) work units and accumulates only the chunks that hit its range.
+constexpr int kR2Blocks = 6;
+constexpr int kR2Px = kR2Blocks * 128;
+constexpr int kR2MaxRanges = 64;
+constexpr int kR2SegChunks = 16;               // chunks (of 64 queries) per work unit
+struct RangePlan {
+  int first_level, nranges;
+  int rbase[MSDA_MAX_LEVELS];                  // id of the first range of level l (l >= first_level)
+  int lo[kR2MaxRanges], hi[kR2MaxRanges];      // pixel interval [lo, hi) of range r
+  int lv0[kR2MaxRanges], lv1[kR2MaxRanges];    // levels [lv0, lv1) that intersect range r
+};
+__device__ inline void plan_ranges(RangePlan& p, const int* sH, const int* sW, const int* sStart, int L, int S, int max_levels) {
+  p.first_level = L;
+  p.nranges = 0;
+  int end = S, l = L - 1;
+  while (l >= 0 && L - l <= max_levels) {
+    const int px = sH[l] * sW[l];
+    if (px <= 0 || sStart[l] + px != end) break;                 // not the cumulative layout: stop here
+    if (px > kR2Px) {
+      const int nr = (px + kR2Px - 1) / kR2Px;
+      if (p.nranges + nr > kR2MaxRanges) break;
+      p.rbase[l] = p.nranges;
+      for (int k = 0; k < nr; ++k) {
+        const int r = p.nranges + k;
+        p.lo[r] = sStart[l] + k * kR2Px;
+        p.hi[r] = (p.lo[r] + kR2Px < end) ? p.lo[r] + kR2Px : end;
+        p.lv0[r] = l;
+        p.lv1[r] = l + 1;
+      }
+      p.nranges += nr;
+      p.first_level = l;
+      end = sStart[l];
+      --l;
+    } else {
+      if (p.nranges + 1 > kR2MaxRanges) break;
+      // merge group: levels l, l-1, ... while they stay contiguous, small, at most 4 and within the level budget
+      const int r = p.nranges, g_hi = end, g_lv1 = l + 1;
+      int total = 0, cnt = 0;
+      while (l >= 0 && L - l <= max_levels && cnt < 4) {
+        const int q = sH[l] * sW[l];
+        if (q <= 0 || sStart[l] + q != end || total + q > kR2Px) break;
+        p.rbase[l] = r;
+        total += q;
+        end = sStart[l];
+        ++cnt;
+        --l;
+      }
+      if (cnt == 0) break;
+      p.lo[r] = end; p.hi[r] = g_hi; p.lv0[r] = l + 1; p.lv1[r] = g_lv1;
+      p.first_level = l + 1;
+      ++p.nranges;
+    }
+  }
 }
 
 // Unit (b, q, m) handled by lane-group `j` of pass `pass`.  A pass covers `tile` consecutive units in

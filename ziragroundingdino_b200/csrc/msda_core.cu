@@ -142,14 +142,14 @@ struct FuseQ {
   int is_half;
 };
 
-template <typename VT, int D, typename V, bool FUSEQ>
+template <typename VT, int D, typename V, bool FUSEQ, bool HITS>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
                     float* __restrict__ grad_value, float* __restrict__ grad_loc,
                     float* __restrict__ grad_aw, int S, int M, int L, int Lq, long long units,
-                    int passes, int q_fast, int mma_tail, FuseQ fq) {
+                    int passes, int q_fast, int mma_mode, int mma_levels, unsigned long long* __restrict__ hit, FuseQ fq) {
   constexpr int CH = V::CH;
   constexpr int LPG = D / CH;
   constexpr int UPW = 32 / LPG;
@@ -160,16 +160,23 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
 
   __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
   __shared__ int sRedLevels;
+  __shared__ RangePlan plan;       // HITS (mma_mode 2) only; the compiler drops it otherwise
   if (threadIdx.x < L) {
     sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
     sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
   }
   __syncthreads();
-  // mma_tail: the grad_value contributions of levels >= red_levels are accumulated by msda_scatter_mma_kernel
-  if (threadIdx.x == 0) sRedLevels = mma_tail ? coarse_first_level(sH, sW, sStart, L, S) : L;
+  // mma_mode 1: the grad_value contributions of the coarse tail (levels >= red_levels) are accumulated by
+  // msda_scatter_mma_kernel; mma_mode 2: those of the last `mma_levels` levels by msda_scatter_mma2_kernel, which needs
+  // to know which pixel ranges each 64-query chunk touches -- this kernel has every tap in hand and ORs the bits into `hit`
+  if (threadIdx.x == 0) {
+    if (HITS) { plan_ranges(plan, sH, sW, sStart, L, S, mma_levels); sRedLevels = plan.first_level; }
+    else sRedLevels = mma_mode == 1 ? coarse_first_level(sH, sW, sStart, L, S) : L;
+  }
   __syncthreads();
   const int red_levels = sRedLevels;
+  const int cpq = (Lq + 63) >> 6;
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int lig = lane % LPG;
@@ -224,6 +231,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
     // or grad_attn of point lig/2 (odd lanes); they are kept until the softmax dot product over all 16 samples is known.
     float fq_a[4], fq_b[4], fq_aw[4];
     float fq_dot = 0.f;
+    unsigned long long hit_bits = 0ull;      // mma_mode 2: ranges touched by this unit's samples
 
     for (int l = 0; l < L; ++l) {
       const int H = sH[l], W = sW[l];
@@ -235,11 +243,13 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
       const float as[4] = {a4.x, a4.y, a4.z, a4.w};
       const bool do_red = l < red_levels;
+      int o_min = 0x7fffffff, o_max = -1;    // clamped corner-offset extent of this level's inside samples (mma_mode 2)
       float red[16];
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         Tap<float> t = make_tap<float>(xs[p], ys[p], H, W);
         t.c1 = t.c1 && active; t.c2 = t.c2 && active; t.c3 = t.c3 && active; t.c4 = t.c4 && active;
+        if (HITS && t.ok) { o_min = min(o_min, t.o1); o_max = max(o_max, t.o4); }
         float v1[CH], v2[CH], v3[CH], v4[CH];
         const long long e1 = static_cast<long long>(t.o1) * row, e2 = static_cast<long long>(t.o2) * row;
         const long long e3 = static_cast<long long>(t.o3) * row, e4 = static_cast<long long>(t.o4) * row;
@@ -277,6 +287,14 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           if (do_red && t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
         }
       }
+      if (HITS && !do_red && o_max >= 0) {
+        // every valid corner of the level's samples lies in [max(o_min, 0), min(o_max, H*W - 1)]; ranges are contiguous
+        // pixel intervals, so the ranges touched are (a subset of) rid(lo) .. rid(hi): a clear bit is exact, a set one
+        // may be a false positive (costs an empty product, never a wrong result)
+        const int lo_ = max(o_min, 0), hi_ = min(o_max, H * W - 1);
+        const int r_lo = plan.rbase[l] + lo_ / kR2Px, r_hi = plan.rbase[l] + hi_ / kR2Px;
+        hit_bits |= (2ull << r_hi) - (1ull << r_lo);
+      }
       reduce_scatter16<LPG>(red, lig);
       if constexpr (FUSEQ) {
         // LPG == 8, R == 2: red[0], red[1] = entries 2*lig, 2*lig+1 of (w, h, a, pad) x 4 points
@@ -295,6 +313,8 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         }
       }
     }
+    if (HITS && active && lig == 0 && hit_bits != 0ull)
+      atomicOr(hit + ((b * M + m) * cpq + (static_cast<int>(bq % Lq) >> 6)), hit_bits);
     if constexpr (FUSEQ) {
       // softmax dot product over the unit's 16 samples: the 4 odd lanes hold 4 terms each
       fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 1);
@@ -465,6 +485,17 @@ template <typename VT>
 cudaError_t launch_scatter_mma(const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
                                const VT* grad_out, float* gv, int N, int S, int M, int L, int Lq, cudaStream_t st);
 
+template <typename VT>
+cudaError_t launch_scatter_mma2(const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                                const VT* grad_out, float* gv, const unsigned long long* hit, int N, int S, int M, int L,
+                                int Lq, int max_levels, cudaStream_t st);
+
+// Caller-provided scratch of the current backward call (msda_backward_16_ws); null for the entry points without one.
+thread_local void* t_workspace = nullptr;
+thread_local long long t_workspace_bytes = 0;
+
+long long backward_workspace_bytes(int N, int M, int Lq) { return static_cast<long long>(N) * M * ((Lq + 63) / 64) * 8; }
+
 template <typename VT, int D, typename V, bool FUSEQ>
 static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                     const float* loc, const float* aw, const VT* grad_out, float* gv,
@@ -476,14 +507,39 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   // 16-bit storage, D = 32: the coarse tail of the level list accumulates in tensor memory (msda_scatter_mma.cu); this
   // kernel then skips those reductions.  Both kernels derive the same split from the device-side shapes.
-  int mma_tail = 0;
-  if constexpr (sizeof(VT) == 2 && D == 32) mma_tail = (g_tuning.bwd_mma && units >= g_tuning.bwd_mma_min_units) ? 1 : 0;
+  int mma_mode = 0;
+  unsigned long long* hit = nullptr;
+  if constexpr (sizeof(VT) == 2 && D == 32) {
+    if (g_tuning.bwd_mma && units >= g_tuning.bwd_mma_min_units) {
+      mma_mode = 1;
+      if (g_tuning.bwd_mma_levels > 0 && t_workspace != nullptr && t_workspace_bytes >= backward_workspace_bytes(N, M, Lq) &&
+          (reinterpret_cast<uintptr_t>(t_workspace) & 7u) == 0) {
+        mma_mode = 2;
+        hit = static_cast<unsigned long long*>(t_workspace);
+        cudaError_t ez = cudaMemsetAsync(hit, 0, static_cast<size_t>(backward_workspace_bytes(N, M, Lq)), st);
+        if (ez != cudaSuccess) return ez;
+      }
+    }
+  }
   ++g_launches;
-  msda_bwd_vec_kernel<VT, D, V, FUSEQ><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
-      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_tail, fq);
+  bool launched = false;
+  if constexpr (sizeof(VT) == 2 && D == 32) {
+    if (mma_mode == 2) {
+      msda_bwd_vec_kernel<VT, D, V, FUSEQ, true><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+          value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,
+          g_tuning.bwd_mma_levels, hit, fq);
+      launched = true;
+    }
+  }
+  if (!launched)
+    msda_bwd_vec_kernel<VT, D, V, FUSEQ, false><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+        value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,
+        g_tuning.bwd_mma_levels, hit, fq);
   cudaError_t e = cudaGetLastError();
   if constexpr (sizeof(VT) == 2 && D == 32) {
-    if (e == cudaSuccess && mma_tail) e = launch_scatter_mma<VT>(shapes, lstart, loc, aw, grad_out, gv, N, S, M, L, Lq, st);
+    if (e == cudaSuccess && mma_mode == 1) e = launch_scatter_mma<VT>(shapes, lstart, loc, aw, grad_out, gv, N, S, M, L, Lq, st);
+    if (e == cudaSuccess && mma_mode == 2)
+      e = launch_scatter_mma2<VT>(shapes, lstart, loc, aw, grad_out, gv, hit, N, S, M, L, Lq, g_tuning.bwd_mma_levels, st);
   }
   return e;
 }

@@ -91,11 +91,19 @@ def backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, grad_co
     Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
     grad_value = torch.empty(value.shape, dtype=torch.float32, device=value.device)
     dq = torch.empty((N * Lq, 3 * M * L * P), dtype=value.dtype, device=value.device)
+    ws = _C.backward_workspace(value, N, M, D, Lq, P)
     with torch.cuda.device(value.device):
-        rc = _lib.lib().msda_backward_fusedq_16(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+        if ws is not None:
+            rc = _lib.lib().msda_backward_16_ws(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                                                 loc.data_ptr(), aw.data_ptr(), grad_core.data_ptr(), ref.data_ptr(), ref_dim, N, S,
-                                                M, D, L, Lq, P, grad_value.data_ptr(), dq.data_ptr(), 1,
-                                                1 if value.dtype == torch.float16 else 0, _stream(value))
+                                                M, D, L, Lq, P, grad_value.data_ptr(), 0, 0, dq.data_ptr(), 1,
+                                                1 if value.dtype == torch.float16 else 0, ws.data_ptr(), ws.numel() * 8,
+                                                _stream(value))
+        else:
+            rc = _lib.lib().msda_backward_fusedq_16(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                                    loc.data_ptr(), aw.data_ptr(), grad_core.data_ptr(), ref.data_ptr(), ref_dim, N,
+                                                    S, M, D, L, Lq, P, grad_value.data_ptr(), dq.data_ptr(), 1,
+                                                    1 if value.dtype == torch.float16 else 0, _stream(value))
     _lib.check(rc, "msda_backward_fusedq_16")
     return grad_value, dq
 
