@@ -249,6 +249,27 @@ int msda_group_norm_bwd_16(const void *dy, long long dy_image_stride, const void
                            const float *gamma, const float *mean_rstd, int N, long long HW, int C, int G, void *dx,
                            long long dx_image_stride, double *scratch, int is_half, void *stream);
 
+/* ---- the steps either side of the stacks --------------------------------------------
+ * msda_flatten_levels: transformer_for_adapter.py:238-262 as one launch.  src_levels / pos_levels / mask_levels are HOST
+ *   arrays of L device pointers: per level an NCHW map [N, C, H*W] (dtype: 0 bf16, 1 f16, 2 f32), its position embedding
+ *   (same shape; pos_levels may be NULL) and its padding mask [N, H*W] bytes (mask_levels may be NULL); level_hw[l] = H*W.
+ *   Writes src_out [N, S, C], pos_out [N, S, C] = pos + level_embed[l] (level_embed [L, C] device, may be NULL) and
+ *   mask_out [N, S].  Any of the three outputs may be NULL.
+ * msda_level_valid_counts: counts[n][l] = (valid_W, valid_H) = unmasked pixels of the first row / first column of level l
+ *   (utils.py:74-75; divided by (W, H) they are get_valid_ratio, transformer_for_adapter.py:216-223).
+ * msda_encoder_proposals: gen_encoder_output_proposals (utils.py:56-116): proposals_out [N, S, 4] fp32 = inverse sigmoid of
+ *   ((x + 0.5) / valid_W, (y + 0.5) / valid_H, wh_base * 2^level), +inf where the token is padded or any component leaves
+ *   (0.01, 0.99); memory_out = memory with exactly those rows zeroed.  wh_base: 2 device floats (0.05, 0.05 or
+ *   sigmoid(learnedwh)); rows are row_bytes long (multiple of 16). */
+int msda_flatten_levels(const void *const *src_levels, const void *const *pos_levels, const uint8_t *const *mask_levels,
+                        const int *level_hw, int L, int N, int C, const void *level_embed, int dtype, void *src_out,
+                        void *pos_out, uint8_t *mask_out, void *stream);
+int msda_level_valid_counts(const uint8_t *mask_flatten, const int64_t *spatial_shapes, const int64_t *level_start_index, int N,
+                            int S, int L, int *counts, void *stream);
+int msda_encoder_proposals(const void *memory, const uint8_t *mask_flatten, const int64_t *spatial_shapes,
+                           const int64_t *level_start_index, const int *counts, const float *wh_base, int N, int S, int L,
+                           int row_bytes, void *memory_out, float *proposals_out, void *stream);
+
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
  * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =
  * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */

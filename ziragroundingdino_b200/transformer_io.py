@@ -3,12 +3,29 @@
 (transformer_for_adapter.py:228-262 flatten / level embedding / valid ratios; :300-340 two-stage proposals and top-k
 query selection; utils.py:56-116 ``gen_encoder_output_proposals``).
 
-Host-side PyTorch plumbing, B200-first in two ways: level shapes stay **on the host** as Python ints (the reference
-iterates a CUDA ``spatial_shapes`` tensor, which costs a device->host sync per level per call, utils.py:72), and the
-flattened ``[N, S, C]`` layout produced by ``ZiRaInputProj.forward_rows`` is consumed as is (no per-level
-``flatten(2).transpose(1, 2)`` copies).
+B200-first in three ways: level shapes stay **on the host** as Python ints (the reference iterates a CUDA
+``spatial_shapes`` tensor, which costs a device->host sync per level per call, utils.py:72); the flattened ``[N, S, C]``
+layout produced by ``ZiRaInputProj.forward_rows`` is consumed as is (no per-level ``flatten(2).transpose(1, 2)`` copies);
+and on CUDA tensors the two bulk steps are single kernels (csrc/layer_io.cu): ``flatten_levels`` = one tiled
+NCHW -> [N, S, C] transposition of all levels with the level embedding added on the way (instead of ~6 eager kernels per
+level), ``gen_encoder_output_proposals`` = one pass over the encoder memory (instead of ~40 eager kernels and five
+[N, S, 4] temporaries).  CPU tensors take the eager PyTorch restatement (host plumbing, used by the CPU fixture test).
 """
+import ctypes
+
 import torch
+
+from . import _lib
+
+_DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _device_path(*tensors):
+    return all(t.is_cuda for t in tensors) and tensors[0].dtype in _DT and all(t.dtype == tensors[0].dtype for t in tensors)
 
 
 def get_valid_ratio(mask):
@@ -30,6 +47,9 @@ def flatten_levels(srcs, masks, pos_embeds, level_embed=None):
     embeddings -> (src_flatten [N, S, C], mask_flatten [N, S], lvl_pos_embed_flatten [N, S, C], shapes (host list),
     spatial_shapes, level_start_index, valid_ratios [N, L, 2])."""
     shapes = [tuple(s.shape[-2:]) for s in srcs]
+    if (_device_path(*srcs, *pos_embeds) and (level_embed is None or (level_embed.is_cuda and level_embed.dtype == srcs[0].dtype))
+            and all(m.is_cuda and m.dtype == torch.bool for m in masks) and not any(t.requires_grad for t in (*srcs, *pos_embeds))):
+        return _flatten_levels_device(srcs, masks, pos_embeds, level_embed, shapes)
     src_flatten = torch.cat([s.flatten(2).transpose(1, 2) for s in srcs], 1)
     mask_flatten = torch.cat([m.flatten(1) for m in masks], 1)
     pos = []
@@ -39,6 +59,37 @@ def flatten_levels(srcs, masks, pos_embeds, level_embed=None):
     spatial_shapes, level_start_index = level_tensors(shapes, src_flatten.device)
     valid_ratios = torch.stack([get_valid_ratio(m) for m in masks], 1)
     return src_flatten, mask_flatten, torch.cat(pos, 1), shapes, spatial_shapes, level_start_index, valid_ratios
+
+
+def _flatten_levels_device(srcs, masks, pos_embeds, level_embed, shapes):
+    """flatten_levels on CUDA tensors: msda_flatten_levels + msda_level_valid_counts (no autograd: inputs are detached
+    backbone features / position embeddings; level_embed is frozen in the ZiRa configuration)."""
+    N, C = srcs[0].shape[:2]
+    L = len(srcs)
+    dev, dt = srcs[0].device, srcs[0].dtype
+    S = sum(h * w for h, w in shapes)
+    srcs = [t.contiguous() for t in srcs]
+    poss = [t.contiguous() for t in pos_embeds]
+    mks = [m.contiguous().view(torch.uint8) for m in masks]
+    src_flatten = torch.empty((N, S, C), dtype=dt, device=dev)
+    pos_flatten = torch.empty((N, S, C), dtype=dt, device=dev)
+    mask_u8 = torch.empty((N, S), dtype=torch.uint8, device=dev)
+    arr = lambda ts: (ctypes.c_void_p * L)(*[t.data_ptr() for t in ts])
+    hw = (ctypes.c_int * L)(*[h * w for h, w in shapes])
+    le = None if level_embed is None else level_embed.detach().contiguous()
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = lib.msda_flatten_levels(arr(srcs), arr(poss), arr(mks), hw, L, N, C, 0 if le is None else le.data_ptr(), _DT[dt],
+                                     src_flatten.data_ptr(), pos_flatten.data_ptr(), mask_u8.data_ptr(), _stream(src_flatten))
+        _lib.check(rc, "msda_flatten_levels")
+        spatial_shapes, level_start_index = level_tensors(shapes, dev)
+        counts = torch.empty((N, L, 2), dtype=torch.int32, device=dev)
+        rc = lib.msda_level_valid_counts(mask_u8.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), N, S, L,
+                                         counts.data_ptr(), _stream(src_flatten))
+        _lib.check(rc, "msda_level_valid_counts")
+    wh = torch.tensor([[w, h] for h, w in shapes], dtype=torch.float32, device=dev)
+    valid_ratios = counts.float() / wh[None]
+    return src_flatten, mask_u8.view(torch.bool), pos_flatten, shapes, spatial_shapes, level_start_index, valid_ratios
 
 
 def add_level_embed_rows(pos_rows, level_embed, shapes):
@@ -53,6 +104,9 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, shapes, learnedwh=
     """utils.py:56-116 with host ``shapes`` [(H, W), ...]: (output_memory [N, S, C], output_proposals [N, S, 4] unsigmoid).
     Same arithmetic, one level at a time; no device->host synchronisation."""
     N = memory.shape[0]
+    if (memory.is_cuda and memory.dtype in _DT and memory_padding_mask.is_cuda and memory_padding_mask.dtype == torch.bool
+            and not memory.requires_grad and (memory.shape[-1] * memory.element_size()) % 16 == 0):
+        return _proposals_device(memory, memory_padding_mask, shapes, learnedwh)
     proposals, cur = [], 0
     for lvl, (H, W) in enumerate(shapes):
         m = memory_padding_mask[:, cur:cur + H * W].view(N, H, W)
@@ -76,6 +130,32 @@ def gen_encoder_output_proposals(memory, memory_padding_mask, shapes, learnedwh=
     output_proposals = output_proposals.masked_fill(drop, float("inf"))
     output_memory = memory.masked_fill(drop, float(0))
     return output_memory, output_proposals
+
+
+def _proposals_device(memory, memory_padding_mask, shapes, learnedwh):
+    """gen_encoder_output_proposals on CUDA tensors: msda_level_valid_counts + msda_encoder_proposals (inference /
+    detached use; with a memory that requires grad the eager path keeps autograd -- output_memory is a masked copy)."""
+    N, S, C = memory.shape
+    L = len(shapes)
+    dev = memory.device
+    memory = memory.contiguous()
+    mask_u8 = memory_padding_mask.contiguous().view(torch.uint8)
+    spatial_shapes, level_start_index = level_tensors(shapes, dev)
+    counts = torch.empty((N, L, 2), dtype=torch.int32, device=dev)
+    wh_base = (learnedwh.detach().float().sigmoid().reshape(2).contiguous() if learnedwh is not None
+               else torch.full((2,), 0.05, dtype=torch.float32, device=dev))
+    out_mem = torch.empty_like(memory)
+    out_prop = torch.empty((N, S, 4), dtype=torch.float32, device=dev)
+    lib = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = lib.msda_level_valid_counts(mask_u8.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(), N, S, L,
+                                         counts.data_ptr(), _stream(memory))
+        _lib.check(rc, "msda_level_valid_counts")
+        rc = lib.msda_encoder_proposals(memory.data_ptr(), mask_u8.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
+                                        counts.data_ptr(), wh_base.data_ptr(), N, S, L, C * memory.element_size(),
+                                        out_mem.data_ptr(), out_prop.data_ptr(), _stream(memory))
+        _lib.check(rc, "msda_encoder_proposals")
+    return out_mem, out_prop
 
 
 def select_topk_queries(output_memory, class_logits, coord_unselected, output_proposals, num_queries):
