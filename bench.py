@@ -643,7 +643,9 @@ def run_ours(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
-    bwd_kernel = "msda_bwd_vec_kernel<bf16,32,FUSEQ>" + ({2: " + msda_scatter_mma_kernel<bf16>", 3: " + memset + msda_scatter_mma2_kernel<bf16>"}.get(bwd_launches, ""))
+    bwd_kernel = "msda_bwd_vec_kernel<bf16,32,FUSEQ>"
+    if bwd_launches == 2:      # the tensor-memory scatter owns some levels (tuning keys bwd_mma / bwd_mma_levels)
+        bwd_kernel += " + msda_scatter_mma2_kernel<bf16>" if _lib.get_tuning("bwd_mma_levels") > 0 else " + msda_scatter_mma_kernel<bf16>"
     traffic, traffic_src = None, None
     try:   # DRAM bytes per launch of the dominant kernel, from the committed `ncu --set full` capture of the same launch
         ent = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[bwd_kernel]
