@@ -124,6 +124,8 @@ int msda_backward_16_ws(const void *value, const int64_t *spatial_shapes, const 
  *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64)
  *   key "bwd_narrow"        : 16-bit storage, 1 = 4 channels per lane in the backward kernel (one full-line
  *                             reduction per corner), 0 = 8 channels per lane
+ *   key "tap_share"         : 1 = the four sampling taps of a level are computed once per lane group and exchanged with
+ *                             shuffles (bit-identical values) instead of once per lane; vector kernels with >= 4 lanes per unit
  *   key "bwd_mma"           : 16-bit storage, D = 32, P = 4: 1 = the coarse tail of the level list (<= 1536 pixels, <= 4
  *                             levels) accumulates grad_value in tensor memory (tcgen05) and leaves the SM once per
  *                             (image, head) instead of once per bilinear corner; 0 = every corner is a reduction

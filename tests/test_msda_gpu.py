@@ -449,3 +449,26 @@ def test_mma2_scatter_full_size_and_fused_query(regime):
                 assert d < 1e-2
     finally:
         _lib.set_tuning(**keep)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("D", [32, 64, 16])
+def test_tap_share_is_bit_identical(dtype, D):
+    """tap_share=1 computes a level's four taps once per lane group and exchanges them by shuffles: the forward output,
+    grad_sampling_loc and grad_attn_weight must be BIT-identical to the per-lane form (grad_value only up to the order of
+    the atomics), including inactive tail groups (unit count not a multiple of the CTA tile) and border / outside samples."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import _lib
+    dev = _dev()
+    value, sh, lsi, loc, aw, gout = _mk([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, D, 333, 4, seed=70 + D, dtype=dtype, lo=-0.2, hi=1.2)
+    res = {}
+    keep = {k: _lib.get_tuning(k) for k in ("tap_share", "bwd_mma")}
+    try:
+        for ts in (0, 1):
+            _lib.set_tuning(tap_share=ts, bwd_mma=0)
+            res[ts] = _run(value, sh, lsi, loc, aw, gout, dev)
+    finally:
+        _lib.set_tuning(**keep)
+    assert torch.equal(res[0][0], res[1][0])
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+    assert rel_err(res[1][1].float(), res[0][1].float()) < 1e-5

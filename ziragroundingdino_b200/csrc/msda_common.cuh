@@ -20,6 +20,7 @@ struct Tuning {
   int bwd_q_fast = 1;
   int bwd_passes = 1;
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
+  int tap_share = 0;         // taps of a level computed once per lane group and exchanged by shuffles (shared_taps())
   int bwd_mma = 1;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu)
   int bwd_mma_levels = 0;    // > 0 and a workspace given: the last `bwd_mma_levels` levels go through the range-planned
                              // second-generation kernel (msda_scatter_mma2.cu) instead; 0 = first-generation tail only
@@ -251,6 +252,32 @@ __device__ inline void plan_ranges(RangePlan& p, const int* sH, const int* sW, c
       p.first_level = l + 1;
       ++p.nranges;
     }
+  }
+}
+
+// The four taps of a level, computed ONCE per lane group instead of once per lane: lane `lig` of the group evaluates the
+// tap of point lig & 3 and the group exchanges (corner offset, guards, lh, lw) with 16 shuffles; every lane then rebuilds
+// o2..o4 / hh / hw with the same two subtractions make_tap() does, so the values are bit-identical to the unshared form.
+// Needs LPG >= 4 lanes per group (all 32 lanes of the warp must call it).
+template <int LPG>
+__device__ __forceinline__ void shared_taps(const float (&xs)[4], const float (&ys)[4], int H, int W, int lig, Tap<float> (&t)[4]) {
+  static_assert(LPG >= 4, "tap sharing needs at least four lanes per unit");
+  const int pm = lig & 3;
+  const float x = pm == 0 ? xs[0] : (pm == 1 ? xs[1] : (pm == 2 ? xs[2] : xs[3]));
+  const float y = pm == 0 ? ys[0] : (pm == 1 ? ys[1] : (pm == 2 ? ys[2] : ys[3]));
+  const Tap<float> mine = make_tap<float>(x, y, H, W);
+  const int flags = (mine.c1 ? 1 : 0) | (mine.c2 ? 2 : 0) | (mine.c3 ? 4 : 0) | (mine.c4 ? 8 : 0) | (mine.ok ? 16 : 0);
+  const int base = (threadIdx.x & 31) & ~(LPG - 1);     // first lane of this group
+#pragma unroll
+  for (int p = 0; p < 4; ++p) {
+    const int o1 = __shfl_sync(0xffffffffu, mine.o1, base + p);
+    const int f = __shfl_sync(0xffffffffu, flags, base + p);
+    t[p].lh = __shfl_sync(0xffffffffu, mine.lh, base + p);
+    t[p].lw = __shfl_sync(0xffffffffu, mine.lw, base + p);
+    t[p].hh = 1.f - t[p].lh;
+    t[p].hw = 1.f - t[p].lw;
+    t[p].o1 = o1; t[p].o2 = o1 + 1; t[p].o3 = o1 + W; t[p].o4 = o1 + W + 1;
+    t[p].c1 = (f & 1) != 0; t[p].c2 = (f & 2) != 0; t[p].c3 = (f & 4) != 0; t[p].c4 = (f & 8) != 0; t[p].ok = (f & 16) != 0;
   }
 }
 

@@ -27,7 +27,7 @@ namespace msda {
 // =================================================================================================
 // forward, vectorised: D in {16, 32, 64, 128}, P == 4
 // =================================================================================================
-template <typename VT, int D, int SB>
+template <typename VT, int D, int SB, bool SHARE>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -53,9 +53,14 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   const int j = warp * UPW + lane / LPG;            // unit slot inside the pass tile
   const int row = M * D;                            // elements between neighbouring pixels
 
+  constexpr bool SH = SHARE && LPG >= 4;   // taps computed once per lane group (shared_taps): every lane stays in the loop
   for (int it = 0; it < passes; ++it) {
-    const long long u = unit_of(static_cast<long long>(blockIdx.x) * passes + it, j, TILE, M, q_fast != 0);
-    if (u >= units) continue;
+    long long u = unit_of(static_cast<long long>(blockIdx.x) * passes + it, j, TILE, M, q_fast != 0);
+    const bool active = u < units;
+    if (!active) {
+      if (!SH) continue;
+      u = 0;
+    }
     const int m = static_cast<int>(u % M);
     const long long bq = u / M;
     const long long b = bq / Lq;
@@ -75,13 +80,16 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
       const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
       const float as[4] = {a4.x, a4.y, a4.z, a4.w};
+      Tap<float> t4[4];
+      if constexpr (SH) shared_taps<LPG>(xs, ys, H, W, lig, t4);
 #pragma unroll
       for (int p0 = 0; p0 < P; p0 += SB) {
         float v[SB][4][CH];
         float k[SB][4];
 #pragma unroll
         for (int s = 0; s < SB; ++s) {
-          const Tap<float> t = make_tap<float>(xs[p0 + s], ys[p0 + s], H, W);
+          Tap<float> t;
+          if constexpr (SH) t = t4[p0 + s]; else t = make_tap<float>(xs[p0 + s], ys[p0 + s], H, W);
           // 32-bit element offsets (S*M*D < 2^31 is checked on the host): one IMAD + three adds per sample
           const int e1 = t.o1 * row, e3 = e1 + wrow;
           Vec<VT>::load(vl + e1, t.c1, v[s][0]);
@@ -104,7 +112,7 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         }
       }
     }
-    Vec<VT>::store(out + static_cast<size_t>(u) * D + lig * CH, acc);
+    if (active) Vec<VT>::store(out + static_cast<size_t>(u) * D + lig * CH, acc);
   }
 }
 
@@ -142,7 +150,7 @@ struct FuseQ {
   int is_half;
 };
 
-template <typename VT, int D, typename V, bool FUSEQ, bool HITS>
+template <typename VT, int D, typename V, bool FUSEQ, bool HITS, bool SHARE>
 __global__ void __launch_bounds__(kThreads)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -245,9 +253,13 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const bool do_red = l < red_levels;
       int o_min = 0x7fffffff, o_max = -1;    // clamped corner-offset extent of this level's inside samples (mma_mode 2)
       float red[16];
+      constexpr bool SH = SHARE && LPG >= 4;
+      Tap<float> t4[4];
+      if constexpr (SH) shared_taps<LPG>(xs, ys, H, W, lig, t4);
 #pragma unroll
       for (int p = 0; p < P; ++p) {
-        Tap<float> t = make_tap<float>(xs[p], ys[p], H, W);
+        Tap<float> t;
+        if constexpr (SH) t = t4[p]; else t = make_tap<float>(xs[p], ys[p], H, W);
         t.c1 = t.c1 && active; t.c2 = t.c2 && active; t.c3 = t.c3 && active; t.c4 = t.c4 && active;
         if (HITS && t.ok) { o_min = min(o_min, t.o1); o_max = max(o_max, t.o4); }
         float v1[CH], v2[CH], v3[CH], v4[CH];
@@ -473,10 +485,14 @@ static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const 
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   const dim3 grid(static_cast<unsigned>(blocks));
   ++g_launches;
+  if (g_tuning.tap_share && g_tuning.fwd_sample_batch == 4) {
+    msda_fwd_vec_kernel<VT, D, 4, true><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast);
+    return cudaGetLastError();
+  }
   switch (g_tuning.fwd_sample_batch) {
-    case 1: msda_fwd_vec_kernel<VT, D, 1><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
-    case 4: msda_fwd_vec_kernel<VT, D, 4><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
-    default: msda_fwd_vec_kernel<VT, D, 2><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    case 1: msda_fwd_vec_kernel<VT, D, 1, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    case 4: msda_fwd_vec_kernel<VT, D, 4, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    default: msda_fwd_vec_kernel<VT, D, 2, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
   }
   return cudaGetLastError();
 }
@@ -523,18 +539,21 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   }
   ++g_launches;
   bool launched = false;
+  const dim3 grid(static_cast<unsigned>(blocks));
+#define MSDA_BWD_LAUNCH(HITS_, SHARE_)                                                                               \
+  msda_bwd_vec_kernel<VT, D, V, FUSEQ, HITS_, SHARE_><<<grid, kThreads, 0, st>>>(                                   \
+      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,            \
+      g_tuning.bwd_mma_levels, hit, fq)
   if constexpr (sizeof(VT) == 2 && D == 32) {
     if (mma_mode == 2) {
-      msda_bwd_vec_kernel<VT, D, V, FUSEQ, true><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
-          value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,
-          g_tuning.bwd_mma_levels, hit, fq);
+      if (g_tuning.tap_share) MSDA_BWD_LAUNCH(true, true); else MSDA_BWD_LAUNCH(true, false);
       launched = true;
     }
   }
-  if (!launched)
-    msda_bwd_vec_kernel<VT, D, V, FUSEQ, false><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
-        value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,
-        g_tuning.bwd_mma_levels, hit, fq);
+  if (!launched) {
+    if (g_tuning.tap_share) MSDA_BWD_LAUNCH(false, true); else MSDA_BWD_LAUNCH(false, false);
+  }
+#undef MSDA_BWD_LAUNCH
   cudaError_t e = cudaGetLastError();
   if constexpr (sizeof(VT) == 2 && D == 32) {
     if (e == cudaSuccess && mma_mode == 1) e = launch_scatter_mma<VT>(shapes, lstart, loc, aw, grad_out, gv, N, S, M, L, Lq, st);
