@@ -16,6 +16,7 @@ for lv in 0 2 3 4; do
 done
 MSDA_B200_TUNING=tap_share=1 run 300 python bench.py --config 2 --steps 10 --warmup 3 --no-cpu-baseline --no-config5 > $O/r2_bench_c2_tapshare.json 2> $O/r2_bench_c2_tapshare.err
 MSDA_B200_TUNING=tap_share=1,bwd_mma_levels=4 run 300 python bench.py --config 2 --steps 10 --warmup 3 --no-cpu-baseline --no-config5 > $O/r2_bench_c2_tapshare_lv4.json 2> $O/r2_bench_c2_tapshare_lv4.err
+MSDA_B200_OWN_K_FFN=1 run 300 python bench.py --config 2 --steps 10 --warmup 3 --no-cpu-baseline --no-config5 > $O/r2_bench_c2_ownkffn.json 2> $O/r2_bench_c2_ownkffn.err
 MSDA_B200_TUNING=bwd_mma=0 run 300 python bench.py --config 2 --steps 10 --warmup 3 --no-cpu-baseline --no-config5 > $O/r2_bench_c2_nomma.json 2> $O/r2_bench_c2_nomma.err
 run 300 python bench.py --gaps --config 4 2> $O/r2_gaps_c4.txt
 run 300 python bench.py --gaps --config 2 2> $O/r2_gaps_c2.txt

@@ -16,6 +16,19 @@ from . import _C, _lib, fused
 from .layer_ops import _linear_act_bits16, _stream, derived
 
 
+import os
+
+# The two FFN products with K = d_ffn (linear2 forward, linear1 dgrad): library GEMMs by default -- their 1 MB weight
+# does not stay resident in shared memory and the library's 2-CTA multicast kernel streams it at half the L2 traffic.
+# MSDA_B200_OWN_K_FFN=1 (or blocks.OWN_K_FFN = True) runs them on the tcgen05 GEMM of csrc/proj_gemm.cu as well, so that
+# no library kernel is left in the encoder layer (A/B in profiles/).
+OWN_K_FFN = os.environ.get("MSDA_B200_OWN_K_FFN", "0") == "1"
+
+
+def own_k_ffn():
+    return OWN_K_FFN
+
+
 def _add_ln_fwd(x2, r2, g32, b32, eps):
     R, C = x2.shape
     z, y = torch.empty_like(x2), torch.empty_like(x2)
@@ -107,7 +120,10 @@ class FFNBlockFunction(Function):
         x2d = x.reshape(-1, shape[-1]).contiguous()
         bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
         h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
-        y2 = torch.nn.functional.linear(h, w2, b2)
+        if own_k_ffn():      # K = d_ffn on the tcgen05 GEMM too (W2 streams through the ring): no library kernel in the block
+            y2 = fused.linear16(h, w2.contiguous(), derived(b2, "f32"))
+        else:
+            y2 = torch.nn.functional.linear(h, w2, b2)
         z, y, mean, rstd = _add_ln_fwd(x2d, y2, g32, b32, eps)
         ctx.save_for_backward(bits, w1, w2, z, g32, mean, rstd)
         ctx.shape = shape
@@ -119,7 +135,10 @@ class FFNBlockFunction(Function):
         bits, w1, w2, z, g32, mean, rstd = ctx.saved_tensors
         dz = _add_ln_bwd(dy.reshape(z.shape).contiguous(), z, g32, mean, rstd)
         dh = _linear_act_bits16(dz, derived(w2, "t"), None, gate_bits=bits)
-        dx = dz.addmm_(dh, w1)      # in place (beta = 1): the out-of-place form first copies dz into its output (a 45 MB memcpy)
+        if own_k_ffn():
+            dx = linear_accum16(dh, derived(w1, "t"), dz)      # dz += dh W1, accumulated in the GEMM epilogue
+        else:
+            dx = dz.addmm_(dh, w1)      # in place (beta = 1): the out-of-place form first copies dz into its output (a 45 MB memcpy)
         return (dx.view(ctx.shape),) + (None,) * 7
 
 
