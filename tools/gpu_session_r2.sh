@@ -7,6 +7,8 @@ run() { local t=$1; shift; timeout $t "$@"; echo "[rc=$?] $*" >> $O/r2_session.l
 : > $O/r2_session.log
 run 420 python -m pytest tests/test_msda_gpu.py -m gpu -q -s -k "mma" > $O/r2_tests_mma.log 2>&1
 tail -4 $O/r2_tests_mma.log
+run 300 python tools/debug_mma_scatter.py --time > $O/r2_debug_mma.log 2>&1
+tail -30 $O/r2_debug_mma.log
 run 900 python bench.py --steps 20 --warmup 5 > $O/r2_bench1.json 2> $O/r2_bench1.err
 cut -c1-400 $O/r2_bench1.json
 run 1500 python -m pytest tests -m gpu -q -s > $O/r2_tests_full.log 2>&1
