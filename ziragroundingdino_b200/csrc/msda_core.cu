@@ -150,8 +150,10 @@ struct FuseQ {
   int is_half;
 };
 
+// HITS: the hit-mask bookkeeping would otherwise cost ~25 registers (80 -> 104: 3 -> 2 resident CTAs per SM); capped at
+// the plain kernel's 80 it spills 8-36 bytes, which is cheaper than the lost occupancy.
 template <typename VT, int D, typename V, bool FUSEQ, bool HITS, bool SHARE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, HITS ? 3 : 1)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
