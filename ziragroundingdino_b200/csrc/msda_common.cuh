@@ -185,7 +185,7 @@ constexpr int kMmaMaxLevels = 4;               // two levels per builder thread
 // map and fit the accumulators; L when none does (or level_start is not the cumulative layout the reference builds,
 // transformer_for_adapter.py:254-256).  Evaluated identically by msda_bwd_vec_kernel (which skips those reductions) and
 // msda_scatter_mma_kernel (which owns them).
-__device__ __forceinline__ int coarse_first_level(const int* sH, const int* sW, const int* sStart, int L, int S) {
+__host__ __device__ __forceinline__ int coarse_first_level(const int* sH, const int* sW, const int* sStart, int L, int S) {
   int first = L, end = S;
   for (int l = L - 1; l >= 0 && L - l <= kMmaMaxLevels; --l) {
     if (sStart[l] + sH[l] * sW[l] != end || S - sStart[l] > kMmaMaxPixels) break;
@@ -211,7 +211,7 @@ struct RangePlan {
   int lo[kR2MaxRanges], hi[kR2MaxRanges];      // pixel interval [lo, hi) of range r
   int lv0[kR2MaxRanges], lv1[kR2MaxRanges];    // levels [lv0, lv1) that intersect range r
 };
-__device__ inline void plan_ranges(RangePlan& p, const int* sH, const int* sW, const int* sStart, int L, int S, int max_levels) {
+__host__ __device__ inline void plan_ranges(RangePlan& p, const int* sH, const int* sW, const int* sStart, int L, int S, int max_levels) {
   p.first_level = L;
   p.nranges = 0;
   int end = S, l = L - 1;
