@@ -251,6 +251,18 @@ int msda_group_norm_bwd_16(const void *dy, long long dy_image_stride, const void
                            const float *gamma, const float *mean_rstd, int N, long long HW, int C, int G, void *dx,
                            long long dx_image_stride, double *scratch, int is_half, void *stream);
 
+/* ---- the whole FFN of the layer as ONE launch per direction (row N1; transformer_for_adapter.py:876-885) ------------
+ * msda_ffn_chain_fwd_16: out[R, C] = relu(x W1^T + b1) W2^T + b2 with the [R, F] hidden activation kept on chip (128 rows
+ *   x 128 hidden columns at a time: TMEM -> registers -> shared memory -> second tcgen05 product); relu_bits_out [F/32, R]
+ *   receives one bit per hidden activation (same layout as msda_linear_act_bits_16).  x, W1 [F, C], W2 [C, F], out 16-bit;
+ *   b1 [F], b2 [C] fp32.  C == 256, F % 128 == 0.
+ * msda_ffn_chain_bwd_16: dx[R, C] = accum + gate(dy W2) W1 with the same chaining: w2_t = W2^T [F, C], w1_t = W1^T [C, F],
+ *   gate_bits from the forward; accum (16-bit [R, C], may be NULL) and dx may alias dy. */
+int msda_ffn_chain_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R, int C,
+                          int F, void *out, uint32_t *relu_bits_out, int is_half, void *stream);
+int msda_ffn_chain_bwd_16(const void *dy, const void *w2_t, const void *w1_t, const uint32_t *gate_bits, const void *accum,
+                          long long R, int C, int F, void *dx, int is_half, void *stream);
+
 /* ---- the steps either side of the stacks --------------------------------------------
  * msda_flatten_levels: transformer_for_adapter.py:238-262 as one launch.  src_levels / pos_levels / mask_levels are HOST
  *   arrays of L device pointers: per level an NCHW map [N, C, H*W] (dtype: 0 bf16, 1 f16, 2 f32), its position embedding

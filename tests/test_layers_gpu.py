@@ -177,3 +177,69 @@ def test_linear_accum16_in_place_and_out_of_place():
                     _lib.lib().msda_b200_gemm_set_staged(1)
                 assert (out.double() - want).abs().max().item() <= eps * want.abs().max().item() * 1.05
                 assert torch.equal(out, a2)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("R", [1, 127, 128, 1000, 22223])
+def test_ffn_chain_forward_and_backward_vs_fp64(dtype, R):
+    """Chained FFN kernel (hidden activation never leaves the SM) vs fp64 on the same 16-bit operands, with the SAME
+    intermediate rounding the two-launch path has (hidden rounded to the storage type before the second product):
+    forward y = relu(x W1^T + b1) W2^T + b2, the 1-bit ReLU mask, and backward dx = dz + ((dz W2) * mask) W1 in place."""
+    from ziragroundingdino_b200 import blocks
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(5 + R)
+    C, F = 256, 2048
+    x = torch.randn(R, C, generator=g).to(dtype).to(dev)
+    w1 = (torch.randn(F, C, generator=g) * 0.06).to(dtype).to(dev)
+    w2 = (torch.randn(C, F, generator=g) * 0.02).to(dtype).to(dev)
+    b1 = (torch.randn(F, generator=g) * 0.1).to(dev)
+    b2 = (torch.randn(C, generator=g) * 0.1).to(dev)
+    bits = torch.zeros((F // 32, R), dtype=torch.int32, device=dev)
+    y = blocks.ffn_chain_fwd16(x, w1, b1, w2, b2, bits)
+    h64 = torch.relu(x.double() @ w1.double().t() + b1.double())
+    h16 = h64.to(dtype).double()
+    want = h16 @ w2.double().t() + b2.double()
+    eps = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert (y.double() - want).abs().max().item() <= 2 * eps * want.abs().max().item()
+    # bits: exact wherever the pre-activation is not within rounding distance of zero
+    pre = x.double() @ w1.double().t() + b1.double()
+    got = ((bits.t().contiguous().view(R, F // 32, 1) >> torch.arange(32, device=dev).view(1, 1, 32)) & 1).reshape(R, F).bool()
+    sure = pre.abs() > 1e-3
+    assert torch.equal(got[sure], (pre > 0)[sure])
+    dz = torch.randn(R, C, generator=g).to(dtype).to(dev)
+    dz_in = dz.clone()
+    dx = blocks.ffn_chain_bwd16(dz, w2.t().contiguous(), w1.t().contiguous(), bits)
+    assert dx.data_ptr() == dz.data_ptr()
+    dh = ((dz_in.double() @ w2.double()) * got.double()).to(dtype).double()
+    want_dx = dz_in.double() + dh @ w1.double()
+    assert (dx.double() - want_dx).abs().max().item() <= 2 * eps * want_dx.abs().max().item()
+
+
+def test_encoder_layer_with_chained_ffn_matches_unchained():
+    """The frozen encoder layer with blocks.FFN_CHAIN on vs off: same outputs and input gradients to 16-bit rounding."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import blocks, encoder, synthetic as syn
+    dev = "cuda:0"
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    sh, lsi = syn.level_tensors(shapes, dev)
+    torch.manual_seed(9)
+    layer = encoder.DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4).to(dev).bfloat16()
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    refp = syn.encoder_reference_points(shapes, torch.ones(2, 4, 2, device=dev), dev)
+    x0 = torch.randn(2, S, 256, device=dev).bfloat16()
+    pos = torch.randn(2, S, 256, device=dev).bfloat16()
+    res = {}
+    keep = blocks.FFN_CHAIN
+    try:
+        for chain in (False, True):
+            blocks.FFN_CHAIN = chain
+            x = x0.clone().requires_grad_(True)
+            out, _ = layer(x, pos, refp, sh, lsi, None)
+            out.float().square().mean().backward()
+            res[chain] = (out.detach().float(), x.grad.float())
+    finally:
+        blocks.FFN_CHAIN = keep
+    assert (res[True][0] - res[False][0]).abs().max().item() < 3 * 2 ** -8 * res[False][0].abs().max().item()
+    assert (res[True][1] - res[False][1]).abs().max().item() < 2e-2 * res[False][1].abs().max().item()

@@ -222,7 +222,8 @@ def test_full_size_properties(shapes, N, tag, dtype):
     gv, gl, ga = zb._C.ms_deform_attn_backward(v, sh, lsi, loc, aw, gout, 64)
     lhs = (o.double() * gout.double()).sum().item()
     rhs = (v.double() * gv.double()).sum().item()
-    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < (1e-5 if dtype == torch.float32 else 2e-3)
+    # bf16: the two sides round differently (output rounding vs gradient / weight rounding): north_star's 1e-2
+    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < (1e-5 if dtype == torch.float32 else 1e-2)
     # (4)
     idx = torch.randperm(Lq, generator=torch.Generator().manual_seed(1))[: max(Lq // 64, 8)].sort().values
     sub_loc = loc[:1, idx.to(dev)].contiguous().cpu()
@@ -383,7 +384,7 @@ def test_mma_scatter_full_size_encoder(regime):
     o = zb._C.ms_deform_attn_forward(*a, 64)
     lhs = (o.double() * inp["grad_out"].double()).sum().item()
     rhs = (inp["value"].double() * gv1.double()).sum().item()
-    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < 2e-3
+    assert abs(lhs - rhs) / max(abs(lhs), 1.0) < 1e-2
 
 
 def _bwd16_v2(value, sh, lsi, loc, aw, gout, dev, levels):
@@ -471,4 +472,5 @@ def test_tap_share_is_bit_identical(dtype, D):
         _lib.set_tuning(**keep)
     assert torch.equal(res[0][0], res[1][0])
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
-    assert rel_err(res[1][1].float(), res[0][1].float()) < 1e-5
+    # grad_value: same fp32 contributions in a different atomic order, then (for 16-bit storage) one rounding to bf16
+    assert rel_err(res[1][1].float(), res[0][1].float()) < (1e-5 if dtype == torch.float32 else 2 ** -8)

@@ -49,7 +49,9 @@ def test_proposals_and_topk_on_cuda_match_reference():
                                                    t("output_proposals"), nq)
     # top-k over distinct logits: same set in the same (sorted) order
     assert torch.equal(idx, t("topk_proposals")) and torch.equal(tgt, t("tgt_undetach"))
-    assert torch.equal(ref_u, t("refpoint_embed_undetach")) and torch.equal(box, t("init_box_proposal"))
+    assert torch.equal(ref_u, t("refpoint_embed_undetach"))
+    # sigmoid of proposals that may differ from the CPU fixture in the last ulp of logf
+    assert (box - t("init_box_proposal")).abs().max().item() < 1e-6
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])

@@ -61,6 +61,8 @@ def lib():
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]
     L.msda_linear_f32.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp]
     L.msda_query_proj_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]
+    L.msda_ffn_chain_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]
+    L.msda_ffn_chain_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp]
     L.msda_flatten_levels.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]
     L.msda_level_valid_counts.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]
     L.msda_encoder_proposals.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]

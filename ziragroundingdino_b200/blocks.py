@@ -29,6 +29,38 @@ def own_k_ffn():
     return OWN_K_FFN
 
 
+# MSDA_B200_FFN_CHAIN=1 (or blocks.FFN_CHAIN = True): the whole FFN as ONE launch per direction with the hidden
+# activation kept on chip (csrc/layer_ffn_chain.cu): linear1 -> ReLU (+ 1-bit mask) -> linear2 forward, and
+# gate(dz W2) W1 + dz backward.  d_model = 256, d_ffn % 128 == 0.
+FFN_CHAIN = os.environ.get("MSDA_B200_FFN_CHAIN", "0") == "1"
+
+
+def ffn_chain_ok(C, F):
+    return FFN_CHAIN and C == 256 and F % 128 == 0 and F <= 8192
+
+
+def ffn_chain_fwd16(x2d, w1, b1_f32, w2, b2_f32, bits):
+    R, C = x2d.shape
+    F = w1.shape[0]
+    out = torch.empty((R, C), dtype=x2d.dtype, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_ffn_chain_fwd_16(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C, F,
+                                              out.data_ptr(), bits.data_ptr(), 1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_ffn_chain_fwd_16")
+    return out
+
+
+def ffn_chain_bwd16(dz, w2_t, w1_t, bits):
+    """dz <- dz + gate(dz W2) W1, in place (w2_t = W2^T [d_ffn, d_model], w1_t = W1^T [d_model, d_ffn])."""
+    R, C = dz.shape
+    F = w2_t.shape[0]
+    with torch.cuda.device(dz.device):
+        rc = _lib.lib().msda_ffn_chain_bwd_16(dz.data_ptr(), w2_t.data_ptr(), w1_t.data_ptr(), bits.data_ptr(), dz.data_ptr(), R, C, F,
+                                              dz.data_ptr(), 1 if dz.dtype == torch.float16 else 0, _stream(dz))
+    _lib.check(rc, "msda_ffn_chain_bwd_16")
+    return dz
+
+
 def _add_ln_fwd(x2, r2, g32, b32, eps):
     R, C = x2.shape
     z, y = torch.empty_like(x2), torch.empty_like(x2)
@@ -119,6 +151,13 @@ class FFNBlockFunction(Function):
         shape = x.shape
         x2d = x.reshape(-1, shape[-1]).contiguous()
         bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
+        ctx.chain = ffn_chain_ok(x2d.shape[1], w1.shape[0])
+        if ctx.chain:
+            y2 = ffn_chain_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"), bits)
+            z, y, mean, rstd = _add_ln_fwd(x2d, y2, g32, b32, eps)
+            ctx.save_for_backward(bits, w1, w2, z, g32, mean, rstd)
+            ctx.shape = shape
+            return y.view(shape)
         h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
         if own_k_ffn():      # K = d_ffn on the tcgen05 GEMM too (W2 streams through the ring): no library kernel in the block
             y2 = fused.linear16(h, w2.contiguous(), derived(b2, "f32"))
@@ -134,6 +173,8 @@ class FFNBlockFunction(Function):
     def backward(ctx, dy):
         bits, w1, w2, z, g32, mean, rstd = ctx.saved_tensors
         dz = _add_ln_bwd(dy.reshape(z.shape).contiguous(), z, g32, mean, rstd)
+        if ctx.chain:
+            return (ffn_chain_bwd16(dz, derived(w2, "t"), derived(w1, "t"), bits).view(ctx.shape),) + (None,) * 7
         dh = _linear_act_bits16(dz, derived(w2, "t"), None, gate_bits=bits)
         if own_k_ffn():
             dx = linear_accum16(dh, derived(w1, "t"), dz)      # dz += dh W1, accumulated in the GEMM epilogue

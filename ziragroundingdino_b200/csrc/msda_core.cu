@@ -150,10 +150,14 @@ struct FuseQ {
   int is_half;
 };
 
-// HITS: the hit-mask bookkeeping would otherwise cost ~25 registers (80 -> 104: 3 -> 2 resident CTAs per SM); capped at
-// the plain kernel's 80 it spills 8-36 bytes, which is cheaper than the lost occupancy.
-template <typename VT, int D, typename V, bool FUSEQ, bool HITS, bool SHARE>
-__global__ void __launch_bounds__(kThreads, HITS ? 3 : 1)
+// 3 resident CTAs per SM (<= 85 registers): the kernel needs its occupancy to keep enough reductions and corner loads in
+// flight.  The plain variant fits in 80 without spilling; the hit-mask bookkeeping (HITS) would take ~25
+// more and spills 8-36 bytes instead, which is cheaper than dropping to 2 CTAs.
+// MODE: 0 = every corner is a reduction (the round-1 kernel, unchanged); 1 = the coarse tail of the level list is owned by
+// msda_scatter_mma_kernel; 2 = the last `mma_levels` levels are owned by msda_scatter_mma2_kernel and this kernel also
+// writes the per-chunk hit masks it needs.
+template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE>
+__global__ void __launch_bounds__(kThreads, 3)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
@@ -166,6 +170,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   constexpr int TILE = UPW * kWarpsPerBlock;
   constexpr int P = 4;
   constexpr int R = 16 / LPG;
+  constexpr bool HITS = MODE == 2;
   static_assert(LPG >= 1 && LPG <= 16 && (LPG & (LPG - 1)) == 0, "D / CH must be a power of two <= 16");
 
   __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
@@ -243,7 +248,12 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
     float fq_dot = 0.f;
     unsigned long long hit_bits = 0ull;      // mma_mode 2: ranges touched by this unit's samples
 
-    for (int l = 0; l < L; ++l) {
+    // One level.  DO_RED is a COMPILE-TIME property of the call: with a run-time `if (l < red_levels)` around the reductions
+    // the compiler fences each group of reductions off in its own branch region and can no longer hoist the next point's
+    // corner loads above them -- measured: 959 -> 1527 us per launch at config 2 (profiles/r2_*).  Two loops over the two
+    // level classes keep each body straight-line.
+    auto level_body = [&](const int l, auto red_tag) {
+      constexpr bool do_red = decltype(red_tag)::value;
       const int H = sH[l], W = sW[l];
       const size_t loff = static_cast<size_t>(sStart[l]) * row;
       const VT* vl = vb + loff;
@@ -252,7 +262,6 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
       const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
       const float as[4] = {a4.x, a4.y, a4.z, a4.w};
-      const bool do_red = l < red_levels;
       int o_min = 0x7fffffff, o_max = -1;    // clamped corner-offset extent of this level's inside samples (mma_mode 2)
       float red[16];
       constexpr bool SH = SHARE && LPG >= 4;
@@ -326,6 +335,15 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           }
         }
       }
+    };
+    if constexpr (MODE == 0) {
+      for (int l = 0; l < L; ++l) level_body(l, std::true_type{});
+    } else {
+      int l = 0;
+#pragma unroll 1
+      for (; l < red_levels; ++l) level_body(l, std::true_type{});
+#pragma unroll 1
+      for (; l < L; ++l) level_body(l, std::false_type{});
     }
     if (HITS && active && lig == 0 && hit_bits != 0ull)
       atomicOr(hit + ((b * M + m) * cpq + (static_cast<int>(bq % Lq) >> 6)), hit_bits);
@@ -542,18 +560,21 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   ++g_launches;
   bool launched = false;
   const dim3 grid(static_cast<unsigned>(blocks));
-#define MSDA_BWD_LAUNCH(HITS_, SHARE_)                                                                               \
-  msda_bwd_vec_kernel<VT, D, V, FUSEQ, HITS_, SHARE_><<<grid, kThreads, 0, st>>>(                                   \
+#define MSDA_BWD_LAUNCH(MODE_, SHARE_)                                                                               \
+  msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_><<<grid, kThreads, 0, st>>>(                                   \
       value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,            \
       g_tuning.bwd_mma_levels, hit, fq)
   if constexpr (sizeof(VT) == 2 && D == 32) {
     if (mma_mode == 2) {
-      if (g_tuning.tap_share) MSDA_BWD_LAUNCH(true, true); else MSDA_BWD_LAUNCH(true, false);
+      if (g_tuning.tap_share) MSDA_BWD_LAUNCH(2, true); else MSDA_BWD_LAUNCH(2, false);
+      launched = true;
+    } else if (mma_mode == 1) {
+      if (g_tuning.tap_share) MSDA_BWD_LAUNCH(1, true); else MSDA_BWD_LAUNCH(1, false);
       launched = true;
     }
   }
   if (!launched) {
-    if (g_tuning.tap_share) MSDA_BWD_LAUNCH(false, true); else MSDA_BWD_LAUNCH(false, false);
+    if (g_tuning.tap_share) MSDA_BWD_LAUNCH(0, true); else MSDA_BWD_LAUNCH(0, false);
   }
 #undef MSDA_BWD_LAUNCH
   cudaError_t e = cudaGetLastError();
