@@ -199,7 +199,7 @@ def test_five_level_training_backward_through_im2col_level():
     y3 = F_.conv2d(x, d(m.input_proj[3][0].weight), d(m.input_proj[3][0].bias), stride=2, padding=1) \
         + d(a3.scaling) * F_.conv2d(x, w3, d(a3.bias), stride=2, padding=1) + F_.conv2d(x, d(a3.freeze_conv.weight), d(a3.freeze_conv.bias), stride=2, padding=1)
     s3 = F_.group_norm(y3, 32, d(m.input_proj[3][1].weight), d(m.input_proj[3][1].bias), 1e-5)
-    s3 = s3.to(torch.bfloat16).double() + (s3 - s3.detach())          # the bf16 rounding of the stored level
+    s3 = s3.detach().to(torch.bfloat16).double() + (s3 - s3.detach())   # value: the bf16-rounded stored level; gradient: identity
     y4 = F_.conv2d(s3, d(m.input_proj[4][0].weight), d(m.input_proj[4][0].bias), stride=2, padding=1) \
         + d(a4.scaling) * F_.conv2d(s3, d(a4.weight), d(a4.bias), stride=2, padding=1) + F_.conv2d(s3, d(a4.freeze_conv.weight), d(a4.freeze_conv.bias), stride=2, padding=1)
     s4 = F_.group_norm(y4, 32, d(m.input_proj[4][1].weight), d(m.input_proj[4][1].bias), 1e-5)

@@ -474,3 +474,36 @@ def test_tap_share_is_bit_identical(dtype, D):
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
     # grad_value: same fp32 contributions in a different atomic order, then (for 16-bit storage) one rounding to bf16
     assert rel_err(res[1][1].float(), res[0][1].float()) < (1e-5 if dtype == torch.float32 else 2 ** -8)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("D,M", [(32, 8), (64, 4), (16, 5), (128, 2)])
+def test_bwd_dots_formulation_vs_oracle(dtype, D, M):
+    """bwd_dots=1: grad_sampling_loc / grad_attn_weight formed from the four corner dot products of a sample instead of
+    per-channel bilinear derivatives -- same mathematics, different association.  Against the C oracle (fp32) / the fp64
+    oracle on the rounded inputs (16-bit) at north_star's 1e-4, every lane-group width (R = 1, 2, 4, 8), samples on, inside
+    and outside the borders; grad_value is untouched by the switch."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import _lib
+    if D == 128 and dtype == torch.float32:
+        pytest.skip("D = 128 is a vector shape for 16-bit storage only")
+    dev = _dev()
+    value, sh, lsi, loc, aw, gout = _mk([(20, 30), (10, 15), (5, 8), (3, 4)], 2, M, D, 333, 4, seed=80 + D, dtype=dtype, lo=-0.2, hi=1.2)
+    keep = {k: _lib.get_tuning(k) for k in ("bwd_dots", "bwd_mma", "bwd_narrow")}
+    res = {}
+    try:
+        for narrow in (1, 0):
+            for dots in (0, 1):
+                _lib.set_tuning(bwd_dots=dots, bwd_mma=0, bwd_narrow=narrow)
+                res[(narrow, dots)] = _run(value, sh, lsi, loc, aw, gout, dev)
+    finally:
+        _lib.set_tuning(**keep)
+    if dtype == torch.float32:
+        o_gv, o_gl, o_ga = O.c_backward(value.numpy(), sh.numpy(), loc.numpy(), aw.numpy(), gout.numpy())
+    else:
+        o_gv, o_gl, o_ga = O.c_backward(value.double().numpy(), sh.numpy(), loc.double().numpy(), aw.double().numpy(), gout.double().numpy())
+    for key, (out, gv, gl, ga) in res.items():
+        assert rel_err(gl, o_gl) < 1e-4 and rel_err(ga, o_ga) < 1e-4, key
+        assert torch.equal(out, res[(1, 0)][0])
+    print("bwd_dots %s D=%d: grad_loc rel err per-channel %.1e / dots %.1e; grad_aw %.1e / %.1e" % (
+        str(dtype).split(".")[-1], D, rel_err(res[(1, 0)][2], o_gl), rel_err(res[(1, 1)][2], o_gl), rel_err(res[(1, 0)][3], o_ga), rel_err(res[(1, 1)][3], o_ga)))

@@ -58,10 +58,11 @@ def timings():
     for regime in ("local", "uniform"):
         sets = [syn.core_inputs(syn.SWIN_T_800x1333, 4, dtype=torch.bfloat16, regime=regime, device=dev, seed=5 + i) for i in range(3)]
         refs = [syn.encoder_reference_points(syn.SWIN_T_800x1333, torch.ones(4, 4, 2, device=dev), dev).contiguous() for _ in sets]
-        for tun in (dict(bwd_mma=0), dict(bwd_mma=1, bwd_mma_levels=0), dict(bwd_mma=1, bwd_mma_levels=2), dict(bwd_mma=1, bwd_mma_levels=3),
-                    dict(bwd_mma=1, bwd_mma_levels=4), dict(bwd_mma=0, tap_share=1), dict(bwd_mma=1, bwd_mma_levels=0, tap_share=1),
-                    dict(bwd_mma=1, bwd_mma_levels=4, tap_share=1)):
-            _lib.set_tuning(**dict(dict(bwd_mma=1, bwd_mma_levels=0, tap_share=0), **tun))
+        for tun in (dict(bwd_mma=0), dict(bwd_mma=0, bwd_dots=1), dict(bwd_mma=1, bwd_mma_levels=0), dict(bwd_mma=1, bwd_mma_levels=0, bwd_dots=1),
+                    dict(bwd_mma=1, bwd_mma_levels=2), dict(bwd_mma=1, bwd_mma_levels=2, bwd_dots=1), dict(bwd_mma=1, bwd_mma_levels=3, bwd_dots=1),
+                    dict(bwd_mma=1, bwd_mma_levels=4, bwd_dots=1), dict(bwd_mma=0, bwd_dots=1, bwd_narrow=0),
+                    dict(bwd_mma=1, bwd_mma_levels=4, bwd_dots=1, bwd_narrow=0)):
+            _lib.set_tuning(**dict(dict(bwd_mma=1, bwd_mma_levels=0, tap_share=0, bwd_dots=0, bwd_narrow=1), **tun))
             fns = [(lambda i_=i_, r=r: fused.backward_fusedq16(i_["value"], i_["shapes"], i_["level_start"], i_["loc"], i_["aw"], i_["grad_out"], r, 2))
                    for i_, r in zip(sets, refs)]
             ffn = [(lambda i_=i_: zb._C.ms_deform_attn_forward(i_["value"], i_["shapes"], i_["level_start"], i_["loc"], i_["aw"], 64)) for i_ in sets]
@@ -77,7 +78,7 @@ def timings():
                 res[nm] = a.elapsed_time(b) * 1e3 / 12
             rec = dict(regime=regime, tuning=tun, **res)
             print(rec); out.append(rec)
-    _lib.set_tuning(bwd_mma=1, bwd_mma_levels=0, tap_share=0)
+    _lib.set_tuning(bwd_mma=1, bwd_mma_levels=0, tap_share=0, bwd_dots=0, bwd_narrow=1)
     with open(os.path.join(ROOT, "gpurun_out", "r2_scatter_variants.jsonl"), "w") as f:
         for r in out:
             f.write(json.dumps(r) + "\n")

@@ -20,6 +20,7 @@ struct Tuning {
   int bwd_q_fast = 1;
   int bwd_passes = 1;
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
+  int bwd_dots = 0;          // backward: per-sample sums from the four corner dot products (combine_dots) instead of per channel
   int tap_share = 0;         // taps of a level computed once per lane group and exchanged by shuffles (shared_taps())
   int bwd_mma = 1;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu)
   int bwd_mma_levels = 0;    // > 0 and a workspace given: the last `bwd_mma_levels` levels go through the range-planned

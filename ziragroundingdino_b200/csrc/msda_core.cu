@@ -139,6 +139,53 @@ __device__ __forceinline__ void reduce_scatter16(float (&v)[16], int lig) {
   }
 }
 
+__device__ __forceinline__ float sel4(const float (&a)[4], int p) { return p == 0 ? a[0] : (p == 1 ? a[1] : (p == 2 ? a[2] : a[3])); }
+
+// DOTS formulation of the per-sample sums.  The reference accumulates, per channel, d(bilinear)/dw * top_grad etc.
+// (im2col.cuh:123-151); all three sums are linear in the four corner dot products d_i = <grad_out row, value row of
+// corner i> (guarded-off corners contribute 0):
+//     grad_aw = k1 d1 + k2 d2 + k3 d3 + k4 d4
+//     grad_x  = W a [hh (d2 - d1) + lh (d4 - d3)]        grad_y = H a [hw (d3 - d1) + lw (d4 - d2)]
+// so a lane only accumulates 4 FMAs per channel instead of 14 operations, the group reduce-scatters the 16 dots of a
+// level (4 points x 4 corners: the slot that used to be padding now carries d4), and the lanes that end up holding a
+// point's dots finish the three sums.  combine_dots() turns v[] from the dots layout into the (w, h, a, pad) layout the
+// rest of the kernel expects.  Same mathematics, different association: fp32 round-off moves by ~1e-6 relative.
+template <int LPG>
+__device__ __forceinline__ void combine_dots(float (&v)[16], int lig, const float (&lh)[4], const float (&lw)[4],
+                                             const float (&as)[4], float Wf, float Hf) {
+  constexpr int R = 16 / LPG;
+  auto finish = [&](int p, float d1, float d2, float d3, float d4, float& gx, float& gy, float& ga) {
+    const float h_l = sel4(lh, p), w_l = sel4(lw, p), a = sel4(as, p);
+    const float h_h = 1.f - h_l, w_h = 1.f - w_l;
+    ga = (h_h * w_h) * d1 + (h_h * w_l) * d2 + (h_l * w_h) * d3 + (h_l * w_l) * d4;
+    gx = Wf * a * (h_h * (d2 - d1) + h_l * (d4 - d3));
+    gy = Hf * a * (w_h * (d3 - d1) + w_l * (d4 - d2));
+  };
+  if constexpr (R >= 4) {
+#pragma unroll
+    for (int r0 = 0; r0 < R; r0 += 4) {
+      float gx, gy, ga;
+      finish(((lig * R + r0) >> 2) & 3, v[r0], v[r0 + 1], v[r0 + 2], v[r0 + 3], gx, gy, ga);
+      v[r0] = gx; v[r0 + 1] = gy; v[r0 + 2] = ga; v[r0 + 3] = 0.f;
+    }
+  } else if constexpr (R == 2) {
+    const float o0 = __shfl_xor_sync(0xffffffffu, v[0], 1), o1 = __shfl_xor_sync(0xffffffffu, v[1], 1);
+    const bool odd = (lig & 1) != 0;
+    float gx, gy, ga;
+    finish((lig >> 1) & 3, odd ? o0 : v[0], odd ? o1 : v[1], odd ? v[0] : o0, odd ? v[1] : o1, gx, gy, ga);
+    v[0] = odd ? ga : gx;
+    v[1] = odd ? 0.f : gy;
+  } else {
+    const int base = (threadIdx.x & 31) & ~3;
+    const float d1 = __shfl_sync(0xffffffffu, v[0], base), d2 = __shfl_sync(0xffffffffu, v[0], base + 1);
+    const float d3 = __shfl_sync(0xffffffffu, v[0], base + 2), d4 = __shfl_sync(0xffffffffu, v[0], base + 3);
+    float gx, gy, ga;
+    finish((lig >> 2) & 3, d1, d2, d3, d4, gx, gy, ga);
+    const int comp = lig & 3;
+    v[0] = comp == 0 ? gx : (comp == 1 ? gy : (comp == 2 ? ga : 0.f));
+  }
+}
+
 // FUSEQ (L == 4, P == 4, 8 lanes per unit): instead of writing grad_sampling_loc / grad_attn_weight in fp32, finish the
 // backward of the query-side epilogue in registers -- d_offset = grad_loc / (W_l, H_l) (2-d reference points) or
 // grad_loc * ref_wh * 0.5 / P (4-d), d_logit = aw * (grad_aw - sum grad_aw * aw) -- and write the 16-bit operand
@@ -156,7 +203,7 @@ struct FuseQ {
 // MODE: 0 = every corner is a reduction (the round-1 kernel, unchanged); 1 = the coarse tail of the level list is owned by
 // msda_scatter_mma_kernel; 2 = the last `mma_levels` levels are owned by msda_scatter_mma2_kernel and this kernel also
 // writes the per-chunk hit masks it needs.
-template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE>
+template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS>
 __global__ void __launch_bounds__(kThreads, 3)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -175,11 +222,16 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
 
   __shared__ int sH[MSDA_MAX_LEVELS], sW[MSDA_MAX_LEVELS], sStart[MSDA_MAX_LEVELS];
   __shared__ int sRedLevels;
+  __shared__ float sInvW[MSDA_MAX_LEVELS], sInvH[MSDA_MAX_LEVELS];     // FUSEQ: 1/W_l, 1/H_l (IEEE division, once per CTA)
   __shared__ RangePlan plan;       // HITS (mma_mode 2) only; the compiler drops it otherwise
   if (threadIdx.x < L) {
     sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
     sStart[threadIdx.x] = static_cast<int>(lstart[threadIdx.x]);
+    if (FUSEQ) {
+      sInvW[threadIdx.x] = 1.f / static_cast<float>(shapes[2 * threadIdx.x + 1]);
+      sInvH[threadIdx.x] = 1.f / static_cast<float>(shapes[2 * threadIdx.x]);
+    }
   }
   __syncthreads();
   // mma_mode 1: the grad_value contributions of the coarse tail (levels >= red_levels) are accumulated by
@@ -244,7 +296,9 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
 
     // FUSEQ: after the reduce-scatter lane `lig` holds, per level, either (grad_x, grad_y) of point lig/2 (even lanes)
     // or grad_attn of point lig/2 (odd lanes); they are kept until the softmax dot product over all 16 samples is known.
-    float fq_a[4], fq_b[4], fq_aw[4];
+    // Even lanes write their (d offset_x, d offset_y) pair inside the level loop; odd lanes keep (grad_attn, attn weight) of
+    // their point for each of the 4 levels in eight scalars (selected by level, so nothing lives in local memory).
+    float fq_g0 = 0.f, fq_g1 = 0.f, fq_g2 = 0.f, fq_g3 = 0.f, fq_w0 = 0.f, fq_w1 = 0.f, fq_w2 = 0.f, fq_w3 = 0.f;
     float fq_dot = 0.f;
     unsigned long long hit_bits = 0ull;      // mma_mode 2: ranges touched by this unit's samples
 
@@ -267,6 +321,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       constexpr bool SH = SHARE && LPG >= 4;
       Tap<float> t4[4];
       if constexpr (SH) shared_taps<LPG>(xs, ys, H, W, lig, t4);
+      float plh[4], plw[4];     // DOTS: fractional parts of the level's four points, for combine_dots()
 #pragma unroll
       for (int p = 0; p < P; ++p) {
         Tap<float> t;
@@ -282,6 +337,16 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         V::load(vl + e4, t.c4, v4);
         const float k1 = t.hh * t.hw, k2 = t.hh * t.lw, k3 = t.lh * t.hw, k4 = t.lh * t.lw;
         const float a = as[p];
+        if constexpr (DOTS) {
+          float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            d1 = fmaf(g[c], v1[c], d1); d2 = fmaf(g[c], v2[c], d2);
+            d3 = fmaf(g[c], v3[c], d3); d4 = fmaf(g[c], v4[c], d4);
+          }
+          red[4 * p + 0] = d1; red[4 * p + 1] = d2; red[4 * p + 2] = d3; red[4 * p + 3] = d4;
+          plh[p] = t.lh; plw[p] = t.lw;
+        } else {
         float s_w = 0.f, s_h = 0.f, s_a = 0.f;
         float tg[CH];
 #pragma unroll
@@ -299,6 +364,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         red[4 * p + 1] = s_h * static_cast<float>(H);
         red[4 * p + 2] = s_a;
         red[4 * p + 3] = 0.f;
+        }
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 4) {
           // element offset of this 4-channel slice relative to the lane's load slice (see `gr` above)
@@ -319,12 +385,28 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         hit_bits |= (2ull << r_hi) - (1ull << r_lo);
       }
       reduce_scatter16<LPG>(red, lig);
+      if constexpr (DOTS) combine_dots<LPG>(red, lig, plh, plw, as, static_cast<float>(W), static_cast<float>(H));
       if constexpr (FUSEQ) {
         // LPG == 8, R == 2: red[0], red[1] = entries 2*lig, 2*lig+1 of (w, h, a, pad) x 4 points
         const int p = lig >> 1;
         const float my_aw = p == 0 ? as[0] : (p == 1 ? as[1] : (p == 2 ? as[2] : as[3]));
-        if (l < 4) { fq_a[l] = red[0]; fq_b[l] = red[1]; fq_aw[l] = my_aw; }
-        if (lig & 1) fq_dot = fmaf(red[0], my_aw, fq_dot);      // odd lanes hold grad_attn of point p
+        if (lig & 1) {                                           // odd lanes hold grad_attn of point p
+          fq_dot = fmaf(red[0], my_aw, fq_dot);
+          fq_g0 = l == 0 ? red[0] : fq_g0; fq_g1 = l == 1 ? red[0] : fq_g1; fq_g2 = l == 2 ? red[0] : fq_g2; fq_g3 = l == 3 ? red[0] : fq_g3;
+          fq_w0 = l == 0 ? my_aw : fq_w0; fq_w1 = l == 1 ? my_aw : fq_w1; fq_w2 = l == 2 ? my_aw : fq_w2; fq_w3 = l == 3 ? my_aw : fq_w3;
+        } else if (active && l < 4) {                            // even lanes hold (grad_x, grad_y) of point p: d(offset) goes out now
+          float sx, sy;
+          if (fq.ref_dim == 2) { sx = sInvW[l]; sy = sInvH[l]; }
+          else {
+            const float* rp = fq.ref + static_cast<size_t>(bq) * 4 * fq.ref_dim;
+            sx = rp[l * 4 + 2] * 0.125f; sy = rp[l * 4 + 3] * 0.125f;      // * 0.5 / P with P == 4
+          }
+          const float dx = red[0] * sx, dy = red[1] * sy;
+          uint32_t w32;
+          if (fq.is_half) { __half2 t2 = __floats2half2_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t2); }
+          else { __nv_bfloat162 t2 = __floats2bfloat162_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t2); }
+          *reinterpret_cast<uint32_t*>(fq.dq + static_cast<size_t>(bq) * (3 * M * 16) + m * 32 + (l * 4 + p) * 2) = w32;
+        }
       } else {
         if (active) {
 #pragma unroll
@@ -352,30 +434,18 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 1);
       fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 2);
       fq_dot += __shfl_xor_sync(0xffffffffu, fq_dot, 4);
-      if (active) {
+      if (active && (lig & 1)) {
         const int p = lig >> 1;
-        const int n_aw = M * 16, ld = 3 * n_aw;
-        uint16_t* orow = fq.dq + static_cast<size_t>(bq) * ld;
-        const float* rp = fq.ref + static_cast<size_t>(bq) * 4 * fq.ref_dim;
-        const bool hf = fq.is_half != 0;
+        const int n_aw = M * 16;
+        uint16_t* orow = fq.dq + static_cast<size_t>(bq) * (3 * n_aw) + 2 * n_aw + m * 16 + p;
+        const float gs[4] = {fq_g0, fq_g1, fq_g2, fq_g3}, ws[4] = {fq_w0, fq_w1, fq_w2, fq_w3};
 #pragma unroll
         for (int l = 0; l < 4; ++l) {
-          if (lig & 1) {
-            const float d = fq_aw[l] * (fq_a[l] - fq_dot);
-            uint16_t w16;
-            if (hf) { __half t = __float2half_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t); }
-            else { __nv_bfloat16 t = __float2bfloat16_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t); }
-            orow[2 * n_aw + m * 16 + l * 4 + p] = w16;
-          } else {
-            float sx, sy;
-            if (fq.ref_dim == 2) { sx = 1.f / static_cast<float>(sW[l]); sy = 1.f / static_cast<float>(sH[l]); }
-            else { sx = rp[l * 4 + 2] * 0.125f; sy = rp[l * 4 + 3] * 0.125f; }     // * 0.5 / P with P == 4
-            const float dx = fq_a[l] * sx, dy = fq_b[l] * sy;
-            uint32_t w32;
-            if (hf) { __half2 t = __floats2half2_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t); }
-            else { __nv_bfloat162 t = __floats2bfloat162_rn(dx, dy); w32 = *reinterpret_cast<uint32_t*>(&t); }
-            *reinterpret_cast<uint32_t*>(orow + m * 32 + (l * 4 + p) * 2) = w32;
-          }
+          const float d = ws[l] * (gs[l] - fq_dot);
+          uint16_t w16;
+          if (fq.is_half) { __half t2 = __float2half_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t2); }
+          else { __nv_bfloat16 t2 = __float2bfloat16_rn(d); w16 = *reinterpret_cast<uint16_t*>(&t2); }
+          orow[l * 4] = w16;
         }
       }
     }
@@ -561,9 +631,16 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   bool launched = false;
   const dim3 grid(static_cast<unsigned>(blocks));
 #define MSDA_BWD_LAUNCH(MODE_, SHARE_)                                                                               \
-  msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_><<<grid, kThreads, 0, st>>>(                                   \
-      value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,            \
-      g_tuning.bwd_mma_levels, hit, fq)
+  do {                                                                                                               \
+    if (g_tuning.bwd_dots)                                                                                           \
+      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, true><<<grid, kThreads, 0, st>>>(                          \
+          value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,        \
+          g_tuning.bwd_mma_levels, hit, fq);                                                                         \
+    else                                                                                                             \
+      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, false><<<grid, kThreads, 0, st>>>(                         \
+          value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,        \
+          g_tuning.bwd_mma_levels, hit, fq);                                                                         \
+  } while (0)
   if constexpr (sizeof(VT) == 2 && D == 32) {
     if (mma_mode == 2) {
       if (g_tuning.tap_share) MSDA_BWD_LAUNCH(2, true); else MSDA_BWD_LAUNCH(2, false);

@@ -194,14 +194,14 @@ msda_scatter_mma2_kernel(const int64_t* __restrict__ shapes, const int64_t* __re
           const uint4* gp = reinterpret_cast<const uint4*>(grad_out + un * 32 + 16 * slot);
           g0 = __ldg(gp); g1 = __ldg(gp + 1);
         }
-        if (pending) {
-          mbar_wait(bar_done, ph_done);
-          ph_done ^= 1;
-          tc_fence_after();
-          restore();
-        }
+        // ---- taps of this chunk -> registers (pixel ids + weights), BEFORE waiting for the previous product: the coordinate
+        // math overlaps the tensor core; only the shared-memory traffic below sits on the chunk-to-chunk critical path ----
+        uint32_t npix[2][8];
+        float nwgt[2][16];
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) npix[i][j] = 0xffffffffu;
           const int l = lv0 + slot + 2 * i;
           if (l < lv1 && valid) {
             const int H = sH[l], W = sW[l], base = sStart[l] - lo;
@@ -213,24 +213,41 @@ msda_scatter_mma2_kernel(const int64_t* __restrict__ shapes, const int64_t* __re
               const Tap<float> t = make_tap<float>(xs[p], ys[p], H, W);
               const float a = as[p];
               const int px[4] = {base + t.o1, base + t.o2, base + t.o3, base + t.o4};
-              // a corner belongs to this unit when its guard holds AND it lies inside the range (a split level's
-              // neighbouring range picks up the others)
               const bool cg[4] = {t.c1 && px[0] >= 0 && px[0] < npx, t.c2 && px[1] >= 0 && px[1] < npx,
-                                  t.c3 && px[2] >= 0 && px[2] < npx, t.c4 && px[3] >= 0 && px[3] < npx};
-              const float kw[4] = {t.hh * t.hw * a, t.hh * t.lw * a, t.lh * t.hw * a, t.lh * t.lw * a};
-              uint32_t old[4], addr[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                addr[k] = a_addr(cg[k] ? px[k] : 0);
-                old[k] = cg[k] ? lds_u16(addr[k]) : 0u;
-              }
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (cg[k]) sts_u16(addr[k], f32_to_w<VT>(w_to_f32<VT>(old[k]) + kw[k]));
-              saved[i][2 * p] = (cg[0] ? static_cast<uint32_t>(px[0]) : 0xffffu) | ((cg[1] ? static_cast<uint32_t>(px[1]) : 0xffffu) << 16);
-              saved[i][2 * p + 1] = (cg[2] ? static_cast<uint32_t>(px[2]) : 0xffffu) | ((cg[3] ? static_cast<uint32_t>(px[3]) : 0xffffu) << 16);
+                                      t.c3 && px[2] >= 0 && px[2] < npx, t.c4 && px[3] >= 0 && px[3] < npx};
+              nwgt[i][4 * p] = t.hh * t.hw * a; nwgt[i][4 * p + 1] = t.hh * t.lw * a;
+              nwgt[i][4 * p + 2] = t.lh * t.hw * a; nwgt[i][4 * p + 3] = t.lh * t.lw * a;
+              npix[i][2 * p] = (cg[0] ? static_cast<uint32_t>(px[0]) : 0xffffu) | ((cg[1] ? static_cast<uint32_t>(px[1]) : 0xffffu) << 16);
+              npix[i][2 * p + 1] = (cg[2] ? static_cast<uint32_t>(px[2]) : 0xffffu) | ((cg[3] ? static_cast<uint32_t>(px[3]) : 0xffffu) << 16);
             }
           }
+        }
+        if (pending) {
+          mbar_wait(bar_done, ph_done);
+          ph_done ^= 1;
+          tc_fence_after();
+          restore();
+        }
+        // ---- A: read-modify-write the new entries (a point's four corners are distinct pixels; points are serialised because
+        // two points of one query may share a pixel) ----
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p) {
+            const uint32_t w0 = npix[i][2 * p], w1 = npix[i][2 * p + 1];
+            const uint32_t pid[4] = {w0 & 0xffffu, w0 >> 16, w1 & 0xffffu, w1 >> 16};
+            uint32_t old[4], addr[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              addr[k] = a_addr(pid[k] != 0xffffu ? static_cast<int>(pid[k]) : 0);
+              old[k] = pid[k] != 0xffffu ? lds_u16(addr[k]) : 0u;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (pid[k] != 0xffffu) sts_u16(addr[k], f32_to_w<VT>(w_to_f32<VT>(old[k]) + nwgt[i][4 * p + k]));
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) saved[i][j] = npix[i][j];
         }
         {
           const uint32_t w[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
