@@ -363,20 +363,22 @@ def test_mma_scatter_nonstandard_level_start_falls_back():
 
 @pytest.mark.parametrize("regime", ["local", "uniform"])
 def test_mma_scatter_full_size_encoder(regime):
-    """Config 2's launch (4 images, Swin-T 800x1333, Lq = S, bf16): tensor-memory path (default at this size) vs the
+    """Config 2's launch (4 images, Swin-T 800x1333, Lq = S, bf16): tensor-memory path (bwd_mma=1) vs the
     all-reductions kernel, and the adjoint identity <f(v), g> == <v, grad_value(g)> with the shipped path."""
     import ziragroundingdino_b200 as zb
     from ziragroundingdino_b200 import synthetic as syn
     dev = _dev()
     inp = syn.core_inputs(SWIN_T, 4, dtype=torch.bfloat16, regime=regime, device=dev, seed=21)
     a = (inp["value"], inp["shapes"], inp["level_start"], inp["loc"], inp["aw"])
-    gv1, gl1, ga1 = zb._C.ms_deform_attn_backward(*a, inp["grad_out"], 64)
     from ziragroundingdino_b200 import _lib
+    keep = _lib.get_tuning("bwd_mma")
     try:
+        _lib.set_tuning(bwd_mma=1)
+        gv1, gl1, ga1 = zb._C.ms_deform_attn_backward(*a, inp["grad_out"], 64)
         _lib.set_tuning(bwd_mma=0)
         gv0, gl0, ga0 = zb._C.ms_deform_attn_backward(*a, inp["grad_out"], 64)
     finally:
-        _lib.set_tuning(bwd_mma=1)
+        _lib.set_tuning(bwd_mma=keep)
     assert torch.equal(gl1, gl0) and torch.equal(ga1, ga0)
     d = (gv1.float() - gv0.float()).abs().max().item() / gv0.float().abs().max().item()
     print("full-size %s: mma vs reductions grad_value max rel diff %.2e" % (regime, d))

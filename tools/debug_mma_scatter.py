@@ -50,7 +50,7 @@ def check():
         torch.cuda.synchronize()
         print("%-12s per-level rel err vs fp64: %s  finite=%s" % (name, ["%.1e" % e for e in per_level(gv.cpu(), o_gv, shapes)],
                                                                   bool(torch.isfinite(gv).all())))
-    _lib.set_tuning(bwd_mma=1, bwd_mma_levels=0, bwd_mma_min_units=131072)
+    _lib.set_tuning(bwd_mma=0, bwd_mma_levels=0, bwd_mma_min_units=131072)
 
 
 def timings():
@@ -78,7 +78,7 @@ def timings():
                 res[nm] = a.elapsed_time(b) * 1e3 / 12
             rec = dict(regime=regime, tuning=tun, **res)
             print(rec); out.append(rec)
-    _lib.set_tuning(bwd_mma=1, bwd_mma_levels=0, tap_share=0, bwd_dots=0, bwd_narrow=1)
+    _lib.set_tuning(bwd_mma=0, bwd_mma_levels=0, tap_share=0, bwd_dots=1, bwd_narrow=1)
     with open(os.path.join(ROOT, "gpurun_out", "r2_scatter_variants.jsonl"), "w") as f:
         for r in out:
             f.write(json.dumps(r) + "\n")

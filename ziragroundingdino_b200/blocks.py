@@ -29,10 +29,10 @@ def own_k_ffn():
     return OWN_K_FFN
 
 
-# MSDA_B200_FFN_CHAIN=1 (or blocks.FFN_CHAIN = True): the whole FFN as ONE launch per direction with the hidden
+# Default (MSDA_B200_FFN_CHAIN=0 / blocks.FFN_CHAIN = False turns it off): the whole FFN as ONE launch per direction with the hidden
 # activation kept on chip (csrc/layer_ffn_chain.cu): linear1 -> ReLU (+ 1-bit mask) -> linear2 forward, and
 # gate(dz W2) W1 + dz backward.  d_model = 256, d_ffn % 128 == 0.
-FFN_CHAIN = os.environ.get("MSDA_B200_FFN_CHAIN", "0") == "1"
+FFN_CHAIN = os.environ.get("MSDA_B200_FFN_CHAIN", "1") == "1"
 
 
 def ffn_chain_ok(C, F):

@@ -20,9 +20,12 @@ struct Tuning {
   int bwd_q_fast = 1;
   int bwd_passes = 1;
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
-  int bwd_dots = 0;          // backward: per-sample sums from the four corner dot products (combine_dots) instead of per channel
+  int bwd_dots = 1;          // backward: per-sample sums from the four corner dot products (combine_dots) instead of per channel
+                             // (measured -13 % on the scatter kernel, same parity: profiles/r2_scatter_variants.jsonl)
   int tap_share = 0;         // taps of a level computed once per lane group and exchanged by shuffles (shared_taps())
-  int bwd_mma = 1;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu)
+  int bwd_mma = 0;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu).
+                             // Opt-in: correct (tests), but the scatter kernel is issue-bound, not reduction-bound, so dropping
+                             // half of its reductions saves less (~125 us) than the accumulation kernel costs (~160-190 us)
   int bwd_mma_levels = 0;    // > 0 and a workspace given: the last `bwd_mma_levels` levels go through the range-planned
                              // second-generation kernel (msda_scatter_mma2.cu) instead; 0 = first-generation tail only
   int bwd_mma_min_units = 131072;   // ... when N*Lq*M is at least this (below it the reductions it saves do not pay for a launch)
