@@ -1,0 +1,18 @@
+#!/bin/bash
+O=gpurun_out
+mkdir -p $O
+run() { local t=$1; shift; timeout $t "$@"; echo "[rc=$?] $*" >> $O/r2e_session.log; }
+: > $O/r2e_session.log
+run 600 python -m pytest tests -m gpu -q > $O/r2e_tests_full.log 2>&1
+tail -4 $O/r2e_tests_full.log | cut -c1-200
+run 900 python bench.py --steps 20 --warmup 5 > $O/r2e_bench.json 2> $O/r2e_bench.err
+run 300 python bench.py --impl reference --steps 2 --warmup 1 > $O/r2e_bench_reference.json 2> $O/r2e_bench_reference.err
+run 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/r2e_launches_c2.csv python bench.py --profile-step --config 2 > /dev/null 2>&1
+run 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $O/r2e_launches_c4.csv python bench.py --profile-step --config 4 > /dev/null 2>&1
+# full ncu captures, one kernel family per report, ONE launch each (reports stay small: no --import-source)
+for k in msda_bwd_vec msda_fwd_vec ffn_chain linear_tf32x3 flatten_levels encoder_proposals; do
+  run 400 ncu --set full --clock-control none -k regex:$k -c 1 -s 1 -o $O/r2e_$k python tools/prof_r2.py > $O/r2e_ncu_$k.log 2>&1
+done
+MSDA_B200_TUNING=bwd_mma=1 run 400 ncu --set full --clock-control none -k regex:'msda_bwd_vec|msda_scatter_mma' -c 2 -s 2 -o $O/r2e_scatter_mma python tools/prof_r2.py > $O/r2e_ncu_scatter_mma.log 2>&1
+ls -la $O/*.ncu-rep; du -sh $O
+cat $O/r2e_session.log
