@@ -147,8 +147,6 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       mbar_wait(x_full, ph_x);
       ph_x ^= 1;
-      mbar_wait(a2_free, ph_a2 ^ 1);       // the previous tile's result has been read out of acc2
-      ph_a2 ^= 1;
       tc_fence_after();
       for (int j = 0; j <= nchunk; ++j) {
         if (j < nchunk) {
@@ -182,6 +180,10 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         }
         if (j >= 1) {
           const int jj = j - 1, b = jj & 1;
+          if (jj == 0) {                       // first product into acc2: the previous tile's result must have been read out.
+            mbar_wait(a2_free, ph_a2 ^ 1);     // Waiting HERE (not at the top of the tile) lets GEMM1_0 / GEMM1_1 of this tile
+            ph_a2 ^= 1;                        // overlap the previous tile's final stage.
+          }
           mbar_wait(h_full + b, ph_hfull[b]);
           ph_hfull[b] ^= 1;
           tc_fence_after();
