@@ -127,8 +127,6 @@ int msda_backward_16_ws(const void *value, const int64_t *spatial_shapes, const 
  *   key "bwd_dots"          : 1 = the backward forms grad_sampling_loc / grad_attn_weight from the four corner dot products
  *                             <grad_out row, value row> of a sample (4 FMAs per channel) instead of per-channel bilinear
  *                             derivatives (14 operations per channel); same mathematics, fp32 round-off moves by ~1e-6
- *   key "pk2"               : 1 = per-channel arithmetic of the vector kernels as packed fp32x2 instructions (FMUL2 / FFMA2,
- *                             sm_100): two channels per issue slot; the forward stays bit-identical
  *   key "tap_share"         : 1 = the four sampling taps of a level are computed once per lane group and exchanged with
  *                             shuffles (bit-identical values) instead of once per lane; vector kernels with >= 4 lanes per unit
  *   key "bwd_mma"           : 16-bit storage, D = 32, P = 4: 1 = the coarse tail of the level list (<= 1536 pixels, <= 4

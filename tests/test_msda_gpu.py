@@ -508,26 +508,3 @@ def test_bwd_dots_formulation_vs_oracle(dtype, D, M):
         assert torch.equal(out, res[(1, 0)][0])
     print("bwd_dots %s D=%d: grad_loc rel err per-channel %.1e / dots %.1e; grad_aw %.1e / %.1e" % (
         str(dtype).split(".")[-1], D, rel_err(res[(1, 0)][2], o_gl), rel_err(res[(1, 1)][2], o_gl), rel_err(res[(1, 0)][3], o_ga), rel_err(res[(1, 1)][3], o_ga)))
-
-
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("D", [32, 64, 16])
-def test_pk2_packed_math(dtype, D):
-    """pk2=1 issues the per-channel arithmetic as packed fp32x2 instructions: the forward must stay BIT-identical (each
-    lane of a pair performs the scalar sequence); the backward (dot products packed across corners, reduction values
-    packed across channels) stays within 1e-4 of the fp32 C oracle and grad_value within atomic-order noise."""
-    from ziragroundingdino_b200 import _lib
-    dev = _dev()
-    value, sh, lsi, loc, aw, gout = _mk([(20, 30), (10, 15), (5, 8), (3, 4)], 2, 8, D, 333, 4, seed=90 + D, dtype=dtype, lo=-0.2, hi=1.2)
-    keep = {k: _lib.get_tuning(k) for k in ("pk2", "bwd_mma", "bwd_dots")}
-    res = {}
-    try:
-        for pk in (0, 1):
-            _lib.set_tuning(pk2=pk, bwd_mma=0, bwd_dots=1)
-            res[pk] = _run(value, sh, lsi, loc, aw, gout, dev)
-    finally:
-        _lib.set_tuning(**keep)
-    assert torch.equal(res[0][0], res[1][0])
-    o_gv, o_gl, o_ga = O.c_backward(value.float().numpy(), sh.numpy(), loc.numpy(), aw.numpy(), gout.float().numpy())
-    assert rel_err(res[1][2], o_gl) < 1e-4 and rel_err(res[1][3], o_ga) < 1e-4
-    assert rel_err(res[1][1].float(), res[0][1].float()) < (1e-5 if dtype == torch.float32 else 2 ** -8)

@@ -108,7 +108,6 @@ static int* tuning_slot(const char* key) {
   if (!strcmp(key, "bwd_passes")) return &msda::g_tuning.bwd_passes;
   if (!strcmp(key, "bwd_narrow")) return &msda::g_tuning.bwd_narrow;
   if (!strcmp(key, "bwd_dots")) return &msda::g_tuning.bwd_dots;
-  if (!strcmp(key, "pk2")) return &msda::g_tuning.pk2;
   if (!strcmp(key, "tap_share")) return &msda::g_tuning.tap_share;
   if (!strcmp(key, "bwd_mma")) return &msda::g_tuning.bwd_mma;
   if (!strcmp(key, "bwd_mma_min_units")) return &msda::g_tuning.bwd_mma_min_units;

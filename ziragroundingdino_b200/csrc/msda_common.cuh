@@ -22,7 +22,6 @@ struct Tuning {
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
   int bwd_dots = 1;          // backward: per-sample sums from the four corner dot products (combine_dots) instead of per channel
                              // (measured -13 % on the scatter kernel, same parity: profiles/r2_scatter_variants.jsonl)
-  int pk2 = 0;               // per-channel arithmetic as packed fp32x2 instructions (FMUL2 / FFMA2): bit-identical forward
   int tap_share = 0;         // taps of a level computed once per lane group and exchanged by shuffles (shared_taps())
   int bwd_mma = 0;           // 16-bit storage, D = 32, P = 4: coarse levels accumulate in tensor memory (msda_scatter_mma.cu).
                              // Opt-in: correct (tests), but the scatter kernel is issue-bound, not reduction-bound, so dropping

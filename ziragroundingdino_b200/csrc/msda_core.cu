@@ -27,10 +27,7 @@ namespace msda {
 // =================================================================================================
 // forward, vectorised: D in {16, 32, 64, 128}, P == 4
 // =================================================================================================
-// PK2: the per-channel arithmetic as packed fp32x2 instructions (FMUL2 / FFMA2, sm_100): two channels per issue slot in a
-// kernel that is bound by issue slots.  Each lane of a pair performs exactly the scalar sequence (one multiply, three
-// fused multiply-adds, one more for the attention weight), so the results are bit-identical.
-template <typename VT, int D, int SB, bool SHARE, bool PK2>
+template <typename VT, int D, int SB, bool SHARE>
 __global__ void __launch_bounds__(kThreads)
 msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -107,24 +104,10 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           // weight.  Folding the weight into the four taps saves one FMA per channel but moves the result ~1e-5 away
           // from the reference op at sigma = 1 inputs (measured: profiles/r1_parity_table.txt), i.e. onto the parity bar.
           const float a = as[p0 + s];
-          if constexpr (PK2) {
-            const float2 k0 = make_float2(k[s][0], k[s][0]), k1 = make_float2(k[s][1], k[s][1]);
-            const float2 k2 = make_float2(k[s][2], k[s][2]), k3 = make_float2(k[s][3], k[s][3]), a2 = make_float2(a, a);
-#pragma unroll
-            for (int c = 0; c < CH; c += 2) {
-              float2 val = __fmul2_rn(k0, make_float2(v[s][0][c], v[s][0][c + 1]));
-              val = __ffma2_rn(k1, make_float2(v[s][1][c], v[s][1][c + 1]), val);
-              val = __ffma2_rn(k2, make_float2(v[s][2][c], v[s][2][c + 1]), val);
-              val = __ffma2_rn(k3, make_float2(v[s][3][c], v[s][3][c + 1]), val);
-              const float2 r = __ffma2_rn(val, a2, make_float2(acc[c], acc[c + 1]));
-              acc[c] = r.x; acc[c + 1] = r.y;
-            }
-          } else {
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
             const float val = k[s][0] * v[s][0][c] + k[s][1] * v[s][1][c] + k[s][2] * v[s][2][c] + k[s][3] * v[s][3][c];
             acc[c] = fmaf(val, a, acc[c]);
-          }
           }
         }
       }
@@ -220,7 +203,7 @@ struct FuseQ {
 // MODE: 0 = every corner is a reduction (the round-1 kernel, unchanged); 1 = the coarse tail of the level list is owned by
 // msda_scatter_mma_kernel; 2 = the last `mma_levels` levels are owned by msda_scatter_mma2_kernel and this kernel also
 // writes the per-chunk hit masks it needs.
-template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS, bool PK2>
+template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS>
 __global__ void __launch_bounds__(kThreads, 3)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -354,18 +337,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         V::load(vl + e4, t.c4, v4);
         const float k1 = t.hh * t.hw, k2 = t.hh * t.lw, k3 = t.lh * t.hw, k4 = t.lh * t.lw;
         const float a = as[p];
-        if constexpr (DOTS && PK2) {
-          // packed fp32x2: (d1, d2) += (g, g) * (v1, v2) and (d3, d4) += (g, g) * (v3, v4): two FFMA2 per channel
-          float2 d12 = make_float2(0.f, 0.f), d34 = make_float2(0.f, 0.f);
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const float2 gg = make_float2(g[c], g[c]);
-            d12 = __ffma2_rn(gg, make_float2(v1[c], v2[c]), d12);
-            d34 = __ffma2_rn(gg, make_float2(v3[c], v4[c]), d34);
-          }
-          red[4 * p + 0] = d12.x; red[4 * p + 1] = d12.y; red[4 * p + 2] = d34.x; red[4 * p + 3] = d34.y;
-          plh[p] = t.lh; plw[p] = t.lw;
-        } else if constexpr (DOTS) {
+        if constexpr (DOTS) {
           float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
 #pragma unroll
           for (int c = 0; c < CH; ++c) {
@@ -397,29 +369,11 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         for (int c0 = 0; c0 < CH; c0 += 4) {
           // element offset of this 4-channel slice relative to the lane's load slice (see `gr` above)
           const int ro = (CH == 4) ? 0 : ((c0 == 0 ? 4 * lig : 4 * LPG + 4 * lig) - CH * lig);
-          if constexpr (PK2) {
-            if constexpr (do_red) {
-              const float2 aa = make_float2(a, a);
-              const float2 r01 = __fmul2_rn(make_float2(gr[c0], gr[c0 + 1]), aa), r23 = __fmul2_rn(make_float2(gr[c0 + 2], gr[c0 + 3]), aa);
-              const float ks[4] = {k1, k2, k3, k4};
-              const bool cs[4] = {t.c1, t.c2, t.c3, t.c4};
-              const long long es[4] = {e1, e2, e3, e4};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                if (cs[i]) {
-                  const float2 kk = make_float2(ks[i], ks[i]);
-                  const float2 x01 = __fmul2_rn(kk, r01), x23 = __fmul2_rn(kk, r23);
-                  red_add_v4(gvl + es[i] + ro, x01.x, x01.y, x23.x, x23.y);
-                }
-              }
-            }
-          } else {
           const float r0 = gr[c0] * a, r1 = gr[c0 + 1] * a, r2 = gr[c0 + 2] * a, r3 = gr[c0 + 3] * a;
           if (do_red && t.c1) red_add_v4(gvl + e1 + ro, k1 * r0, k1 * r1, k1 * r2, k1 * r3);
           if (do_red && t.c2) red_add_v4(gvl + e2 + ro, k2 * r0, k2 * r1, k2 * r2, k2 * r3);
           if (do_red && t.c3) red_add_v4(gvl + e3 + ro, k3 * r0, k3 * r1, k3 * r2, k3 * r3);
           if (do_red && t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
-          }
         }
       }
       if (HITS && !do_red && o_max >= 0) {
@@ -622,17 +576,13 @@ static cudaError_t launch_fwd_vec(const VT* value, const int64_t* shapes, const 
   const dim3 grid(static_cast<unsigned>(blocks));
   ++g_launches;
   if (g_tuning.tap_share && g_tuning.fwd_sample_batch == 4) {
-    msda_fwd_vec_kernel<VT, D, 4, true, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast);
-    return cudaGetLastError();
-  }
-  if (g_tuning.pk2 && g_tuning.fwd_sample_batch == 4) {
-    msda_fwd_vec_kernel<VT, D, 4, false, true><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast);
+    msda_fwd_vec_kernel<VT, D, 4, true><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast);
     return cudaGetLastError();
   }
   switch (g_tuning.fwd_sample_batch) {
-    case 1: msda_fwd_vec_kernel<VT, D, 1, false, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
-    case 4: msda_fwd_vec_kernel<VT, D, 4, false, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
-    default: msda_fwd_vec_kernel<VT, D, 2, false, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    case 1: msda_fwd_vec_kernel<VT, D, 1, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    case 4: msda_fwd_vec_kernel<VT, D, 4, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
+    default: msda_fwd_vec_kernel<VT, D, 2, false><<<grid, kThreads, 0, st>>>(value, shapes, lstart, loc, aw, out, S, M, L, Lq, units, passes, q_fast); break;
   }
   return cudaGetLastError();
 }
@@ -682,16 +632,12 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   const dim3 grid(static_cast<unsigned>(blocks));
 #define MSDA_BWD_LAUNCH(MODE_, SHARE_)                                                                               \
   do {                                                                                                               \
-    if (g_tuning.bwd_dots && g_tuning.pk2 && !(SHARE_))                                                              \
-      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, false, true, true><<<grid, kThreads, 0, st>>>(                     \
-          value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,        \
-          g_tuning.bwd_mma_levels, hit, fq);                                                                         \
-    else if (g_tuning.bwd_dots)                                                                                      \
-      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, true, false><<<grid, kThreads, 0, st>>>(                   \
+    if (g_tuning.bwd_dots)                                                                                           \
+      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, true><<<grid, kThreads, 0, st>>>(                          \
           value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,        \
           g_tuning.bwd_mma_levels, hit, fq);                                                                         \
     else                                                                                                             \
-      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, false, false><<<grid, kThreads, 0, st>>>(                  \
+      msda_bwd_vec_kernel<VT, D, V, FUSEQ, MODE_, SHARE_, false><<<grid, kThreads, 0, st>>>(                         \
           value, shapes, lstart, loc, aw, grad_out, gv, gl, ga, S, M, L, Lq, units, passes, q_fast, mma_mode,        \
           g_tuning.bwd_mma_levels, hit, fq);                                                                         \
   } while (0)
