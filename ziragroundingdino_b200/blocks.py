@@ -50,15 +50,18 @@ def ffn_chain_fwd16(x2d, w1, b1_f32, w2, b2_f32, bits):
     return out
 
 
-def ffn_chain_bwd16(dz, w2_t, w1_t, bits):
-    """dz <- dz + gate(dz W2) W1, in place (w2_t = W2^T [d_ffn, d_model], w1_t = W1^T [d_model, d_ffn])."""
+def ffn_chain_bwd16(dz, w2_t, w1_t, bits, accumulate=True):
+    """accumulate: dz <- dz + gate(dz W2) W1, in place (the residual path of the encoder block); otherwise returns
+    gate(dz W2) W1 in a new tensor.  w2_t = W2^T [d_ffn, d_model], w1_t = W1^T [d_model, d_ffn]."""
     R, C = dz.shape
     F = w2_t.shape[0]
+    out = dz if accumulate else torch.empty_like(dz)
     with torch.cuda.device(dz.device):
-        rc = _lib.lib().msda_ffn_chain_bwd_16(dz.data_ptr(), w2_t.data_ptr(), w1_t.data_ptr(), bits.data_ptr(), dz.data_ptr(), R, C, F,
-                                              dz.data_ptr(), 1 if dz.dtype == torch.float16 else 0, _stream(dz))
+        rc = _lib.lib().msda_ffn_chain_bwd_16(dz.data_ptr(), w2_t.data_ptr(), w1_t.data_ptr(), bits.data_ptr(),
+                                              dz.data_ptr() if accumulate else 0, R, C, F, out.data_ptr(),
+                                              1 if dz.dtype == torch.float16 else 0, _stream(dz))
     _lib.check(rc, "msda_ffn_chain_bwd_16")
-    return dz
+    return out
 
 
 def _add_ln_fwd(x2, r2, g32, b32, eps):

@@ -196,9 +196,14 @@ class FFN16Function(Function):
         ctx.bits = (FFN16Function.bit_gate_when_frozen and FFN16Function.fuse_relu_backward and not any(ctx.needs_input_grad[1:])
                     and w1.shape[0] % 32 == 0)
         if ctx.bits:
+            from . import blocks      # the chained kernel's wrappers live beside the block Functions
             bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
-            h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
-            y = torch.nn.functional.linear(h, w2, b2)
+            ctx.chain = blocks.ffn_chain_ok(x2d.shape[1], w1.shape[0]) and w2.shape[0] == x2d.shape[1]
+            if ctx.chain:     # linear1 -> ReLU -> linear2 in one launch, hidden activation kept on chip (csrc/layer_ffn_chain.cu)
+                y = blocks.ffn_chain_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"), bits)
+            else:
+                h = _linear_act_bits16(x2d, w1.contiguous(), derived(b1, "f32"), relu_bits=bits)
+                y = torch.nn.functional.linear(h, w2, b2)
             ctx.save_for_backward(bits, w1, w2)
             return y.view(*shape[:-1], w2.shape[0])
         h = _linear_act16(x2d, w1.contiguous(), derived(b1, "f32"), relu=True)
@@ -212,9 +217,14 @@ class FFN16Function(Function):
         dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
         if ctx.bits:
             bits, w1, w2 = ctx.saved_tensors
+            if not ctx.needs_input_grad[0]:
+                return None, None, None, None, None
+            if ctx.chain:
+                from . import blocks
+                dx = blocks.ffn_chain_bwd16(dy2, derived(w2, "t"), derived(w1, "t"), bits, accumulate=False)
+                return dx.view(ctx.shape), None, None, None, None
             dh = _linear_act_bits16(dy2, derived(w2, "t"), None, gate_bits=bits)
-            dx = (dh @ w1).view(ctx.shape) if ctx.needs_input_grad[0] else None
-            return dx, None, None, None, None
+            return (dh @ w1).view(ctx.shape), None, None, None, None
         x2d, h, w1, w2 = ctx.saved_tensors
         if FFN16Function.fuse_relu_backward:
             dh = _linear_act16(dy2, derived(w2, "t"), None, gate=h)    # (dy W2) gated by relu'(.) in the GEMM epilogue
