@@ -400,6 +400,16 @@ class ZiraStep:
         self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         cur.synchronize()
 
+    def close(self):
+        """Release the captured graphs before the process group goes away: a live CUDA graph that holds captured NCCL
+        kernels keeps the communicator busy and destroy_process_group() then blocks (the round-1 "hang" with a captured
+        all-reduce was this teardown, not the capture: profiles/r2_bench_n2_graph_allreduce.json)."""
+        import gc
+        self.graph = self.graph_upd = None
+        self._fwd_bwd = self._update = self.step_eager = None
+        gc.collect()
+        self.torch.cuda.synchronize()
+
     @property
     def h2d_bytes(self):
         return self.host_feat.numel() * 2 + self.host_pos.numel() * 2 + self.host_mask.numel()
@@ -512,6 +522,7 @@ def run_ours(args):
     h2d = wl.h2d_bytes
     N = wl.N
     use_graph = wl.graph is not None
+    wl.close()
     del wl, run
     torch.cuda.empty_cache()
 
@@ -537,6 +548,7 @@ def run_ours(args):
                      "images_per_gpu": IMAGES[oc], "gpu_launches": w2.launches_per_step * args.steps,
                      "e2e": {"value": img2 / (ms2_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": w2.h2d_bytes, "d2h_bytes_per_step": 4},
                      "workload": workload_config(world, oc)["workload"]}
+            w2.close()
             del w2
         except Exception as e:      # noqa: BLE001
             errors["other_workload"] = repr(e)[:300]

@@ -203,8 +203,11 @@ struct FuseQ {
 // MODE: 0 = every corner is a reduction (the round-1 kernel, unchanged); 1 = the coarse tail of the level list is owned by
 // msda_scatter_mma_kernel; 2 = the last `mma_levels` levels are owned by msda_scatter_mma2_kernel and this kernel also
 // writes the per-chunk hit masks it needs.
+#ifndef MSDA_BWD_MINB
+#define MSDA_BWD_MINB 3      // resident CTAs per SM the scatter kernel is compiled for (A/B: -DMSDA_BWD_MINB=4 -> 64 registers)
+#endif
 template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, MSDA_BWD_MINB)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
                     const float* __restrict__ aw, const VT* __restrict__ grad_out,
