@@ -57,8 +57,15 @@ def config1(f):
             src.grad = None
             fwd().float().square().mean().backward()
         t_fb = timeit(fb)
+        for p_ in m.parameters():          # the ZiRa configuration: the module's own linears are frozen (no weight-gradient GEMMs)
+            p_.requires_grad_(False)
+        n0 = _lib.launch_count()
+        fb()
+        launches = _lib.launch_count() - n0
+        t_fb_frozen = timeit(fb)
         rec = dict(config=1, what="single MSDeformAttn module, N=1, Swin-T 800x1333, Lq=S=22223", dtype=str(dtype),
-                   fwd_us=t_f, fwd_bwd_us=t_fb, fused=m._use_fused(src, refp))
+                   fwd_us=t_f, fwd_bwd_us=t_fb, fwd_bwd_frozen_us=t_fb_frozen, own_launches_fwd_bwd_frozen=launches,
+                   fused=bool(m._use_fused(src, refp) or m._use_fused32(src, refp)))
         print(rec); f.write(json.dumps(rec) + "\n"); f.flush()
 
 
