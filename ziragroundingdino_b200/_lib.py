@@ -70,6 +70,9 @@ def lib():
     L.msda_backward_workspace_bytes.argtypes = [_i, _i, _i]
     L.msda_backward_16_ws.argtypes = [_vp] * 7 + [_i] * 8 + [_vp] * 4 + [_i, _i, _vp, _ll, _vp]
     L.msda_query_post_f32.argtypes = [_vp, _vp, _i, _vp, _ll, _i, _i, _i, _vp, _vp, _vp]
+    L.msda_biattn_splits.argtypes = [_i, _i]
+    L.msda_biattn_pv_16.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]
+    L.msda_biattn_combine_16.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     L.msda_b200_probe_scatter.argtypes = [_vp, _ll, _i, _i, _i, _vp]
     _lib = L

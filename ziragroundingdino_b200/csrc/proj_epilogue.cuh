@@ -190,6 +190,9 @@ extern thread_local char t_err[256];
 // row-major [rows, cols] matrix, box = box_rows x box_cols (box_cols * element size == 128 bytes), 128-byte swizzle.
 // dtype: 0 bf16, 1 f16, 2 f32.
 int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, int box_rows, int box_cols, int dtype);
+// [batch, rows, cols] tensor of 16-bit elements (row stride = cols), box = 1 x box_rows x 64 columns, 128-byte swizzle;
+// rows beyond `rows` read as zeros and are clipped on store (per batch entry -- the reason for the third dimension).
+int make_map3(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows, int dtype);
 // in-place softmax over runs of `lp` consecutive fp32 values (L*P does not divide the 32-column epilogue chunk)
 int softmax_rows(float* x, long long runs, int lp, cudaStream_t st);
 
