@@ -65,8 +65,10 @@ def test_pv_online_matches_softmax_attention(LA, LB, nsplit, masked, dtype):
         cm[1, -9:] = True
     out, stat = biattn.pv(a, b, x, H, scale, biattn._pad_mask(cm, B, LB, DEV), nsplit=nsplit)
     ro, rs = _ref_online(a, b, x, H, scale, cm)
-    e, es = rel_err(out.double(), ro), (stat.double() - rs).abs().max().item()
+    e = rel_err(out.double(), ro)
+    es = (stat[:, :, :LA].double() - rs).abs().max().item()
     assert e < 1e-2 and es < 2e-3, (e, es)
+    assert torch.isinf(stat[:, :, LA:]).all()
 
 
 def test_pv_online_rescales_when_later_tiles_dominate():
@@ -79,7 +81,7 @@ def test_pv_online_rescales_when_later_tiles_dominate():
     for nsplit in (1, 2):
         out, stat = biattn.pv(a, b, x, H, scale, biattn._pad_mask(None, B, LB, DEV), nsplit=nsplit)
         ro, rs = _ref_online(a, b, x, H, scale, None)
-        e, es = rel_err(out.double(), ro), (stat.double() - rs).abs().max().item()
+        e, es = rel_err(out.double(), ro), (stat[:, :, :LA].double() - rs).abs().max().item()
         assert e < 1e-2 and es < 5e-3, (nsplit, e, es)
 
 
@@ -93,8 +95,42 @@ def test_pv_given_statistics_reproduces_transposed_probabilities(LA, LB, nsplit)
     # statistics of the other direction: softmax over the rows (axis LA) of each column, masked rows excluded
     s2 = _logits2(a, b, H, scale).masked_fill(rm[:, None, :, None], float("-inf"))
     col_stat = (torch.logsumexp(s2 * math.log(2.0), dim=2) / math.log(2.0)).float().contiguous()      # [B, H, LB]
-    out, _ = biattn.pv(a, b, x, H, scale, biattn._pad_mask(rm, B, LA, DEV), col_stat=col_stat, nsplit=nsplit)
+    out, _ = biattn.pv(a, b, x, H, scale, biattn._pad_mask(rm, B, LA, DEV), col_stat=biattn.pad_stat(col_stat, float("inf")), nsplit=nsplit)
     ro = _ref_given(a, b, x, H, scale, col_stat, rm)
     e = rel_err(out.double(), ro)
     assert e < 1e-2, e
     assert out[1, 5:40].abs().max().item() == 0.0
+
+
+def _ref_core(q, k, vv, vl, mv, ml, H, scale):
+    """fp64 autograd restatement of both directions (reference fuse_modules.py:172-227 without the no-op clamps)."""
+    s = (_heads(q, H) @ _heads(k, H).transpose(-1, -2)) * scale                       # [B, H, S, T]
+    sv = s if ml is None else s.masked_fill(ml[:, None, None, :], float("-inf"))
+    sl = s.transpose(-1, -2)
+    sl = sl if mv is None else sl.masked_fill(mv[:, None, None, :], float("-inf"))
+    ov = torch.softmax(sv, -1) @ _heads(vl, H)
+    ol = torch.softmax(sl, -1) @ _heads(vv, H)
+    B, _, S, hd = ov.shape
+    return ov.transpose(1, 2).reshape(B, S, H * hd), ol.transpose(1, 2).reshape(B, ol.shape[2], H * hd)
+
+
+@pytest.mark.parametrize("S,T,masked", [(300, 200, True), (1000, 256, False), (2500, 48, True)])
+def test_core_function_forward_backward_vs_fp64(S, T, masked):
+    from ziragroundingdino_b200 import biattn
+    B, H, scale, dtype = 2, 2, 1.0 / 16, torch.bfloat16
+    q, k = _mk(B, S, H, dtype, seed=11).requires_grad_(True), _mk(B, T, H, dtype, seed=12).requires_grad_(True)
+    vv, vl = _mk(B, S, H, dtype, seed=13).requires_grad_(True), _mk(B, T, H, dtype, seed=14).requires_grad_(True)
+    mv = ml = None
+    if masked:
+        mv = torch.zeros(B, S, dtype=torch.bool, device=DEV); mv[1, -S // 5:] = True
+        ml = torch.zeros(B, T, dtype=torch.bool, device=DEV); ml[0, -7:] = True
+    ov, ol = biattn.bi_attention_core(q, k, vv, vl, mv, ml, H, scale)
+    gv, gl = _mk(B, S, H, dtype, seed=15), _mk(B, T, H, dtype, seed=16)
+    torch.autograd.backward([ov, ol], [gv, gl])
+    ref_in = [t.detach().double().requires_grad_(True) for t in (q, k, vv, vl)]
+    rv, rl = _ref_core(*ref_in, mv, ml, H, scale)
+    torch.autograd.backward([rv, rl], [gv.double(), gl.double()])
+    errs = {"out_v": rel_err(ov.double(), rv.detach()), "out_l": rel_err(ol.double(), rl.detach())}
+    for name, t, r in zip(("d_q", "d_k", "d_val_v", "d_val_l"), (q, k, vv, vl), ref_in):
+        errs[name] = rel_err(t.grad.double(), r.grad)
+    assert all(e < 1e-2 for e in errs.values()), errs

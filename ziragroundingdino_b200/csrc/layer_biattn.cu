@@ -65,8 +65,9 @@ struct PvParams {
   float scale_log2;            // logits scale x log2(e)
   const uint8_t* mask;         // online: [B, ctiles*128] 1 = column masked (padding columns are 1)
                                // given : [B, mtiles*128] 1 = lane masked (padding lanes are 1)
-  const float* col_stat;       // given: [B, H, LB] log2-domain log-sum-exp of each column's softmax (over the lanes)
-  float* lane_stat;            // online, nsplit == 1: [B, H, LA] log2-domain log-sum-exp per lane (may be null)
+  const float* col_stat;       // given: [B, H, ctiles*128] log2-domain log-sum-exp of each column's softmax (over the
+                               // lanes); +inf in the padding (and for columns that attend to nothing)
+  float* lane_stat;            // online, nsplit == 1: [B, H, mtiles*128] log2-domain log-sum-exp per lane (may be null)
   float* part_o;               // nsplit > 1: [items, 128, 256] fp32 un-normalised partial results
   float* part_m;               // nsplit > 1, online: [items, 128] running reference;  part_l: [items, 128] partial sums
   float* part_l;
@@ -321,15 +322,17 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           ref_use = m_ref == -CUDART_INF_F ? 0.f : m_ref;
         } else {
-          const float4* cp = reinterpret_cast<const float4*>(p.col_stat + (static_cast<size_t>(b) * p.H + h) * p.LB);
-          const float* cs = p.col_stat + (static_cast<size_t>(b) * p.H + h) * p.LB;
-          (void)cp;
+          const float4* cs = reinterpret_cast<const float4*>(p.col_stat + (static_cast<size_t>(b) * p.H + h) * lb_pad + col0);
 #pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const int col = col0 + c;
-            const float raw = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
-            const float st = col < p.LB ? __ldg(cs + col) : CUDART_INF_F;
-            s[c] = lane_ok ? raw * p.scale_log2 - st : -CUDART_INF_F;
+          for (int c4 = 0; c4 < 16; ++c4) {
+            const float4 st = __ldg(cs + c4);
+            const float stv[4] = {st.x, st.y, st.z, st.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int c = c4 * 4 + i;
+              const float raw = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
+              s[c] = lane_ok ? raw * p.scale_log2 - stv[i] : -CUDART_INF_F;
+            }
           }
           ref_use = 0.f;
         }
@@ -367,7 +370,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (p.nsplit == 1) {
         const float inv = p.given ? 1.f : (l_tot > 0.f ? 1.f / l_tot : 0.f);
         if (!p.given && p.lane_stat != nullptr && half == 0 && live)
-          p.lane_stat[(static_cast<size_t>(b) * p.H + h) * p.LA + arow] = l_tot > 0.f ? m_ref + log2f(l_tot) : CUDART_INF_F;
+          p.lane_stat[(static_cast<size_t>(b) * p.H + h) * la_pad + arow] = l_tot > 0.f ? m_ref + log2f(l_tot) : CUDART_INF_F;
 #pragma unroll 1
         for (int gq = 0; gq < 2; ++gq) {
           const int gc = half * 128 + gq * 64;
@@ -447,7 +450,7 @@ __global__ void biattn_combine_kernel(const float* __restrict__ part_o, const fl
       acc += part_o[((item0 + c) * BM + tr) * HD + d] * w;
     }
     inv = lstar > 0.f ? 1.f / lstar : 0.f;
-    if (d == 0 && lane_stat != nullptr) lane_stat[static_cast<size_t>(bh) * LA + a] = lstar > 0.f ? mstar + log2f(lstar) : CUDART_INF_F;
+    if (d == 0 && lane_stat != nullptr) lane_stat[static_cast<size_t>(bh) * mtiles * BM + a] = lstar > 0.f ? mstar + log2f(lstar) : CUDART_INF_F;
   } else {
     for (int c = 0; c < nsplit; ++c) acc += part_o[((item0 + c) * BM + tr) * HD + d];
   }
