@@ -73,6 +73,7 @@ def parse():
                     "forward+backward and the update (capture_error_mode=thread_local, so the NCCL watchdog thread's event "
                     "queries do not invalidate the capture -- the round-1 hang) instead of an eager call between two graphs")
     ap.add_argument("--no-config5", action="store_true", help="skip the Swin-B stride-4 (HBM-bound) core-op timing")
+    ap.add_argument("--no-fusion", action="store_true", help="skip the image<->text fusion block leg (row N4)")
     a = ap.parse_args()
     set_config(a.config if a.config is not None else 4)
     return a
@@ -618,6 +619,48 @@ def run_ours(args):
         errors["config5_stride4"] = repr(e)[:300]
         c5 = None
 
+    # row N4 (image <-> text fusion, one BiAttentionBlock per encoder layer): forward+backward at this workload's image
+    # count with frozen weights (the ZiRa configuration), the tcgen05 attention core against the library formulation
+    fusion = None
+    if rank == 0 and not args.no_fusion:
+      try:
+        from ziragroundingdino_b200.fuse_modules import BiAttentionBlock, BiMultiHeadAttention
+        S5 = sum(h * w for h, w in syn.SWIN_T_800x1333)
+        torch.manual_seed(3)
+        blk = BiAttentionBlock(256, 256, 1024, 4, dropout=0.0, drop_path=0.0).to(dev).to(torch.bfloat16)
+        for prm in blk.parameters():
+            prm.requires_grad_(False)
+        fv = torch.randn(KN, S5, 256, device=dev).to(torch.bfloat16).requires_grad_(True)
+        fl = torch.randn(KN, 256, 256, device=dev).to(torch.bfloat16).requires_grad_(True)
+        fmv = torch.zeros(KN, S5, dtype=torch.bool, device=dev); fmv[-1, -3000:] = True
+        fml = torch.zeros(KN, 256, dtype=torch.bool, device=dev); fml[:, -56:] = True
+        gfv, gfl = torch.randn_like(fv), torch.randn_like(fl)
+
+        def fus_step():
+            ov, ol = blk(fv, fl, fmv, fml)
+            torch.autograd.backward([ov, ol], [gfv, gfl])
+
+        def fus_fwd():
+            with torch.no_grad():
+                blk(fv, fl, fmv, fml)
+        fusion = {"workload": "BiAttentionBlock fwd+bwd, %d images, S=%d image tokens, 256 text tokens, 4 heads x 256, bf16, "
+                              "frozen weights, upstream gradients given" % (KN, S5)}
+        was = BiMultiHeadAttention.use_kernel
+        for name, flag in (("kernel", True), ("library", False)):
+            BiMultiHeadAttention.use_kernel = flag
+            n0 = _lib.launch_count()
+            fus_step()
+            fusion[name + "_own_launches"] = _lib.launch_count() - n0
+            fusion[name + "_fwd_us"] = kernel_us([fus_fwd], 5)
+            fusion[name + "_fwd_bwd_us"] = kernel_us([fus_step], 5)
+        BiMultiHeadAttention.use_kernel = was
+        fusion["speedup_fwd"] = fusion["library_fwd_us"] / fusion["kernel_fwd_us"]
+        fusion["speedup_fwd_bwd"] = fusion["library_fwd_bwd_us"] / fusion["kernel_fwd_bwd_us"]
+        del blk, fv, fl, gfv, gfl
+      except Exception as e:      # noqa: BLE001
+        errors["fusion_block"] = repr(e)[:300]
+        fusion = None
+
     # the reference's own CUDA op (oracle/_ref/ref_C.so, built in place from the unmodified sources) on the same box and
     # the same launch, fp32 (it has no bf16): a BASELINE leg like cpu_baseline -- reported beside ours, never on the path
     ref_ab = None
@@ -699,7 +742,7 @@ def run_ours(args):
                                 "note": "reduction_bytes = one 128-byte fp32 row per bilinear corner (N*Lq*M*L*P*4 rows), the "
                                         "ALGORITHMIC scatter; a kernel that combines rows on the SM before they leave sends fewer "
                                         "and can exceed 1.0 of this instruction-shape probe"},
-        "config5_stride4": c5, "ref_cuda_us_per_layer": ref_ab,
+        "config5_stride4": c5, "ref_cuda_us_per_layer": ref_ab, "fusion_block": fusion,
     }
     if errors:
         out["errors"] = errors

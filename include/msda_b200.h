@@ -287,6 +287,45 @@ int msda_encoder_proposals(const void *memory, const uint8_t *mask_flatten, cons
                            const int64_t *level_start_index, const int *counts, const float *wh_base, int N, int S, int L,
                            int row_bytes, void *memory_out, float *proposals_out, void *stream);
 
+/* ---- image <-> text fusion attention -------------------------------------------------
+ * Replaces the attention core of BiMultiHeadAttention.forward (reference fuse_modules.py:172-227: fp32 logits
+ * [B*heads, n_img, n_text], their transpose, two softmaxes, two batched products) and autograd through it.  Heads are 256
+ * wide; operands are the projections as they leave their GEMMs, [B, L, H*256] 16-bit, heads addressed by column offset.
+ * Both directions share the logits s = scale * a . b^T, so every entry point exists in two ORIENTATIONS: `a` is the
+ * stationary side (LA rows, 128 per CTA), `b` / `x` the streamed side (LB rows).  Statistics are log2-domain
+ * log-sum-exp values, fp32 [B, H, pad128(L)] with +inf in the padding; masks are bytes [B, pad128(L)], 1 = masked, padding 1.
+ *
+ * msda_biattn_pv_16: out[B, LA, H*256] = P . x.
+ *   col_stat == NULL ("online"): P = softmax over the LB axis of s (mask_padded masks streamed rows); lane_stat receives
+ *     the statistics.  out_v = pv(q, k, val_l, mask_l), out_l = pv(k, q, val_v, mask_v).
+ *   col_stat != NULL ("given"):  P[i, j] = exp2(s2[i, j] - col_stat[j]), zero for masked stationary rows i (mask_padded
+ *     masks stationary rows): the other direction's probabilities, transposed -- d val_l = pv(k, q, d out_v, stat_v),
+ *     d val_v = pv(q, k, d out_l, stat_l).
+ *   nsplit > 1 splits the streamed axis over CTAs: partial results go to part_o [items, 128, 256] fp32 (+ part_m, part_l
+ *   [items, 128] online), items = B * H * ceil(LA/128) * msda_biattn_splits(LB, nsplit); msda_biattn_combine_16 merges
+ *   them (softmax-weighted when given == 0, plain sum otherwise) into out16 / lane_stat.
+ * msda_biattn_rowdot_16: delta[B, H, lpad] = per-head dot product of d_o and o ([B, L, H*256]).
+ * msda_biattn_ds_16: d a[B, LA, H*256] = scale * dS . b with dS[i, j] = P1 (d_oa[i].xb[j] - lane_delta[i]) +
+ *   P2 (xa[i].d_ob[j] - col_delta[j]), P1 = exp2(s2 - lane_stat[i]) masked by mask_b (streamed rows), P2 = exp2(s2 -
+ *   col_stat[j]) masked by mask_a (stationary rows).  d q = ds(q, d out_v, val_v, k, val_l, d out_l, ...),
+ *   d k = ds(k, d out_l, val_l, q, val_v, d out_v, ...).  nsplit as above (64-row column tiles; msda_biattn_ds_splits),
+ *   partials merged by msda_biattn_combine_16(given = 1).
+ * msda_biattn_set_trace: debug -- 16 int64 cycle counters per CTA of the next msda_biattn_pv_16 launches (NULL = off). */
+int msda_biattn_splits(int LB, int nsplit);
+int msda_biattn_pv_16(const void *a, const void *b, const void *x, int B, int H, int LA, int LB, float scale,
+                      const uint8_t *mask_padded, const float *col_stat, void *out16, float *lane_stat, float *part_o,
+                      float *part_m, float *part_l, int nsplit, int is_half, void *stream);
+int msda_biattn_combine_16(const float *part_o, const float *part_m, const float *part_l, int B, int H, int LA, int nsplit,
+                           int given, void *out16, float *lane_stat, int is_half, void *stream);
+int msda_biattn_rowdot_16(const void *d_o, const void *o, int B, int L, int H, int lpad, float *delta, int is_half,
+                          void *stream);
+int msda_biattn_ds_splits(int LB, int nsplit);
+int msda_biattn_ds_16(const void *a, const void *d_oa, const void *xa, const void *b, const void *xb, const void *d_ob, int B,
+                      int H, int LA, int LB, float scale, const uint8_t *mask_a_padded, const uint8_t *mask_b_padded,
+                      const float *lane_stat, const float *lane_delta, const float *col_stat, const float *col_delta,
+                      void *out16, float *part_o, int nsplit, int is_half, void *stream);
+void msda_biattn_set_trace(long long *buf);
+
 /* Measurement aid: random seg_bytes-aligned (64, 128 or 512) segment reads from `buf` (bytes long,
  * keep it L2-sized), `iters` segments per lane group, `blocks` CTAs of 256 threads.  Bytes moved =
  * blocks * 256 * 16 * iters (iters rounded up to a multiple of 8).  `sink` is 4 writable bytes. */

@@ -1,5 +1,5 @@
 """GPU: row N4 -- BiAttentionBlock at the model's dimensions (v_dim = l_dim = 256, embed 1024, 4 heads of 256) in bf16 on
-the library's fused attention kernels, against the oracle restatement (materialised attention matrix, fp64, CPU) on the
+the tcgen05 attention core (and the two library formulations), against the oracle restatement (materialised attention matrix, fp64, CPU) on the
 same parameters.  Outputs are LayerNorm-normalised inputs plus a gamma-scaled delta: bar 3e-2 absolute, 2e-2 relative
 (Frobenius) on the deltas' input gradients."""
 import pytest
@@ -11,12 +11,15 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("use_sdpa", [False, True])
+@pytest.mark.parametrize("core", ["kernel", "matmul", "sdpa"])
 @pytest.mark.parametrize("masked", [True, False])
-def test_bi_attention_block_bf16_vs_oracle(masked, use_sdpa, monkeypatch):
+def test_bi_attention_block_bf16_vs_oracle(masked, core, monkeypatch):
     from oracle import cpu_encoder
+    from ziragroundingdino_b200 import _lib
     from ziragroundingdino_b200.fuse_modules import BiAttentionBlock, BiMultiHeadAttention
-    monkeypatch.setattr(BiMultiHeadAttention, "use_sdpa", use_sdpa)
+    monkeypatch.setattr(BiMultiHeadAttention, "use_kernel", core == "kernel")
+    monkeypatch.setattr(BiMultiHeadAttention, "use_sdpa", core == "sdpa")
+    launches0 = _lib.launch_count()
     torch.manual_seed(9)
     B, n_img, n_text, C, E, H = 2, 1500, 48, 256, 1024, 4
     blk = BiAttentionBlock(v_dim=C, l_dim=C, embed_dim=E, num_heads=H, dropout=0.0, drop_path=0.0)
@@ -32,6 +35,8 @@ def test_bi_attention_block_bf16_vs_oracle(masked, use_sdpa, monkeypatch):
     ov, ol = blk(v, l, attention_mask_v=mv, attention_mask_l=ml)
     gv, gl = torch.randn_like(ov), torch.randn_like(ol)
     ((ov.float() * gv.float()).sum() + (ol.float() * gl.float()).sum()).backward()
+    # kernel core: 2 products + combine forward; 2 row-dots, 2 value products (+ combine), 2 logits-gradient products (+ combine)
+    assert (_lib.launch_count() - launches0 >= 9) == (core == "kernel")
     d = lambda t: t.detach().double().cpu()
     p = {k: d(t) for k, t in blk.state_dict().items()}
     vd, ld = d(v).requires_grad_(True), d(l).requires_grad_(True)

@@ -44,12 +44,21 @@ def pad_stat(stat, fill):
 
 
 def default_splits(B, heads, LA, LB, dev, tile=TILE):
-    """Column splits for the orientation with few stationary tiles: enough work items to fill the SMs about twice."""
+    """Column splits for the orientation with few stationary tiles: the split count whose work items (each a persistent
+    CTA's share) finish in the fewest column tiles -- rounds of items over the SMs times tiles per item."""
     sms = torch.cuda.get_device_properties(dev).multi_processor_count
     units = B * heads * ((LA + TILE - 1) // TILE)
+    ctiles = (LB + tile - 1) // tile
     if units >= sms:
         return 1
-    return max(1, min((LB + tile - 1) // tile, (2 * sms + units - 1) // units))
+    best, best_cost = 1, None
+    for ns in range(1, min(ctiles, (4 * sms) // units + 1) + 1):
+        tps = (ctiles + ns - 1) // ns
+        real = (ctiles + tps - 1) // tps
+        cost = ((units * real + sms - 1) // sms) * tps + 0.02 * real      # small penalty per split: the combine pass
+        if best_cost is None or cost < best_cost:
+            best, best_cost = real, cost
+    return best
 
 
 def _ptr(t):

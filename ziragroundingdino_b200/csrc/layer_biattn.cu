@@ -27,7 +27,9 @@
 // log2-domain log-sum-exp per lane is saved.  GIVEN (backward, dVal = P^T dO): the statistics of the OTHER direction are
 // supplied per column, p = exp2(s - stat[column]) exactly reproduces that direction's probabilities, transposed.
 //
-//   warp 0      TMA producer: the stationary tile once per work item, then B / X k-blocks through a ring of 16 KiB slots
+//   warp 0      TMA producer 1: the stationary tile once per work item, then B k-blocks through ring 1 (16 KiB slots)
+//   warp 10     TMA producer 2: X slabs through ring 2 -- separate rings and producers, so that slabs waiting for their
+//               probability tile never hold back the prefetch of the next logits operands
 //   warp 1      MMA issuer (GEMM1_{j+1} is issued before GEMM2_j); owns the 512 TMEM columns (2 x 128 + 256)
 //   warps 2-9   mid / final stages: two warps per TMEM lane quarter, each 64 of a tile's 128 columns
 #include <cuda.h>
@@ -67,39 +69,46 @@ struct PvParams {
                                // given : [B, mtiles*128] 1 = lane masked (padding lanes are 1)
   const float* col_stat;       // given: [B, H, ctiles*128] log2-domain log-sum-exp of each column's softmax (over the
                                // lanes); +inf in the padding (and for columns that attend to nothing)
+  void* out16;                 // nsplit == 1: [B, LA, H*256] 16-bit result
   float* lane_stat;            // online, nsplit == 1: [B, H, mtiles*128] log2-domain log-sum-exp per lane (may be null)
   float* part_o;               // nsplit > 1: [items, 128, 256] fp32 un-normalised partial results
   float* part_m;               // nsplit > 1, online: [items, 128] running reference;  part_l: [items, 128] partial sums
   float* part_l;
   int half_in;
+  long long* trace;            // debug: per-CTA cycle counters of the pipeline waits (null = off)
 };
 
-template <int NSLOT>
-struct PvSmem {
-  static constexpr int kBytes = 1024 + A_BYTES + NSLOT * SLOT + 2 * P_BYTES + 2 * 2 * BM * 4 + 2 * BM * 4 + 512;
-};
+constexpr int NS1 = 3, NS2 = 2;         // ring depths: logits operands (B k-blocks, 16 KiB) / value half-tiles (X, 32 KiB)
+constexpr int SLOT2 = 2 * SLOT;         // two 64-column slabs of X, contiguous: GEMM2 runs as N = 128 instructions
+constexpr int PV_THREADS = THREADS + 32; // + the second TMA producer warp
+constexpr int PV_SMEM = 1024 + A_BYTES + NS1 * SLOT + NS2 * SLOT2 + P_BYTES + 2 * 2 * BM * 4 + 2 * BM * 4 + 512;
 
-template <int NSLOT>
-__global__ void __launch_bounds__(THREADS, 1)
+#define TWAIT(bar, par, ctr) do { const long long t0_ = clock64(); mbar_wait(bar, par); (ctr) += clock64() - t0_; } while (0)
+
+template <bool HALF, bool GIVEN>
+__global__ void __launch_bounds__(PV_THREADS, 1)
 biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmOut, PvParams p) {
+                 const __grid_constant__ CUtensorMap tmX, PvParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
-  uint8_t* sRing = sA + A_BYTES;
-  uint8_t* sP = sRing + NSLOT * SLOT;
-  float* sMax = reinterpret_cast<float*>(sP + 2 * P_BYTES);      // [2 buffers][2 halves][128]
+  uint8_t* sRing1 = sA + A_BYTES;
+  uint8_t* sRing2 = sRing1 + NS1 * SLOT;
+  uint8_t* sP = sRing2 + NS2 * SLOT2;                               // ONE probability tile: the next tile's exponentials are
+  float* sMax = reinterpret_cast<float*>(sP + P_BYTES);            // computed while GEMM2 still reads it; [2][2 halves][128]
   float* sSum = sMax + 2 * 2 * BM;                                 // [2 halves][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sSum + 2 * BM);
-  uint64_t* full = bars;              // [NSLOT]
-  uint64_t* empty = full + NSLOT;     // [NSLOT]
-  uint64_t* x_full = empty + NSLOT;   // stationary tile landed
+  uint64_t* full1 = bars;             // [NS1]
+  uint64_t* empty1 = full1 + NS1;     // [NS1]
+  uint64_t* full2 = empty1 + NS1;     // [NS2]
+  uint64_t* empty2 = full2 + NS2;     // [NS2]
+  uint64_t* x_full = empty2 + NS2;    // stationary tile landed
   uint64_t* x_free = x_full + 1;      // last GEMM1 of the work item retired
   uint64_t* a1_full = x_free + 1;     // [2] logits tile complete
   uint64_t* a1_free = a1_full + 2;    // [2] mid stage has read it
-  uint64_t* h_full = a1_free + 2;     // [2] probability tile written to shared memory
-  uint64_t* h_free = h_full + 2;      // [2] GEMM2 has read it (== GEMM2 of that tile complete)
-  uint64_t* a2_full = h_free + 2;     // result complete
+  uint64_t* h_full = a1_free + 2;     // probability tile written to shared memory
+  uint64_t* h_free = h_full + 1;      // GEMM2 has read it (== GEMM2 of that tile complete)
+  uint64_t* a2_full = h_free + 1;     // result complete
   uint64_t* a2_free = a2_full + 1;    // final stage has read it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_free + 1);
 
@@ -110,9 +119,11 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmX)) : "memory");
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < NS1; ++i) { mbar_init(full1 + i, 1); mbar_init(empty1 + i, 1); }
+    for (int i = 0; i < NS2; ++i) { mbar_init(full2 + i, 1); mbar_init(empty2 + i, 1); }
     mbar_init(x_full, 1); mbar_init(x_free, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); mbar_init(h_full + i, EPI_WARPS); mbar_init(h_free + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); }
+    mbar_init(h_full, EPI_WARPS); mbar_init(h_free, 1);
     mbar_init(a2_full, 1); mbar_init(a2_free, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -141,11 +152,10 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer 1: the stationary tile, then the logits operands (ring 1) =====
     if (elect_one()) {
       int slot = 0;
       uint32_t ph_slot = 0, ph_x = 0;
-      auto next_slot = [&]() { if (++slot == NSLOT) { slot = 0; ph_slot ^= 1; } };
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int b, h, mt, j0, n;
         decode(item, b, h, mt, j0, n);
@@ -153,106 +163,120 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ph_x ^= 1;
         mbar_expect_tx(x_full, A_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_3d(&tmA, x_full, sA + kb * 16384, h * HD + kb * 64, mt * BM, b);
-        for (int jj = 0; jj <= n; ++jj) {
-          if (jj < n) {
-            for (int kb = 0; kb < 4; ++kb) {
-              mbar_wait(empty + slot, ph_slot ^ 1);
-              mbar_expect_tx(full + slot, SLOT);
-              tma_load_3d(&tmB, full + slot, sRing + slot * SLOT, h * HD + kb * 64, (j0 + jj) * BN, b);
-              next_slot();
-            }
+        for (int jj = 0; jj < n; ++jj) {
+          for (int kb = 0; kb < 4; ++kb) {
+            mbar_wait(empty1 + slot, ph_slot ^ 1);
+            mbar_expect_tx(full1 + slot, SLOT);
+            tma_load_3d(&tmB, full1 + slot, sRing1 + slot * SLOT, h * HD + kb * 64, (j0 + jj) * BN, b);
+            if (++slot == NS1) { slot = 0; ph_slot ^= 1; }
           }
-          if (jj >= 1) {
-            for (int sl = 0; sl < 4; ++sl) {
-              mbar_wait(empty + slot, ph_slot ^ 1);
-              mbar_expect_tx(full + slot, SLOT);
-              tma_load_3d(&tmX, full + slot, sRing + slot * SLOT, h * HD + sl * 64, (j0 + jj - 1) * BN, b);
-              next_slot();
-            }
+        }
+      }
+    }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ===== TMA producer 2: the value slabs (ring 2) -- its own warp, so waiting for GEMM2 never holds back ring 1 =====
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph_slot = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int b, h, mt, j0, n;
+        decode(item, b, h, mt, j0, n);
+        for (int jj = 0; jj < n; ++jj) {
+          for (int sl = 0; sl < 2; ++sl) {     // half a value tile: head-dim columns [sl*128, +128) as two 64-column slabs
+            mbar_wait(empty2 + slot, ph_slot ^ 1);
+            mbar_expect_tx(full2 + slot, SLOT2);
+            tma_load_3d(&tmX, full2 + slot, sRing2 + slot * SLOT2, h * HD + sl * 128, (j0 + jj) * BN, b);
+            tma_load_3d(&tmX, full2 + slot, sRing2 + slot * SLOT2 + SLOT, h * HD + sl * 128 + 64, (j0 + jj) * BN, b);
+            if (++slot == NS2) { slot = 0; ph_slot ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc1 = umma_idesc(BM, BN, p.half_in != 0);
-    const uint32_t idesc2 = umma_idesc(BM, 64, p.half_in != 0) | kIdescBMn;
-    int slot = 0;
-    uint32_t ph_slot = 0, ph_x = 0, ph_a2 = 0, g1 = 0, g2 = 0;     // g1 / g2: running tile counters of GEMM1 / GEMM2
-    uint32_t ph_a1free[2] = {0, 0}, ph_hfull[2] = {0, 0};
-    auto next_slot = [&]() { if (++slot == NSLOT) { slot = 0; ph_slot ^= 1; } };
+    const uint32_t idesc1 = umma_idesc(BM, BN, HALF);
+    const uint32_t idesc2 = umma_idesc(BM, 128, HALF) | kIdescBMn;
+    int slot1 = 0, slot2 = 0;
+    uint32_t ph1 = 0, ph2 = 0, ph_x = 0, ph_a2 = 0, ph_hfull = 0, g1 = 0;     // g1: running tile counter of GEMM1
+    uint32_t ph_a1free[2] = {0, 0};
+    long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b_, h_, mt_, j0_, n;
       decode(item, b_, h_, mt_, j0_, n);
-      mbar_wait(x_full, ph_x);
+      TWAIT(x_full, ph_x, tc[0]);
       ph_x ^= 1;
       tc_fence_after();
       for (int jj = 0; jj <= n; ++jj) {
         if (jj < n) {
           const int b = g1 & 1;
           ++g1;
-          mbar_wait(a1_free + b, ph_a1free[b] ^ 1);
+          TWAIT(a1_free + b, ph_a1free[b] ^ 1, tc[1]);
           ph_a1free[b] ^= 1;
           tc_fence_after();
           for (int kb = 0; kb < 4; ++kb) {
-            mbar_wait(full + slot, ph_slot);
+            TWAIT(full1 + slot1, ph1, tc[2]);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
                 const uint64_t da = umma_desc_sw128(sA + kb * 16384, k * 32);
-                const uint64_t db = umma_desc_sw128(sRing + slot * SLOT, k * 32);
+                const uint64_t db = umma_desc_sw128(sRing1 + slot1 * SLOT, k * 32);
                 umma_f16(t_acc1 + static_cast<uint32_t>(b * BN), da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
               }
-              umma_commit(empty + slot);
+              umma_commit(empty1 + slot1);
               if (kb == 3) {
                 umma_commit(a1_full + b);
                 if (jj == n - 1) umma_commit(x_free);
               }
             }
             __syncwarp();
-            next_slot();
+            if (++slot1 == NS1) { slot1 = 0; ph1 ^= 1; }
           }
         }
         if (jj >= 1) {
-          const int t = jj - 1, b = g2 & 1;
-          ++g2;
+          const int t = jj - 1;
           if (t == 0) {                        // first product into acc2: the previous item's result must have been read out
-            mbar_wait(a2_free, ph_a2 ^ 1);
+            TWAIT(a2_free, ph_a2 ^ 1, tc[3]);
             ph_a2 ^= 1;
           }
-          mbar_wait(h_full + b, ph_hfull[b]);
-          ph_hfull[b] ^= 1;
+          TWAIT(h_full, ph_hfull, tc[4]);
+          ph_hfull ^= 1;
           tc_fence_after();
-          for (int sl = 0; sl < 4; ++sl) {
-            mbar_wait(full + slot, ph_slot);
+          for (int sl = 0; sl < 2; ++sl) {
+            TWAIT(full2 + slot2, ph2, tc[5]);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 8; ++k) {    // K = 128 streamed rows, 16 per instruction
-                const uint64_t da = umma_desc_sw128(sP + b * P_BYTES + (k >> 2) * 16384, (k & 3) * 32);
-                const uint64_t db = umma_desc_mn_sw128(sRing + slot * SLOT, k * 2048, 16384u);
-                umma_f16(t_acc2 + static_cast<uint32_t>(sl * 64), da, db, idesc2, (t | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 8; ++k) {    // K = 128 streamed rows, 16 per instruction; N = 128: two slabs 16 KiB apart
+                const uint64_t da = umma_desc_sw128(sP + (k >> 2) * 16384, (k & 3) * 32);
+                const uint64_t db = umma_desc_mn_sw128(sRing2 + slot2 * SLOT2, k * 2048, 16384u);
+                umma_f16(t_acc2 + static_cast<uint32_t>(sl * 128), da, db, idesc2, (t | k) != 0 ? 1u : 0u);
               }
-              umma_commit(empty + slot);
-              if (sl == 3) {
-                umma_commit(h_free + b);
+              umma_commit(empty2 + slot2);
+              if (sl == 1) {
+                umma_commit(h_free);
                 if (t == n - 1) umma_commit(a2_full);
               }
             }
             __syncwarp();
-            next_slot();
+            if (++slot2 == NS2) { slot2 = 0; ph2 ^= 1; }
           }
         }
       }
+    }
+    if (p.trace != nullptr && lane == 0) {
+      tc[6] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) p.trace[blockIdx.x * 16 + i] = tc[i];
     }
   } else {
     // ===== mid / final stages =====
     const int quarter = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter; which 64 of a tile's 128 columns
     const int trow = quarter * 32 + lane;                     // row inside the stationary tile == TMEM lane
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0, g = 0;
-    uint8_t* stile = sP + (half * 4 + quarter) * 4096;        // the 4 KiB of P buffer 0 only this warp ever writes
+    uint32_t ph_a1full[2] = {0, 0}, ph_hfree = 0, ph_a2 = 0, g = 0;
+    long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
     const int lb_pad = p.ctiles * BN, la_pad = p.mtiles * BM;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b, h, mt, j0, n;
@@ -260,69 +284,81 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int arow = mt * BM + trow;                        // row of the stationary operand
       const bool live = arow < p.LA;
       bool lane_ok = live;
-      if (p.given && p.mask != nullptr) lane_ok = lane_ok && p.mask[static_cast<size_t>(b) * la_pad + arow] == 0;
+      if (GIVEN && p.mask != nullptr) lane_ok = lane_ok && p.mask[static_cast<size_t>(b) * la_pad + arow] == 0;
       float m_ref = -CUDART_INF_F, l_part = 0.f;
       for (int jj = 0; jj < n; ++jj, ++g) {
         const int bb = g & 1;
-        mbar_wait(a1_full + bb, ph_a1full[bb]);
+        const int col0 = (j0 + jj) * BN + half * 64;          // first streamed row (= logits column) this thread handles
+        // the tile's mask bytes / column statistics are fetched before waiting for its logits (an L2 round trip otherwise
+        // sits between the TMEM load and the first use)
+        uint4 mk[4];
+        const float4* cs = nullptr;
+        if (!GIVEN) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(b) * lb_pad + col0);
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) mk[q4] = __ldg(mp + q4);
+        } else {                                              // 256 bytes of statistics: pull the two lines into L1
+          cs = reinterpret_cast<const float4*>(p.col_stat + (static_cast<size_t>(b) * p.H + h) * lb_pad + col0);
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(cs));
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(cs + 8));
+        }
+        TWAIT(a1_full + bb, ph_a1full[bb], te[0]);
         ph_a1full[bb] ^= 1;
         tc_fence_after();
         uint32_t r0[32], r1[32];
         const uint32_t t_s = t_acc1 + lane_bits + static_cast<uint32_t>(bb * BN + half * 64);
-        tmem_ld32(t_s, r0);
-        tmem_ld32(t_s + 32u, r1);
+        { const long long t0_ = clock64();
+        tmem_ld32_nowait(t_s, r0);
+        tmem_ld32_nowait(t_s + 32u, r1);
+        tmem_ld_wait();
+        te[5] += clock64() - t0_; }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_free + bb);             // logits are in registers: GEMM1 of tile g + 2 may overwrite them
-        const int col0 = (j0 + jj) * BN + half * 64;          // first streamed row (= logits column) this thread handles
         float s[64];
-        float ref_use;
-        if (!p.given) {
-          const uint4* mp = reinterpret_cast<const uint4*>(p.mask + static_cast<size_t>(b) * lb_pad + col0);
-          float tmax = -CUDART_INF_F;
+        float sc = 1.f;
+        bool need = false;
+        if (!GIVEN) {
+          uint32_t any_mask = 0u;
 #pragma unroll
-          for (int q4 = 0; q4 < 4; ++q4) {
-            const uint4 mk = __ldg(mp + q4);
-            const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+          for (int q4 = 0; q4 < 4; ++q4) any_mask |= mk[q4].x | mk[q4].y | mk[q4].z | mk[q4].w;
+          // raw logits (masked ones -> -inf) stay in s[]; the scale is positive, so max(raw) * scale is the scaled maximum
+          float rm[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};     // independent chains
+          if (any_mask == 0u) {                               // uniform across the warp: the mask is per column
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = q4 * 16 + i;
-              const float raw = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
-              const bool masked = ((w[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0u;
-              s[c] = masked ? -CUDART_INF_F : raw * p.scale_log2;
-              tmax = fmaxf(tmax, s[c]);
+            for (int c = 0; c < 64; ++c) {
+              s[c] = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
+              rm[c & 3] = fmaxf(rm[c & 3], s[c]);
+            }
+          } else {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              const uint32_t w[4] = {mk[q4].x, mk[q4].y, mk[q4].z, mk[q4].w};
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const int c = q4 * 16 + i;
+                const float raw = __uint_as_float(c < 32 ? r0[c & 31] : r1[c & 31]);
+                const bool masked = ((w[i >> 2] >> ((i & 3) * 8)) & 0xffu) != 0u;
+                s[c] = masked ? -CUDART_INF_F : raw;
+                rm[c & 3] = fmaxf(rm[c & 3], s[c]);
+              }
             }
           }
+          float tmax = fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * p.scale_log2;
           float* mx = sMax + bb * 2 * BM;
           mx[half * BM + trow] = tmax;
-          named_bar(1 + quarter, 64);
+          { const long long t0_ = clock64(); named_bar(1 + quarter, 64); te[1] += clock64() - t0_; }
           tmax = fmaxf(tmax, mx[(half ^ 1) * BM + trow]);
-          const bool need = tmax > m_ref + kRaise;            // also true for the first finite tile (m_ref = -inf)
-          float sc = 1.f;
+          need = tmax > m_ref + kRaise;                       // also true for the first finite tile (m_ref = -inf)
           if (need) {
             sc = ex2(m_ref - tmax);                            // 0 when m_ref = -inf
             l_part *= sc;
             m_ref = tmax;
           }
-          if (jj > 0 && __any_sync(0xffffffffu, need)) {
-            // raise the reference: rescale this warp's half of the accumulator once GEMM2 of the previous tile has retired
-            const int pb = (g - 1) & 1;
-            mbar_wait(h_free + pb, ph_hfree[pb] ^ 1);          // peek: the toggle happens at tile g + 1 as usual
-            tc_fence_after();
-#pragma unroll 1
-            for (int q4 = 0; q4 < 4; ++q4) {
-              uint32_t o[32];
-              const uint32_t t_o = t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32);
-              tmem_ld32(t_o, o);
+          const float ref_use = m_ref == -CUDART_INF_F ? 0.f : m_ref;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
-              tmem_st32(t_o, o);
-            }
-            tmem_st_wait();
-          }
-          ref_use = m_ref == -CUDART_INF_F ? 0.f : m_ref;
+          for (int c = 0; c < 64; ++c) s[c] = fmaf(s[c], p.scale_log2, -ref_use);
         } else {
-          const float4* cs = reinterpret_cast<const float4*>(p.col_stat + (static_cast<size_t>(b) * p.H + h) * lb_pad + col0);
 #pragma unroll
           for (int c4 = 0; c4 < 16; ++c4) {
             const float4 st = __ldg(cs + c4);
@@ -334,66 +370,83 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               s[c] = lane_ok ? raw * p.scale_log2 - stv[i] : -CUDART_INF_F;
             }
           }
-          ref_use = 0.f;
         }
-        mbar_wait(h_free + bb, ph_hfree[bb] ^ 1);             // GEMM2 of tile g - 2 has finished reading this P buffer
-        ph_hfree[bb] ^= 1;
-        uint8_t* pk_base = sP + bb * P_BYTES + half * 16384;
+        // exponentials and packing overlap GEMM2 of the previous tile, which still reads the P tile
+        const long long t_exp = clock64();
+        uint4 pk[8];
+        float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           float v[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            v[i] = ex2(s[hf * 32 + i] - ref_use);
-            l_part += v[i];
+            v[i] = ex2(s[hf * 32 + i]);
+            ls[i & 3] += v[i];
           }
-          uint4 pk[4];
-          pack_16(v, p.half_in != 0, false, pk);
+          uint4 o4[4];
+          pack_16(v, HALF, false, o4);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(pk_base, trow, 4 * hf + i)) = pk[i];
+          for (int i = 0; i < 4; ++i) pk[hf * 4 + i] = o4[i];
         }
+        l_part += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+        te[7] += clock64() - t_exp;
+        TWAIT(h_free, ph_hfree ^ 1, te[2]);                      // GEMM2 of tile g - 1 retired: P tile and accumulator are ours
+        ph_hfree ^= 1;
+        if (jj > 0 && __any_sync(0xffffffffu, need)) {
+          // raise the reference: rescale this warp's half of the accumulator before the next product is added to it
+          tc_fence_after();
+#pragma unroll 1
+          for (int q4 = 0; q4 < 4; ++q4) {
+            uint32_t o[32];
+            const uint32_t t_o = t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32);
+            tmem_ld32(t_o, o);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * sc);
+            tmem_st32(t_o, o);
+          }
+          tmem_st_wait();
+        }
+        uint8_t* pk_base = sP + half * 16384;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(swz(pk_base, trow, i)) = pk[i];
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_full + bb);
+        if (lane == 0) mbar_arrive(h_full);
       }
       // ---- final stage ----
       if (n > 0) {
-        mbar_wait(a2_full, ph_a2);
+        TWAIT(a2_full, ph_a2, te[3]);
         ph_a2 ^= 1;
         tc_fence_after();
       }
+      const long long t_fin = clock64();
       sSum[half * BM + trow] = l_part;
       named_bar(1 + quarter, 64);
       const float l_tot = l_part + sSum[(half ^ 1) * BM + trow];
       named_bar(1 + quarter, 64);
       if (p.nsplit == 1) {
-        const float inv = p.given ? 1.f : (l_tot > 0.f ? 1.f / l_tot : 0.f);
-        if (!p.given && p.lane_stat != nullptr && half == 0 && live)
+        const float inv = GIVEN ? 1.f : (l_tot > 0.f ? 1.f / l_tot : 0.f);
+        if (!GIVEN && p.lane_stat != nullptr && half == 0 && live)
           p.lane_stat[(static_cast<size_t>(b) * p.H + h) * la_pad + arow] = l_tot > 0.f ? m_ref + log2f(l_tot) : CUDART_INF_F;
+        // 16-bit result straight from registers: 64 contiguous bytes per thread and 32-column group (whole sectors); the
+        // TMEM loads are warp-collective, only the stores are predicated
+        uint8_t* orow = static_cast<uint8_t*>(p.out16) +
+                        ((static_cast<size_t>(b) * p.LA + (live ? arow : 0)) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
 #pragma unroll 1
-        for (int gq = 0; gq < 2; ++gq) {
-          const int gc = half * 128 + gq * 64;
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t r[32];
+          float v[32];
+          tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32), r);
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t r[32];
-            float v[32];
-            if (n > 0) tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(gc + 32 * hf), r);
+          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv;
+          uint4 o4[4];
+          pack_16(v, HALF, false, o4);
+          if (live) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = n > 0 ? __uint_as_float(r[i]) * inv : 0.f;
-            uint4 pk[4];
-            pack_16(v, p.half_in != 0, false, pk);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(stile, lane, 4 * hf + i)) = pk[i];
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + q4 * 64)[i] = o4[i];
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) tma_store_3d(&tmOut, stile, h * HD + gc, mt * BM + quarter * 32, b);
         }
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
       } else {
         float* po = p.part_o + (static_cast<size_t>(item) * BM + trow) * HD + half * 128;
 #pragma unroll 1
@@ -406,7 +459,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             dst[i] = n > 0 ? make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))
                            : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        if (!p.given && half == 0) {
+        if (!GIVEN && half == 0) {
           p.part_m[static_cast<size_t>(item) * BM + trow] = m_ref;
           p.part_l[static_cast<size_t>(item) * BM + trow] = l_tot;
         }
@@ -416,8 +469,12 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_free);
       }
+      te[4] += clock64() - t_fin;
     }
-    if (lane == 0) tma_store_wait_all();
+    if (p.trace != nullptr && warp == 2 && lane == 0) {
+      te[6] = clock64() - t_begin;
+      for (int i = 0; i < 8; ++i) p.trace[blockIdx.x * 16 + 8 + i] = te[i];
+    }
   }
 
   tc_fence_before();
@@ -460,7 +517,7 @@ __global__ void biattn_combine_kernel(const float* __restrict__ part_o, const fl
   else static_cast<__nv_bfloat16*>(out16)[o] = __float2bfloat16_rn(v);
 }
 
-constexpr int kSlots = 5;
+long long* g_pv_trace = nullptr;
 
 static int launch_pv(const void* a, const void* b, const void* x, void* out16, PvParams p, cudaStream_t st) {
   if (!a || !b || !x) { snprintf(t_err, sizeof(t_err), "null operand"); return MSDA_ERR_NULL_POINTER; }
@@ -477,14 +534,12 @@ static int launch_pv(const void* a, const void* b, const void* x, void* out16, P
   if (p.given && !p.col_stat) { snprintf(t_err, sizeof(t_err), "given mode needs column statistics"); return MSDA_ERR_NULL_POINTER; }
   const int dt = p.half_in ? 1 : 0;
   const long long E = static_cast<long long>(p.H) * HD;
-  CUtensorMap tmA, tmB, tmX, tmOut;
+  CUtensorMap tmA, tmB, tmX;
   int rc = make_map3(&tmA, a, p.B, p.LA, E, BM, dt);
   if (rc) return rc;
   rc = make_map3(&tmB, b, p.B, p.LB, E, BN, dt);
   if (rc) return rc;
   rc = make_map3(&tmX, x, p.B, p.LB, E, BN, dt);
-  if (rc) return rc;
-  rc = make_map3(&tmOut, out16 ? out16 : a, p.B, p.LA, E, 32, dt);
   if (rc) return rc;
   int dev_id = 0;
   cudaGetDevice(&dev_id);
@@ -493,15 +548,26 @@ static int launch_pv(const void* a, const void* b, const void* x, void* out16, P
   const long long items = static_cast<long long>(p.B) * p.H * p.mtiles * p.nsplit;
   if (items >= (1ll << 31)) return MSDA_ERR_BAD_SHAPE;
   const int grid = items < sms_of[dev_id & 63] ? static_cast<int>(items) : sms_of[dev_id & 63];
-  constexpr int smem = PvSmem<kSlots>::kBytes;
+  constexpr int smem = PV_SMEM;
   static bool configured[64] = {};
   if (!configured[dev_id & 63]) {
-    cudaError_t cfg = cudaFuncSetAttribute(biattn_pv_kernel<kSlots>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaError_t cfg = cudaFuncSetAttribute(biattn_pv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cfg == cudaSuccess) cfg = cudaFuncSetAttribute(biattn_pv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cfg == cudaSuccess) cfg = cudaFuncSetAttribute(biattn_pv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (cfg == cudaSuccess) cfg = cudaFuncSetAttribute(biattn_pv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
     configured[dev_id & 63] = true;
   }
+  p.trace = g_pv_trace;
+  p.out16 = out16;
   ++msda::g_launches;
-  biattn_pv_kernel<kSlots><<<grid, THREADS, smem, st>>>(tmA, tmB, tmX, tmOut, p);
+  if (p.half_in) {
+    if (p.given) biattn_pv_kernel<true, true><<<grid, PV_THREADS, smem, st>>>(tmA, tmB, tmX, p);
+    else biattn_pv_kernel<true, false><<<grid, PV_THREADS, smem, st>>>(tmA, tmB, tmX, p);
+  } else {
+    if (p.given) biattn_pv_kernel<false, true><<<grid, PV_THREADS, smem, st>>>(tmA, tmB, tmX, p);
+    else biattn_pv_kernel<false, false><<<grid, PV_THREADS, smem, st>>>(tmA, tmB, tmX, p);
+  }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "biattn_pv_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return p.nsplit;
@@ -511,6 +577,9 @@ static int launch_pv(const void* a, const void* b, const void* x, void* out16, P
 }  // namespace pg
 
 extern "C" {
+
+// Debug: device buffer of 16 int64 per CTA receiving the pipeline wait counters of the next launches (null = off).
+void msda_biattn_set_trace(long long* buf) { pg::bia::g_pv_trace = buf; }
 
 // Number of column splits msda_biattn_pv_16 will use for a requested `nsplit` (it never leaves a split empty).
 int msda_biattn_splits(int LB, int nsplit) {

@@ -15,10 +15,12 @@
 // into the same TMEM result, which is rounded once.
 //
 //   GEMM1_t  S_t  (64 TMEM columns) = A . B_t^T ;  dP_t (64 columns) = A2 . X2_t^T         (double-buffered pairs)
-//   mid      dS_t = exp2(s2 - stat) * (dP - delta), masked, 16 bit -> shared memory (K-major, 128-byte rows)
+//   mid      dS_t = exp2(s2 - stat) * (dP - delta), masked, 16 bit -> ONE shared-memory tile (K-major, 128-byte rows;
+//            the arithmetic of tile t+1 overlaps GEMM2_t, only the store waits for it)
 //   GEMM2_t  acc (256 columns) += dS_t[128, 64] . B_t[64, 256]      (B_t again, read MN-major as TMA delivers it)
 //
-//   warp 0 TMA producer, warp 1 MMA issuer, warps 2-9 mid / final stages (two per TMEM lane quarter, 32 columns each)
+//   warp 0 TMA producer 1 (stationary operands + GEMM1 operands, ring 1), warp 10 TMA producer 2 (GEMM2 operand, ring 2),
+//   warp 1 MMA issuer, warps 2-9 mid / final stages (two per TMEM lane quarter, 32 columns each)
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <cuda_runtime.h>
@@ -42,11 +44,13 @@ namespace bid {
 
 constexpr int HD = 256, BM = 128, BN = 64;
 constexpr int A_BYTES = 4 * 16384;       // one stationary operand: 4 k-blocks of 128 rows x 128 bytes
-constexpr int SLOT = 8192, NSLOT = 8;    // streamed k-block / slab: 64 rows x 128 bytes
-constexpr int P_BYTES = 16384;           // one dS tile: 128 rows x 64 columns, 16 bit
+constexpr int SLOT = 8192;               // streamed k-block / slab: 64 rows x 128 bytes
+constexpr int NS1 = 6, NS2 = 2;          // ring depths: GEMM1 operands (B, X2 k-blocks, 8 KiB) / GEMM2 operand (B half-tiles, 16 KiB)
+constexpr int SLOT2 = 2 * SLOT;          // two 64-column slabs, contiguous: GEMM2 runs as N = 128 instructions
+constexpr int P_BYTES = 16384;           // the dS tile: 128 rows x 64 columns, 16 bit
 constexpr int EPI_WARPS = 8;
-constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_BYTES = 1024 + 2 * A_BYTES + NSLOT * SLOT + 2 * P_BYTES + 512;
+constexpr int THREADS = 96 + 32 * EPI_WARPS;     // producer 1, MMA issuer, 8 mid/final warps, producer 2
+constexpr int SMEM_BYTES = 1024 + 2 * A_BYTES + NS1 * SLOT + NS2 * SLOT2 + P_BYTES + 512;
 
 struct DsParams {
   int B, H, LA, LB;
@@ -59,33 +63,37 @@ struct DsParams {
   const float* lane_delta;       // [B, H, la_pad] rowsum(dO * O) of that direction        (pass 0)
   const float* col_stat;         // [B, H, lb_pad]                                          (pass 1)
   const float* col_delta;        // [B, H, lb_pad]                                          (pass 1)
+  void* out16;                   // nsplit == 1: [B, LA, H*256] 16-bit result
   float* part_o;                 // nsplit > 1: [items, 128, 256] fp32 partial results (already scaled)
   int half_in;
 };
 
+template <bool HALF>
 __global__ void __launch_bounds__(THREADS, 1)
 biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2a,
                  const __grid_constant__ CUtensorMap tmA2b, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmX2a, const __grid_constant__ CUtensorMap tmX2b,
-                 const __grid_constant__ CUtensorMap tmOut, DsParams p) {
+                 const __grid_constant__ CUtensorMap tmX2a, const __grid_constant__ CUtensorMap tmX2b, DsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sA2 = sA + A_BYTES;
-  uint8_t* sRing = sA2 + A_BYTES;
-  uint8_t* sP = sRing + NSLOT * SLOT;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * P_BYTES);
-  uint64_t* full = bars;              // [NSLOT]
-  uint64_t* empty = full + NSLOT;     // [NSLOT]
-  uint64_t* x_full = empty + NSLOT;   // A landed (once per item)
+  uint8_t* sRing1 = sA2 + A_BYTES;
+  uint8_t* sRing2 = sRing1 + NS1 * SLOT;
+  uint8_t* sP = sRing2 + NS2 * SLOT2;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + P_BYTES);
+  uint64_t* full1 = bars;             // [NS1]
+  uint64_t* empty1 = full1 + NS1;     // [NS1]
+  uint64_t* full2 = empty1 + NS1;     // [NS2]
+  uint64_t* empty2 = full2 + NS2;     // [NS2]
+  uint64_t* x_full = empty2 + NS2;    // A landed (once per item)
   uint64_t* x_free = x_full + 1;      // last GEMM1 of the item retired
   uint64_t* x2_full = x_free + 1;     // second stationary operand landed (twice per item)
   uint64_t* x2_free = x2_full + 1;    // last GEMM1 of a pass retired
   uint64_t* a1_full = x2_free + 1;    // [2]
   uint64_t* a1_free = a1_full + 2;    // [2]
-  uint64_t* h_full = a1_free + 2;     // [2]
-  uint64_t* h_free = h_full + 2;      // [2]
-  uint64_t* a2_full = h_free + 2;
+  uint64_t* h_full = a1_free + 2;     // dS tile written
+  uint64_t* h_free = h_full + 1;      // GEMM2 of that tile retired
+  uint64_t* a2_full = h_free + 1;
   uint64_t* a2_free = a2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_free + 1);
 
@@ -95,9 +103,11 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
-    for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
+    for (int i = 0; i < NS1; ++i) { mbar_init(full1 + i, 1); mbar_init(empty1 + i, 1); }
+    for (int i = 0; i < NS2; ++i) { mbar_init(full2 + i, 1); mbar_init(empty2 + i, 1); }
     mbar_init(x_full, 1); mbar_init(x_free, 1); mbar_init(x2_full, 1); mbar_init(x2_free, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); mbar_init(h_full + i, EPI_WARPS); mbar_init(h_free + i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); }
+    mbar_init(h_full, EPI_WARPS); mbar_init(h_free, 1);
     mbar_init(a2_full, 1); mbar_init(a2_free, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -125,16 +135,15 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   };
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer 1: stationary operands, then the GEMM1 operands (ring 1) =====
     if (elect_one()) {
       int slot = 0;
       uint32_t ph_slot = 0, ph_x = 0, ph_x2 = 0;
-      auto next_slot = [&]() { if (++slot == NSLOT) { slot = 0; ph_slot ^= 1; } };
       auto stream = [&](const CUtensorMap* tm, int c0, int r0, int b) {
-        mbar_wait(empty + slot, ph_slot ^ 1);
-        mbar_expect_tx(full + slot, SLOT);
-        tma_load_3d(tm, full + slot, sRing + slot * SLOT, c0, r0, b);
-        next_slot();
+        mbar_wait(empty1 + slot, ph_slot ^ 1);
+        mbar_expect_tx(full1 + slot, SLOT);
+        tma_load_3d(tm, full1 + slot, sRing1 + slot * SLOT, c0, r0, b);
+        if (++slot == NS1) { slot = 0; ph_slot ^= 1; }
       };
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int b, h, mt, j0, n;
@@ -144,33 +153,47 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_expect_tx(x_full, A_BYTES);
         for (int kb = 0; kb < 4; ++kb) tma_load_3d(&tmA, x_full, sA + kb * 16384, h * HD + kb * 64, mt * BM, b);
         const int total = 2 * n;
-        for (int tt = 0; tt <= total; ++tt) {
-          if (tt < total) {
-            const int pass = tt >= n ? 1 : 0, j = j0 + (pass ? tt - n : tt);
-            if (tt == 0 || tt == n) {
-              mbar_wait(x2_free, ph_x2 ^ 1);
-              ph_x2 ^= 1;
-              mbar_expect_tx(x2_full, A_BYTES);
-              for (int kb = 0; kb < 4; ++kb) tma_load_3d(pass ? &tmA2b : &tmA2a, x2_full, sA2 + kb * 16384, h * HD + kb * 64, mt * BM, b);
-            }
-            for (int kb = 0; kb < 4; ++kb) stream(&tmB, h * HD + kb * 64, j * BN, b);
-            for (int kb = 0; kb < 4; ++kb) stream(pass ? &tmX2b : &tmX2a, h * HD + kb * 64, j * BN, b);
+        for (int tt = 0; tt < total; ++tt) {
+          const int pass = tt >= n ? 1 : 0, j = j0 + (pass ? tt - n : tt);
+          if (tt == 0 || tt == n) {
+            mbar_wait(x2_free, ph_x2 ^ 1);
+            ph_x2 ^= 1;
+            mbar_expect_tx(x2_full, A_BYTES);
+            for (int kb = 0; kb < 4; ++kb) tma_load_3d(pass ? &tmA2b : &tmA2a, x2_full, sA2 + kb * 16384, h * HD + kb * 64, mt * BM, b);
           }
-          if (tt >= 1) {
-            const int t = tt - 1, j = j0 + (t >= n ? t - n : t);
-            for (int sl = 0; sl < 4; ++sl) stream(&tmB, h * HD + sl * 64, j * BN, b);
+          for (int kb = 0; kb < 4; ++kb) stream(&tmB, h * HD + kb * 64, j * BN, b);
+          for (int kb = 0; kb < 4; ++kb) stream(pass ? &tmX2b : &tmX2a, h * HD + kb * 64, j * BN, b);
+        }
+      }
+    }
+  } else if (warp == 2 + EPI_WARPS) {
+    // ===== TMA producer 2: the GEMM2 operand (B_t again, as slabs) through ring 2 =====
+    if (elect_one()) {
+      int slot = 0;
+      uint32_t ph_slot = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        int b, h, mt, j0, n;
+        decode(item, b, h, mt, j0, n);
+        const int total = 2 * n;
+        for (int t = 0; t < total; ++t) {
+          const int j = j0 + (t >= n ? t - n : t);
+          for (int sl = 0; sl < 2; ++sl) {
+            mbar_wait(empty2 + slot, ph_slot ^ 1);
+            mbar_expect_tx(full2 + slot, SLOT2);
+            tma_load_3d(&tmB, full2 + slot, sRing2 + slot * SLOT2, h * HD + sl * 128, j * BN, b);
+            tma_load_3d(&tmB, full2 + slot, sRing2 + slot * SLOT2 + SLOT, h * HD + sl * 128 + 64, j * BN, b);
+            if (++slot == NS2) { slot = 0; ph_slot ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc1 = umma_idesc(BM, BN, p.half_in != 0);
-    const uint32_t idesc2 = umma_idesc(BM, 64, p.half_in != 0) | kIdescBMn;
-    int slot = 0;
-    uint32_t ph_slot = 0, ph_x = 0, ph_x2 = 0, ph_a2 = 0, g1 = 0, g2 = 0;
-    uint32_t ph_a1free[2] = {0, 0}, ph_hfull[2] = {0, 0};
-    auto next_slot = [&]() { if (++slot == NSLOT) { slot = 0; ph_slot ^= 1; } };
+    const uint32_t idesc1 = umma_idesc(BM, BN, HALF);
+    const uint32_t idesc2 = umma_idesc(BM, 128, HALF) | kIdescBMn;
+    int slot1 = 0, slot2 = 0;
+    uint32_t ph1 = 0, ph2 = 0, ph_x = 0, ph_x2 = 0, ph_a2 = 0, ph_hfull = 0, g1 = 0;
+    uint32_t ph_a1free[2] = {0, 0};
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b_, h_, mt_, j0_, n;
       decode(item, b_, h_, mt_, j0_, n);
@@ -193,16 +216,16 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint8_t* stat_op = prod ? sA2 : sA;
             const uint32_t t_d = t_acc1 + static_cast<uint32_t>(b * 128 + prod * 64);
             for (int kb = 0; kb < 4; ++kb) {
-              mbar_wait(full + slot, ph_slot);
+              mbar_wait(full1 + slot1, ph1);
               tc_fence_after();
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                   const uint64_t da = umma_desc_sw128(stat_op + kb * 16384, k * 32);
-                  const uint64_t db = umma_desc_sw128(sRing + slot * SLOT, k * 32);
+                  const uint64_t db = umma_desc_sw128(sRing1 + slot1 * SLOT, k * 32);
                   umma_f16(t_d, da, db, idesc1, (kb | k) != 0 ? 1u : 0u);
                 }
-                umma_commit(empty + slot);
+                umma_commit(empty1 + slot1);
                 if (prod == 1 && kb == 3) {
                   umma_commit(a1_full + b);
                   if (tt == n - 1 || tt == total - 1) umma_commit(x2_free);
@@ -210,38 +233,37 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 }
               }
               __syncwarp();
-              next_slot();
+              if (++slot1 == NS1) { slot1 = 0; ph1 ^= 1; }
             }
           }
         }
         if (tt >= 1) {
-          const int t = tt - 1, b = g2 & 1;
-          ++g2;
+          const int t = tt - 1;
           if (t == 0) {
             mbar_wait(a2_free, ph_a2 ^ 1);
             ph_a2 ^= 1;
           }
-          mbar_wait(h_full + b, ph_hfull[b]);
-          ph_hfull[b] ^= 1;
+          mbar_wait(h_full, ph_hfull);
+          ph_hfull ^= 1;
           tc_fence_after();
-          for (int sl = 0; sl < 4; ++sl) {
-            mbar_wait(full + slot, ph_slot);
+          for (int sl = 0; sl < 2; ++sl) {
+            mbar_wait(full2 + slot2, ph2);
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {                 // K = 64 streamed rows, 16 per instruction
-                const uint64_t da = umma_desc_sw128(sP + b * P_BYTES, k * 32);
-                const uint64_t db = umma_desc_mn_sw128(sRing + slot * SLOT, k * 2048, 8192u);
-                umma_f16(t_acc2 + static_cast<uint32_t>(sl * 64), da, db, idesc2, (t | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < 4; ++k) {                 // K = 64 streamed rows, 16 per instruction; N = 128: two slabs 8 KiB apart
+                const uint64_t da = umma_desc_sw128(sP, k * 32);
+                const uint64_t db = umma_desc_mn_sw128(sRing2 + slot2 * SLOT2, k * 2048, 8192u);
+                umma_f16(t_acc2 + static_cast<uint32_t>(sl * 128), da, db, idesc2, (t | k) != 0 ? 1u : 0u);
               }
-              umma_commit(empty + slot);
-              if (sl == 3) {
-                umma_commit(h_free + b);
+              umma_commit(empty2 + slot2);
+              if (sl == 1) {
+                umma_commit(h_free);
                 if (t == total - 1) umma_commit(a2_full);
               }
             }
             __syncwarp();
-            next_slot();
+            if (++slot2 == NS2) { slot2 = 0; ph2 ^= 1; }
           }
         }
       }
@@ -251,8 +273,7 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int quarter = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter; which 32 of a tile's 64 columns
     const int trow = quarter * 32 + lane;
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
-    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0, g = 0;
-    uint8_t* stile = sP + (half * 4 + quarter) * 4096;        // final-stage staging; shared with the partner warp's mid stage
+    uint32_t ph_a1full[2] = {0, 0}, ph_hfree = 0, ph_a2 = 0, g = 0;
     const int la_pad = p.mtiles * BM, lb_pad = (p.ctiles * BN + 127) / 128 * 128;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b, h, mt, j0, n;
@@ -265,23 +286,35 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tt = 0; tt < total; ++tt, ++g) {
         const int bb = g & 1;
         const int pass = tt >= n ? 1 : 0, j = j0 + (pass ? tt - n : tt);
+        const int col0 = j * BN + half * 32;
+        // per-column inputs of this tile are fetched before waiting for its accumulators
+        uint4 mk[2];
+        float4 cst[8], cdl[8];
+        if (pass == 0) {
+          const uint4* mp = reinterpret_cast<const uint4*>(p.mask_b + static_cast<size_t>(b) * lb_pad + col0);
+          mk[0] = __ldg(mp); mk[1] = __ldg(mp + 1);
+        } else {
+          const size_t sb = (static_cast<size_t>(b) * p.H + h) * lb_pad + col0;
+          const float4* cs = reinterpret_cast<const float4*>(p.col_stat + sb);
+          const float4* cd = reinterpret_cast<const float4*>(p.col_delta + sb);
+#pragma unroll
+          for (int c4 = 0; c4 < 8; ++c4) { cst[c4] = __ldg(cs + c4); cdl[c4] = __ldg(cd + c4); }
+        }
         mbar_wait(a1_full + bb, ph_a1full[bb]);
         ph_a1full[bb] ^= 1;
         tc_fence_after();
         uint32_t rs[32], rd[32];
-        tmem_ld32(t_acc1 + lane_bits + static_cast<uint32_t>(bb * 128 + half * 32), rs);
-        tmem_ld32(t_acc1 + lane_bits + static_cast<uint32_t>(bb * 128 + 64 + half * 32), rd);
+        tmem_ld32_nowait(t_acc1 + lane_bits + static_cast<uint32_t>(bb * 128 + half * 32), rs);
+        tmem_ld32_nowait(t_acc1 + lane_bits + static_cast<uint32_t>(bb * 128 + 64 + half * 32), rd);
+        tmem_ld_wait();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_free + bb);
-        const int col0 = j * BN + half * 32;
         float v[32];
         if (pass == 0) {
-          const uint4* mp = reinterpret_cast<const uint4*>(p.mask_b + static_cast<size_t>(b) * lb_pad + col0);
 #pragma unroll
           for (int q4 = 0; q4 < 2; ++q4) {
-            const uint4 mk = __ldg(mp + q4);
-            const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+            const uint32_t w[4] = {mk[q4].x, mk[q4].y, mk[q4].z, mk[q4].w};
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               const int c = q4 * 16 + i;
@@ -291,12 +324,9 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else {
-          const size_t sb = (static_cast<size_t>(b) * p.H + h) * lb_pad + col0;
-          const float4* cs = reinterpret_cast<const float4*>(p.col_stat + sb);
-          const float4* cd = reinterpret_cast<const float4*>(p.col_delta + sb);
 #pragma unroll
           for (int c4 = 0; c4 < 8; ++c4) {
-            const float4 st = __ldg(cs + c4), dl = __ldg(cd + c4);
+            const float4 st = cst[c4], dl = cdl[c4];
             const float stv[4] = {st.x, st.y, st.z, st.w}, dlv[4] = {dl.x, dl.y, dl.z, dl.w};
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -306,45 +336,40 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        mbar_wait(h_free + bb, ph_hfree[bb] ^ 1);
-        ph_hfree[bb] ^= 1;
         uint4 pk[4];
-        pack_16(v, p.half_in != 0, false, pk);
+        pack_16(v, HALF, false, pk);
+        mbar_wait(h_free, ph_hfree ^ 1);                      // GEMM2 of the previous tile has finished reading the dS tile
+        ph_hfree ^= 1;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(sP + bb * P_BYTES, trow, 4 * half + i)) = pk[i];
+        for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(sP, trow, 4 * half + i)) = pk[i];
         tc_fence_before();
         fence_async_smem();
         __syncwarp();
-        if (lane == 0) mbar_arrive(h_full + bb);
+        if (lane == 0) mbar_arrive(h_full);
       }
       // ---- final stage: acc2 * scale -> 16 bit (direct) or fp32 partial ----
       mbar_wait(a2_full, ph_a2);
       ph_a2 ^= 1;
       tc_fence_after();
       if (p.nsplit == 1) {
+        // 16-bit result straight from registers: 64 contiguous bytes per thread and 32-column group (whole sectors)
+        const bool live = arow < p.LA;          // the TMEM loads are warp-collective: only the stores are predicated
+        uint8_t* orow = static_cast<uint8_t*>(p.out16) +
+                        ((static_cast<size_t>(b) * p.LA + (live ? arow : 0)) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
 #pragma unroll 1
-        for (int gq = 0; gq < 2; ++gq) {
-          const int gc = half * 128 + gq * 64;
-          if (lane == 0) tma_store_wait_read();
-          __syncwarp();
+        for (int q4 = 0; q4 < 4; ++q4) {
+          uint32_t r[32];
+          float o[32];
+          tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32), r);
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            uint32_t r[32];
-            float o[32];
-            tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(gc + 32 * hf), r);
+          for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]) * p.scale;
+          uint4 pk[4];
+          pack_16(o, HALF, false, pk);
+          if (live) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]) * p.scale;
-            uint4 pk[4];
-            pack_16(o, p.half_in != 0, false, pk);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(stile, lane, 4 * hf + i)) = pk[i];
+            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + q4 * 64)[i] = pk[i];
           }
-          fence_async_smem();
-          __syncwarp();
-          if (lane == 0) tma_store_3d(&tmOut, stile, h * HD + gc, mt * BM + quarter * 32, b);
         }
-        if (lane == 0) tma_store_wait_read();
-        __syncwarp();
       } else {
         float* po = p.part_o + (static_cast<size_t>(item) * BM + trow) * HD + half * 128;
 #pragma unroll 1
@@ -359,10 +384,9 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      named_bar(1 + quarter, 64);          // the staging tile overlaps rows the partner warp writes in the next mid stage
+      __syncwarp();
       if (lane == 0) mbar_arrive(a2_free);
     }
-    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -442,12 +466,12 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
   p.scale = scale; p.scale_log2 = scale * 1.4426950408889634f;
   p.mask_a = mask_a_padded; p.mask_b = mask_b_padded;
   p.lane_stat = lane_stat; p.lane_delta = lane_delta; p.col_stat = col_stat; p.col_delta = col_delta;
-  p.part_o = part_o; p.half_in = is_half;
+  p.out16 = out16; p.part_o = part_o; p.half_in = is_half;
   if (p.nsplit == 1 && !out16) { snprintf(t_err, sizeof(t_err), "null output"); return MSDA_ERR_NULL_POINTER; }
   if (p.nsplit > 1 && !part_o) { snprintf(t_err, sizeof(t_err), "null partial buffer"); return MSDA_ERR_NULL_POINTER; }
   const int dt = is_half ? 1 : 0;
   const long long E = static_cast<long long>(H) * HD;
-  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmOut;
+  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b;
   int rc;
   if ((rc = make_map3(&tmA, a, B, LA, E, BM, dt))) return rc;
   if ((rc = make_map3(&tmA2a, d_oa, B, LA, E, BM, dt))) return rc;
@@ -455,7 +479,6 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
   if ((rc = make_map3(&tmB, b, B, LB, E, BN, dt))) return rc;
   if ((rc = make_map3(&tmX2a, xb, B, LB, E, BN, dt))) return rc;
   if ((rc = make_map3(&tmX2b, d_ob, B, LB, E, BN, dt))) return rc;
-  if ((rc = make_map3(&tmOut, out16 ? out16 : a, B, LA, E, 32, dt))) return rc;
   int dev_id = 0;
   cudaGetDevice(&dev_id);
   static int sms_of[64] = {};
@@ -465,12 +488,14 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
   const int grid = items < sms_of[dev_id & 63] ? static_cast<int>(items) : sms_of[dev_id & 63];
   static bool configured[64] = {};
   if (!configured[dev_id & 63]) {
-    cudaError_t cfg = cudaFuncSetAttribute(biattn_ds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t cfg = cudaFuncSetAttribute(biattn_ds_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (cfg == cudaSuccess) cfg = cudaFuncSetAttribute(biattn_ds_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
     if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
     configured[dev_id & 63] = true;
   }
   ++msda::g_launches;
-  biattn_ds_kernel<<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmOut, p);
+  if (is_half) biattn_ds_kernel<true><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, p);
+  else biattn_ds_kernel<false><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "biattn_ds_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;

@@ -14,12 +14,20 @@ exp(-50000) = 0 -- as long as each row's own maximum lies within 50 000 of the g
 trained model produces (they are O(10); tested up to spreads of thousands).  Outside that window the reference itself
 degenerates (a row entirely below the window is clamped flat and attends uniformly); that quirk is not reproduced.  So each
 direction is a plain softmax attention: computed from logits kept in the activation dtype (default), or as
-two fused scaled-dot-product-attention calls that never materialise it (``use_sdpa``).  Dense, tensor-core work: library
-kernels by design -- this row is not on the path SURVEY.md 8 names, it completes the encoder layer loop around it.
+two fused scaled-dot-product-attention calls that never materialise it (``use_sdpa``).
+
+Default for 16-bit CUDA tensors with 256-wide heads and no attention dropout (the reference configs: fusion_dropout = 0.0):
+the attention core runs on this package's own tcgen05 kernels (``biattn.py`` / csrc/layer_biattn*.cu) -- both directions
+from the projections' natural [B, L, heads*256] layout, logits and probabilities never leaving the SM, backward by
+recomputation from per-row log-sum-exp statistics.  The six projections are plain GEMMs and stay on the library.
 """
+import os
+
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
+
+from . import biattn
 
 
 class DropPath(nn.Module):
@@ -42,6 +50,8 @@ class BiMultiHeadAttention(nn.Module):
     # measured at the model's sizes, see tools/bench_fusion.py).  True: two fused scaled-dot-product-attention calls -- nothing of size n_img x n_text is ever
     # materialised (memory-lean; its backward for the 256-query x 22 223-key direction parallelises poorly today).
     use_sdpa = False
+    # True (default): the tcgen05 attention core when the tensors qualify (see the module docstring); the paths above otherwise
+    use_kernel = os.environ.get("MSDA_B200_BIATTN", "1") == "1"
 
     def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, cfg=None):
         super().__init__()
@@ -79,6 +89,15 @@ class BiMultiHeadAttention(nn.Module):
         bsz, n_img, _ = v.shape
         n_text = l.shape[1]
         n_img_in = n_img
+        p_drop = self.dropout if self.training else 0.0
+        if self.use_kernel and v.is_cuda and self.head_dim == biattn.HD and p_drop == 0.0:
+            q = self.v_proj(v)                      # the 1/sqrt(head_dim) scale is applied to the logits inside the kernel
+            if q.dtype in (torch.bfloat16, torch.float16):
+                k, val_v, val_l = self.l_proj(l), self.values_v_proj(v), self.values_l_proj(l)
+                if k.dtype == q.dtype == val_v.dtype == val_l.dtype:
+                    out_v, out_l = biattn.bi_attention_core(q, k, val_v, val_l, attention_mask_v, attention_mask_l,
+                                                            self.num_heads, self.scale)
+                    return self.out_v_proj(out_v), self.out_l_proj(out_l)
         if not self.use_sdpa and n_img % 8 and v.is_cuda:
             # S = 22 223 is odd: a [.., n_text, S] logits matrix then has rows that are not 16-byte aligned and the library
             # falls back to its unaligned GEMM / softmax kernels.  Pad the image tokens to a multiple of 8 with masked rows.
