@@ -429,35 +429,42 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const float inv = GIVEN ? 1.f : (l_tot > 0.f ? 1.f / l_tot : 0.f);
         if (!GIVEN && p.lane_stat != nullptr && half == 0 && live)
           p.lane_stat[(static_cast<size_t>(b) * p.H + h) * la_pad + arow] = l_tot > 0.f ? m_ref + log2f(l_tot) : CUDART_INF_F;
-        // 16-bit result straight from registers: 64 contiguous bytes per thread and 32-column group (whole sectors); the
-        // TMEM loads are warp-collective, only the stores are predicated
-        uint8_t* orow = static_cast<uint8_t*>(p.out16) +
-                        ((static_cast<size_t>(b) * p.LA + (live ? arow : 0)) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
+        // 16-bit result: TMEM -> registers -> this warp's 4 KiB of the (idle) P tile -> coalesced global stores
+        uint8_t* stage = sP + (half * 4 + quarter) * 4096;    // rows only this warp writes in the mid stage
+        const int row0 = mt * BM + quarter * 32;
+        const int rows_valid = p.LA - row0;
+        uint8_t* gbase = static_cast<uint8_t*>(p.out16) +
+                         ((static_cast<size_t>(b) * p.LA + row0) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
 #pragma unroll 1
-        for (int q4 = 0; q4 < 4; ++q4) {
-          uint32_t r[32];
-          float v[32];
-          tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32), r);
+        for (int gq = 0; gq < 2; ++gq) {
+          uint4 pk8[8];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv;
-          uint4 o4[4];
-          pack_16(v, HALF, false, o4);
-          if (live) {
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            float v[32];
+            tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + gq * 64 + hf * 32), r);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + q4 * 64)[i] = o4[i];
+            for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]) * inv;
+            uint4 o4[4];
+            pack_16(v, HALF, false, o4);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pk8[hf * 4 + i] = o4[i];
           }
+          store_rows_128B(stage, pk8, gbase + gq * 128, static_cast<size_t>(p.H) * HD * 2, lane, rows_valid);
         }
       } else {
-        float* po = p.part_o + (static_cast<size_t>(item) * BM + trow) * HD + half * 128;
+        // fp32 partial result of this warp's 32 rows x 128 columns, 32 columns (128 bytes per row) per staging pass
+        uint8_t* stage = sP + (half * 4 + quarter) * 4096;
+        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.part_o + (static_cast<size_t>(item) * BM + quarter * 32) * HD + half * 128);
 #pragma unroll 1
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t r[32];
           if (n > 0) tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32), r);
-          float4* dst = reinterpret_cast<float4*>(po + q4 * 32);
+          uint4 pk8[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            dst[i] = n > 0 ? make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]))
-                           : make_float4(0.f, 0.f, 0.f, 0.f);
+            pk8[i] = n > 0 ? make_uint4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]) : make_uint4(0u, 0u, 0u, 0u);
+          store_rows_128B(stage, pk8, gbase + q4 * 128, HD * 4, lane, 32);
         }
         if (!GIVEN && half == 0) {
           p.part_m[static_cast<size_t>(item) * BM + trow] = m_ref;

@@ -353,9 +353,12 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       if (p.nsplit == 1) {
         // 16-bit result straight from registers: 64 contiguous bytes per thread and 32-column group (whole sectors)
-        const bool live = arow < p.LA;          // the TMEM loads are warp-collective: only the stores are predicated
-        uint8_t* orow = static_cast<uint8_t*>(p.out16) +
-                        ((static_cast<size_t>(b) * p.LA + (live ? arow : 0)) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
+        // 16-bit result: TMEM -> registers -> 2 KiB of the (idle) dS tile per warp -> coalesced global stores
+        uint8_t* stage = sP + (warp - 2) * 2048;
+        const int row0 = mt * BM + quarter * 32;
+        const int rows_valid = p.LA - row0;
+        uint8_t* gbase = static_cast<uint8_t*>(p.out16) +
+                         ((static_cast<size_t>(b) * p.LA + row0) * (static_cast<size_t>(p.H) * HD) + h * HD + half * 128) * 2;
 #pragma unroll 1
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t r[32];
@@ -365,26 +368,29 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(r[i]) * p.scale;
           uint4 pk[4];
           pack_16(o, HALF, false, pk);
-          if (live) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow + q4 * 64)[i] = pk[i];
-          }
+          store_rows_64B(stage, pk, gbase + q4 * 64, static_cast<size_t>(p.H) * HD * 2, lane, rows_valid);
         }
       } else {
-        float* po = p.part_o + (static_cast<size_t>(item) * BM + trow) * HD + half * 128;
+        // fp32 partial result (already scaled): 16 columns (64 bytes per row) per staging pass
+        uint8_t* stage = sP + (warp - 2) * 2048;
+        uint8_t* gbase = reinterpret_cast<uint8_t*>(p.part_o + (static_cast<size_t>(item) * BM + quarter * 32) * HD + half * 128);
 #pragma unroll 1
         for (int q4 = 0; q4 < 4; ++q4) {
           uint32_t r[32];
           tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(half * 128 + q4 * 32), r);
-          float4* dst = reinterpret_cast<float4*>(po + q4 * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            dst[i] = make_float4(__uint_as_float(r[4 * i]) * p.scale, __uint_as_float(r[4 * i + 1]) * p.scale,
-                                 __uint_as_float(r[4 * i + 2]) * p.scale, __uint_as_float(r[4 * i + 3]) * p.scale);
+          for (int hq = 0; hq < 2; ++hq) {
+            uint4 pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              pk[i] = make_uint4(__float_as_uint(__uint_as_float(r[hq * 16 + 4 * i]) * p.scale), __float_as_uint(__uint_as_float(r[hq * 16 + 4 * i + 1]) * p.scale),
+                                 __float_as_uint(__uint_as_float(r[hq * 16 + 4 * i + 2]) * p.scale), __float_as_uint(__uint_as_float(r[hq * 16 + 4 * i + 3]) * p.scale));
+            store_rows_64B(stage, pk, gbase + q4 * 128 + hq * 64, HD * 4, lane, 32);
+          }
         }
       }
       tc_fence_before();
-      __syncwarp();
+      named_bar(1, 32 * EPI_WARPS);        // the staging pieces lie in rows other warps write in the next mid stage
       if (lane == 0) mbar_arrive(a2_free);
     }
   }

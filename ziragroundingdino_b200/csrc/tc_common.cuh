@@ -155,6 +155,35 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// A warp's 32 rows x 64 16-bit columns (lane = row, 8 x 16 bytes each) -> global memory, row stride ld_bytes, through a
+// 4 KiB shared staging tile so that every store instruction covers four whole 128-byte rows instead of 32 partial ones.
+__device__ __forceinline__ void store_rows_128B(uint8_t* stage, const uint4 (&pk)[8], uint8_t* gbase, size_t ld_bytes, int lane,
+                                                int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<uint4*>(swz(stage, lane, i)) = pk[i];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = (lane >> 3) + 4 * i, c = lane & 7;
+    const uint4 v = *reinterpret_cast<const uint4*>(swz(stage, r, c));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(r) * ld_bytes + c * 16) = v;
+  }
+  __syncwarp();
+}
+// the 64-byte-row variant (32 rows x 32 columns, 2 KiB staging): eight 64-byte row pieces per store instruction
+__device__ __forceinline__ void store_rows_64B(uint8_t* stage, const uint4 (&pk)[4], uint8_t* gbase, size_t ld_bytes, int lane,
+                                               int rows_valid) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + lane * 64 + ((i ^ ((lane >> 1) & 3)) << 4)) = pk[i];
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i, c = lane & 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 64 + ((c ^ ((r >> 1) & 3)) << 4));
+    if (r < rows_valid) *reinterpret_cast<uint4*>(gbase + static_cast<size_t>(r) * ld_bytes + c * 16) = v;
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void named_bar(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 }  // namespace pg
