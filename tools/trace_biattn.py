@@ -1,5 +1,6 @@
 """Pipeline-wait breakdown of biattn_pv_kernel (debug counters, cycles summed per CTA): where the MMA issuer and one
-mid-stage warp spend their time, rows and tokens orientation at the model's size."""
+mid-stage warp spend their time, rows and tokens orientation at the model's size.
+Needs a traced build: MSDA_NVCC_EXTRA=-DBIA_TRACE bash ziragroundingdino_b200/csrc/build.sh (the default build has no counters)."""
 import ctypes, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

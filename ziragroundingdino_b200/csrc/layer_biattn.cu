@@ -83,7 +83,15 @@ constexpr int SLOT2 = 2 * SLOT;         // two 64-column slabs of X, contiguous:
 constexpr int PV_THREADS = THREADS + 32; // + the second TMA producer warp
 constexpr int PV_SMEM = A_BYTES + NS1 * SLOT + NS2 * SLOT2 + P_BYTES + 2 * 2 * BM * 4 + 256;     // 231 680 of 232 448 bytes
 
+// -DBIA_TRACE (MSDA_NVCC_EXTRA=-DBIA_TRACE csrc/build.sh) builds the pipeline-wait counters in for tools/trace_biattn.py;
+// otherwise the waits are plain and the counters fold away
+#ifdef BIA_TRACE
 #define TWAIT(bar, par, ctr) do { const long long t0_ = clock64(); mbar_wait(bar, par); (ctr) += clock64() - t0_; } while (0)
+#define TCLK() clock64()
+#else
+#define TWAIT(bar, par, ctr) mbar_wait(bar, par)
+#define TCLK() 0ll
+#endif
 
 template <bool HALF, bool GIVEN>
 __global__ void __launch_bounds__(PV_THREADS, 1)
@@ -202,7 +210,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t ph1 = 0, ph2 = 0, ph_x = 0, ph_a2 = 0, ph_hfull = 0, g1 = 0;     // g1: running tile counter of GEMM1
     uint32_t ph_a1free[2] = {0, 0};
     long long tc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
+    const long long t_begin = TCLK();
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b_, h_, mt_, j0_, n;
       decode(item, b_, h_, mt_, j0_, n);
@@ -268,7 +276,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
     if (p.trace != nullptr && lane == 0) {
-      tc[6] = clock64() - t_begin;
+      tc[6] = TCLK() - t_begin;
       for (int i = 0; i < 8; ++i) p.trace[blockIdx.x * 16 + i] = tc[i];
     }
   } else {
@@ -278,7 +286,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
     uint32_t ph_a1full[2] = {0, 0}, ph_hfree = 0, ph_a2 = 0, g = 0;
     long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
+    const long long t_begin = TCLK();
     const int lb_pad = p.ctiles * BN, la_pad = p.mtiles * BM;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int b, h, mt, j0, n;
@@ -309,11 +317,11 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         uint32_t r0[32], r1[32];
         const uint32_t t_s = t_acc1 + lane_bits + static_cast<uint32_t>(bb * BN + half * 64);
-        { const long long t0_ = clock64();
+        { const long long t0_ = TCLK();
         tmem_ld32_nowait(t_s, r0);
         tmem_ld32_nowait(t_s + 32u, r1);
         tmem_ld_wait();
-        te[5] += clock64() - t0_; }
+        te[5] += TCLK() - t0_; }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(a1_free + bb);             // logits are in registers: GEMM1 of tile g + 2 may overwrite them
@@ -349,7 +357,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           float tmax = fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * p.scale_log2;
           float* mx = sMax + bb * 2 * BM;
           mx[half * BM + trow] = tmax;
-          { const long long t0_ = clock64(); named_bar(1 + quarter, 64); te[1] += clock64() - t0_; }
+          { const long long t0_ = TCLK(); named_bar(1 + quarter, 64); te[1] += TCLK() - t0_; }
           tmax = fmaxf(tmax, mx[(half ^ 1) * BM + trow]);
           need = tmax > m_ref + kRaise;                       // also true for the first finite tile (m_ref = -inf)
           if (need) {
@@ -374,7 +382,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         // exponentials and packing overlap GEMM2 of the previous tile, which still reads the P tile
-        const long long t_exp = clock64();
+        const long long t_exp = TCLK();
         uint4 pk[8];
         float ls[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -391,7 +399,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int i = 0; i < 4; ++i) pk[hf * 4 + i] = o4[i];
         }
         l_part += (ls[0] + ls[1]) + (ls[2] + ls[3]);
-        te[7] += clock64() - t_exp;
+        te[7] += TCLK() - t_exp;
         TWAIT(h_free, ph_hfree ^ 1, te[2]);                      // GEMM2 of tile g - 1 retired: P tile and accumulator are ours
         ph_hfree ^= 1;
         if (jj > 0 && __any_sync(0xffffffffu, need)) {
@@ -422,7 +430,7 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ph_a2 ^= 1;
         tc_fence_after();
       }
-      const long long t_fin = clock64();
+      const long long t_fin = TCLK();
       sSum[half * BM + trow] = l_part;
       named_bar(1 + quarter, 64);
       const float l_tot = l_part + sSum[(half ^ 1) * BM + trow];
@@ -478,10 +486,10 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(a2_free);
       }
-      te[4] += clock64() - t_fin;
+      te[4] += TCLK() - t_fin;
     }
     if (p.trace != nullptr && warp == 2 && lane == 0) {
-      te[6] = clock64() - t_begin;
+      te[6] = TCLK() - t_begin;
       for (int i = 0; i < 8; ++i) p.trace[blockIdx.x * 16 + 8 + i] = te[i];
     }
   }
