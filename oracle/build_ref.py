@@ -7,7 +7,7 @@ incompatibility with torch 2.11 (csrc/MsDeformAttn/ms_deform_attn_cuda.cu:65,:13
 force-including `oracle/ref_shim.h`; the reference's own build system (setup.py) is not run.
 
 The resulting `.so` is a torch extension for sm_100a.  It is only ever *loaded* by the `-m gpu`
-tests and by `bench.py --ab-ref` as the GPU-side A/B oracle; the product never imports it.
+tests and by `bench.py (key `ref_cuda_us_per_layer`)` as the GPU-side A/B oracle; the product never imports it.
 """
 import os
 import subprocess
