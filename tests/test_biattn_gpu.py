@@ -114,9 +114,11 @@ def _ref_core(q, k, vv, vl, mv, ml, H, scale):
     return ov.transpose(1, 2).reshape(B, S, H * hd), ol.transpose(1, 2).reshape(B, ol.shape[2], H * hd)
 
 
+@pytest.mark.parametrize("store_ds", [True, False])
 @pytest.mark.parametrize("S,T,masked", [(300, 200, True), (1000, 256, False), (2500, 48, True)])
-def test_core_function_forward_backward_vs_fp64(S, T, masked):
+def test_core_function_forward_backward_vs_fp64(S, T, masked, store_ds, monkeypatch):
     from ziragroundingdino_b200 import biattn
+    monkeypatch.setattr(biattn, "STORE_DS", store_ds)
     B, H, scale, dtype = 2, 2, 1.0 / 16, torch.bfloat16
     q, k = _mk(B, S, H, dtype, seed=11).requires_grad_(True), _mk(B, T, H, dtype, seed=12).requires_grad_(True)
     vv, vl = _mk(B, S, H, dtype, seed=13).requires_grad_(True), _mk(B, T, H, dtype, seed=14).requires_grad_(True)

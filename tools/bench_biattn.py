@@ -76,6 +76,7 @@ ov, sv = biattn.pv(q, k, vl, H, scale, mlp)
 ol, sl = biattn.pv(k, q, vv, H, scale, mvp, nsplit=ns)
 dv, dl = biattn.rowdot(gv, ov, H), biattn.rowdot(gl, ol, H)
 unit = 2.0 * B * H * S * T * 256          # one logits-sized product, FLOP
+_, terms_ = biattn.ds(q, gv, vv, k, vl, gl, H, scale, mvp, mlp, sv, dv, sl, dl, want_terms=True)
 legs = [
     ("pv rows online (out_v)", lambda: biattn.pv(q, k, vl, H, scale, mlp), 2),
     ("pv tokens online (out_l) + combine, nsplit=%d" % ns, lambda: biattn.pv(k, q, vv, H, scale, mvp, nsplit=ns), 2),
@@ -83,12 +84,14 @@ legs = [
     ("pv tokens given (d_val_l) + combine", lambda: biattn.pv(k, q, gv, H, scale, mlp, col_stat=sv, nsplit=ns), 2),
     ("pv rows given (d_val_v)", lambda: biattn.pv(q, k, gl, H, scale, mvp, col_stat=sl), 2),
     ("ds rows (d_q)", lambda: biattn.ds(q, gv, vv, k, vl, gl, H, scale, mvp, mlp, sv, dv, sl, dl), 6),
-    ("ds tokens (d_k) + combine, nsplit=%d" % ns64, lambda: biattn.ds(k, gl, vl, q, vv, gv, H, scale, mlp, mvp, sl, dl, sv, dv, nsplit=ns64), 6),
+    ("ds rows (d_q) storing dS terms", lambda: biattn.ds(q, gv, vv, k, vl, gl, H, scale, mvp, mlp, sv, dv, sl, dl, want_terms=True), 6),
+    ("tn (d_k from stored terms) + combine", lambda: biattn.tn(terms_, q, H, scale, T), 2),
+    ("ds tokens (d_k, recompute) + combine, nsplit=%d" % ns64, lambda: biattn.ds(k, gl, vl, q, vv, gv, H, scale, mlp, mvp, sl, dl, sv, dv, nsplit=ns64), 6),
 ]
 tot_f = tot_b = 0.0
 for i, (name, fn, units) in enumerate(legs):
     us = t(fn)
     emit(dict(kernel=name, us=us, tflops=units * unit / us / 1e6 if units else None))
     if i < 2: tot_f += us
-    else: tot_b += us
+    elif "recompute" not in name and name != "ds rows (d_q)": tot_b += us
 emit(dict(core_fwd_us=tot_f, core_bwd_us=tot_b, logits_product_gflop=unit / 1e9))

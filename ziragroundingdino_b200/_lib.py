@@ -75,6 +75,9 @@ def lib():
     L.msda_biattn_combine_16.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp]
     L.msda_biattn_ds_splits.argtypes = [_i, _i]
     L.msda_biattn_ds_16.argtypes = [_vp] * 6 + [_i] * 4 + [ctypes.c_float] + [_vp] * 8 + [_i, _i, _vp]
+    L.msda_biattn_ds_terms_16.argtypes = [_vp] * 6 + [_i] * 4 + [ctypes.c_float] + [_vp] * 8 + [_i, _vp]
+    L.msda_biattn_tn_splits.argtypes = [_i, _i]
+    L.msda_biattn_tn_16.argtypes = [_vp, _vp, _i, _i, _i, _i, ctypes.c_float, _vp, _vp, _i, _i, _vp]
     L.msda_biattn_rowdot_16.argtypes = [_vp, _vp, _i, _i, _i, _i, _vp, _i, _vp]
     L.msda_b200_probe_gather.argtypes = [_vp, _ll, _i, _i, _i, _vp, _vp]
     L.msda_b200_probe_scatter.argtypes = [_vp, _ll, _i, _i, _i, _vp]

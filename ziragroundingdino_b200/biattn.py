@@ -118,8 +118,11 @@ def rowdot(d_o, o, heads):
     return delta
 
 
-def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat, col_delta, nsplit=1):
-    """dA[B, LA, E] = scale * dS . b with dS the logits gradient of both softmax directions (csrc/layer_biattn_bwd.cu)."""
+def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat, col_delta, nsplit=1,
+       want_terms=False):
+    """dA[B, LA, E] = scale * dS . b with dS the logits gradient of both softmax directions (csrc/layer_biattn_bwd.cu).
+    want_terms: also return the two terms of dS as a 16-bit [2, B, H, LA, ceil(LB/64)*64] tensor (unsplit launches only) --
+    `tn` turns them into the gradient of the streamed side without recomputing anything."""
     B, LA, E = a.shape
     LB = b.shape[1]
     for t in (a, d_oa, xa, b, xb, d_ob):
@@ -132,6 +135,16 @@ def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lan
     nsplit = L.msda_biattn_ds_splits(LB, int(nsplit))
     out = torch.empty((B, LA, E), dtype=a.dtype, device=dev)
     is_half = 1 if a.dtype == torch.float16 else 0
+    if want_terms:
+        assert nsplit == 1
+        terms = torch.empty((2, B, heads, LA, (LB + 63) // 64 * 64), dtype=a.dtype, device=dev)
+        with torch.cuda.device(dev):
+            rc = L.msda_biattn_ds_terms_16(a.data_ptr(), d_oa.data_ptr(), xa.data_ptr(), b.data_ptr(), xb.data_ptr(), d_ob.data_ptr(), B,
+                                           heads, LA, LB, float(scale), mask_a_padded.data_ptr(), mask_b_padded.data_ptr(),
+                                           lane_stat.data_ptr(), lane_delta.data_ptr(), col_stat.data_ptr(), col_delta.data_ptr(),
+                                           out.data_ptr(), terms.data_ptr(), is_half, _stream(a))
+        _lib.check(rc, "msda_biattn_ds_terms_16")
+        return out, terms
     po = None
     if nsplit > 1:
         po = torch.empty((B * heads * ((LA + TILE - 1) // TILE) * nsplit, TILE, HD), dtype=torch.float32, device=dev)
@@ -145,6 +158,35 @@ def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lan
             rc = L.msda_biattn_combine_16(_ptr(po), 0, 0, B, heads, LA, nsplit, 1, out.data_ptr(), 0, is_half, _stream(a))
             _lib.check(rc, "msda_biattn_combine_16")
     return out
+
+
+def tn(terms, q, heads, scale, T, nsplit=None):
+    """d k[B, T, E] = scale * (terms[0] + terms[1])^T . q per head (csrc/layer_biattn_tn.cu); terms from ds(..., want_terms=True)."""
+    _, B, H, S, tpad = terms.shape
+    assert terms.is_contiguous() and q.is_contiguous() and H == heads and tuple(q.shape) == (B, S, heads * HD) and tpad == (T + 63) // 64 * 64
+    L = _lib.lib()
+    dev = q.device
+    if nsplit is None:
+        nsplit = default_splits(B, heads, T, S, dev, tile=64)
+    nsplit = L.msda_biattn_tn_splits(S, int(nsplit))
+    out = torch.empty((B, T, heads * HD), dtype=q.dtype, device=dev)
+    is_half = 1 if q.dtype == torch.float16 else 0
+    po = None
+    if nsplit > 1:
+        po = torch.empty((B * heads * ((T + TILE - 1) // TILE) * nsplit, TILE, HD), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.msda_biattn_tn_16(terms.data_ptr(), q.data_ptr(), B, heads, S, T, float(scale), out.data_ptr(), _ptr(po), nsplit, is_half,
+                                 _stream(q))
+        _lib.check(rc, "msda_biattn_tn_16")
+        if nsplit > 1:
+            rc = L.msda_biattn_combine_16(_ptr(po), 0, 0, B, heads, T, nsplit, 1, out.data_ptr(), 0, is_half, _stream(q))
+            _lib.check(rc, "msda_biattn_combine_16")
+    return out
+
+
+# True (default): the rows-orientation logits-gradient launch stores its dS tiles (16 bit, 2 x B*H*S*256 elements) and d k is
+# one product over them; False: d k recomputes logits and dP in the tokens orientation (nothing logits-sized in memory).
+STORE_DS = __import__("os").environ.get("MSDA_B200_BIATTN_STORE_DS", "1") == "1"
 
 
 class BiAttentionCoreFunction(Function):
@@ -181,9 +223,13 @@ class BiAttentionCoreFunction(Function):
         d_val_l, _ = pv(k, q, d_out_v, heads, scale, ml, col_stat=stat_v, nsplit=ns_tok)
         d_val_v, _ = pv(q, k, d_out_l, heads, scale, mv, col_stat=stat_l)
         # queries / keys: the logits gradient of both directions times the other operand
-        d_q = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l)
-        d_k = ds(k, d_out_l, val_l, q, val_v, d_out_v, heads, scale, ml, mv, stat_l, delta_l, stat_v, delta_v,
-                 nsplit=default_splits(B, heads, T, S, dev, tile=64))
+        if STORE_DS:
+            d_q, terms = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l, want_terms=True)
+            d_k = tn(terms, q, heads, scale, T)
+        else:
+            d_q = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l)
+            d_k = ds(k, d_out_l, val_l, q, val_v, d_out_v, heads, scale, ml, mv, stat_l, delta_l, stat_v, delta_v,
+                     nsplit=default_splits(B, heads, T, S, dev, tile=64))
         return d_q, d_k, d_val_v, d_val_l, None, None, None, None
 
 

@@ -64,6 +64,7 @@ struct DsParams {
   const float* col_stat;         // [B, H, lb_pad]                                          (pass 1)
   const float* col_delta;        // [B, H, lb_pad]                                          (pass 1)
   void* out16;                   // nsplit == 1: [B, LA, H*256] 16-bit result
+  int store_terms;               // also write the two dS terms (16 bit, [B, H, LA, ctiles*64] each) through tmT0 / tmT1
   float* part_o;                 // nsplit > 1: [items, 128, 256] fp32 partial results (already scaled)
   int half_in;
 };
@@ -72,7 +73,8 @@ template <bool HALF>
 __global__ void __launch_bounds__(THREADS, 1)
 biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2a,
                  const __grid_constant__ CUtensorMap tmA2b, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmX2a, const __grid_constant__ CUtensorMap tmX2b, DsParams p) {
+                 const __grid_constant__ CUtensorMap tmX2a, const __grid_constant__ CUtensorMap tmX2b,
+                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, DsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -93,7 +95,8 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* a1_free = a1_full + 2;    // [2]
   uint64_t* h_full = a1_free + 2;     // dS tile written
   uint64_t* h_free = h_full + 1;      // GEMM2 of that tile retired
-  uint64_t* a2_full = h_free + 1;
+  uint64_t* st_free = h_free + 1;     // the dS tile has been read by its TMA store (store_terms only)
+  uint64_t* a2_full = st_free + 1;
   uint64_t* a2_free = a2_full + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_free + 1);
 
@@ -107,7 +110,7 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int i = 0; i < NS2; ++i) { mbar_init(full2 + i, 1); mbar_init(empty2 + i, 1); }
     mbar_init(x_full, 1); mbar_init(x_free, 1); mbar_init(x2_full, 1); mbar_init(x2_free, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); }
-    mbar_init(h_full, EPI_WARPS); mbar_init(h_free, 1);
+    mbar_init(h_full, EPI_WARPS); mbar_init(h_free, 1); mbar_init(st_free, 1);
     mbar_init(a2_full, 1); mbar_init(a2_free, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -167,16 +170,17 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 2 + EPI_WARPS) {
-    // ===== TMA producer 2: the GEMM2 operand (B_t again, as slabs) through ring 2 =====
+    // ===== TMA producer 2: the GEMM2 operand (B_t again, as half-tiles) through ring 2; with store_terms it also sends each
+    // finished dS tile to global memory (the tokens-orientation product reads it back instead of recomputing it) =====
     if (elect_one()) {
       int slot = 0;
-      uint32_t ph_slot = 0;
+      uint32_t ph_slot = 0, ph_hfull = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         int b, h, mt, j0, n;
         decode(item, b, h, mt, j0, n);
         const int total = 2 * n;
         for (int t = 0; t < total; ++t) {
-          const int j = j0 + (t >= n ? t - n : t);
+          const int pass = t >= n ? 1 : 0, j = j0 + (pass ? t - n : t);
           for (int sl = 0; sl < 2; ++sl) {
             mbar_wait(empty2 + slot, ph_slot ^ 1);
             mbar_expect_tx(full2 + slot, SLOT2);
@@ -184,8 +188,16 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tma_load_3d(&tmB, full2 + slot, sRing2 + slot * SLOT2 + SLOT, h * HD + sl * 128 + 64, j * BN, b);
             if (++slot == NS2) { slot = 0; ph_slot ^= 1; }
           }
+          if (p.store_terms) {
+            mbar_wait(h_full, ph_hfull);          // the mid stage has written (and proxy-fenced) the tile
+            ph_hfull ^= 1;
+            tma_store_4d(pass ? &tmT1 : &tmT0, sP, j * BN, mt * BM, h, b);
+            tma_store_wait_read();
+            mbar_arrive(st_free);
+          }
         }
       }
+      if (p.store_terms) tma_store_wait_all();
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -340,6 +352,7 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         pack_16(v, HALF, false, pk);
         mbar_wait(h_free, ph_hfree ^ 1);                      // GEMM2 of the previous tile has finished reading the dS tile
         ph_hfree ^= 1;
+        if (p.store_terms) mbar_wait(st_free, ph_hfree);      // ... and so has its store (same phase sequence as h_free)
 #pragma unroll
         for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(sP, trow, 4 * half + i)) = pk[i];
         tc_fence_before();
@@ -351,6 +364,7 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(a2_full, ph_a2);
       ph_a2 ^= 1;
       tc_fence_after();
+      if (p.store_terms) mbar_wait(st_free, ph_hfree ^ 1);  // the last tile's store has read the dS tile: it becomes staging space
       if (p.nsplit == 1) {
         // 16-bit result straight from registers: 64 contiguous bytes per thread and 32-column group (whole sectors)
         // 16-bit result: TMEM -> registers -> 2 KiB of the (idle) dS tile per warp -> coalesced global stores
@@ -450,10 +464,10 @@ int msda_biattn_ds_splits(int LB, int nsplit) {
   return (ctiles + tps - 1) / tps;
 }
 
-int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const void* b, const void* xb, const void* d_ob, int B,
-                      int H, int LA, int LB, float scale, const uint8_t* mask_a_padded, const uint8_t* mask_b_padded,
-                      const float* lane_stat, const float* lane_delta, const float* col_stat, const float* col_delta,
-                      void* out16, float* part_o, int nsplit, int is_half, void* stream) {
+static int biattn_ds_impl(const void* a, const void* d_oa, const void* xa, const void* b, const void* xb, const void* d_ob, int B,
+                          int H, int LA, int LB, float scale, const uint8_t* mask_a_padded, const uint8_t* mask_b_padded,
+                          const float* lane_stat, const float* lane_delta, const float* col_stat, const float* col_delta,
+                          void* out16, float* part_o, void* terms, int nsplit, int is_half, void* stream) {
   using namespace pg;
   using namespace pg::bid;
   t_err[0] = 0;
@@ -477,7 +491,7 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
   if (p.nsplit > 1 && !part_o) { snprintf(t_err, sizeof(t_err), "null partial buffer"); return MSDA_ERR_NULL_POINTER; }
   const int dt = is_half ? 1 : 0;
   const long long E = static_cast<long long>(H) * HD;
-  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b;
+  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1;
   int rc;
   if ((rc = make_map3(&tmA, a, B, LA, E, BM, dt))) return rc;
   if ((rc = make_map3(&tmA2a, d_oa, B, LA, E, BM, dt))) return rc;
@@ -485,6 +499,15 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
   if ((rc = make_map3(&tmB, b, B, LB, E, BN, dt))) return rc;
   if ((rc = make_map3(&tmX2a, xb, B, LB, E, BN, dt))) return rc;
   if ((rc = make_map3(&tmX2b, d_ob, B, LB, E, BN, dt))) return rc;
+  p.store_terms = terms != nullptr;
+  if (p.store_terms && p.nsplit != 1) { snprintf(t_err, sizeof(t_err), "dS terms are only written by unsplit launches"); return MSDA_ERR_UNSUPPORTED; }
+  {
+    const long long tpad = static_cast<long long>(p.ctiles) * BN;
+    const void* t0 = terms ? terms : a;        // placeholders keep the maps valid when nothing is stored
+    const void* t1 = terms ? static_cast<const uint8_t*>(terms) + static_cast<size_t>(B) * H * LA * tpad * 2 : a;
+    if ((rc = make_map4(&tmT0, t0, terms ? B : 1, terms ? H : 1, terms ? LA : BM, terms ? tpad : 64, BM, dt))) return rc;
+    if ((rc = make_map4(&tmT1, t1, terms ? B : 1, terms ? H : 1, terms ? LA : BM, terms ? tpad : 64, BM, dt))) return rc;
+  }
   int dev_id = 0;
   cudaGetDevice(&dev_id);
   static int sms_of[64] = {};
@@ -500,11 +523,28 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
     configured[dev_id & 63] = true;
   }
   ++msda::g_launches;
-  if (is_half) biattn_ds_kernel<true><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, p);
-  else biattn_ds_kernel<false><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, p);
+  if (is_half) biattn_ds_kernel<true><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1, p);
+  else biattn_ds_kernel<false><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "biattn_ds_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;
+}
+
+int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const void* b, const void* xb, const void* d_ob, int B,
+                      int H, int LA, int LB, float scale, const uint8_t* mask_a_padded, const uint8_t* mask_b_padded,
+                      const float* lane_stat, const float* lane_delta, const float* col_stat, const float* col_delta,
+                      void* out16, float* part_o, int nsplit, int is_half, void* stream) {
+  return biattn_ds_impl(a, d_oa, xa, b, xb, d_ob, B, H, LA, LB, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat,
+                        col_delta, out16, part_o, nullptr, nsplit, is_half, stream);
+}
+
+int msda_biattn_ds_terms_16(const void* a, const void* d_oa, const void* xa, const void* b, const void* xb, const void* d_ob, int B,
+                            int H, int LA, int LB, float scale, const uint8_t* mask_a_padded, const uint8_t* mask_b_padded,
+                            const float* lane_stat, const float* lane_delta, const float* col_stat, const float* col_delta,
+                            void* out16, void* terms16, int is_half, void* stream) {
+  if (!terms16) { snprintf(pg::t_err, sizeof(pg::t_err), "null terms buffer"); return MSDA_ERR_NULL_POINTER; }
+  return biattn_ds_impl(a, d_oa, xa, b, xb, d_ob, B, H, LA, LB, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat,
+                        col_delta, out16, nullptr, terms16, 1, is_half, stream);
 }
 
 int msda_biattn_rowdot_16(const void* d_o, const void* o, int B, int L, int H, int lpad, float* delta, int is_half, void* stream) {

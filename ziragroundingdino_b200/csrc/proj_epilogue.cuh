@@ -193,6 +193,8 @@ int make_map(CUtensorMap* map, const void* base, long long rows, long long cols,
 // [batch, rows, cols] tensor of 16-bit elements (row stride = cols), box = 1 x box_rows x 64 columns, 128-byte swizzle;
 // rows beyond `rows` read as zeros and are clipped on store (per batch entry -- the reason for the third dimension).
 int make_map3(CUtensorMap* map, const void* base, long long batch, long long rows, long long cols, int box_rows, int dtype);
+// [d3, d2, rows, cols] dense tensor of 16-bit elements, box = 1 x 1 x box_rows x 64 columns, 128-byte swizzle
+int make_map4(CUtensorMap* map, const void* base, long long d3, long long d2, long long rows, long long cols, int box_rows, int dtype);
 // in-place softmax over runs of `lp` consecutive fp32 values (L*P does not divide the 32-column epilogue chunk)
 int softmax_rows(float* x, long long runs, int lp, cudaStream_t st);
 

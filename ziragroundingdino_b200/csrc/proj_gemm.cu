@@ -566,6 +566,23 @@ int make_map3(CUtensorMap* map, const void* base, long long batch, long long row
   return 0;
 }
 
+int make_map4(CUtensorMap* map, const void* base, long long d3, long long d2, long long rows, long long cols, int box_rows, int dtype) {
+  thread_local bool ctx_bound = false;
+  if (!ctx_bound) { cudaFree(nullptr); ctx_bound = true; }
+  auto fn = encode_fn();
+  if (!fn) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled unavailable"); return MSDA_ERR_NO_DEVICE; }
+  cuuint64_t gdim[4] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(d2), static_cast<cuuint64_t>(d3)};
+  const cuuint64_t rb = static_cast<cuuint64_t>(cols) * 2;
+  cuuint64_t gstride[3] = {rb, rb * static_cast<cuuint64_t>(rows), rb * static_cast<cuuint64_t>(rows) * static_cast<cuuint64_t>(d2)};
+  cuuint32_t box[4] = {64u, static_cast<cuuint32_t>(box_rows), 1u, 1u};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = fn(map, dt, 4, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(t_err, sizeof(t_err), "cuTensorMapEncodeTiled (4-d) failed (%d)", static_cast<int>(r)); return MSDA_ERR_BAD_SHAPE; }
+  return 0;
+}
+
 // Widest n-block (multiple of `unit`, dividing Nout, <= 256 columns so two accumulators fit TMEM) whose slice of W
 // (block_n x K 16-bit) still fits in shared memory beside the activation ring; the smallest legal block otherwise.
 static int pick_block_n(int Nout, int K, int unit, bool f32_out) {
