@@ -310,9 +310,9 @@ int msda_encoder_proposals(const void *memory, const uint8_t *mask_flatten, cons
  *   col_stat[j]) masked by mask_a (stationary rows).  d q = ds(q, d out_v, val_v, k, val_l, d out_l, ...),
  *   d k = ds(k, d out_l, val_l, q, val_v, d out_v, ...).  nsplit as above (64-row column tiles; msda_biattn_ds_splits),
  *   partials merged by msda_biattn_combine_16(given = 1).
- * msda_biattn_ds_terms_16: the unsplit msda_biattn_ds_16 that also stores the two terms of dS (16 bit, two [B, H, LA,
- *   ceil(LB/64)*64] tensors back to back in terms16); msda_biattn_tn_16: d b = scale * (term0 + term1)^T . a from those, i.e.
- *   d k = tn(terms of the d q launch, q) without a second recomputation (image axis split as above, msda_biattn_tn_splits).
+ * msda_biattn_ds_terms_16: the unsplit msda_biattn_ds_16 that also stores dS (16 bit, [B, H, LA, ceil(LB/64)*64]; pass 0
+ *   stores its term, pass 1 adds its own with a TMA reduction); msda_biattn_tn_16: d b = scale * dS^T . a from it, i.e.
+ *   d k = tn(dS of the d q launch, q) without a second recomputation (image axis split as above, msda_biattn_tn_splits).
  * msda_biattn_set_trace: debug -- 16 int64 cycle counters per CTA of the next msda_biattn_pv_16 launches (NULL = off). */
 int msda_biattn_splits(int LB, int nsplit);
 int msda_biattn_pv_16(const void *a, const void *b, const void *x, int B, int H, int LA, int LB, float scale,
@@ -330,9 +330,9 @@ int msda_biattn_ds_16(const void *a, const void *d_oa, const void *xa, const voi
 int msda_biattn_ds_terms_16(const void *a, const void *d_oa, const void *xa, const void *b, const void *xb, const void *d_ob,
                             int B, int H, int LA, int LB, float scale, const uint8_t *mask_a_padded,
                             const uint8_t *mask_b_padded, const float *lane_stat, const float *lane_delta, const float *col_stat,
-                            const float *col_delta, void *out16, void *terms16, int is_half, void *stream);
+                            const float *col_delta, void *out16, void *ds16, int is_half, void *stream);
 int msda_biattn_tn_splits(int S, int nsplit);
-int msda_biattn_tn_16(const void *terms16, const void *q, int B, int H, int S, int T, float scale, void *out16, float *part_o,
+int msda_biattn_tn_16(const void *ds16, const void *q, int B, int H, int S, int T, float scale, void *out16, float *part_o,
                       int nsplit, int is_half, void *stream);
 void msda_biattn_set_trace(long long *buf);
 

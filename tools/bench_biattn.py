@@ -85,7 +85,7 @@ legs = [
     ("pv rows given (d_val_v)", lambda: biattn.pv(q, k, gl, H, scale, mvp, col_stat=sl), 2),
     ("ds rows (d_q)", lambda: biattn.ds(q, gv, vv, k, vl, gl, H, scale, mvp, mlp, sv, dv, sl, dl), 6),
     ("ds rows (d_q) storing dS terms", lambda: biattn.ds(q, gv, vv, k, vl, gl, H, scale, mvp, mlp, sv, dv, sl, dl, want_terms=True), 6),
-    ("tn (d_k from stored terms) + combine", lambda: biattn.tn(terms_, q, H, scale, T), 2),
+    ("tn (d_k from stored dS) + combine", lambda: biattn.tn(terms_, q, H, scale, T), 1),
     ("ds tokens (d_k, recompute) + combine, nsplit=%d" % ns64, lambda: biattn.ds(k, gl, vl, q, vv, gv, H, scale, mlp, mvp, sl, dl, sv, dv, nsplit=ns64), 6),
 ]
 tot_f = tot_b = 0.0

@@ -121,8 +121,8 @@ def rowdot(d_o, o, heads):
 def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat, col_delta, nsplit=1,
        want_terms=False):
     """dA[B, LA, E] = scale * dS . b with dS the logits gradient of both softmax directions (csrc/layer_biattn_bwd.cu).
-    want_terms: also return the two terms of dS as a 16-bit [2, B, H, LA, ceil(LB/64)*64] tensor (unsplit launches only) --
-    `tn` turns them into the gradient of the streamed side without recomputing anything."""
+    want_terms: also return dS as a 16-bit [B, H, LA, ceil(LB/64)*64] tensor (unsplit launches only; the second pass adds
+    onto the first with a TMA reduction).  `tn` turns it into the gradient of the streamed side without recomputing anything."""
     B, LA, E = a.shape
     LB = b.shape[1]
     for t in (a, d_oa, xa, b, xb, d_ob):
@@ -137,7 +137,7 @@ def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lan
     is_half = 1 if a.dtype == torch.float16 else 0
     if want_terms:
         assert nsplit == 1
-        terms = torch.empty((2, B, heads, LA, (LB + 63) // 64 * 64), dtype=a.dtype, device=dev)
+        terms = torch.empty((B, heads, LA, (LB + 63) // 64 * 64), dtype=a.dtype, device=dev)
         with torch.cuda.device(dev):
             rc = L.msda_biattn_ds_terms_16(a.data_ptr(), d_oa.data_ptr(), xa.data_ptr(), b.data_ptr(), xb.data_ptr(), d_ob.data_ptr(), B,
                                            heads, LA, LB, float(scale), mask_a_padded.data_ptr(), mask_b_padded.data_ptr(),
@@ -161,13 +161,13 @@ def ds(a, d_oa, xa, b, xb, d_ob, heads, scale, mask_a_padded, mask_b_padded, lan
 
 
 def tn(terms, q, heads, scale, T, nsplit=None):
-    """d k[B, T, E] = scale * (terms[0] + terms[1])^T . q per head (csrc/layer_biattn_tn.cu); terms from ds(..., want_terms=True)."""
-    _, B, H, S, tpad = terms.shape
+    """d k[B, T, E] = scale * dS^T . q per head (csrc/layer_biattn_tn.cu); terms = the dS of ds(..., want_terms=True)."""
+    B, H, S, tpad = terms.shape
     assert terms.is_contiguous() and q.is_contiguous() and H == heads and tuple(q.shape) == (B, S, heads * HD) and tpad == (T + 63) // 64 * 64
     L = _lib.lib()
     dev = q.device
-    if nsplit is None:
-        nsplit = default_splits(B, heads, T, S, dev, tile=64)
+    if nsplit is None:      # work items cover two 128-token tiles each
+        nsplit = default_splits(B, heads, (T + 1) // 2, S, dev, tile=64)
     nsplit = L.msda_biattn_tn_splits(S, int(nsplit))
     out = torch.empty((B, T, heads * HD), dtype=q.dtype, device=dev)
     is_half = 1 if q.dtype == torch.float16 else 0
@@ -184,7 +184,7 @@ def tn(terms, q, heads, scale, T, nsplit=None):
     return out
 
 
-# True (default): the rows-orientation logits-gradient launch stores its dS tiles (16 bit, 2 x B*H*S*256 elements) and d k is
+# True (default): the rows-orientation logits-gradient launch stores its dS tiles (16 bit, B*H*S*256 elements) and d k is
 # one product over them; False: d k recomputes logits and dP in the tokens orientation (nothing logits-sized in memory).
 STORE_DS = __import__("os").environ.get("MSDA_B200_BIATTN_STORE_DS", "1") == "1"
 

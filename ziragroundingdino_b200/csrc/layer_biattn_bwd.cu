@@ -64,7 +64,8 @@ struct DsParams {
   const float* col_stat;         // [B, H, lb_pad]                                          (pass 1)
   const float* col_delta;        // [B, H, lb_pad]                                          (pass 1)
   void* out16;                   // nsplit == 1: [B, LA, H*256] 16-bit result
-  int store_terms;               // also write the two dS terms (16 bit, [B, H, LA, ctiles*64] each) through tmT0 / tmT1
+  int store_terms;               // also write dS (16 bit, [B, H, LA, ctiles*64]) through tmT0: pass 0 stores its term,
+                                 // pass 1 adds its own with a TMA reduction
   float* part_o;                 // nsplit > 1: [items, 128, 256] fp32 partial results (already scaled)
   int half_in;
 };
@@ -74,7 +75,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2a,
                  const __grid_constant__ CUtensorMap tmA2b, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmX2a, const __grid_constant__ CUtensorMap tmX2b,
-                 const __grid_constant__ CUtensorMap tmT0, const __grid_constant__ CUtensorMap tmT1, DsParams p) {
+                 const __grid_constant__ CUtensorMap tmT0, DsParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
@@ -191,7 +192,12 @@ biattn_ds_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (p.store_terms) {
             mbar_wait(h_full, ph_hfull);          // the mid stage has written (and proxy-fenced) the tile
             ph_hfull ^= 1;
-            tma_store_4d(pass ? &tmT1 : &tmT0, sP, j * BN, mt * BM, h, b);
+            if (pass == 0) {
+              tma_store_4d(&tmT0, sP, j * BN, mt * BM, h, b);
+            } else {
+              if (t == n) tma_store_wait_all();     // every pass-0 store of this item has landed before anything is added to it
+              tma_reduce_add_4d(&tmT0, sP, j * BN, mt * BM, h, b);
+            }
             tma_store_wait_read();
             mbar_arrive(st_free);
           }
@@ -491,7 +497,7 @@ static int biattn_ds_impl(const void* a, const void* d_oa, const void* xa, const
   if (p.nsplit > 1 && !part_o) { snprintf(t_err, sizeof(t_err), "null partial buffer"); return MSDA_ERR_NULL_POINTER; }
   const int dt = is_half ? 1 : 0;
   const long long E = static_cast<long long>(H) * HD;
-  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1;
+  CUtensorMap tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0;
   int rc;
   if ((rc = make_map3(&tmA, a, B, LA, E, BM, dt))) return rc;
   if ((rc = make_map3(&tmA2a, d_oa, B, LA, E, BM, dt))) return rc;
@@ -504,9 +510,7 @@ static int biattn_ds_impl(const void* a, const void* d_oa, const void* xa, const
   {
     const long long tpad = static_cast<long long>(p.ctiles) * BN;
     const void* t0 = terms ? terms : a;        // placeholders keep the maps valid when nothing is stored
-    const void* t1 = terms ? static_cast<const uint8_t*>(terms) + static_cast<size_t>(B) * H * LA * tpad * 2 : a;
     if ((rc = make_map4(&tmT0, t0, terms ? B : 1, terms ? H : 1, terms ? LA : BM, terms ? tpad : 64, BM, dt))) return rc;
-    if ((rc = make_map4(&tmT1, t1, terms ? B : 1, terms ? H : 1, terms ? LA : BM, terms ? tpad : 64, BM, dt))) return rc;
   }
   int dev_id = 0;
   cudaGetDevice(&dev_id);
@@ -523,8 +527,8 @@ static int biattn_ds_impl(const void* a, const void* d_oa, const void* xa, const
     configured[dev_id & 63] = true;
   }
   ++msda::g_launches;
-  if (is_half) biattn_ds_kernel<true><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1, p);
-  else biattn_ds_kernel<false><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, tmT1, p);
+  if (is_half) biattn_ds_kernel<true><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, p);
+  else biattn_ds_kernel<false><<<grid, THREADS, SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmA, tmA2a, tmA2b, tmB, tmX2a, tmX2b, tmT0, p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { snprintf(t_err, sizeof(t_err), "biattn_ds_kernel launch: %s", cudaGetErrorString(e)); return static_cast<int>(e); }
   return 0;
@@ -541,10 +545,10 @@ int msda_biattn_ds_16(const void* a, const void* d_oa, const void* xa, const voi
 int msda_biattn_ds_terms_16(const void* a, const void* d_oa, const void* xa, const void* b, const void* xb, const void* d_ob, int B,
                             int H, int LA, int LB, float scale, const uint8_t* mask_a_padded, const uint8_t* mask_b_padded,
                             const float* lane_stat, const float* lane_delta, const float* col_stat, const float* col_delta,
-                            void* out16, void* terms16, int is_half, void* stream) {
-  if (!terms16) { snprintf(pg::t_err, sizeof(pg::t_err), "null terms buffer"); return MSDA_ERR_NULL_POINTER; }
+                            void* out16, void* ds16, int is_half, void* stream) {
+  if (!ds16) { snprintf(pg::t_err, sizeof(pg::t_err), "null dS buffer"); return MSDA_ERR_NULL_POINTER; }
   return biattn_ds_impl(a, d_oa, xa, b, xb, d_ob, B, H, LA, LB, scale, mask_a_padded, mask_b_padded, lane_stat, lane_delta, col_stat,
-                        col_delta, out16, nullptr, terms16, 1, is_half, stream);
+                        col_delta, out16, nullptr, ds16, 1, is_half, stream);
 }
 
 int msda_biattn_rowdot_16(const void* d_o, const void* o, int B, int L, int H, int lpad, float* delta, int is_half, void* stream) {

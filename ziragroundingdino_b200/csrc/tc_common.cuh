@@ -134,6 +134,12 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// element-wise add of a shared-memory tile into global memory (the tensor map's element type; fp16 / bf16 here)
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 // MN-major operand tile with 128-byte swizzle: the tile is stored [k][64 elements of M or N] (128-byte rows, one row per
 // k index) -- i.e. a row-major [k, mn] matrix as TMA delivers it.  Eight k-rows form a 1024-byte group (stride byte
 // offset); further 64-element slabs along M/N lie `lbo_bytes` apart (leading byte offset).
