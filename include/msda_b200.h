@@ -237,6 +237,11 @@ int msda_b200_gemm_set_store_bufs(int bufs, int prefer_resident);
  * and r).  C % 8 == 0, C <= 1024.  gamma / beta fp32. */
 int msda_add_layernorm_fwd_16(const void *x, const void *r, const float *gamma, const float *beta, long long R, int C,
                               float eps, void *z, void *y, float *mean, float *rstd, int is_half, void *stream);
+/* Plain LayerNorm with the same kernel (no residual operand): y = LN(x); optionally y2 = y + shift2[column] as a second output
+ * (the residual operand of an output projection whose bias has been folded into it, fuse_modules.py).  Its backward is
+ * msda_add_layernorm_bwd_16 with z = x. */
+int msda_layernorm_fwd_16(const void *x, const float *gamma, const float *beta, long long R, int C, float eps, void *y,
+                          void *y2, const float *shift2, float *mean, float *rstd, int is_half, void *stream);
 int msda_add_layernorm_bwd_16(const void *dy, const void *z, const float *gamma, const float *mean, const float *rstd,
                               long long R, int C, void *dz, int is_half, void *stream);
 

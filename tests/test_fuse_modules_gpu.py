@@ -11,12 +11,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-@pytest.mark.parametrize("core", ["kernel", "matmul", "sdpa"])
+@pytest.mark.parametrize("core", ["kernel", "kernel-frozen", "matmul", "sdpa"])
 @pytest.mark.parametrize("masked", [True, False])
 def test_bi_attention_block_bf16_vs_oracle(masked, core, monkeypatch):
     from oracle import cpu_encoder
     from ziragroundingdino_b200 import _lib
     from ziragroundingdino_b200.fuse_modules import BiAttentionBlock, BiMultiHeadAttention
+    frozen = core == "kernel-frozen"
+    core = "kernel" if frozen else core
     monkeypatch.setattr(BiMultiHeadAttention, "use_kernel", core == "kernel")
     monkeypatch.setattr(BiMultiHeadAttention, "use_sdpa", core == "sdpa")
     launches0 = _lib.launch_count()
@@ -26,6 +28,9 @@ def test_bi_attention_block_bf16_vs_oracle(masked, core, monkeypatch):
     with torch.no_grad():
         blk.gamma_v.fill_(0.5); blk.gamma_l.fill_(0.5)
     blk = blk.to(DEV).to(torch.bfloat16)
+    if frozen:      # the whole block as one autograd node (FrozenBiAttentionBlockFunction)
+        for prm in blk.parameters():
+            prm.requires_grad_(False)
     v = torch.randn(B, n_img, C, device=DEV).to(torch.bfloat16).requires_grad_(True)
     l = torch.randn(B, n_text, C, device=DEV).to(torch.bfloat16).requires_grad_(True)
     mv = ml = None
@@ -36,7 +41,7 @@ def test_bi_attention_block_bf16_vs_oracle(masked, core, monkeypatch):
     gv, gl = torch.randn_like(ov), torch.randn_like(ol)
     ((ov.float() * gv.float()).sum() + (ol.float() * gl.float()).sum()).backward()
     # kernel core: 2 products + combine forward; 2 row-dots, 2 value products (+ combine), 2 logits-gradient products (+ combine)
-    assert (_lib.launch_count() - launches0 >= 9) == (core == "kernel")
+    assert (_lib.launch_count() - launches0 >= (13 if frozen else 9)) == (core == "kernel")
     d = lambda t: t.detach().double().cpu()
     p = {k: d(t) for k, t in blk.state_dict().items()}
     vd, ld = d(v).requires_grad_(True), d(l).requires_grad_(True)

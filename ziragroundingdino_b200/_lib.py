@@ -55,6 +55,7 @@ def lib():
     L.msda_zira_linear_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_zira_bwd_prep_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _vp, _vp, _i, _vp]
     L.msda_add_layernorm_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _ll, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _vp]
+    L.msda_layernorm_fwd_16.argtypes = [_vp, _vp, _vp, _ll, _i, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_add_layernorm_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _vp, _i, _vp]
     L.msda_group_norm_fwd_16.argtypes = [_vp, _ll, _vp, _vp, _i, _ll, _i, _i, ctypes.c_float, _vp, _ll, _vp, _vp, _i, _vp]
     L.msda_group_norm_bwd_16.argtypes = [_vp, _ll, _vp, _ll, _vp, _vp, _i, _ll, _i, _i, _vp, _ll, _vp, _i, _vp]

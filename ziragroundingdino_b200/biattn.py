@@ -189,6 +189,36 @@ def tn(terms, q, heads, scale, T, nsplit=None):
 STORE_DS = __import__("os").environ.get("MSDA_B200_BIATTN_STORE_DS", "1") == "1"
 
 
+def core_forward(q, k, val_v, val_l, mv, ml, heads, scale):
+    """Both directions from padded byte masks: -> (out_v, out_l, stat_v, stat_l)."""
+    B, S, _ = q.shape
+    T = k.shape[1]
+    out_v, stat_v = pv(q, k, val_l, heads, scale, ml)                                                  # rows orientation
+    out_l, stat_l = pv(k, q, val_v, heads, scale, mv, nsplit=default_splits(B, heads, T, S, q.device))  # tokens orientation
+    return out_v, out_l, stat_v, stat_l
+
+
+def core_backward(q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml, d_out_v, d_out_l, heads, scale):
+    """-> (d_q, d_k, d_val_v, d_val_l)."""
+    B, S, _ = q.shape
+    T = k.shape[1]
+    dev = q.device
+    delta_v, delta_l = rowdot(d_out_v, out_v, heads), rowdot(d_out_l, out_l, heads)
+    ns_tok = default_splits(B, heads, T, S, dev)
+    # values: the transposed probabilities of each direction times the other side's output gradient
+    d_val_l, _ = pv(k, q, d_out_v, heads, scale, ml, col_stat=stat_v, nsplit=ns_tok)
+    d_val_v, _ = pv(q, k, d_out_l, heads, scale, mv, col_stat=stat_l)
+    # queries / keys: the logits gradient of both directions times the other operand
+    if STORE_DS:
+        d_q, terms = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l, want_terms=True)
+        d_k = tn(terms, q, heads, scale, T)
+    else:
+        d_q = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l)
+        d_k = ds(k, d_out_l, val_l, q, val_v, d_out_v, heads, scale, ml, mv, stat_l, delta_l, stat_v, delta_v,
+                 nsplit=default_splits(B, heads, T, S, dev, tile=64))
+    return d_q, d_k, d_val_v, d_val_l
+
+
 class BiAttentionCoreFunction(Function):
     """(q [B,S,E], k [B,T,E], val_v [B,S,E], val_l [B,T,E]) -> (out_v [B,S,E], out_l [B,T,E]).
 
@@ -202,8 +232,7 @@ class BiAttentionCoreFunction(Function):
         dev = q.device
         q, k, val_v, val_l = q.contiguous(), k.contiguous(), val_v.contiguous(), val_l.contiguous()
         mv, ml = _pad_mask(mask_v, B, S, dev), _pad_mask(mask_l, B, T, dev)
-        out_v, stat_v = pv(q, k, val_l, heads, scale, ml)                                          # rows orientation
-        out_l, stat_l = pv(k, q, val_v, heads, scale, mv, nsplit=default_splits(B, heads, T, S, dev))  # tokens orientation
+        out_v, out_l, stat_v, stat_l = core_forward(q, k, val_v, val_l, mv, ml, heads, scale)
         ctx.save_for_backward(q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml)
         ctx.heads, ctx.scale = heads, scale
         return out_v, out_l
@@ -212,25 +241,9 @@ class BiAttentionCoreFunction(Function):
     @once_differentiable
     def backward(ctx, d_out_v, d_out_l):
         q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml = ctx.saved_tensors
-        heads, scale = ctx.heads, ctx.scale
-        B, S, _ = q.shape
-        T = k.shape[1]
-        dev = q.device
-        d_out_v, d_out_l = d_out_v.contiguous(), d_out_l.contiguous()
-        delta_v, delta_l = rowdot(d_out_v, out_v, heads), rowdot(d_out_l, out_l, heads)
-        ns_tok = default_splits(B, heads, T, S, dev)
-        # values: the transposed probabilities of each direction times the other side's output gradient
-        d_val_l, _ = pv(k, q, d_out_v, heads, scale, ml, col_stat=stat_v, nsplit=ns_tok)
-        d_val_v, _ = pv(q, k, d_out_l, heads, scale, mv, col_stat=stat_l)
-        # queries / keys: the logits gradient of both directions times the other operand
-        if STORE_DS:
-            d_q, terms = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l, want_terms=True)
-            d_k = tn(terms, q, heads, scale, T)
-        else:
-            d_q = ds(q, d_out_v, val_v, k, val_l, d_out_l, heads, scale, mv, ml, stat_v, delta_v, stat_l, delta_l)
-            d_k = ds(k, d_out_l, val_l, q, val_v, d_out_v, heads, scale, ml, mv, stat_l, delta_l, stat_v, delta_v,
-                     nsplit=default_splits(B, heads, T, S, dev, tile=64))
-        return d_q, d_k, d_val_v, d_val_l, None, None, None, None
+        grads = core_backward(q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml, d_out_v.contiguous(), d_out_l.contiguous(),
+                              ctx.heads, ctx.scale)
+        return grads + (None, None, None, None)
 
 
 def bi_attention_core(q, k, val_v, val_l, mask_v, mask_l, heads, scale):

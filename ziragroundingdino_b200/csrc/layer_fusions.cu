@@ -26,7 +26,10 @@ template <int kMaxVec>
 __global__ void __launch_bounds__(256)
 add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r, const float* __restrict__ gamma,
                   const float* __restrict__ beta, long long R, int C, float eps, int is_half, uint16_t* __restrict__ z,
-                  uint16_t* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+                  uint16_t* __restrict__ y, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                  uint16_t* __restrict__ y2, const float* __restrict__ shift2) {
+  // r == nullptr: plain LayerNorm(x) (z is not written);  y2 != nullptr: a second output y2 = y + shift2[column], the
+  // residual operand of a GEMM whose bias is folded in here (fuse_modules.py)
   const long long row = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
   if (row >= R) return;
   const int lane = threadIdx.x & 31;
@@ -40,13 +43,18 @@ add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r
     if (i < nvec && c < C) {
       float a[8], b[8];
       unpack8(__ldg(reinterpret_cast<const uint4*>(x + row * C + c)), h, a);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(r + row * C + c)), h, b);
+      if (r != nullptr) {
+        unpack8(__ldg(reinterpret_cast<const uint4*>(r + row * C + c)), h, b);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[i][j] = a[j] + b[j];
-      // LayerNorm sees the 16-bit rounded sum, exactly as the unfused add -> LayerNorm sequence does
-      const uint4 zz = pack8(v[i], h);
-      *reinterpret_cast<uint4*>(z + row * C + c) = zz;
-      unpack8(zz, h, v[i]);
+        for (int j = 0; j < 8; ++j) v[i][j] = a[j] + b[j];
+        // LayerNorm sees the 16-bit rounded sum, exactly as the unfused add -> LayerNorm sequence does
+        const uint4 zz = pack8(v[i], h);
+        *reinterpret_cast<uint4*>(z + row * C + c) = zz;
+        unpack8(zz, h, v[i]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] = a[j];
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) sum += v[i][j];
     }
@@ -73,7 +81,16 @@ add_ln_fwd_kernel(const uint16_t* __restrict__ x, const uint16_t* __restrict__ r
       const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf((v[i][j] - mean) * rstd, gg[j], bb[j]);
-      *reinterpret_cast<uint4*>(y + row * C + c) = pack8(o, h);
+      const uint4 yy = pack8(o, h);
+      *reinterpret_cast<uint4*>(y + row * C + c) = yy;
+      if (y2 != nullptr) {          // from the ROUNDED y, as the unfused `y + shift` would
+        unpack8(yy, h, o);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift2 + c)), s1 = __ldg(reinterpret_cast<const float4*>(shift2 + c + 4));
+        const float ss[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += ss[j];
+        *reinterpret_cast<uint4*>(y2 + row * C + c) = pack8(o, h);
+      }
     }
   }
   if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
@@ -134,7 +151,22 @@ int msda_add_layernorm_fwd_16(const void* x, const void* r, const float* gamma, 
   const unsigned grid = static_cast<unsigned>((R + 7) / 8);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define LN_FWD(NV) add_ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), static_cast<const uint16_t*>(r), \
-      gamma, beta, R, C, eps, is_half, static_cast<uint16_t*>(z), static_cast<uint16_t*>(y), mean, rstd)
+      gamma, beta, R, C, eps, is_half, static_cast<uint16_t*>(z), static_cast<uint16_t*>(y), mean, rstd, nullptr, nullptr)
+  if (C <= 256) LN_FWD(1); else if (C <= 512) LN_FWD(2); else LN_FWD(4);
+#undef LN_FWD
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+int msda_layernorm_fwd_16(const void* x, const float* gamma, const float* beta, long long R, int C, float eps, void* y,
+                          void* y2, const float* shift2, float* mean, float* rstd, int is_half, void* stream) {
+  if (!x || !gamma || !beta || !y || !mean || !rstd || (y2 && !shift2)) return MSDA_ERR_NULL_POINTER;
+  if (R <= 0 || C <= 0 || C % 8 || C > 1024) return MSDA_ERR_BAD_SHAPE;
+  ++msda::g_launches;
+  const unsigned grid = static_cast<unsigned>((R + 7) / 8);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define LN_FWD(NV) add_ln_fwd_kernel<NV><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(x), nullptr, gamma, beta, R, C, eps, is_half, \
+      nullptr, static_cast<uint16_t*>(y), mean, rstd, static_cast<uint16_t*>(y2), shift2)
   if (C <= 256) LN_FWD(1); else if (C <= 512) LN_FWD(2); else LN_FWD(4);
 #undef LN_FWD
   cudaError_t e = cudaGetLastError();

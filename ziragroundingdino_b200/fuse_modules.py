@@ -27,7 +27,11 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import biattn
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib, biattn
+from .layer_ops import _stream, derived
 
 
 class DropPath(nn.Module):
@@ -135,6 +139,90 @@ class BiMultiHeadAttention(nn.Module):
         return self.out_v_proj(out_v[:, :n_img_in]), self.out_l_proj(out_l)
 
 
+def _layer_norm16(x2, norm, shift=None):
+    """LayerNorm on the package's kernel: -> (y, y + shift or None, mean, rstd)."""
+    R, C = x2.shape
+    y = torch.empty_like(x2)
+    y2 = torch.empty_like(x2) if shift is not None else None
+    mean = torch.empty(R, dtype=torch.float32, device=x2.device)
+    rstd = torch.empty(R, dtype=torch.float32, device=x2.device)
+    g32, b32 = derived(norm.weight, "f32"), derived(norm.bias, "f32")
+    with torch.cuda.device(x2.device):
+        rc = _lib.lib().msda_layernorm_fwd_16(x2.data_ptr(), g32.data_ptr(), b32.data_ptr(), R, C, float(norm.eps), y.data_ptr(),
+                                              0 if y2 is None else y2.data_ptr(), 0 if shift is None else shift.data_ptr(),
+                                              mean.data_ptr(), rstd.data_ptr(), 1 if x2.dtype == torch.float16 else 0, _stream(x2))
+    _lib.check(rc, "msda_layernorm_fwd_16")
+    return y, y2, mean, rstd, g32
+
+
+def _layer_norm16_bwd(dy2, x2, g32, mean, rstd):
+    dx = torch.empty_like(x2)
+    R, C = x2.shape
+    with torch.cuda.device(x2.device):
+        rc = _lib.lib().msda_add_layernorm_bwd_16(dy2.data_ptr(), x2.data_ptr(), g32.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, C,
+                                                  dx.data_ptr(), 1 if x2.dtype == torch.float16 else 0, _stream(x2))
+    _lib.check(rc, "msda_add_layernorm_bwd_16")
+    return dx
+
+
+class FrozenBiAttentionBlockFunction(Function):
+    """The whole BiAttentionBlock (reference fuse_modules.py:258-307) as ONE autograd node when none of its parameters is
+    trained (the ZiRa configuration: gradients only flow THROUGH the fusion layers) and dropout / drop-path are inactive:
+    LayerNorms on the package's kernel (the image-side one also emits `LN(v) + gamma_v * b_out`), gamma folded into the
+    output projections so that `v + gamma * (x W^T + b)` is one GEMM with a residual operand, and in the backward the three
+    gradients reaching LN(v) -- residual, q projection, value projection -- are accumulated by the dgrad GEMMs themselves.
+    Removes 2 multiplies, 4 adds and 2 slow LayerNorm kernels per direction from the eager composition."""
+
+    @staticmethod
+    def forward(ctx, v, l, mask_v, mask_l, blk):
+        a = blk.attn
+        H, E = a.num_heads, a.embed_dim
+        B, S, C = v.shape
+        T = l.shape[1]
+        dev = v.device
+        v2, l2 = v.reshape(B * S, C).contiguous(), l.reshape(B * T, l.shape[-1]).contiguous()
+        w_ov = (blk.gamma_v[:, None] * a.out_v_proj.weight).contiguous()            # [v_dim, E]
+        w_ol = (blk.gamma_l[:, None] * a.out_l_proj.weight).contiguous()
+        shift_v = blk.gamma_v.float() * a.out_v_proj.bias.float()
+        shift_l = blk.gamma_l.float() * a.out_l_proj.bias.float()
+        v_ln, v_res, mean_v, rstd_v, g_v = _layer_norm16(v2, blk.layer_norm_v, shift_v)
+        l_ln, l_res, mean_l, rstd_l, g_l = _layer_norm16(l2, blk.layer_norm_l, shift_l)
+        q = F.linear(v_ln, a.v_proj.weight, a.v_proj.bias).view(B, S, E)           # unscaled: the kernel scales the logits
+        val_v = F.linear(v_ln, a.values_v_proj.weight, a.values_v_proj.bias).view(B, S, E)
+        k = F.linear(l_ln, a.l_proj.weight, a.l_proj.bias).view(B, T, E)
+        val_l = F.linear(l_ln, a.values_l_proj.weight, a.values_l_proj.bias).view(B, T, E)
+        mv, ml = biattn._pad_mask(mask_v, B, S, dev), biattn._pad_mask(mask_l, B, T, dev)
+        out_v, out_l, stat_v, stat_l = biattn.core_forward(q, k, val_v, val_l, mv, ml, H, a.scale)
+        v_out = torch.addmm(v_res, out_v.view(B * S, E), w_ov.t())
+        l_out = torch.addmm(l_res, out_l.view(B * T, E), w_ol.t())
+        ctx.save_for_backward(v2, l2, q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml, mean_v, rstd_v, mean_l, rstd_l,
+                              g_v, g_l, w_ov, w_ol)
+        ctx.blk = blk
+        ctx.shapes = (v.shape, l.shape)
+        return v_out.view(v.shape), l_out.view(l.shape)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_v_out, g_l_out):
+        (v2, l2, q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml, mean_v, rstd_v, mean_l, rstd_l, g_v, g_l, w_ov,
+         w_ol) = ctx.saved_tensors
+        a = ctx.blk.attn
+        B, S, E = q.shape
+        T = k.shape[1]
+        gv2, gl2 = g_v_out.reshape(v2.shape).contiguous(), g_l_out.reshape(l2.shape).contiguous()
+        d_out_v = torch.mm(gv2, w_ov).view(B, S, E)
+        d_out_l = torch.mm(gl2, w_ol).view(B, T, E)
+        d_q, d_k, d_val_v, d_val_l = biattn.core_backward(q, k, val_v, val_l, out_v, out_l, stat_v, stat_l, mv, ml, d_out_v, d_out_l,
+                                                          a.num_heads, a.scale)
+        d_vln = torch.addmm(gv2, d_q.view(B * S, E), a.v_proj.weight)
+        d_vln.addmm_(d_val_v.view(B * S, E), a.values_v_proj.weight)
+        d_lln = torch.addmm(gl2, d_k.view(B * T, E), a.l_proj.weight)
+        d_lln.addmm_(d_val_l.view(B * T, E), a.values_l_proj.weight)
+        d_v = _layer_norm16_bwd(d_vln, v2, g_v, mean_v, rstd_v).view(ctx.shapes[0])
+        d_l = _layer_norm16_bwd(d_lln, l2, g_l, mean_l, rstd_l).view(ctx.shapes[1])
+        return d_v, d_l, None, None, None
+
+
 class BiAttentionBlock(nn.Module):
     def __init__(self, v_dim, l_dim, embed_dim, num_heads, dropout=0.1, drop_path=0.0, init_values=1e-4, cfg=None):
         super().__init__()
@@ -145,7 +233,18 @@ class BiAttentionBlock(nn.Module):
         self.gamma_v = nn.Parameter(init_values * torch.ones((v_dim)), requires_grad=True)
         self.gamma_l = nn.Parameter(init_values * torch.ones((l_dim)), requires_grad=True)
 
+    def _fused_ok(self, v, l):
+        a = self.attn
+        dp = self.drop_path
+        return (a.use_kernel and v.is_cuda and v.dtype in (torch.bfloat16, torch.float16) and l.dtype == v.dtype
+                and a.head_dim == biattn.HD and not (self.training and a.dropout > 0.0)
+                and (isinstance(dp, nn.Identity) or not self.training or dp.drop_prob == 0.0)
+                and not torch.is_autocast_enabled() and v.shape[-1] % 8 == 0 and l.shape[-1] % 8 == 0
+                and all(p.dtype == v.dtype and not p.requires_grad for p in self.parameters()))
+
     def forward(self, v, l, attention_mask_v=None, attention_mask_l=None):
+        if self._fused_ok(v, l):
+            return FrozenBiAttentionBlockFunction.apply(v, l, attention_mask_v, attention_mask_l, self)
         v = self.layer_norm_v(v)
         l = self.layer_norm_l(l)
         delta_v, delta_l = self.attn(v, l, attention_mask_v=attention_mask_v, attention_mask_l=attention_mask_l)
