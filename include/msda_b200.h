@@ -268,6 +268,11 @@ int msda_group_norm_bwd_16(const void *dy, long long dy_image_stride, const void
  *   gate_bits from the forward; accum (16-bit [R, C], may be NULL) and dx may alias dy. */
 int msda_ffn_chain_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R, int C,
                           int F, void *out, uint32_t *relu_bits_out, int is_half, void *stream);
+/* msda_ffn_chain_ln_fwd_16: the same launch with the layer's `src = norm2(src + src2)` (transformer_for_adapter.py:882-885) in its
+ * final stage: z = x + ffn(x) (16 bit; LayerNorm's saved input), y = LayerNorm(z) * gamma + beta, mean / rstd [R] fp32. */
+int msda_ffn_chain_ln_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R, int C,
+                             int F, const float *gamma, const float *beta, float eps, void *z, void *y, float *mean,
+                             float *rstd, uint32_t *relu_bits_out, int is_half, void *stream);
 int msda_ffn_chain_bwd_16(const void *dy, const void *w2_t, const void *w1_t, const uint32_t *gate_bits, const void *accum,
                           long long R, int C, int F, void *dx, int is_half, void *stream);
 

@@ -143,7 +143,9 @@ def test_encoder_layer_block_functions_vs_stagewise(dtype, with_mask):
             res[blocks_on] = (y.detach(), x.grad)
         finally:
             zb.DeformableTransformerEncoderLayer.block_functions = True
-    assert torch.equal(res[True][0], res[False][0])
+    # the block form keeps x + ffn(x) in fp32 until LayerNorm's input is rounded (the stage-wise path rounds ffn(x) first)
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert (res[True][0].float() - res[False][0].float()).abs().max().item() <= 4 * ulp * res[False][0].float().abs().max().item()
     assert rel_err(res[True][1].float().cpu(), res[False][1].float().cpu()) < 2e-2
     # fp64 truth of the same layer
     d = lambda t: t.detach().double().cpu()
@@ -224,12 +226,17 @@ def test_encoder_layer_with_chained_ffn_matches_unchained():
     S = sum(h * w for h, w in shapes)
     sh, lsi = syn.level_tensors(shapes, dev)
     torch.manual_seed(9)
-    layer = encoder.DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4).to(dev).bfloat16()
+    layer = encoder.DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4)
+    with torch.no_grad():      # (the gradient of mean(out^2) through a LayerNorm with gamma = 1, beta = 0 is exactly zero: use
+        for nrm in (layer.norm1, layer.norm2):      # a random affine and a random upstream gradient instead of rounding noise)
+            nrm.weight.normal_(1, 0.2); nrm.bias.normal_(0, 0.2)
+    layer = layer.to(dev).bfloat16()
     for p in layer.parameters():
         p.requires_grad_(False)
     refp = syn.encoder_reference_points(shapes, torch.ones(2, 4, 2, device=dev), dev)
     x0 = torch.randn(2, S, 256, device=dev).bfloat16()
     pos = torch.randn(2, S, 256, device=dev).bfloat16()
+    gout = torch.randn(2, S, 256, device=dev).bfloat16()
     res = {}
     keep = blocks.FFN_CHAIN
     try:
@@ -237,9 +244,77 @@ def test_encoder_layer_with_chained_ffn_matches_unchained():
             blocks.FFN_CHAIN = chain
             x = x0.clone().requires_grad_(True)
             out, _ = layer(x, pos, refp, sh, lsi, None)
-            out.float().square().mean().backward()
+            out.backward(gout)
             res[chain] = (out.detach().float(), x.grad.float())
     finally:
         blocks.FFN_CHAIN = keep
+    assert (res[True][0] - res[False][0]).abs().max().item() < 3 * 2 ** -8 * res[False][0].abs().max().item()
+    assert (res[True][1] - res[False][1]).abs().max().item() < 2e-2 * res[False][1].abs().max().item()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("R", [1, 127, 128, 1000, 22223])
+def test_ffn_chain_with_fused_residual_layernorm_vs_fp64(dtype, R):
+    """The chained FFN with `norm2(x + ffn(x))` in its final stage: z (LayerNorm's saved input, 16 bit), y, mean, rstd against
+    fp64 on the same operands (hidden activation rounded to the storage type, as in the kernel)."""
+    from ziragroundingdino_b200 import blocks
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(11 + R)
+    C, F = 256, 2048
+    x = torch.randn(R, C, generator=g).to(dtype).to(dev)
+    w1 = (torch.randn(F, C, generator=g) * 0.06).to(dtype).to(dev)
+    w2 = (torch.randn(C, F, generator=g) * 0.02).to(dtype).to(dev)
+    b1 = (torch.randn(F, generator=g) * 0.1).to(dev)
+    b2 = (torch.randn(C, generator=g) * 0.1).to(dev)
+    gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+    beta = (0.1 * torch.randn(C, generator=g)).to(dev)
+    bits = torch.zeros((F // 32, R), dtype=torch.int32, device=dev)
+    z, y, mean, rstd = blocks.ffn_chain_ln_fwd16(x, w1, b1, w2, b2, gamma, beta, 1e-5, bits)
+    h16 = torch.relu(x.double() @ w1.double().t() + b1.double()).to(dtype).double()
+    z64 = x.double() + h16 @ w2.double().t() + b2.double()
+    eps = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    assert (z.double() - z64).abs().max().item() <= 2 * eps * z64.abs().max().item()
+    zr = z.double()                       # LayerNorm is defined on the ROUNDED sum
+    m64, v64 = zr.mean(1), zr.var(1, unbiased=False)
+    assert (mean.double() - m64).abs().max().item() < 1e-5 * max(1.0, m64.abs().max().item())
+    assert ((rstd.double() - (v64 + 1e-5).rsqrt()).abs() * (v64 + 1e-5).sqrt()).max().item() < 1e-4
+    y64 = (zr - m64[:, None]) * (v64 + 1e-5).rsqrt()[:, None] * gamma.double() + beta.double()
+    assert (y.double() - y64).abs().max().item() <= 2 * eps * y64.abs().max().item()
+    # same ReLU mask as the plain chain
+    bits2 = torch.zeros_like(bits)
+    blocks.ffn_chain_fwd16(x, w1, b1, w2, b2, bits2)
+    assert torch.equal(bits, bits2)
+
+
+def test_encoder_layer_with_fused_ffn_layernorm_matches_separate():
+    """The frozen encoder layer with blocks.FFN_LN on vs off: same outputs and input gradients to 16-bit rounding."""
+    from ziragroundingdino_b200 import blocks, encoder, synthetic as syn
+    dev = "cuda:0"
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    sh, lsi = syn.level_tensors(shapes, dev)
+    torch.manual_seed(10)
+    layer = encoder.DeformableTransformerEncoderLayer(256, 2048, 0.0, "relu", 4, 8, 4)
+    with torch.no_grad():      # (the gradient of mean(out^2) through a LayerNorm with gamma = 1, beta = 0 is exactly zero: use
+        for nrm in (layer.norm1, layer.norm2):      # a random affine and a random upstream gradient instead of rounding noise)
+            nrm.weight.normal_(1, 0.2); nrm.bias.normal_(0, 0.2)
+    layer = layer.to(dev).bfloat16()
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    refp = syn.encoder_reference_points(shapes, torch.ones(2, 4, 2, device=dev), dev)
+    x0 = torch.randn(2, S, 256, device=dev).bfloat16()
+    pos = torch.randn(2, S, 256, device=dev).bfloat16()
+    gout = torch.randn(2, S, 256, device=dev).bfloat16()
+    res = {}
+    keep = blocks.FFN_LN
+    try:
+        for fused_ln in (False, True):
+            blocks.FFN_LN = fused_ln
+            x = x0.clone().requires_grad_(True)
+            out, _ = layer(x, pos, refp, sh, lsi, None)
+            out.backward(gout)
+            res[fused_ln] = (out.detach().float(), x.grad.float())
+    finally:
+        blocks.FFN_LN = keep
     assert (res[True][0] - res[False][0]).abs().max().item() < 3 * 2 ** -8 * res[False][0].abs().max().item()
     assert (res[True][1] - res[False][1]).abs().max().item() < 2e-2 * res[False][1].abs().max().item()

@@ -50,6 +50,27 @@ def ffn_chain_fwd16(x2d, w1, b1_f32, w2, b2_f32, bits):
     return out
 
 
+# Default on: the residual + LayerNorm that follows the FFN runs in the chained kernel's final stage (MSDA_B200_FFN_LN=0 keeps the
+# separate add+LayerNorm launch).
+FFN_LN = os.environ.get("MSDA_B200_FFN_LN", "1") == "1"
+
+
+def ffn_chain_ln_fwd16(x2d, w1, b1_f32, w2, b2_f32, g32, b32, eps, bits):
+    """-> (z = x + ffn(x), y = LayerNorm(z), mean, rstd) in one launch."""
+    R, C = x2d.shape
+    F = w1.shape[0]
+    z, y = torch.empty_like(x2d), torch.empty_like(x2d)
+    mean = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_ffn_chain_ln_fwd_16(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C,
+                                                 F, g32.data_ptr(), b32.data_ptr(), float(eps), z.data_ptr(), y.data_ptr(),
+                                                 mean.data_ptr(), rstd.data_ptr(), bits.data_ptr(),
+                                                 1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_ffn_chain_ln_fwd_16")
+    return z, y, mean, rstd
+
+
 def ffn_chain_bwd16(dz, w2_t, w1_t, bits, accumulate=True):
     """accumulate: dz <- dz + gate(dz W2) W1, in place (the residual path of the encoder block); otherwise returns
     gate(dz W2) W1 in a new tensor.  w2_t = W2^T [d_ffn, d_model], w1_t = W1^T [d_model, d_ffn]."""
@@ -156,8 +177,12 @@ class FFNBlockFunction(Function):
         bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
         ctx.chain = ffn_chain_ok(x2d.shape[1], w1.shape[0])
         if ctx.chain:
-            y2 = ffn_chain_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"), bits)
-            z, y, mean, rstd = _add_ln_fwd(x2d, y2, g32, b32, eps)
+            if FFN_LN:
+                z, y, mean, rstd = ffn_chain_ln_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"),
+                                                      g32, b32, eps, bits)
+            else:
+                y2 = ffn_chain_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"), bits)
+                z, y, mean, rstd = _add_ln_fwd(x2d, y2, g32, b32, eps)
             ctx.save_for_backward(bits, w1, w2, z, g32, mean, rstd)
             ctx.shape = shape
             return y.view(shape)

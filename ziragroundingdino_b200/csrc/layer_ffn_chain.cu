@@ -47,7 +47,7 @@ constexpr int SLOT = 32768, NSLOT = 3;
 constexpr int H_BYTES = 2 * 16384;       // one hidden chunk: 2 k-blocks of 128 rows x 128 bytes
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT + 2 * H_BYTES + 512;
+constexpr int SMEM_BYTES = X_BYTES + NSLOT * SLOT + 2 * H_BYTES + 512 + 1024;      // operands, barriers, LayerNorm exchange
 
 struct Params {
   int R, F;                  // rows, hidden width (multiple of 128)
@@ -57,14 +57,24 @@ struct Params {
   uint32_t* bits;            // [F/32, R] word-major: written (forward) / read (backward)
   const void* accum;         // backward: 16-bit [R, C] added to the result (may alias the output)
   int half_in;
+  // forward with the layer's residual + LayerNorm fused into the final stage (LN = true): z = x + ffn(x) and y = LN(z)
+  const float* ln_gamma;     // [C]
+  const float* ln_beta;      // [C]
+  float ln_eps;
+  float* ln_mean;            // [R]
+  float* ln_rstd;            // [R]
 };
 
-template <bool BWD, bool HALF>
+template <bool BWD, bool HALF, bool LN>
 __global__ void __launch_bounds__(THREADS, 1)
 ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut, Params p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                 const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr, Params p) {
+  // no room for a run-time alignment pad: the dynamic window of a kernel without static shared memory starts 1024-aligned
+  // (what the 128-byte swizzle needs); checked, not assumed
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
+  uint8_t* smem = smem_raw;
   uint8_t* sX = smem;
   uint8_t* sRing = sX + X_BYTES;
   uint8_t* sH = sRing + NSLOT * SLOT;
@@ -79,7 +89,9 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* h_free = h_full + 2;      // [2] GEMM2 has read it
   uint64_t* a2_full = h_free + 2;     // result tile complete
   uint64_t* a2_free = a2_full + 1;    // final stage has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_free + 1);
+  uint64_t* res_full = a2_free + 1;   // [EPI_WARPS] LN: a warp's residual pieces have landed in its staging tiles
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + EPI_WARPS);
+  float2* sStat = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(bars) + 512);     // [128 rows] LN partial sums / statistics
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunk = p.F / HC;
@@ -91,6 +103,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(x_full, 1); mbar_init(x_free, 1);
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(res_full + i, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, EPI_WARPS); mbar_init(h_full + i, EPI_WARPS); mbar_init(h_free + i, 1); }
     mbar_init(a2_full, 1); mbar_init(a2_free, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -212,7 +225,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   } else {
     // ===== mid / final stages =====
     const int quarter = warp & 3, half = (warp - 2) >> 2;     // TMEM lane quarter; which 64 of a chunk's 128 columns
-    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0;
+    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0, ph_res = 0;
     // final stage: per-warp 32 x 128-byte store tile inside H[0] (idle by then) -- the SAME 4 KiB this warp writes in the mid
     // stage (k-block `half`, rows of `quarter`), so only the warp itself ever reuses it, after its own store has been read
     uint8_t* stile = sH + (half * 4 + quarter) * 4096;
@@ -266,6 +279,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       mbar_wait(a2_full, ph_a2);
       ph_a2 ^= 1;
       tc_fence_after();
+      if (!LN) {
 #pragma unroll 1
       for (int g = 0; g < 2; ++g) {
         const int gc = half * 128 + g * 64;
@@ -302,6 +316,103 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         __syncwarp();
         if (lane == 0) tma_store_2d(&tmOut, stile, gc, static_cast<int>(row0));
       }
+      } else {
+        // ---- residual + LayerNorm in the final stage (reference transformer_for_adapter.py:882-885): z = x + ffn(x) rounded to
+        // 16 bit (what LayerNorm's backward keeps), y = LN(z).  Each warp fetches its 32 x 128 piece of the residual x by TMA
+        // straight into its two staging tiles (the X operand tile is NOT held back: the next tile's products overlap this
+        // stage), turns it into z in place, stores z, and -- after the two warps of a lane quarter have exchanged partial sums
+        // of the ROUNDED values -- normalises the packed z row it kept in registers and stores y.
+        uint8_t* stile1 = stile + H_BYTES;              // this warp's 4 KiB of H[1]
+        if (lane == 0) {
+          tma_store_wait_read();                        // the previous tile's stores have read both staging tiles
+          mbar_expect_tx(res_full + (warp - 2), 2 * 4096);
+          tma_load_2d(&tmXr, res_full + (warp - 2), stile, half * 128, static_cast<int>(row0));
+          tma_load_2d(&tmXr, res_full + (warp - 2), stile1, half * 128 + 64, static_cast<int>(row0));
+        }
+        __syncwarp();
+        mbar_wait(res_full + (warp - 2), ph_res);
+        ph_res ^= 1;
+        uint4 zk[2][2][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int gc = half * 128 + g * 64;
+          uint8_t* st = g ? stile1 : stile;
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            float v[32];
+            tmem_ld32(t_acc2 + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(gc + 32 * hf), r);
+            const float4* bp = reinterpret_cast<const float4*>(p.bias2 + gc + 32 * hf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 bb = __ldg(bp + i);
+              v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+            }
+            uint4 xin[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xin[i] = *reinterpret_cast<const uint4*>(swz(st, lane, 4 * hf + i));
+            add_packed16(v, reinterpret_cast<const uint32_t*>(xin), HALF);
+            pack_16(v, HALF, false, zk[g][hf]);
+            float zr[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zr[i] = 0.f;
+            add_packed16(zr, reinterpret_cast<const uint32_t*>(zk[g][hf]), HALF);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) { s1 += zr[i]; s2 = fmaf(zr[i], zr[i], s2); }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(st, lane, 4 * hf + i)) = zk[g][hf][i];
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmZ, st, gc, static_cast<int>(row0));
+        }
+        // half 1 hands its partial sums to half 0, which returns mean / rstd through the same slots
+        const int trow = quarter * 32 + lane;
+        if (half == 1) sStat[trow] = make_float2(s1, s2);
+        named_bar(1 + quarter, 64);
+        float mean = 0.f, rstd = 0.f;
+        if (half == 0) {
+          const float2 o = sStat[trow];
+          mean = (s1 + o.x) * (1.f / C);
+          rstd = rsqrtf(fmaxf((s2 + o.y) * (1.f / C) - mean * mean, 0.f) + p.ln_eps);
+          sStat[trow] = make_float2(mean, rstd);
+          if (live) { p.ln_mean[row] = mean; p.ln_rstd[row] = rstd; }
+        }
+        named_bar(1 + quarter, 64);
+        if (half == 1) { const float2 o = sStat[trow]; mean = o.x; rstd = o.y; }
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int gc = half * 128 + g * 64;
+          uint8_t* st = g ? stile1 : stile;
+          if (lane == 0) tma_store_wait_read1();        // both z stores are older than the one still allowed in flight
+          __syncwarp();
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            float zr[32], v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) zr[i] = 0.f;
+            add_packed16(zr, reinterpret_cast<const uint32_t*>(zk[g][hf]), HALF);
+            const float4* gp = reinterpret_cast<const float4*>(p.ln_gamma + gc + 32 * hf);
+            const float4* bp = reinterpret_cast<const float4*>(p.ln_beta + gc + 32 * hf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 gg = __ldg(gp + i), bb = __ldg(bp + i);
+              v[4 * i] = fmaf((zr[4 * i] - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((zr[4 * i + 1] - mean) * rstd, gg.y, bb.y);
+              v[4 * i + 2] = fmaf((zr[4 * i + 2] - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((zr[4 * i + 3] - mean) * rstd, gg.w, bb.w);
+            }
+            uint4 pk[4];
+            pack_16(v, HALF, false, pk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(st, lane, 4 * hf + i)) = pk[i];
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmOut, st, gc, static_cast<int>(row0));
+        }
+        named_bar(1 + quarter, 64);                     // the exchange slots are free for the next tile
+      }
       if (lane == 0) tma_store_wait_read();      // the store tiles live in the H buffers: drained before the next tile's mid stage
       __syncwarp();
       tc_fence_before();
@@ -318,11 +429,11 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   }
 }
 
-static int launch(const void* x, const void* wa, const void* wb, void* out, const Params& p, cudaStream_t st) {
+static int launch(const void* x, const void* wa, const void* wb, void* out, void* z_out, const Params& p, cudaStream_t st) {
   if (!x || !wa || !wb || !out) { snprintf(t_err, sizeof(t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
   if (p.R <= 0 || p.F <= 0 || p.F % HC || p.F > 8192) { snprintf(t_err, sizeof(t_err), "chained FFN needs d_ffn %% 128 == 0 (R=%d F=%d)", p.R, p.F); return MSDA_ERR_UNSUPPORTED; }
   const int dt = p.half_in ? 1 : 0;
-  CUtensorMap tmX, tmA, tmB, tmOut;
+  CUtensorMap tmX, tmA, tmB, tmOut, tmZ, tmXr;
   int rc = make_map(&tmX, x, p.R, C, BM, 64, dt);
   if (rc) return rc;
   rc = make_map(&tmA, wa, p.F, C, HC, 64, dt);
@@ -330,6 +441,10 @@ static int launch(const void* x, const void* wa, const void* wb, void* out, cons
   rc = make_map(&tmB, wb, C, p.F, C, 64, dt);
   if (rc) return rc;
   rc = make_map(&tmOut, out, p.R, C, 32, 64, dt);
+  if (rc) return rc;
+  rc = make_map(&tmZ, z_out ? z_out : out, p.R, C, 32, 64, dt);
+  if (rc) return rc;
+  rc = make_map(&tmXr, x, p.R, C, 32, 64, dt);      // the residual, in the final stage's 32-row pieces
   if (rc) return rc;
   int dev_id = 0;
   cudaGetDevice(&dev_id);
@@ -339,17 +454,18 @@ static int launch(const void* x, const void* wa, const void* wb, void* out, cons
   const int grid = tiles < sms_of[dev_id & 63] ? tiles : sms_of[dev_id & 63];
   cudaError_t cfg = cudaSuccess;
   ++msda::g_launches;
-#define FFN_LAUNCH(BWD, HALF)                                                                                         \
-  do {                                                                                                                 \
-    static bool configured[64] = {};                                                                                   \
-    if (!configured[dev_id & 63]) {                                                                                    \
-      cfg = cudaFuncSetAttribute(ffn_chain_kernel<BWD, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES); \
-      configured[dev_id & 63] = cfg == cudaSuccess;                                                                    \
-    }                                                                                                                  \
-    if (cfg == cudaSuccess) ffn_chain_kernel<BWD, HALF><<<grid, THREADS, SMEM_BYTES, st>>>(tmX, tmA, tmB, tmOut, p);    \
+#define FFN_LAUNCH(BWD, HALF, LN)                                                                                          \
+  do {                                                                                                                      \
+    static bool configured[64] = {};                                                                                        \
+    if (!configured[dev_id & 63]) {                                                                                         \
+      cfg = cudaFuncSetAttribute(ffn_chain_kernel<BWD, HALF, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+      configured[dev_id & 63] = cfg == cudaSuccess;                                                                         \
+    }                                                                                                                       \
+    if (cfg == cudaSuccess) ffn_chain_kernel<BWD, HALF, LN><<<grid, THREADS, SMEM_BYTES, st>>>(tmX, tmA, tmB, tmOut, tmZ, tmXr, p); \
   } while (0)
-  if (p.backward) { if (p.half_in) FFN_LAUNCH(true, true); else FFN_LAUNCH(true, false); }
-  else { if (p.half_in) FFN_LAUNCH(false, true); else FFN_LAUNCH(false, false); }
+  if (p.backward) { if (p.half_in) FFN_LAUNCH(true, true, false); else FFN_LAUNCH(true, false, false); }
+  else if (z_out) { if (p.half_in) FFN_LAUNCH(false, true, true); else FFN_LAUNCH(false, false, true); }
+  else { if (p.half_in) FFN_LAUNCH(false, true, false); else FFN_LAUNCH(false, false, false); }
 #undef FFN_LAUNCH
   if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
   cudaError_t e = cudaGetLastError();
@@ -371,7 +487,23 @@ int msda_ffn_chain_fwd_16(const void* x, const void* w1, const float* b1, const 
   pg::ffn::Params p;
   memset(&p, 0, sizeof(p));
   p.R = static_cast<int>(R); p.F = F; p.backward = 0; p.bias1 = b1; p.bias2 = b2; p.bits = relu_bits_out; p.half_in = is_half;
-  return pg::ffn::launch(x, w1, w2, out, p, static_cast<cudaStream_t>(stream));
+  return pg::ffn::launch(x, w1, w2, out, nullptr, p, static_cast<cudaStream_t>(stream));
+}
+
+// z = x + (relu(x W1^T + b1) W2^T + b2) rounded to 16 bit, y = LayerNorm(z) * gamma + beta, mean / rstd [R] fp32: the FFN half of an
+// encoder layer including `src = norm2(src + src2)` (transformer_for_adapter.py:877-885) in one launch.
+int msda_ffn_chain_ln_fwd_16(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, long long R, int C,
+                             int F, const float* gamma, const float* beta, float eps, void* z, void* y, float* mean, float* rstd,
+                             uint32_t* relu_bits_out, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (C != pg::ffn::C) { snprintf(pg::t_err, sizeof(pg::t_err), "chained FFN is built for d_model = %d (got %d)", pg::ffn::C, C); return MSDA_ERR_UNSUPPORTED; }
+  if (!b1 || !b2 || !gamma || !beta || !z || !mean || !rstd) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  if (R >= (1ll << 31)) return MSDA_ERR_BAD_SHAPE;
+  pg::ffn::Params p;
+  memset(&p, 0, sizeof(p));
+  p.R = static_cast<int>(R); p.F = F; p.backward = 0; p.bias1 = b1; p.bias2 = b2; p.bits = relu_bits_out; p.half_in = is_half;
+  p.ln_gamma = gamma; p.ln_beta = beta; p.ln_eps = eps; p.ln_mean = mean; p.ln_rstd = rstd;
+  return pg::ffn::launch(x, w1, w2, y, z, p, static_cast<cudaStream_t>(stream));
 }
 
 int msda_ffn_chain_bwd_16(const void* dy, const void* w2_t, const void* w1_t, const uint32_t* gate_bits, const void* accum,
@@ -383,7 +515,7 @@ int msda_ffn_chain_bwd_16(const void* dy, const void* w2_t, const void* w1_t, co
   pg::ffn::Params p;
   memset(&p, 0, sizeof(p));
   p.R = static_cast<int>(R); p.F = F; p.backward = 1; p.bits = const_cast<uint32_t*>(gate_bits); p.accum = accum; p.half_in = is_half;
-  return pg::ffn::launch(dy, w2_t, w1_t, dx, p, static_cast<cudaStream_t>(stream));
+  return pg::ffn::launch(dy, w2_t, w1_t, dx, nullptr, p, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
