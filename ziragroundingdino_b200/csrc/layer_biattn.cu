@@ -81,7 +81,7 @@ struct PvParams {
 constexpr int NS1 = 4, NS2 = 2;         // ring depths: logits operands (B k-blocks, 16 KiB) / value half-tiles (X, 32 KiB)
 constexpr int SLOT2 = 2 * SLOT;         // two 64-column slabs of X, contiguous: GEMM2 runs as N = 128 instructions
 constexpr int PV_THREADS = THREADS + 32; // + the second TMA producer warp
-constexpr int PV_SMEM = A_BYTES + NS1 * SLOT + NS2 * SLOT2 + P_BYTES + 2 * 2 * BM * 4 + 256;     // 231 680 of 232 448 bytes
+constexpr int PV_SMEM = 1024 + A_BYTES + NS1 * SLOT + NS2 * SLOT2 + P_BYTES + 2 * BM * 4 + 256;     // 231 680 of 232 448 bytes
 
 // -DBIA_TRACE (MSDA_NVCC_EXTRA=-DBIA_TRACE csrc/build.sh) builds the pipeline-wait counters in for tools/trace_biattn.py;
 // otherwise the waits are plain and the counters fold away
@@ -97,17 +97,15 @@ template <bool HALF, bool GIVEN>
 __global__ void __launch_bounds__(PV_THREADS, 1)
 biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmX, PvParams p) {
-  // every byte of the 227 KiB is spoken for, so there is no room for a run-time alignment pad: the dynamic window of a
-  // kernel without static shared memory starts 1024-aligned (what the 128-byte swizzle needs); checked, not assumed.
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
-  uint8_t* sA = smem_raw;
+  // every byte of the 227 KiB is spoken for: alignment pad, stationary tile, rings, P tile, one exchange buffer, barriers
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sA = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sRing1 = sA + A_BYTES;
   uint8_t* sRing2 = sRing1 + NS1 * SLOT;
   uint8_t* sP = sRing2 + NS2 * SLOT2;                              // ONE probability tile: the next tile's exponentials are
-  float* sMax = reinterpret_cast<float*>(sP + P_BYTES);            // computed while GEMM2 still reads it; [2][2 halves][128]
-  float* sSum = sMax;                                              // [2 halves][128]: final stage only, barriers either side
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 2 * 2 * BM);
+  float* sMax = reinterpret_cast<float*>(sP + P_BYTES);            // computed while GEMM2 still reads it; [2 halves][128]
+  float* sSum = sMax;                                              // final stage only, barriers either side
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMax + 2 * BM);
   uint64_t* full1 = bars;             // [NS1]
   uint64_t* empty1 = full1 + NS1;     // [NS1]
   uint64_t* full2 = empty1 + NS1;     // [NS2]
@@ -355,10 +353,10 @@ biattn_pv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           float tmax = fmaxf(fmaxf(rm[0], rm[1]), fmaxf(rm[2], rm[3])) * p.scale_log2;
-          float* mx = sMax + bb * 2 * BM;
-          mx[half * BM + trow] = tmax;
+          sMax[half * BM + trow] = tmax;
           { const long long t0_ = TCLK(); named_bar(1 + quarter, 64); te[1] += TCLK() - t0_; }
-          tmax = fmaxf(tmax, mx[(half ^ 1) * BM + trow]);
+          tmax = fmaxf(tmax, sMax[(half ^ 1) * BM + trow]);
+          named_bar(1 + quarter, 64);                         // one exchange buffer: both have read before the next tile writes
           need = tmax > m_ref + kRaise;                       // also true for the first finite tile (m_ref = -inf)
           if (need) {
             sc = ex2(m_ref - tmax);                            // 0 when m_ref = -inf

@@ -47,7 +47,7 @@ constexpr int SLOT = 32768, NSLOT = 3;
 constexpr int H_BYTES = 2 * 16384;       // one hidden chunk: 2 k-blocks of 128 rows x 128 bytes
 constexpr int EPI_WARPS = 8;
 constexpr int THREADS = 64 + 32 * EPI_WARPS;
-constexpr int SMEM_BYTES = X_BYTES + NSLOT * SLOT + 2 * H_BYTES + 512 + 1024;      // operands, barriers, LayerNorm exchange
+constexpr int SMEM_BYTES = 1024 + X_BYTES + NSLOT * SLOT + 2 * H_BYTES + 512 + 1024;      // pad, operands, barriers, LayerNorm exchange
 
 struct Params {
   int R, F;                  // rows, hidden width (multiple of 128)
@@ -70,11 +70,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
                  const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr, Params p) {
-  // no room for a run-time alignment pad: the dynamic window of a kernel without static shared memory starts 1024-aligned
-  // (what the 128-byte swizzle needs); checked, not assumed
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  if ((smem_u32(smem_raw) & 1023u) != 0u) __trap();
-  uint8_t* smem = smem_raw;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sX = smem;
   uint8_t* sRing = sX + X_BYTES;
   uint8_t* sH = sRing + NSLOT * SLOT;
