@@ -104,10 +104,28 @@ msda_fwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           // weight.  Folding the weight into the four taps saves one FMA per channel but moves the result ~1e-5 away
           // from the reference op at sigma = 1 inputs (measured: profiles/r1_parity_table.txt), i.e. onto the parity bar.
           const float a = as[p0 + s];
+          if constexpr (sizeof(VT) == 2 && CH % 2 == 0) {
+            // 16-bit storage: the same multiply / fused multiply-add sequence as packed fp32x2 instructions (FMUL2 / FFMA2,
+            // sm_100), two channels per issue slot in a kernel bound by issue slots (-9 % measured, profiles/r2_exp_pk2.txt).
+            // The packed form is not bit-identical to the scalar one on the device, so the fp32 kernel -- whose forward is
+            // bit-identical to the reference CUDA op -- keeps the scalar sequence below.
+            const float2 k0 = make_float2(k[s][0], k[s][0]), k1 = make_float2(k[s][1], k[s][1]);
+            const float2 k2 = make_float2(k[s][2], k[s][2]), k3 = make_float2(k[s][3], k[s][3]), a2 = make_float2(a, a);
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const float val = k[s][0] * v[s][0][c] + k[s][1] * v[s][1][c] + k[s][2] * v[s][2][c] + k[s][3] * v[s][3][c];
-            acc[c] = fmaf(val, a, acc[c]);
+            for (int c = 0; c < CH; c += 2) {
+              float2 val = __fmul2_rn(k0, make_float2(v[s][0][c], v[s][0][c + 1]));
+              val = __ffma2_rn(k1, make_float2(v[s][1][c], v[s][1][c + 1]), val);
+              val = __ffma2_rn(k2, make_float2(v[s][2][c], v[s][2][c + 1]), val);
+              val = __ffma2_rn(k3, make_float2(v[s][3][c], v[s][3][c + 1]), val);
+              const float2 r = __ffma2_rn(val, a2, make_float2(acc[c], acc[c + 1]));
+              acc[c] = r.x; acc[c + 1] = r.y;
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < CH; ++c) {
+              const float val = k[s][0] * v[s][0][c] + k[s][1] * v[s][1][c] + k[s][2] * v[s][2][c] + k[s][3] * v[s][3][c];
+              acc[c] = fmaf(val, a, acc[c]);
+            }
           }
         }
       }
