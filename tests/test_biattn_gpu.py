@@ -136,3 +136,45 @@ def test_core_function_forward_backward_vs_fp64(S, T, masked, store_ds, monkeypa
     for name, t, r in zip(("d_q", "d_k", "d_val_v", "d_val_l"), (q, k, vv, vl), ref_in):
         errs[name] = rel_err(t.grad.double(), r.grad)
     assert all(e < 1e-2 for e in errs.values()), errs
+
+
+@pytest.mark.parametrize("B,H,S,T,dtype", [(1, 1, 50, 7, torch.bfloat16), (1, 3, 700, 300, torch.bfloat16), (2, 4, 129, 64, torch.float16),
+                                           (3, 2, 1024, 513, torch.bfloat16)])
+def test_core_function_edge_shapes(B, H, S, T, dtype):
+    """Fewer image tokens than one tile, more than 256 text tokens (several token tiles / groups), one head, fp16."""
+    from ziragroundingdino_b200 import biattn
+    scale = 1.0 / 16
+    q, k = _mk(B, S, H, dtype, seed=21).requires_grad_(True), _mk(B, T, H, dtype, seed=22).requires_grad_(True)
+    vv, vl = _mk(B, S, H, dtype, seed=23).requires_grad_(True), _mk(B, T, H, dtype, seed=24).requires_grad_(True)
+    mv = torch.zeros(B, S, dtype=torch.bool, device=DEV); mv[0, S // 2:] = True
+    ml = torch.zeros(B, T, dtype=torch.bool, device=DEV); ml[-1, :T // 3] = True
+    ov, ol = biattn.bi_attention_core(q, k, vv, vl, mv, ml, H, scale)
+    gv, gl = _mk(B, S, H, dtype, seed=25), _mk(B, T, H, dtype, seed=26)
+    torch.autograd.backward([ov, ol], [gv, gl])
+    ref_in = [t.detach().double().requires_grad_(True) for t in (q, k, vv, vl)]
+    rv, rl = _ref_core(*ref_in, mv, ml, H, scale)
+    torch.autograd.backward([rv, rl], [gv.double(), gl.double()])
+    errs = {"out_v": rel_err(ov.double(), rv.detach()), "out_l": rel_err(ol.double(), rl.detach())}
+    for name, t, r in zip(("d_q", "d_k", "d_val_v", "d_val_l"), (q, k, vv, vl), ref_in):
+        errs[name] = rel_err(t.grad.double(), r.grad)
+    assert all(e < 1e-2 for e in errs.values()), errs
+
+
+def test_block_under_inference_mode_and_noncontiguous_inputs():
+    from ziragroundingdino_b200 import _lib
+    from ziragroundingdino_b200.fuse_modules import BiAttentionBlock
+    torch.manual_seed(3)
+    blk = BiAttentionBlock(256, 256, 1024, 4, dropout=0.0, drop_path=0.0).to(DEV).bfloat16().eval()
+    v = torch.randn(2, 2, 400, 256, device=DEV).bfloat16()[:, 0]            # a strided view
+    l = torch.randn(2, 33, 256, device=DEV).bfloat16()
+    n0 = _lib.launch_count()
+    with torch.inference_mode():
+        ov, ol = blk(v, l)
+    assert _lib.launch_count() - n0 >= 3
+    blk.attn.use_kernel = False
+    try:
+        with torch.no_grad():
+            rv, rl = blk(v.contiguous(), l)
+    finally:
+        del blk.attn.use_kernel
+    assert (ov.float() - rv.float()).abs().max().item() < 6e-2 and (ol.float() - rl.float()).abs().max().item() < 6e-2
