@@ -273,6 +273,14 @@ int msda_ffn_chain_fwd_16(const void *x, const void *w1, const float *b1, const 
 int msda_ffn_chain_ln_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R, int C,
                              int F, const float *gamma, const float *beta, float eps, void *z, void *y, float *mean,
                              float *rstd, uint32_t *relu_bits_out, int is_half, void *stream);
+/* The same three entry points on CTA pairs (tcgen05 cta_group::2, clusters of two: each SM loads half of every weight tile). */
+int msda_ffn_chain2_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R, int C,
+                           int F, void *out, uint32_t *relu_bits_out, int is_half, void *stream);
+int msda_ffn_chain2_ln_fwd_16(const void *x, const void *w1, const float *b1, const void *w2, const float *b2, long long R,
+                              int C, int F, const float *gamma, const float *beta, float eps, void *z, void *y, float *mean,
+                              float *rstd, uint32_t *relu_bits_out, int is_half, void *stream);
+int msda_ffn_chain2_bwd_16(const void *dy, const void *w2_t, const void *w1_t, const uint32_t *gate_bits, const void *accum,
+                           long long R, int C, int F, void *dx, int is_half, void *stream);
 int msda_ffn_chain_bwd_16(const void *dy, const void *w2_t, const void *w1_t, const uint32_t *gate_bits, const void *accum,
                           long long R, int C, int F, void *dx, int is_half, void *stream);
 

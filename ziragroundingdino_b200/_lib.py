@@ -64,6 +64,9 @@ def lib():
     L.msda_query_proj_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]
     L.msda_ffn_chain_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]
     L.msda_ffn_chain_ln_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+    L.msda_ffn_chain2_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]
+    L.msda_ffn_chain2_ln_fwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _vp, _i, _vp]
+    L.msda_ffn_chain2_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp]
     L.msda_ffn_chain_bwd_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp]
     L.msda_flatten_levels.argtypes = [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _vp, _vp]
     L.msda_level_valid_counts.argtypes = [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]

@@ -35,6 +35,14 @@ def own_k_ffn():
 FFN_CHAIN = os.environ.get("MSDA_B200_FFN_CHAIN", "1") == "1"
 
 
+# The chained FFN on CTA pairs (tcgen05 cta_group::2, csrc/layer_ffn_chain2.cu): each SM streams half of every weight tile.
+FFN_PAIR = os.environ.get("MSDA_B200_FFN_PAIR", "0") == "1"
+
+
+def _chain(name):
+    return getattr(_lib.lib(), ("msda_ffn_chain2_" if FFN_PAIR else "msda_ffn_chain_") + name)
+
+
 def ffn_chain_ok(C, F):
     return FFN_CHAIN and C == 256 and F % 128 == 0 and F <= 8192
 
@@ -44,7 +52,7 @@ def ffn_chain_fwd16(x2d, w1, b1_f32, w2, b2_f32, bits):
     F = w1.shape[0]
     out = torch.empty((R, C), dtype=x2d.dtype, device=x2d.device)
     with torch.cuda.device(x2d.device):
-        rc = _lib.lib().msda_ffn_chain_fwd_16(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C, F,
+        rc = _chain("fwd_16")(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C, F,
                                               out.data_ptr(), bits.data_ptr(), 1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
     _lib.check(rc, "msda_ffn_chain_fwd_16")
     return out
@@ -63,7 +71,7 @@ def ffn_chain_ln_fwd16(x2d, w1, b1_f32, w2, b2_f32, g32, b32, eps, bits):
     mean = torch.empty(R, dtype=torch.float32, device=x2d.device)
     rstd = torch.empty(R, dtype=torch.float32, device=x2d.device)
     with torch.cuda.device(x2d.device):
-        rc = _lib.lib().msda_ffn_chain_ln_fwd_16(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C,
+        rc = _chain("ln_fwd_16")(x2d.data_ptr(), w1.data_ptr(), b1_f32.data_ptr(), w2.data_ptr(), b2_f32.data_ptr(), R, C,
                                                  F, g32.data_ptr(), b32.data_ptr(), float(eps), z.data_ptr(), y.data_ptr(),
                                                  mean.data_ptr(), rstd.data_ptr(), bits.data_ptr(),
                                                  1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
@@ -78,7 +86,7 @@ def ffn_chain_bwd16(dz, w2_t, w1_t, bits, accumulate=True):
     F = w2_t.shape[0]
     out = dz if accumulate else torch.empty_like(dz)
     with torch.cuda.device(dz.device):
-        rc = _lib.lib().msda_ffn_chain_bwd_16(dz.data_ptr(), w2_t.data_ptr(), w1_t.data_ptr(), bits.data_ptr(),
+        rc = _chain("bwd_16")(dz.data_ptr(), w2_t.data_ptr(), w1_t.data_ptr(), bits.data_ptr(),
                                               dz.data_ptr() if accumulate else 0, R, C, F, out.data_ptr(),
                                               1 if dz.dtype == torch.float16 else 0, _stream(dz))
     _lib.check(rc, "msda_ffn_chain_bwd_16")
@@ -177,7 +185,7 @@ class FFNBlockFunction(Function):
         bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
         ctx.chain = ffn_chain_ok(x2d.shape[1], w1.shape[0])
         if ctx.chain:
-            if FFN_LN:
+            if FFN_LN and not FFN_PAIR:      # the pair kernel has no fused LayerNorm
                 z, y, mean, rstd = ffn_chain_ln_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"),
                                                       g32, b32, eps, bits)
             else:

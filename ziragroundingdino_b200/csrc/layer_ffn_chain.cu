@@ -247,15 +247,13 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           const int gc = col0 + 32 * hf;
           if (!BWD) {
             const float4* bp = reinterpret_cast<const float4*>(p.bias1 + gc);
-            uint32_t m = 0u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 bb = __ldg(bp + i);
-              v[4 * i] = fmaxf(__uint_as_float(r[4 * i]) + bb.x, 0.f); v[4 * i + 1] = fmaxf(__uint_as_float(r[4 * i + 1]) + bb.y, 0.f);
-              v[4 * i + 2] = fmaxf(__uint_as_float(r[4 * i + 2]) + bb.z, 0.f); v[4 * i + 3] = fmaxf(__uint_as_float(r[4 * i + 3]) + bb.w, 0.f);
+              v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
             }
-#pragma unroll
-            for (int jx = 0; jx < 32; ++jx) m |= (v[jx] > 0.f ? 1u : 0u) << jx;
+            const uint32_t m = positive_mask32(v);          // the ReLU itself is fused into the 16-bit conversion below
             if (live && p.bits) p.bits[static_cast<size_t>(gc >> 5) * p.R + row] = m;
           } else {
             const uint32_t m = live ? __ldg(p.bits + static_cast<size_t>(gc >> 5) * p.R + row) : 0u;
@@ -263,7 +261,7 @@ ffn_chain_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             for (int jx = 0; jx < 32; ++jx) v[jx] = (m >> jx) & 1u ? __uint_as_float(r[jx]) : 0.f;
           }
           uint4 pk[4];
-          pack_16(v, HALF, false, pk);
+          if (!BWD) pack_16_relu(v, HALF, pk); else pack_16(v, HALF, false, pk);
 #pragma unroll
           for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(hk, quarter * 32 + lane, 4 * hf + i)) = pk[i];
         }

@@ -58,6 +58,23 @@ __device__ __forceinline__ uint32_t pack16(float a, float b, bool half_out) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// max(x, 0) fused into the conversion (cvt.rn.relu): first argument in the low half, like pack16
+__device__ __forceinline__ uint32_t pack16_relu(float a, float b, bool half_out) {
+  uint32_t d;
+  if (half_out) asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  else asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// bit jx of the result = (x[jx] > 0), two instructions per element: the sign of -bits(x) is set exactly for the positive
+// floats (bits in [1, 0x7fffffff]); a funnel shift moves it into the mask.  (-0.0f, bits 0x80000000, would count as
+// positive; a pre-activation is +0 on exact cancellation, never -0, in round-to-nearest.)
+__device__ __forceinline__ uint32_t positive_mask32(const float (&x)[32]) {
+  uint32_t m = 0u;
+#pragma unroll
+  for (int jx = 31; jx >= 0; --jx) m = __funnelshift_l(0u - __float_as_uint(x[jx]), m, 1);
+  return m;
+}
+
 // ---- epilogue -------------------------------------------------------------------------------------
 // tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns per chunk).  Measured in round 1
 // (profiles/r1_gemm_ab.txt): the kernel is bound by the latency of this per-chunk instruction chain on the few epilogue
@@ -98,6 +115,16 @@ __device__ __forceinline__ void pack_16(const float (&v)[32], bool half_out, boo
     o[i].y = zero ? 0u : pack16(v[8 * i + 2], v[8 * i + 3], half_out);
     o[i].z = zero ? 0u : pack16(v[8 * i + 4], v[8 * i + 5], half_out);
     o[i].w = zero ? 0u : pack16(v[8 * i + 6], v[8 * i + 7], half_out);
+  }
+}
+
+__device__ __forceinline__ void pack_16_relu(const float (&v)[32], bool half_out, uint4 (&o)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    o[i].x = pack16_relu(v[8 * i], v[8 * i + 1], half_out);
+    o[i].y = pack16_relu(v[8 * i + 2], v[8 * i + 3], half_out);
+    o[i].z = pack16_relu(v[8 * i + 4], v[8 * i + 5], half_out);
+    o[i].w = pack16_relu(v[8 * i + 6], v[8 * i + 7], half_out);
   }
 }
 
