@@ -318,3 +318,51 @@ def test_encoder_layer_with_fused_ffn_layernorm_matches_separate():
         blocks.FFN_LN = keep
     assert (res[True][0] - res[False][0]).abs().max().item() < 3 * 2 ** -8 * res[False][0].abs().max().item()
     assert (res[True][1] - res[False][1]).abs().max().item() < 2e-2 * res[False][1].abs().max().item()
+
+
+def test_ffn_chain_pair_kernel_bitwise_equals_single_cta_kernel():
+    """The CTA-pair chained FFN (tcgen05 cta_group::2, cross-CTA barriers with relaxed arrivals) must reproduce the single-CTA
+    kernel bit for bit -- same products, same accumulation order, same epilogue arithmetic (the LayerNorm statistics add four
+    partial sums per row instead of two) -- and itself on every repetition (a race in the cross-CTA signalling would show up
+    as a sporadic mismatch)."""
+    from ziragroundingdino_b200 import blocks
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(77)
+    C, F = 256, 2048
+    keep = blocks.FFN_PAIR
+    try:
+        for R in (88892, 1000, 129):
+            x = torch.randn(R, C, generator=g).bfloat16().to(dev)
+            w1 = (torch.randn(F, C, generator=g) * 0.06).bfloat16().to(dev)
+            w2 = (torch.randn(C, F, generator=g) * 0.02).bfloat16().to(dev)
+            b1 = (torch.randn(F, generator=g) * 0.1).to(dev)
+            b2 = (torch.randn(C, generator=g) * 0.1).to(dev)
+            gamma = (1 + 0.2 * torch.randn(C, generator=g)).to(dev)
+            beta = (0.1 * torch.randn(C, generator=g)).to(dev)
+            dz0 = torch.randn(R, C, generator=g).bfloat16().to(dev)
+            w1t, w2t = w1.t().contiguous(), w2.t().contiguous()
+
+            def run():
+                bits = torch.zeros((F // 32, R), dtype=torch.int32, device=dev)
+                y = blocks.ffn_chain_fwd16(x, w1, b1, w2, b2, bits)
+                bits2 = torch.zeros_like(bits)
+                z, yl, mean, rstd = blocks.ffn_chain_ln_fwd16(x, w1, b1, w2, b2, gamma, beta, 1e-5, bits2)
+                dx = blocks.ffn_chain_bwd16(dz0.clone(), w2t, w1t, bits)
+                return y, bits, z, yl, mean, rstd, bits2, dx
+            blocks.FFN_PAIR = False
+            ref = run()
+            blocks.FFN_PAIR = True
+            first = run()
+            names = ("y", "bits", "z", "y_ln", "mean", "rstd", "bits_ln", "dx")
+            for n, a, b in zip(names, ref, first):
+                if n in ("y_ln", "mean", "rstd"):      # four partial sums per row instead of two: last-bit differences allowed
+                    tol = 2 ** -7 if n == "y_ln" else 1e-5
+                    assert (a.double() - b.double()).abs().max().item() <= tol * max(1.0, a.double().abs().max().item()), n
+                else:
+                    assert torch.equal(a, b), n
+            for _ in range(12 if R > 10000 else 40):
+                got = run()
+                for n, a, b in zip(names, first, got):
+                    assert torch.equal(a, b), n
+    finally:
+        blocks.FFN_PAIR = keep

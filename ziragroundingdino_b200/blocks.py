@@ -35,8 +35,10 @@ def own_k_ffn():
 FFN_CHAIN = os.environ.get("MSDA_B200_FFN_CHAIN", "1") == "1"
 
 
-# The chained FFN on CTA pairs (tcgen05 cta_group::2, csrc/layer_ffn_chain2.cu): each SM streams half of every weight tile.
-FFN_PAIR = os.environ.get("MSDA_B200_FFN_PAIR", "0") == "1"
+# The chained FFN on CTA pairs (tcgen05 cta_group::2, csrc/layer_ffn_chain2.cu): each SM streams half of every weight tile and
+# the mid / final stages run on 16 warps.  Default on (bit-identical to the single-CTA kernel of csrc/layer_ffn_chain.cu,
+# 15-20 % faster); MSDA_B200_FFN_PAIR=0 selects the single-CTA kernel.
+FFN_PAIR = os.environ.get("MSDA_B200_FFN_PAIR", "1") == "1"
 
 
 def _chain(name):
@@ -185,7 +187,7 @@ class FFNBlockFunction(Function):
         bits = torch.empty((w1.shape[0] // 32, x2d.shape[0]), dtype=torch.int32, device=x.device)
         ctx.chain = ffn_chain_ok(x2d.shape[1], w1.shape[0])
         if ctx.chain:
-            if FFN_LN and not FFN_PAIR:      # the pair kernel has no fused LayerNorm
+            if FFN_LN:
                 z, y, mean, rstd = ffn_chain_ln_fwd16(x2d, w1.contiguous(), derived(b1, "f32"), w2.contiguous(), derived(b2, "f32"),
                                                       g32, b32, eps, bits)
             else:

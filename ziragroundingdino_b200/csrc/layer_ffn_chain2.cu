@@ -95,10 +95,11 @@ __device__ __forceinline__ void umma2_commit(uint64_t* bar) {
                ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3)) : "memory");
 }
 
-template <bool BWD, bool HALF>
+template <bool BWD, bool HALF, bool LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(THREADS, 1)
 ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmA,
-                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,                  Params p) {
+                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmOut,
+                  const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmXr, Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sX = smem;
@@ -115,7 +116,8 @@ ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   uint64_t* h_free = h_full + 2;      // [2] each CTA: GEMM2 has read it
   uint64_t* a2_full = h_free + 2;     // each CTA: result complete
   uint64_t* a2_free = a2_full + 1;    // leader: both CTAs' final stages have read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a2_free + 1);
+  uint64_t* res_full = a2_free + 1;   // [EPI_WARPS] LN: a warp's residual piece has landed in its staging tile (CTA-local)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + EPI_WARPS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = static_cast<int>(cluster_rank());
@@ -129,6 +131,7 @@ ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     for (int i = 0; i < NSLOT; ++i) { mbar_init(full + i, 1); mbar_init(empty + i, 1); }
     mbar_init(x_full, 1); mbar_init(x_free, 1);
+    for (int i = 0; i < EPI_WARPS; ++i) mbar_init(res_full + i, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(a1_full + i, 1); mbar_init(a1_free + i, 2 * EPI_WARPS); mbar_init(h_full + i, 2 * EPI_WARPS); mbar_init(h_free + i, 1); }
     mbar_init(a2_full, 1); mbar_init(a2_free, 2 * EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -255,7 +258,7 @@ ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     // The single-CTA kernel turned out to be bound by the LATENCY of this stage (the issuer waits for h_full more than half of
     // the time once the weights arrive fast enough), so the pair kernel runs it on twice as many warps. =====
     const int quarter = warp & 3, slice = (warp - 2) >> 2;
-    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0;
+    uint32_t ph_a1full[2] = {0, 0}, ph_hfree[2] = {0, 0}, ph_a2 = 0, ph_res = 0;
     const uint32_t lane_bits = static_cast<uint32_t>(quarter * 32) << 16;
     long long te[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #ifdef FFN2_TRACE
@@ -327,10 +330,10 @@ ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       mbar_wait(a2_full, ph_a2);
       ph_a2 ^= 1;
       tc_fence_after();
-      {
-        constexpr int FC = C / EW;                   // 64 output columns per warp
-        static_assert(FC == 64, "one staging tile per warp");
-        const int gc = slice * FC;
+      constexpr int FC = C / EW;                     // 64 output columns per warp
+      static_assert(FC == 64, "one staging tile per warp");
+      const int gc = slice * FC;
+      if (!LN) {
         uint4 ain[8];
         if (BWD && p.accum != nullptr) {
           const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(p.accum) + row * C + gc);
@@ -355,6 +358,88 @@ ffn_chain2_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
           }
           if (BWD && p.accum != nullptr) add_packed16(v, reinterpret_cast<const uint32_t*>(ain) + 16 * hf, HALF);
+          uint4 pk[4];
+          pack_16(v, HALF, false, pk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(stile, lane, 4 * hf + i)) = pk[i];
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tma_store_2d(&tmOut, stile, gc, static_cast<int>(row0));
+      } else {
+        // ---- residual + LayerNorm (transformer_for_adapter.py:882-885): z = x + ffn(x) rounded to 16 bit, y = LN(z).  The warp
+        // fetches its 32 x 64 piece of the residual by TMA into its staging tile, forms z in registers, exchanges the partial
+        // sums of the ROUNDED values with the three other warps of its lane quarter THROUGH the staging tiles (idle until the
+        // z store), stores z, then normalises the packed row it kept and stores y.
+        if (lane == 0) {
+          tma_store_wait_read();
+          mbar_expect_tx(res_full + (warp - 2), 4096);
+          tma_load_2d(&tmXr, res_full + (warp - 2), stile, gc, static_cast<int>(row0));
+        }
+        __syncwarp();
+        mbar_wait(res_full + (warp - 2), ph_res);
+        ph_res ^= 1;
+        uint4 zk[2][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t r[32];
+          float v[32];
+          tmem_ld32(t_acc2 + lane_bits + static_cast<uint32_t>(gc + 32 * hf), r);
+          const float4* bp = reinterpret_cast<const float4*>(p.bias2 + gc + 32 * hf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bb = __ldg(bp + i);
+            v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+          }
+          uint4 xin[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) xin[i] = *reinterpret_cast<const uint4*>(swz(stile, lane, 4 * hf + i));
+          add_packed16(v, reinterpret_cast<const uint32_t*>(xin), HALF);
+          pack_16(v, HALF, false, zk[hf]);
+          float zr[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) zr[i] = 0.f;
+          add_packed16(zr, reinterpret_cast<const uint32_t*>(zk[hf]), HALF);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { s1 += zr[i]; s2 = fmaf(zr[i], zr[i], s2); }
+        }
+        __syncwarp();                                   // every lane has taken its residual out of the staging tile
+        reinterpret_cast<float2*>(stile)[lane] = make_float2(s1, s2);
+        named_bar(2 + quarter, 32 * EW);
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < EW; ++sl) {
+          const float2 o = reinterpret_cast<const float2*>(sH + (sl * 4 + quarter) * 4096)[lane];
+          t1 += o.x; t2 += o.y;
+        }
+        named_bar(2 + quarter, 32 * EW);               // all four have read: the staging tiles may take z
+        const float mean = t1 * (1.f / C);
+        const float rstd = rsqrtf(fmaxf(t2 * (1.f / C) - mean * mean, 0.f) + p.ln_eps);
+        if (slice == 0 && live) { p.ln_mean[row] = mean; p.ln_rstd[row] = rstd; }
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(stile, lane, 4 * hf + i)) = zk[hf][i];
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(&tmZ, stile, gc, static_cast<int>(row0)); tma_store_wait_read(); }
+        __syncwarp();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float zr[32], v[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) zr[i] = 0.f;
+          add_packed16(zr, reinterpret_cast<const uint32_t*>(zk[hf]), HALF);
+          const float4* gp = reinterpret_cast<const float4*>(p.ln_gamma + gc + 32 * hf);
+          const float4* bp = reinterpret_cast<const float4*>(p.ln_beta + gc + 32 * hf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 gg = __ldg(gp + i), bb = __ldg(bp + i);
+            v[4 * i] = fmaf((zr[4 * i] - mean) * rstd, gg.x, bb.x); v[4 * i + 1] = fmaf((zr[4 * i + 1] - mean) * rstd, gg.y, bb.y);
+            v[4 * i + 2] = fmaf((zr[4 * i + 2] - mean) * rstd, gg.z, bb.z); v[4 * i + 3] = fmaf((zr[4 * i + 3] - mean) * rstd, gg.w, bb.w);
+          }
           uint4 pk[4];
           pack_16(v, HALF, false, pk);
 #pragma unroll
@@ -397,7 +482,7 @@ static int launch(const void* x, const void* wa, const void* wb, void* out, void
   if (!x || !wa || !wb || !out) { snprintf(t_err, sizeof(t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
   if (p.R <= 0 || p.F <= 0 || p.F % HC || p.F > 8192) { snprintf(t_err, sizeof(t_err), "chained FFN needs d_ffn %% 128 == 0 (R=%d F=%d)", p.R, p.F); return MSDA_ERR_UNSUPPORTED; }
   const int dt = p.half_in ? 1 : 0;
-  CUtensorMap tmX, tmA, tmB, tmOut;
+  CUtensorMap tmX, tmA, tmB, tmOut, tmZ, tmXr;
   int rc = make_map(&tmX, x, p.R, C, BM, 64, dt);
   if (rc) return rc;
   rc = make_map(&tmA, wa, p.F, C, 64, 64, dt);           // half of a chunk's 128 rows per CTA
@@ -406,7 +491,10 @@ static int launch(const void* x, const void* wa, const void* wb, void* out, void
   if (rc) return rc;
   rc = make_map(&tmOut, out, p.R, C, 32, 64, dt);
   if (rc) return rc;
-  if (z_out) { snprintf(t_err, sizeof(t_err), "the pair kernel has no fused LayerNorm"); return MSDA_ERR_UNSUPPORTED; }
+  rc = make_map(&tmZ, z_out ? z_out : out, p.R, C, 32, 64, dt);
+  if (rc) return rc;
+  rc = make_map(&tmXr, x, p.R, C, 32, 64, dt);      // the residual, in the final stage's 32 x 64 pieces
+  if (rc) return rc;
   int dev_id = 0;
   cudaGetDevice(&dev_id);
   static int sms_of[64] = {};
@@ -416,17 +504,18 @@ static int launch(const void* x, const void* wa, const void* wb, void* out, void
   const int grid = 2 * (pairs < max_pairs ? pairs : max_pairs);
   cudaError_t cfg = cudaSuccess;
   ++msda::g_launches;
-#define FFN_LAUNCH(BWD, HALF)                                                                                           \
-  do {                                                                                                                   \
-    static bool configured[64] = {};                                                                                     \
-    if (!configured[dev_id & 63]) {                                                                                      \
-      cfg = cudaFuncSetAttribute(ffn_chain2_kernel<BWD, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
-      configured[dev_id & 63] = cfg == cudaSuccess;                                                                      \
-    }                                                                                                                    \
-    if (cfg == cudaSuccess) ffn_chain2_kernel<BWD, HALF><<<grid, THREADS, SMEM_BYTES, st>>>(tmX, tmA, tmB, tmOut, p);     \
+#define FFN_LAUNCH(BWD, HALF, LN)                                                                                           \
+  do {                                                                                                                       \
+    static bool configured[64] = {};                                                                                         \
+    if (!configured[dev_id & 63]) {                                                                                          \
+      cfg = cudaFuncSetAttribute(ffn_chain2_kernel<BWD, HALF, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);  \
+      configured[dev_id & 63] = cfg == cudaSuccess;                                                                          \
+    }                                                                                                                        \
+    if (cfg == cudaSuccess) ffn_chain2_kernel<BWD, HALF, LN><<<grid, THREADS, SMEM_BYTES, st>>>(tmX, tmA, tmB, tmOut, tmZ, tmXr, p); \
   } while (0)
-  if (p.backward) { if (p.half_in) FFN_LAUNCH(true, true); else FFN_LAUNCH(true, false); }
-  else { if (p.half_in) FFN_LAUNCH(false, true); else FFN_LAUNCH(false, false); }
+  if (p.backward) { if (p.half_in) FFN_LAUNCH(true, true, false); else FFN_LAUNCH(true, false, false); }
+  else if (z_out) { if (p.half_in) FFN_LAUNCH(false, true, true); else FFN_LAUNCH(false, false, true); }
+  else { if (p.half_in) FFN_LAUNCH(false, true, false); else FFN_LAUNCH(false, false, false); }
 #undef FFN_LAUNCH
   if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
   cudaError_t e = cudaGetLastError();
