@@ -17,7 +17,7 @@ for k in biattn_pv_kernel biattn_ds_kernel biattn_tn_kernel; do
   python tools/ncu_summary.py gpurun_out/r2z_$k.ncu-rep > gpurun_out/r2z_ncu_$k.txt 2>&1
   rm -f gpurun_out/r2z_$k.ncu-rep
 done
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:ffn_chain_kernel -c 2 -o gpurun_out/r2z_ffn -f python bench.py --config 2 --steps 1 --warmup 1 --no-cpu-baseline --no-config5 --no-fusion --no-graph > gpurun_out/r2z_ncu_ffn.log 2>&1
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:ffn_chain2_kernel -c 2 -o gpurun_out/r2z_ffn -f python bench.py --config 2 --steps 1 --warmup 1 --no-cpu-baseline --no-config5 --no-fusion --no-graph > gpurun_out/r2z_ncu_ffn.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2z_ffn.ncu-rep > gpurun_out/r2z_ncu_ffn_chain.txt 2>&1
 rm -f gpurun_out/r2z_ffn.ncu-rep
 grep -c "==" gpurun_out/r2z_ncu_*.txt
