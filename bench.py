@@ -585,6 +585,12 @@ def run_ours(args):
     bwd_launches = _lib.launch_count() - n0
     us_bwd = kernel_us([(lambda c=c, i_=i_, r=r: fused.backward_fusedq16(*c, i_["grad_out"], r, 2)) for c, i_, r in zip(cargs, sets, refs)])
     us_bwd_plain = kernel_us([(lambda c=c, i_=i_: zb._C.ms_deform_attn_backward(*c, i_["grad_out"], 64)) for c, i_ in zip(cargs, sets)])
+    # opt-in variant (MSDA_B200_F16ACC=1): grad_value accumulated in scaled fp16; amax pass + memset included
+    try:
+        us_bwd_f16acc = kernel_us([(lambda c=c, i_=i_, r=r: fused.backward_fusedq_h16(*c, i_["grad_out"], r, 2)) for c, i_, r in zip(cargs, sets, refs)])
+    except Exception as exc:      # an optional leg must not lose the line
+        us_bwd_f16acc = None
+        sys.stderr.write("bwd_f16acc leg failed: %r\n" % (exc,))
 
     # live probes of the two memory-system limits these kernels run against (nothing but the access shape):
     #   gather : random 64-byte rows (one bf16 head row) read from an L2-resident 22 MB buffer
@@ -720,7 +726,9 @@ def run_ours(args):
                                             **({"padding": "none (all-valid case)"} if args.all_valid else {})), "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": images / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "other_workload": other,
-        "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "bwd_unfused_q": us_bwd_plain, "bwd_launches": bwd_launches,
+        "msda_core_us_per_layer": {"fwd": us_fwd, "bwd": us_bwd, "bwd_unfused_q": us_bwd_plain, "bwd_f16acc_optin": us_bwd_f16acc,
+                                   "grad_value_accumulation": "scaled fp16 (opt-in)" if fused.f16_accumulate else "fp32",
+                                   "bwd_launches": bwd_launches,
                                    "images": KN, "cold_l2": "inputs rotated over 3 sets (> L2)",
                                    "fwd_l2_algorithmic_gbps": ab["fwd_l2"] / us_fwd / 1e3,
                                    "bwd_l2_algorithmic_gbps": ab["bwd_l2"] / us_bwd / 1e3},

@@ -104,6 +104,30 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
                             int N, int S, int M, int D, int L, int Lq, int P, float *grad_value, void *dq,
                             int zero_grad_value, int is_half, void *stream);
 
+/* msda_backward_fusedq_16 with grad_value accumulated in SCALED fp16 instead of fp32 (same reference lines; the
+ * reductions of ms_deform_im2col_cuda.cuh:87-159 leave the SM as 64-byte packed-half rows instead of 128-byte fp32 rows --
+ * the SM->L2 reduction path is byte-bound on this part).
+ *   grad_value_h : device buffer of 2 * N * rows_h * M * D + 128 bytes, rows_h = msda_grad_value_h16_rows(host copy of
+ *                  spatial_shapes, L, Lq): per image, level l is stored as K_l replicas of its H_l*W_l rows (query q adds
+ *                  into replica q mod K_l; K_l = f16acc_replicas(Lq, H_l*W_l) keeps the expected number of contributions
+ *                  per fp16 row <= 96), followed by one 128-byte tail whose first word receives the bits of max |grad_out|.
+ *                  The call zeroes all of it on `stream`, measures the maximum and accumulates scale * contribution with
+ *                  scale = the power of two f16acc_scale(max, Lq) (msda_common.cuh), chosen so that no partial sum can
+ *                  overflow fp16 whatever the sampling pattern.  A rows_h that disagrees with the device-side shapes makes
+ *                  the kernel write nothing and poison the tail (the consumer then yields NaN).
+ * Error vs fp32 accumulation: ~1e-3 of max |grad_value| (fp16 has 11 significand bits; the consumer rounds to bf16's 8
+ * anyway) -- inside the 1e-2 bar of 16-bit storage, outside fp32's 1e-4, so fp32 storage never takes this path.
+ * msda_cast_mask_h16 is the consumer: sum of replicas / scale -> [N*S, cols = M*D] 16-bit rows (out_f32 = 0; padded rows
+ * zeroed: backward of ms_deform_attn.py:287-288) or fp32 rows (out_f32 = 1). */
+long long msda_grad_value_h16_rows(const int64_t *spatial_shapes_host, int L, int Lq);
+int msda_backward_fusedq_h16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
+                             const float *loc, const float *aw, const void *grad_out, const float *ref, int ref_dim,
+                             int N, int S, int M, int D, int L, int Lq, int P, void *grad_value_h, long long rows_h,
+                             void *dq, int is_half, void *stream);
+int msda_cast_mask_h16(const void *grad_value_h, const int64_t *spatial_shapes, const int64_t *level_start_index, int L,
+                       int N, int S, int cols, int Lq, long long rows_h, const uint8_t *row_mask, void *out, int out_f32,
+                       int is_half, void *stream);
+
 /* The 16-bit backward with a caller-provided scratch buffer.  Same results as msda_backward_{bf16,f16} (dq == NULL:
  * grad_loc / grad_aw written, ref ignored) or msda_backward_fusedq_16 (dq != NULL: grad_loc / grad_aw ignored); the
  * scratch lets the tensor-memory scatter own fine levels as well (tuning key "bwd_mma_levels"): the scatter kernel marks

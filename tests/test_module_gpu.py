@@ -65,6 +65,31 @@ def test_module_bf16_within_1e2():
     assert (out.detach().double().cpu() - truth).abs().max().item() < 1e-2 * scale      # north_star: bf16 within 1e-2
 
 
+def test_module_bf16_scaled_fp16_accumulation_switch():
+    """fused.f16_accumulate (opt-in, MSDA_B200_F16ACC=1): the module's input gradients with grad_value accumulated in scaled
+    fp16 against the default fp32 accumulation -- grad_query identical (the query side does not depend on the map),
+    grad_value_in within 1e-2 of its maximum (measured ~1e-3)."""
+    from ziragroundingdino_b200 import fused
+    dev = torch.device("cuda:0")
+    g = load_golden("module_d32")
+    m, (C, M, L, P, bf) = _load_module(g, torch.bfloat16, dev)
+    res = {}
+    keep = fused.f16_accumulate
+    try:
+        for mode in (False, True):
+            fused.f16_accumulate = mode
+            q, v, refp, sh, lsi, mask = _inputs(g, torch.bfloat16, dev, bf)
+            out = m(query=q, value=v, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+            out.backward(torch.from_numpy(g["grad_out"]).to(device=dev, dtype=torch.bfloat16))
+            res[mode] = (out.detach().float(), q.grad.float(), v.grad.float())
+    finally:
+        fused.f16_accumulate = keep
+    assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
+    d = (res[True][2] - res[False][2]).abs().max().item() / res[False][2].abs().max().item()
+    print("module bf16: grad_value_in, scaled-fp16 vs fp32 accumulation: max diff / max = %.2e" % d)
+    assert 0 < d < 1e-2 or (C // M, L, P) != (32, 4, 4)
+
+
 def test_module_errors():
     import ziragroundingdino_b200 as zb
     dev = torch.device("cuda:0")

@@ -165,12 +165,13 @@ class SelfAttnBlockFunction(Function):
         dz = _add_ln_bwd(dy.reshape(N * S, C).contiguous(), z, g32, mean, rstd)     # d(src) via the residual AND d(attn out)
         d_core = fused.linear16(dz, prep.w_o_t)
         if fused.fusedq_ok(M, L, P, C // M):
-            grad_value, dq_cat = fused.backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim)
+            gv16, dq_cat = fused.backward_fusedq_gv16(value, spatial_shapes, level_start_index, loc, aw, d_core, ref, ref_dim,
+                                                      row_mask)
         else:
             grad_value, grad_loc, grad_aw = _C.ms_deform_attn_backward(value, spatial_shapes, level_start_index, loc, aw,
                                                                        d_core.view(N, S, C), im2col_step)
             dq_cat = fused.query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * S, M, L, P, dt)
-        gv16 = fused.cast_mask16(grad_value.view(N * S, C), row_mask, dt)
+            gv16 = fused.cast_mask16(grad_value.view(N * S, C), row_mask, dt)
         d_src = linear_accum16(gv16, prep.w_v_t, dz)            # dz += d(value_proj input)
         d_src = linear_accum16(dq_cat, prep.w_cat_t, d_src)     # dz += d(query) (= d(src) through query = src + pos)
         return (d_src.view(N, S, C),) + (None,) * 13

@@ -12,6 +12,8 @@ template <typename VT>
 cudaError_t backward_f32acc(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 template <typename VT>
 cudaError_t backward_fused_q(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+template <typename VT>
+cudaError_t backward_fused_q_h16(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 cudaError_t forward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t backward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace msda
@@ -192,6 +194,47 @@ int msda_backward_fusedq_16(const void* value, const int64_t* shapes, const int6
     e = msda::backward_fused_q<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(value), shapes, lstart, loc, aw,
                                               static_cast<const __nv_bfloat16*>(grad_out), gv, ref, ref_dim, dq, 0, N, S, M, Lq, st);
   return cuda_status(e, "msda_backward_fusedq launch");
+}
+
+long long msda_grad_value_h16_rows(const int64_t* shapes_host, int L, int Lq) {
+  if (!shapes_host || L <= 0 || L > MSDA_MAX_LEVELS || Lq <= 0) return 0;
+  long long rows = 0;
+  for (int l = 0; l < L; ++l) {
+    const long long hw = shapes_host[2 * l] * shapes_host[2 * l + 1];
+    if (hw <= 0) return 0;
+    rows += hw * msda::f16acc_replicas(Lq, hw);
+  }
+  return rows;
+}
+
+int msda_backward_fusedq_h16(const void* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                             const void* grad_out, const float* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
+                             void* gv_h, long long rows_h, void* dq, int is_half, void* stream) {
+  t_err[0] = 0;
+  int rc = check_common(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, 2);
+  if (rc) return rc;
+  if (!grad_out || !gv_h || !dq || !ref) return fail(MSDA_ERR_NULL_POINTER, "null pointer");
+  if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 4))
+    return fail(MSDA_ERR_UNSUPPORTED, "fused query backward needs D=32, L=4, P=4 (got D=%d L=%d P=%d)", D, L, P);
+  if (rows_h < S || rows_h > 64ll * S) return fail(MSDA_ERR_BAD_SHAPE, "rows_h = %lld is not msda_grad_value_h16_rows() of S = %d", rows_h, S);
+  if (rows_h * M * D >= (1ll << 31)) return fail(MSDA_ERR_BAD_SHAPE, "scaled-fp16 map of %lld rows does not fit 32-bit per-image indexing", rows_h);
+  if (!aligned16(grad_out) || !aligned16(gv_h) || !aligned16(dq) || !aligned16(ref))
+    return fail(MSDA_ERR_MISALIGNED, "pointers must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t map_bytes = 2 * static_cast<size_t>(N) * rows_h * M * D;
+  rc = cuda_status(cudaMemsetAsync(gv_h, 0, map_bytes + 128, st), "grad_value memset");      // the map and the amax word behind it
+  if (rc) return rc;
+  if (N == 0 || Lq == 0) return MSDA_OK;
+  uint32_t* amax = reinterpret_cast<uint32_t*>(static_cast<char*>(gv_h) + map_bytes);
+  cudaError_t e;
+  if (is_half)
+    e = msda::backward_fused_q_h16<__half>(static_cast<const __half*>(value), shapes, lstart, loc, aw, static_cast<const __half*>(grad_out),
+                                           gv_h, rows_h, amax, ref, ref_dim, dq, 1, N, S, M, Lq, st);
+  else
+    e = msda::backward_fused_q_h16<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(value), shapes, lstart, loc, aw,
+                                                  static_cast<const __nv_bfloat16*>(grad_out), gv_h, rows_h, amax, ref, ref_dim, dq, 0, N, S,
+                                                  M, Lq, st);
+  return cuda_status(e, "msda_backward_fusedq_h16 launch");
 }
 
 long long msda_backward_workspace_bytes(int N, int M, int Lq) {

@@ -5,6 +5,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
+#include <cstring>
+
 #include "../../include/msda_b200.h"
 
 namespace msda {
@@ -127,6 +130,46 @@ template <> struct VecQ<__half> {
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.relaxed.gpu.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// 64-bit packed-half reduction (4 channels) into an fp16 map (REDG.E.ADD.F16x2.RN on sm_100a).
+__device__ __forceinline__ void red_add_v2h(__half* p, __half2 a, __half2 b) {
+  asm volatile("red.relaxed.gpu.global.add.noftz.v2.f16x2 [%0], {%1, %2};"
+               :: "l"(p), "r"(*reinterpret_cast<const uint32_t*>(&a)), "r"(*reinterpret_cast<const uint32_t*>(&b)) : "memory");
+}
+
+// Scaled-fp16 accumulation of grad_value: the power of two s with s * amax < 2^floor(log2(60000 / Lq)).  For one
+// (pixel, head) row the contributions of a query sum to at most |grad_out| (its attention weights sum to 1 and a sample
+// touches a pixel with at most one corner of weight <= 1), so every partial sum stays below Lq * s * amax < 60000 < the
+// fp16 maximum: the accumulation cannot overflow whatever the sampling pattern.  Producer and consumers call this with
+// the same (amax bits, Lq) and get the same scale.
+__host__ __device__ inline float f16acc_scale(uint32_t amax_bits, int Lq) {
+  float amax;
+#ifdef __CUDA_ARCH__
+  amax = __uint_as_float(amax_bits);
+#else
+  memcpy(&amax, &amax_bits, 4);
+#endif
+  if (!(amax > 0.f) || amax > 3.0e38f || Lq <= 0) return 1.f;     // zero, NaN or inf gradient: any scale will do
+  int e = 0, be = 0;
+  frexpf(amax, &e);                                               // amax < 2^e
+  frexpf(60000.f / static_cast<float>(Lq), &be);                  // 2^(be-1) <= 60000 / Lq
+  int k = be - 1 - e;
+  k = k < -120 ? -120 : (k > 120 ? 120 : k);
+  return ldexpf(1.f, k);
+}
+
+// fp16 has 11 significand bits: a row that receives n contributions of similar size loses ~log2(n) of them, and the two
+// coarse levels of an encoder launch receive hundreds to thousands per (pixel, head) row (16 * Lq / (H*W) if the samples
+// spread evenly).  The scaled-fp16 map therefore holds K_l REPLICAS of level l's rows -- query q accumulates into replica
+// (q / 4) mod K_l (the four consecutive queries a warp holds keep sharing rows, so their reductions still leave as one
+// request per line), the consumer sums the replicas in fp32 -- with K_l the power of two that brings the expected count per row
+// to <= 96 (Swin-T 800x1333, Lq = 22 223: K = 1, 1, 4, 16; 29 468 map rows per image instead of 22 223).
+__host__ __device__ inline int f16acc_replicas(int Lq, long long hw) {
+  const long long n = 16ll * Lq / (hw > 0 ? hw : 1);
+  int k = 1;
+  while (k < 64 && n > 96ll * k) k <<= 1;
+  return k;
 }
 
 // ---- scalar element access for the generic kernels -----------------------------------------------

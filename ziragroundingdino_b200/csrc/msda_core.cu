@@ -213,6 +213,8 @@ struct FuseQ {
   uint16_t* dq;         // [N*Lq, 3*M*L*P]
   int ref_dim;
   int is_half;
+  uint32_t* amax;        // F16ACC: bits of max |grad_out| (written by grad_amax_kernel), else unused
+  long long rows_h;      // F16ACC: rows per image of the scaled-fp16 map (levels with replicas), as the host sized it
 };
 
 // 3 resident CTAs per SM (<= 85 registers): the kernel needs its occupancy to keep enough reductions and corner loads in
@@ -224,7 +226,10 @@ struct FuseQ {
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 3      // resident CTAs per SM the scatter kernel is compiled for (A/B: -DMSDA_BWD_MINB=4 -> 64 registers)
 #endif
-template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS>
+// F16ACC (16-bit storage, 4 channels per lane): grad_value is a SCALED fp16 map -- every contribution is multiplied by the
+// power of two f16acc_scale(max |grad_out|, Lq) and leaves as red.global.add.noftz.v2.f16x2 (64 bytes per corner row
+// instead of 128: the SM->L2 reduction path is byte-bound).  `grad_value` then points at __half storage.
+template <typename VT, int D, typename V, bool FUSEQ, int MODE, bool SHARE, bool DOTS, bool F16ACC = false>
 __global__ void __launch_bounds__(kThreads, MSDA_BWD_MINB)
 msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ shapes,
                     const int64_t* __restrict__ lstart, const float* __restrict__ loc,
@@ -245,6 +250,11 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   __shared__ int sRedLevels;
   __shared__ float sInvW[MSDA_MAX_LEVELS], sInvH[MSDA_MAX_LEVELS];     // FUSEQ: 1/W_l, 1/H_l (IEEE division, once per CTA)
   __shared__ RangePlan plan;       // HITS (mma_mode 2) only; the compiler drops it otherwise
+  __shared__ float sScale;
+  static_assert(!F16ACC || (FUSEQ && MODE == 0 && V::CH == 4 && sizeof(VT) == 2), "F16ACC: fused-query 16-bit kernel only");
+  __shared__ int sHStart[MSDA_MAX_LEVELS], sHW[MSDA_MAX_LEVELS], sRepMask[MSDA_MAX_LEVELS];   // F16ACC: replica blocks of the map
+  __shared__ long long sRowsH;
+  if (F16ACC && threadIdx.x == 32) sScale = f16acc_scale(*fq.amax, Lq);
   if (threadIdx.x < L) {
     sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
     sW[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x + 1]);
@@ -261,8 +271,25 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   if (threadIdx.x == 0) {
     if (HITS) { plan_ranges(plan, sH, sW, sStart, L, S, mma_levels); sRedLevels = plan.first_level; }
     else sRedLevels = mma_mode == 1 ? coarse_first_level(sH, sW, sStart, L, S) : L;
+    if (F16ACC) {
+      long long at = 0;
+      for (int l = 0; l < L; ++l) {
+        const int hw = sH[l] * sW[l], k = f16acc_replicas(Lq, hw);
+        sHStart[l] = static_cast<int>(at); sHW[l] = hw; sRepMask[l] = k - 1;
+        at += static_cast<long long>(k) * hw;
+      }
+      sRowsH = at;
+    }
   }
   __syncthreads();
+  if constexpr (F16ACC) {
+    // the host sized (and zeroed) the map from ITS copy of the shapes: refuse to write into a buffer laid out differently,
+    // and poison the amax word so that the consumer produces NaN instead of silently wrong gradients
+    if (sRowsH != fq.rows_h) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(fq.amax, 0xffffffffu);
+      return;
+    }
+  }
   const int red_levels = sRedLevels;
   const int cpq = (Lq + 63) >> 6;
 
@@ -281,6 +308,9 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
     const size_t voff = (static_cast<size_t>(b) * S * M + m) * D + lig * CH;
     const VT* vb = value + voff;
     float* gvb = grad_value + voff;
+    __half* gvb_h = reinterpret_cast<__half*>(grad_value);      // F16ACC: image b of the replicated map, head m, this lane's channels
+    const int q_of_unit = static_cast<int>(bq - b * Lq);
+    if constexpr (F16ACC) gvb_h += (static_cast<size_t>(b) * fq.rows_h * M + m) * D + lig * CH;
     const float4* lp = reinterpret_cast<const float4*>(loc + static_cast<size_t>(u) * L * P * 2);
     const float4* ap = reinterpret_cast<const float4*>(aw + static_cast<size_t>(u) * L * P);
     float* glp = grad_loc + static_cast<size_t>(u) * L * P * 2;
@@ -319,6 +349,13 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
     // or grad_attn of point lig/2 (odd lanes); they are kept until the softmax dot product over all 16 samples is known.
     // Even lanes write their (d offset_x, d offset_y) pair inside the level loop; odd lanes keep (grad_attn, attn weight) of
     // their point for each of the 4 levels in eight scalars (selected by level, so nothing lives in local memory).
+    // F16ACC: the lane's four grad_out channels times the scale, as two half2 (exact for 16-bit grad_out unless subnormal)
+    __half2 gh01 = __half2(), gh23 = __half2();
+    if constexpr (F16ACC) {
+      const float sc = sScale;
+      gh01 = __floats2half2_rn(gr[0] * sc, gr[1] * sc);
+      gh23 = __floats2half2_rn(gr[2] * sc, gr[3] * sc);
+    }
     float fq_g0 = 0.f, fq_g1 = 0.f, fq_g2 = 0.f, fq_g3 = 0.f, fq_w0 = 0.f, fq_w1 = 0.f, fq_w2 = 0.f, fq_w3 = 0.f;
     float fq_dot = 0.f;
     unsigned long long hit_bits = 0ull;      // mma_mode 2: ranges touched by this unit's samples
@@ -333,6 +370,8 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
       const size_t loff = static_cast<size_t>(sStart[l]) * row;
       const VT* vl = vb + loff;
       float* gvl = gvb + loff;
+      __half* gvl_h = gvb_h;
+      if constexpr (F16ACC) gvl_h += (static_cast<size_t>(sHStart[l]) + static_cast<size_t>((q_of_unit >> 2) & sRepMask[l]) * sHW[l]) * row;
       const float4 xy01 = __ldg(lp + 2 * l), xy23 = __ldg(lp + 2 * l + 1), a4 = __ldg(ap + l);
       const float xs[4] = {xy01.x, xy01.z, xy23.x, xy23.z};
       const float ys[4] = {xy01.y, xy01.w, xy23.y, xy23.w};
@@ -386,6 +425,13 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
         red[4 * p + 2] = s_a;
         red[4 * p + 3] = 0.f;
         }
+        if constexpr (F16ACC) {
+          // weight (bilinear x attention) in fp32, rounded once to fp16; the two products round once more
+          if (do_red && t.c1) { const __half2 kh = __float2half2_rn(k1 * a); red_add_v2h(gvl_h + e1, __hmul2(kh, gh01), __hmul2(kh, gh23)); }
+          if (do_red && t.c2) { const __half2 kh = __float2half2_rn(k2 * a); red_add_v2h(gvl_h + e2, __hmul2(kh, gh01), __hmul2(kh, gh23)); }
+          if (do_red && t.c3) { const __half2 kh = __float2half2_rn(k3 * a); red_add_v2h(gvl_h + e3, __hmul2(kh, gh01), __hmul2(kh, gh23)); }
+          if (do_red && t.c4) { const __half2 kh = __float2half2_rn(k4 * a); red_add_v2h(gvl_h + e4, __hmul2(kh, gh01), __hmul2(kh, gh23)); }
+        } else {
 #pragma unroll
         for (int c0 = 0; c0 < CH; c0 += 4) {
           // element offset of this 4-channel slice relative to the lane's load slice (see `gr` above)
@@ -395,6 +441,7 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
           if (do_red && t.c2) red_add_v4(gvl + e2 + ro, k2 * r0, k2 * r1, k2 * r2, k2 * r3);
           if (do_red && t.c3) red_add_v4(gvl + e3 + ro, k3 * r0, k3 * r1, k3 * r2, k3 * r3);
           if (do_red && t.c4) red_add_v4(gvl + e4 + ro, k4 * r0, k4 * r1, k4 * r2, k4 * r3);
+        }
         }
       }
       if (HITS && !do_red && o_max >= 0) {
@@ -688,7 +735,7 @@ template <typename VT, int D>
 static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                   const float* loc, const float* aw, const VT* grad_out, float* gv,
                                   float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
-  const FuseQ none{nullptr, nullptr, 0, 0};
+  const FuseQ none{nullptr, nullptr, 0, 0, nullptr, 0};
   // narrow layout needs D/4 <= 16 lanes per unit
   if constexpr (Vec<VT>::CH == 8 && D <= 64) {
     if (g_tuning.bwd_narrow)
@@ -702,11 +749,62 @@ template <typename VT>
 cudaError_t backward_fused_q(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
                              const VT* grad_out, float* gv, const float* ref, int ref_dim, void* dq, int is_half, int N, int S,
                              int M, int Lq, cudaStream_t st) {
-  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half};
+  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, nullptr, 0};
   return launch_bwd_vec_t<VT, 32, VecQ<VT>, true>(value, shapes, lstart, loc, aw, grad_out, gv, nullptr, nullptr, N, S, M, 4, Lq, st, fq);
 }
 template cudaError_t backward_fused_q<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 template cudaError_t backward_fused_q<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+
+// max |grad_out| over a 16-bit tensor, as float bits (monotone for non-negative floats, NaN above inf above finite), by
+// atomicMax into a zero-initialised word: the input of f16acc_scale().
+template <bool IS_HALF>
+__global__ void __launch_bounds__(256) grad_amax_kernel(const uint4* __restrict__ g, long long n8, uint32_t* __restrict__ amax) {
+  uint32_t m = 0u;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 v = __ldg(g + i);
+    m = __vmaxu2(m, __vmaxu2(__vmaxu2(v.x & 0x7fff7fffu, v.y & 0x7fff7fffu), __vmaxu2(v.z & 0x7fff7fffu, v.w & 0x7fff7fffu)));
+  }
+  uint32_t m16 = max(m >> 16, m & 0xffffu);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) m16 = max(m16, __shfl_xor_sync(0xffffffffu, m16, o));
+  __shared__ uint32_t sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m16;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m16 = max(m16, sm[w]);
+    const uint32_t bits = IS_HALF ? __float_as_uint(__half2float(__ushort_as_half(static_cast<unsigned short>(m16)))) : (m16 << 16);
+    if (bits != 0u) atomicMax(amax, bits);
+  }
+}
+
+// 16-bit storage, D == 32, L == 4, P == 4: the fused-query backward with grad_value accumulated in scaled fp16
+// (F16ACC).  gv_h [N*S*M*32] halves and the amax word must arrive zeroed.
+template <typename VT>
+cudaError_t backward_fused_q_h16(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
+                                 const VT* grad_out, void* gv_h, long long rows_h, uint32_t* amax, const float* ref, int ref_dim,
+                                 void* dq, int is_half, int N, int S, int M, int Lq, cudaStream_t st) {
+  using V = VecQ<VT>;
+  constexpr int D = 32;
+  constexpr int TILE = (32 / (D / V::CH)) * kWarpsPerBlock;
+  const long long units = static_cast<long long>(N) * Lq * M;
+  const long long n8 = units * D / 8;
+  const unsigned ablocks = static_cast<unsigned>(std::min<long long>((n8 + 255) / 256, 148 * 8));
+  g_launches += 2;
+  grad_amax_kernel<std::is_same<VT, __half>::value><<<ablocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(grad_out), n8, amax);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, amax, rows_h};
+  const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
+  const int passes = g_tuning.bwd_passes;
+  const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
+  msda_bwd_vec_kernel<VT, D, V, true, 0, false, true, true><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
+      value, shapes, lstart, loc, aw, grad_out, static_cast<float*>(gv_h), nullptr, nullptr, S, M, 4, Lq, units, passes, q_fast, 0, 0,
+      nullptr, fq);
+  return cudaGetLastError();
+}
+template cudaError_t backward_fused_q_h16<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_fused_q_h16<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 
 // Storage types whose locations / weights / gradients are fp32 (float, bf16, half).
 template <typename VT>

@@ -11,11 +11,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/msda_b200.h"
+#include <algorithm>
 
-namespace msda {
-extern long long g_launches;
-}
+#include "msda_common.cuh"
 
 namespace {
 
@@ -155,6 +153,65 @@ cast_mask_kernel(const float* __restrict__ in, const uint8_t* __restrict__ row_m
   w.w = to16(b.z, h) | (static_cast<uint32_t>(to16(b.w, h)) << 16);
   out[i] = zero ? make_uint4(0u, 0u, 0u, 0u) : w;
 }
+// Consumer of the scaled-fp16 grad_value map (msda_backward_fusedq_h16): sum of a pixel's replicas / scale -> 16-bit storage
+// (padded rows zeroed) or fp32.  Scale and replica layout are recomputed from the amax word behind the map and the
+// device-side shapes, exactly as the scatter kernel did.  One thread per 8 channels.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(256)
+cast_mask_h16_kernel(const uint4* __restrict__ in, const uint32_t* __restrict__ amax, const int64_t* __restrict__ shapes,
+                     const int64_t* __restrict__ lstart, int L, int S, long long rows_h, int Lq,
+                     const uint8_t* __restrict__ row_mask, long long n8, int cols8, int is_half, void* __restrict__ out) {
+  __shared__ int sStart[MSDA_MAX_LEVELS], sHStart[MSDA_MAX_LEVELS], sHW[MSDA_MAX_LEVELS], sRep[MSDA_MAX_LEVELS];
+  if (threadIdx.x == 0) {
+    long long at = 0;
+    for (int l = 0; l < L; ++l) {
+      const int hw = static_cast<int>(shapes[2 * l] * shapes[2 * l + 1]), k = msda::f16acc_replicas(Lq, hw);
+      sStart[l] = static_cast<int>(lstart[l]); sHStart[l] = static_cast<int>(at); sHW[l] = hw; sRep[l] = k;
+      at += static_cast<long long>(k) * hw;
+    }
+  }
+  __syncthreads();
+  const float inv = 1.f / msda::f16acc_scale(__ldg(amax), Lq);        // a power of two (NaN if the scatter kernel refused the layout)
+  const long long b = blockIdx.y;
+  const unsigned total = static_cast<unsigned>(S) * cols8;           // image blockIdx.y: 8-channel groups, grid-stride
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int s = static_cast<int>(idx / static_cast<unsigned>(cols8));
+    const int c8 = static_cast<int>(idx - static_cast<unsigned>(s) * cols8);
+    const long long r = b * S + s;
+    const long long i = r * cols8 + c8;
+    int l = 0;
+    while (l + 1 < L && s >= sStart[l + 1]) ++l;
+    const uint4* src = in + ((b * rows_h + sHStart[l] + (s - sStart[l])) * cols8 + c8);
+    const long long rep_stride = static_cast<long long>(sHW[l]) * cols8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+    for (int k = 0; k < sRep[l]; ++k) {
+      const uint4 v = __ldg(src + k * rep_stride);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+        acc[2 * j] += f.x; acc[2 * j + 1] += f.y;
+      }
+    }
+    const bool zero = row_mask != nullptr && row_mask[r] != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = zero ? 0.f : acc[j] * inv;
+    if constexpr (OUT_F32) {
+      float4* o = static_cast<float4*>(out) + 2 * i;
+      o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    } else {
+      const bool h = is_half != 0;
+      uint4 w;
+      w.x = to16(acc[0], h) | (static_cast<uint32_t>(to16(acc[1], h)) << 16);
+      w.y = to16(acc[2], h) | (static_cast<uint32_t>(to16(acc[3], h)) << 16);
+      w.z = to16(acc[4], h) | (static_cast<uint32_t>(to16(acc[5], h)) << 16);
+      w.w = to16(acc[6], h) | (static_cast<uint32_t>(to16(acc[7], h)) << 16);
+      static_cast<uint4*>(out)[i] = w;
+    }
+  }
+}
 __device__ __forceinline__ float from16(uint16_t v, bool is_half) {
   if (is_half) return __half2float(*reinterpret_cast<const __half*>(&v));
   return __uint_as_float(static_cast<uint32_t>(v) << 16);
@@ -292,6 +349,28 @@ int msda_cast_mask_16(const float* in, const uint8_t* row_mask, long long rows, 
   ++msda::g_launches;
   cast_mask_kernel<<<static_cast<unsigned>((n8 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       in, row_mask, n8, cols / 8, is_half, static_cast<uint4*>(out));
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : static_cast<int>(e);
+}
+
+int msda_cast_mask_h16(const void* gv_h, const int64_t* shapes, const int64_t* lstart, int L, int N, int S, int cols, int Lq,
+                       long long rows_h, const uint8_t* row_mask, void* out, int out_f32, int is_half, void* stream) {
+  if (!gv_h || !out || !shapes || !lstart) return MSDA_ERR_NULL_POINTER;
+  if (N <= 0 || N > 65535 || S <= 0 || cols <= 0 || cols % 8 || Lq <= 0 || L <= 0 || L > MSDA_MAX_LEVELS || rows_h < S ||
+      static_cast<long long>(S) * (cols / 8) >= (1ll << 31))
+    return MSDA_ERR_BAD_SHAPE;
+  const long long n8 = static_cast<long long>(N) * S * (cols / 8);
+  const uint32_t* amax = reinterpret_cast<const uint32_t*>(static_cast<const char*>(gv_h) + 2ll * N * rows_h * cols);
+  const long long per_image = (static_cast<long long>(S) * (cols / 8) + 255) / 256;
+  const dim3 blocks(static_cast<unsigned>(std::min<long long>(per_image, (148 * 8 + N - 1) / N)), static_cast<unsigned>(N));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ++msda::g_launches;
+  if (out_f32)
+    cast_mask_h16_kernel<true><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(gv_h), amax, shapes, lstart, L, S, rows_h, Lq, row_mask, n8,
+                                                       cols / 8, 0, out);
+  else
+    cast_mask_h16_kernel<false><<<blocks, 256, 0, st>>>(static_cast<const uint4*>(gv_h), amax, shapes, lstart, L, S, rows_h, Lq, row_mask,
+                                                        n8, cols / 8, is_half, out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : static_cast<int>(e);
 }
