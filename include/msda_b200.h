@@ -189,6 +189,11 @@ int msda_linear_16(const void *x, const void *w, const float *bias, long long R,
  * `out` may alias `accum`.  Nout % 8 == 0. */
 int msda_linear_accum_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout, const void *accum,
                          void *out, int is_half, void *stream);
+/* The same accumulating product over TWO activation operands, K-concatenated without a copy: out = accum + [x1 | x2] w^T,
+ * x1 [R, K1], x2 [R, K2] (K1, K2 multiples of 64), w [Nout, K1 + K2].  The encoder block's two input dgrads
+ * (d value_proj input + d query, ms_deform_attn.py:286 and :290-293 backward) as one launch. */
+int msda_linear_accum2_16(const void *x1, int K1, const void *x2, int K2, const void *w, const float *bias, long long R,
+                          int Nout, const void *accum, void *out, int is_half, void *stream);
 /* FFN companions (row N1; reference transformer_for_adapter.py:876-885): out = relu(x W^T + bias) when relu != 0, and
  * out = (x W^T + bias) where gate > 0 else 0 when gate != NULL (gate: 16-bit [R, Nout]) -- the ReLU backward fused into
  * the dgrad GEMM of linear2.  16-bit output, leading dimension Nout; Nout <= 2048. */
@@ -203,6 +208,12 @@ int msda_linear_act_bits_16(const void *x, const void *w, const float *bias, lon
 int msda_query_proj_16(const void *query, const void *w_cat, const float *bias_cat, const float *ref, int ref_dim,
                        const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
                        float *aw_out, int is_half, void *stream);
+/* msda_query_proj_16 of (query + query_add) without forming the sum: both operands stream against ONE resident copy of
+ * w_cat and the two products accumulate in fp32 (`query = src + pos`, transformer_for_adapter.py:867-869 / :893, folded
+ * into the projection).  query_add == NULL is msda_query_proj_16. */
+int msda_query_proj2_16(const void *query, const void *query_add, const void *w_cat, const float *bias_cat, const float *ref,
+                        int ref_dim, const int64_t *spatial_shapes, long long R, int K, int M, int L, int P, float *loc_out,
+                        float *aw_out, int is_half, void *stream);
 int msda_query_bwd_prep_16(const float *grad_loc, const float *grad_aw, const float *aw, const float *ref, int ref_dim,
                            const int64_t *spatial_shapes, long long R, int M, int L, int P, void *out, int ld_out,
                            int is_half, void *stream);

@@ -146,7 +146,9 @@ def test_encoder_layer_block_functions_vs_stagewise(dtype, with_mask):
     # the block form keeps x + ffn(x) in fp32 until LayerNorm's input is rounded (the stage-wise path rounds ffn(x) first)
     ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
     assert (res[True][0].float() - res[False][0].float()).abs().max().item() <= 4 * ulp * res[False][0].float().abs().max().item()
-    assert rel_err(res[True][1].float().cpu(), res[False][1].float().cpu()) < 2e-2
+    # the block form also projects src + pos WITHOUT rounding the sum to 16 bits (blocks.FOLD_POS): a few sampling
+    # locations land on the other side of a pixel boundary than in the stage-wise path, whose query is the rounded sum
+    assert rel_err(res[True][1].float().cpu(), res[False][1].float().cpu()) < 4e-2
     # fp64 truth of the same layer
     d = lambda t: t.detach().double().cpu()
     p = {(k[len("self_attn."):] if k.startswith("self_attn.") else k): d(v) for k, v in layer.state_dict().items()}
@@ -366,3 +368,106 @@ def test_ffn_chain_pair_kernel_bitwise_equals_single_cta_kernel():
                     assert torch.equal(a, b), n
     finally:
         blocks.FFN_PAIR = keep
+
+
+def test_linear_accum2_two_operands_k_concatenated():
+    """out = accum + [x1 | x2] w^T with the k-blocks of ONE GEMM coming from two activation tensors (msda_linear_accum2_16):
+    against fp64, against the product over a materialised concatenation (bit-equal: same tiles, same order), in place
+    and out of place, rows not a multiple of the tile, resident and streamed W."""
+    from ziragroundingdino_b200 import blocks, _lib
+    for dtype, eps in ((torch.bfloat16, 2 ** -8), (torch.float16, 2 ** -11)):
+        for R, K1, K2, Nout in ((1000, 256, 384, 256), (4 * 22223 + 3, 256, 384, 256), (77, 64, 64, 64), (300, 128, 512, 128)):
+            g = torch.Generator().manual_seed(R + K2)
+            x1 = torch.randn(R, K1, generator=g).to(dtype).to(DEV)
+            x2 = torch.randn(R, K2, generator=g).to(dtype).to(DEV)
+            w = (torch.randn(Nout, K1 + K2, generator=g) * 0.05).to(dtype).to(DEV)
+            acc = torch.randn(R, Nout, generator=g).to(dtype).to(DEV)
+            want = acc.double() + torch.cat([x1, x2], 1).double() @ w.double().t()
+            out = torch.empty_like(acc)
+            for resident in (1, 0):
+                _lib.lib().msda_b200_gemm_set_resident(resident)
+                try:
+                    blocks.linear_accum2_16(x1, x2, w, acc, out)
+                    a2 = acc.clone()
+                    blocks.linear_accum2_16(x1, x2, w, a2)
+                    cat = blocks.linear_accum16(torch.cat([x1, x2], 1).contiguous(), w, acc, torch.empty_like(acc))
+                finally:
+                    _lib.lib().msda_b200_gemm_set_resident(1)
+                assert (out.double() - want).abs().max().item() <= eps * want.abs().max().item() * 1.05
+                assert torch.equal(out, a2) and torch.equal(out, cat)
+
+
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_query_projection_of_a_sum_without_forming_it(dtype, ref_dim):
+    """msda_query_proj2_16(src, pos) = sampling locations / attention weights of (src + pos), the two operands streamed
+    against one resident copy of the stacked weight.  Truth: fp64 on the exact sum; the two-operand form must be at least
+    as close as projecting the rounded 16-bit sum (it skips that rounding)."""
+    from ziragroundingdino_b200 import fused
+    torch.manual_seed(3)
+    C, M, L, P, R = 256, 8, 4, 4, 4 * 1234 + 5
+    shapes = torch.tensor([(20, 30), (10, 15), (5, 8), (3, 4)], device=DEV)
+    src = torch.randn(R, C, device=DEV).to(dtype)
+    pos = torch.randn(R, C, device=DEV).to(dtype)
+    w_cat = (torch.randn(3 * M * L * P, C, device=DEV) * 0.03).to(dtype)
+    b_cat = torch.randn(3 * M * L * P, device=DEV) * 0.1
+    ref = torch.rand(R, L, ref_dim, device=DEV) * 0.6 + 0.2
+    loc2, aw2 = fused.query_proj16(src, w_cat, b_cat, ref, ref_dim, shapes, M, L, P, q_add=pos)
+    loc1, aw1 = fused.query_proj16((src + pos).contiguous(), w_cat, b_cat, ref, ref_dim, shapes, M, L, P)
+    raw = (src.double() + pos.double()) @ w_cat.double().t() + b_cat.double()
+    off = raw[:, :2 * M * L * P].view(R, M, L, P, 2)
+    awt = torch.softmax(raw[:, 2 * M * L * P:].view(R, M, L * P), -1).view(R, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[:, 1], shapes[:, 0]], -1).double()
+        loct = ref.double()[:, None, :, None, :] + off / norm[None, None, :, None, :]
+    else:
+        loct = ref.double()[:, None, :, None, :2] + off / P * ref.double()[:, None, :, None, 2:] * 0.5
+    e2l, e1l = (loc2.double() - loct).abs().max().item(), (loc1.double() - loct).abs().max().item()
+    e2a, e1a = (aw2.double() - awt).abs().max().item(), (aw1.double() - awt).abs().max().item()
+    print("query projection of src + pos (%s, ref_dim %d): loc err two-operand %.2e / rounded sum %.2e; aw %.2e / %.2e" % (dtype, ref_dim, e2l, e1l, e2a, e1a))
+    assert e2l <= e1l * 1.05 + 1e-7 and e2a <= e1a * 1.05 + 1e-7
+    assert e2l < 1e-4 and e2a < 1e-5          # fp32 accumulation of exact 16-bit operands
+
+
+def test_encoder_block_operand_folds_match_the_separate_launches():
+    """blocks.FOLD_POS / blocks.DGRAD_CAT (default on): the encoder's attention block with `src + pos` folded into the query
+    projection and its two input dgrads as one K-concatenated product, against the separate elementwise add and the two
+    accumulating GEMMs.  The fold projects the exact sum (locations 7e-7 from fp64 instead of 2e-3 for the rounded 16-bit
+    sum, see the test above), so some samples move across pixel boundaries: outputs agree to a few 16-bit ulps of the
+    LayerNorm-scale values, the input gradient to 4e-2 (Frobenius) -- the distance the stage-wise comparison also shows."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import blocks
+    torch.manual_seed(9)
+    C, FF, M, L, P, N = 256, 2048, 8, 4, 4, 2
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    layer = zb.DeformableTransformerEncoderLayer(C, FF, 0.0, "relu", L, M, P)
+    with torch.no_grad():
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+        layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+    layer = layer.to(DEV).to(torch.bfloat16)
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    sh = torch.tensor(shapes, device=DEV)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    src0 = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    pos = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    refp = torch.rand(N, S, L, 2, device=DEV)
+    mask = torch.zeros(N, S, dtype=torch.bool, device=DEV)
+    mask[1, S - 150:] = True
+    gy = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    res = {}
+    keep = (blocks.FOLD_POS, blocks.DGRAD_CAT)
+    try:
+        for on in (True, False):
+            blocks.FOLD_POS = blocks.DGRAD_CAT = on
+            x = src0.clone().requires_grad_(True)
+            y, _ = layer(x, pos, refp, sh, lsi, mask)
+            y.backward(gy)
+            res[on] = (y.detach().float(), x.grad.float())
+    finally:
+        blocks.FOLD_POS, blocks.DGRAD_CAT = keep
+    dy = (res[True][0] - res[False][0]).abs().max().item()
+    dg = rel_err(res[True][1].cpu(), res[False][1].cpu())
+    print("encoder block folds on vs off: max |dy| %.2e, rel d(src) %.2e" % (dy, dg))
+    assert dy <= 6e-2 and dg < 4e-2

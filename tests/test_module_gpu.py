@@ -67,27 +67,42 @@ def test_module_bf16_within_1e2():
 
 def test_module_bf16_scaled_fp16_accumulation_switch():
     """fused.f16_accumulate (opt-in, MSDA_B200_F16ACC=1): the module's input gradients with grad_value accumulated in scaled
-    fp16 against the default fp32 accumulation -- grad_query identical (the query side does not depend on the map),
-    grad_value_in within 1e-2 of its maximum (measured ~1e-3)."""
+    fp16 against the default fp32 accumulation -- output and grad_query identical (the query side does not depend on the
+    map), grad_value_in within 1e-2 of its maximum (measured ~1e-3).  256 channels / 8 heads / 4 levels / 4 points: the
+    shape class that takes the fused-query backward."""
+    import ziragroundingdino_b200 as zb
     from ziragroundingdino_b200 import fused
     dev = torch.device("cuda:0")
-    g = load_golden("module_d32")
-    m, (C, M, L, P, bf) = _load_module(g, torch.bfloat16, dev)
+    torch.manual_seed(12)
+    C, M, L, P, N, Lq = 256, 8, 4, 4, 2, 700
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    m = zb.MultiScaleDeformableAttention(C, M, L, P, batch_first=True)
+    with torch.no_grad():
+        m.sampling_offsets.weight.normal_(0, 0.01)
+        m.attention_weights.weight.normal_(0, 0.05)
+    m = m.to(dev).to(torch.bfloat16)
+    sh = torch.tensor(shapes, device=dev)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    q0 = torch.randn(N, Lq, C, device=dev).to(torch.bfloat16)
+    v0 = torch.randn(N, S, C, device=dev).to(torch.bfloat16)
+    refp = torch.rand(N, Lq, L, 2, device=dev)
+    gy = torch.randn(N, Lq, C, device=dev).to(torch.bfloat16)
     res = {}
     keep = fused.f16_accumulate
     try:
         for mode in (False, True):
             fused.f16_accumulate = mode
-            q, v, refp, sh, lsi, mask = _inputs(g, torch.bfloat16, dev, bf)
-            out = m(query=q, value=v, key_padding_mask=mask, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
-            out.backward(torch.from_numpy(g["grad_out"]).to(device=dev, dtype=torch.bfloat16))
+            q, v = q0.clone().requires_grad_(True), v0.clone().requires_grad_(True)
+            out = m(query=q, value=v, reference_points=refp, spatial_shapes=sh, level_start_index=lsi)
+            out.backward(gy)
             res[mode] = (out.detach().float(), q.grad.float(), v.grad.float())
     finally:
         fused.f16_accumulate = keep
     assert torch.equal(res[True][0], res[False][0]) and torch.equal(res[True][1], res[False][1])
     d = (res[True][2] - res[False][2]).abs().max().item() / res[False][2].abs().max().item()
     print("module bf16: grad_value_in, scaled-fp16 vs fp32 accumulation: max diff / max = %.2e" % d)
-    assert 0 < d < 1e-2 or (C // M, L, P) != (32, 4, 4)
+    assert 0 < d < 1e-2
 
 
 def test_module_errors():

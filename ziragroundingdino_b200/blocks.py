@@ -131,6 +131,28 @@ def linear_accum16(x2d, w, accum, out=None):
     return out
 
 
+def linear_accum2_16(x1, x2, w12, accum, out=None):
+    """out = accum + [x1 | x2] @ w12^T (16-bit) without concatenating the activations: ONE GEMM whose k-blocks come from two
+    operands (msda_linear_accum2_16); ``out`` defaults to accumulating in place."""
+    R, K1 = x1.shape
+    K2 = x2.shape[1]
+    Nout = w12.shape[0]
+    out = accum if out is None else out
+    assert x1.is_contiguous() and x2.is_contiguous() and w12.is_contiguous() and accum.is_contiguous()
+    assert x2.shape[0] == R and w12.shape[1] == K1 + K2 and accum.shape == (R, Nout) and accum.dtype == x1.dtype == x2.dtype
+    with torch.cuda.device(x1.device):
+        rc = _lib.lib().msda_linear_accum2_16(x1.data_ptr(), K1, x2.data_ptr(), K2, w12.data_ptr(), 0, R, Nout, accum.data_ptr(),
+                                              out.data_ptr(), 1 if x1.dtype == torch.float16 else 0, _stream(x1))
+    _lib.check(rc, "msda_linear_accum2_16")
+    return out
+
+
+# A/B switches (tests, measurements): `query = src + pos` as a second operand of the query projection instead of an
+# elementwise pass; the two input dgrads of the block as one K-concatenated product.
+FOLD_POS = os.environ.get("MSDA_B200_FOLD_POS", "1") != "0"
+DGRAD_CAT = os.environ.get("MSDA_B200_DGRAD_CAT", "1") != "0"
+
+
 class SelfAttnBlockFunction(Function):
     """``norm1(src + MSDeformAttn(query = src + pos, value = src))`` with every parameter frozen: returns the block
     output; backward returns d(src) only, with the value-projection and query-projection dgrads accumulated onto the
@@ -141,11 +163,16 @@ class SelfAttnBlockFunction(Function):
                 g32, b32, eps):
         N, S, C = src.shape
         src2d = src.reshape(N * S, C).contiguous()
-        q2d = src2d if pos is None else (src + pos).reshape(N * S, C)
         ref = reference_points.to(torch.float32).contiguous()
         ref_dim = ref.shape[-1]
         value = fused.linear16(src2d, prep.w_v, prep.b_v, row_mask).view(N, S, M, C // M)
-        loc, aw = fused.query_proj16(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
+        if pos is not None and FOLD_POS and pos.shape == src.shape and pos.dtype == src.dtype:
+            # (src + pos) W^T = src W^T + pos W^T, both products accumulated in fp32 by the one GEMM (transformer_for_adapter.py:867-869, :893)
+            loc, aw = fused.query_proj16(src2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P,
+                                         q_add=pos.reshape(N * S, C).contiguous())
+        else:
+            q2d = src2d if pos is None else (src + pos).reshape(N * S, C)
+            loc, aw = fused.query_proj16(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
         loc, aw = loc.view(N, S, M, L, P, 2), aw.view(N, S, M, L, P)
         core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
         attn = fused.linear16(core.view(N * S, C), prep.w_o, prep.b_o)
@@ -172,8 +199,12 @@ class SelfAttnBlockFunction(Function):
                                                                        d_core.view(N, S, C), im2col_step)
             dq_cat = fused.query_bwd_prep16(grad_loc, grad_aw, aw, ref, ref_dim, spatial_shapes, N * S, M, L, P, dt)
             gv16 = fused.cast_mask16(grad_value.view(N * S, C), row_mask, dt)
-        d_src = linear_accum16(gv16, prep.w_v_t, dz)            # dz += d(value_proj input)
-        d_src = linear_accum16(dq_cat, prep.w_cat_t, d_src)     # dz += d(query) (= d(src) through query = src + pos)
+        if DGRAD_CAT and dq_cat.shape[1] % 64 == 0 and dq_cat.shape[1] == prep.w_cat_t.shape[1]:
+            # dz += d(value_proj input) + d(query) (= d(src) through query = src + pos): one product over [grad_value | dq]
+            d_src = linear_accum2_16(gv16, dq_cat, prep.w_vq_t, dz)
+        else:
+            d_src = linear_accum16(gv16, prep.w_v_t, dz)            # dz += d(value_proj input)
+            d_src = linear_accum16(dq_cat, prep.w_cat_t, d_src)     # dz += d(query)
         return (d_src.view(N, S, C),) + (None,) * 13
 
 

@@ -61,9 +61,14 @@ bool g_staged_store = true;      // msda_b200_gemm_set_staged(0|1)   // msda_b20
 // ---- the kernel -----------------------------------------------------------------------------------
 template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE, bool TMA_OUT>
 __global__ void __launch_bounds__(THREADS, 1)
-linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC2, int R, int Nout,
-                 int K, int block_n, int b_resident, int stages, int store_bufs, int half_in, EpiParams ep) {
+linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                 const __grid_constant__ CUtensorMap tmC2, int R, int Nout, int K, int k_split, int k_b, int block_n,
+                 int b_resident, int stages, int store_bufs, int half_in, EpiParams ep) {
+  // Two activation operands, K-concatenated: k-blocks [0, k_split) come from tmA, the rest from tmA2 (same rows), so
+  // [x1 | x2] W^T needs no concatenated copy of the activations.  W has k_b k-blocks and k-block kb multiplies W's block
+  // kb % k_b: k_b == K / 64 is the plain product, k_b == k_split == K / 128 is (x1 + x2) W^T = x1 W^T + x2 W^T with ONE
+  // resident copy of W (`query = src + pos`, transformer_for_adapter.py:867-869, folded into the query projection).
   // b_resident: the CTA owns ONE n-block for its whole life and keeps that slice of W (block_n x K) in shared
   // memory, loaded once; only the activation tiles stream through the ring (K = 256, N <= 256: 128 KiB of W).
   // Otherwise A and B tiles stream together (any shape).
@@ -74,7 +79,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int b_tile_bytes = block_n * BLOCK_K * 2;
   const int stage_bytes = b_resident ? SMEM_A : SMEM_A + b_tile_bytes;
   uint8_t* smem_bres = smem + stages * stage_bytes;                       // resident W slice: (K/64) tiles
-  uint8_t* tma_tiles = smem_bres + (b_resident ? (K / BLOCK_K) * b_tile_bytes : 0);   // 1024-aligned (all sizes above are)
+  uint8_t* tma_tiles = smem_bres + (b_resident ? k_b * b_tile_bytes : 0);   // 1024-aligned (all sizes above are)
   uint8_t* aux = tma_tiles + (TMA_OUT ? EPI_WARPS * store_bufs * TMA_TILE_BYTES : 0);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(aux);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -100,6 +105,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    if (k_split < num_k) asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA2)) : "memory");
     for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, EPI_WARPS); }
     mbar_init(bres_bar, 1);
@@ -125,8 +131,8 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       if (b_resident && t_first < t_end) {
-        mbar_expect_tx(bres_bar, static_cast<uint32_t>(num_k * b_tile_bytes));
-        for (int kb = 0; kb < num_k; ++kb) tma_load_2d(&tmB, bres_bar, smem_bres + kb * b_tile_bytes, kb * BLOCK_K, n_fixed);
+        mbar_expect_tx(bres_bar, static_cast<uint32_t>(k_b * b_tile_bytes));
+        for (int kb = 0; kb < k_b; ++kb) tma_load_2d(&tmB, bres_bar, smem_bres + kb * b_tile_bytes, kb * BLOCK_K, n_fixed);
       }
       for (int t = t_first; t < t_end; t += t_step) {
         const int m_idx = (b_resident ? t : t / num_n) * BLOCK_M, n_idx = b_resident ? n_fixed : (t % num_n) * block_n;
@@ -134,8 +140,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_wait(empty_bar + stage, phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           mbar_expect_tx(full_bar + stage, static_cast<uint32_t>(stage_bytes));
-          tma_load_2d(&tmA, full_bar + stage, sa, kb * BLOCK_K, m_idx);
-          if (!b_resident) tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, kb * BLOCK_K, n_idx);
+          if (kb < k_split) tma_load_2d(&tmA, full_bar + stage, sa, kb * BLOCK_K, m_idx);
+          else tma_load_2d(&tmA2, full_bar + stage, sa, (kb - k_split) * BLOCK_K, m_idx);
+          if (!b_resident) tma_load_2d(&tmB, full_bar + stage, sa + SMEM_A, (kb % k_b) * BLOCK_K, n_idx);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -155,7 +162,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         if (elect_one()) {
           const uint8_t* sa = smem + stage * stage_bytes;
-          const uint8_t* sb = b_resident ? smem_bres + kb * b_tile_bytes : sa + SMEM_A;
+          const uint8_t* sb = b_resident ? smem_bres + (kb % k_b) * b_tile_bytes : sa + SMEM_A;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t da = umma_desc_sw128(sa, k * UMMA_K * 2);
@@ -600,9 +607,17 @@ static int pick_block_n(int Nout, int K, int unit, bool f32_out) {
   return smallest ? smallest : unit;
 }
 
+// x2 != nullptr: the activation operand is [x | x2] (K1 and K - K1 columns, both multiples of 64); KB = row length of W
+// (K, or K1 == K / 2 for the shared-weight sum, see the kernel).
 static int launch(const void* x, const void* w, long long R, int K, int Nout, int block_n, bool half_in,
-                  const EpiParams& ep, cudaStream_t st) {
+                  const EpiParams& ep, cudaStream_t st, const void* x2 = nullptr, int K1 = 0, int KB = 0) {
   if (!x || !w) { snprintf(t_err, sizeof(t_err), "null operand"); return MSDA_ERR_NULL_POINTER; }
+  if (!x2) { K1 = K; KB = K; }
+  if (K1 <= 0 || K1 > K || K1 % BLOCK_K || (x2 && K1 == K) || (KB != K && !(x2 && KB == K1 && 2 * K1 == K)) ||
+      (x2 && (reinterpret_cast<uintptr_t>(x2) & 15u))) {
+    snprintf(t_err, sizeof(t_err), "unsupported operand split K=%d K1=%d KB=%d", K, K1, KB);
+    return MSDA_ERR_UNSUPPORTED;
+  }
   if (R <= 0 || R >= (1ll << 31) || K <= 0 || K % BLOCK_K || Nout <= 0 || Nout > MAX_N || block_n % 32 || block_n > 256 ||
       block_n < 32 || Nout % block_n) {
     snprintf(t_err, sizeof(t_err), "unsupported GEMM shape R=%lld K=%d Nout=%d block_n=%d", R, K, Nout, block_n);
@@ -613,10 +628,12 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
     return MSDA_ERR_MISALIGNED;
   }
   const int in_dt = half_in ? 1 : 0;
-  CUtensorMap tmA, tmB, tmC, tmC2;
-  int rc = make_map(&tmA, x, R, K, BLOCK_M, BLOCK_K, in_dt);
+  CUtensorMap tmA, tmA2, tmB, tmC, tmC2;
+  int rc = make_map(&tmA, x, R, K1, BLOCK_M, BLOCK_K, in_dt);
   if (rc) return rc;
-  rc = make_map(&tmB, w, Nout, K, block_n, BLOCK_K, in_dt);
+  tmA2 = tmA;
+  if (x2) { rc = make_map(&tmA2, x2, R, K - K1, BLOCK_M, BLOCK_K, in_dt); if (rc) return rc; }
+  rc = make_map(&tmB, w, Nout, KB, block_n, BLOCK_K, in_dt);
   if (rc) return rc;
   tmC = tmA; tmC2 = tmA;   // placeholders when the epilogue does not store through TMA
   // TMA-store epilogue: plain 16-bit stores in 64-column steps, and the fp32 query outputs in 32-column steps
@@ -642,7 +659,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
   const int sms = sms_of[dev_id & 63];
   const int num_n = Nout / block_n;
   const long long num_m = (R + BLOCK_M - 1) / BLOCK_M;
-  const int bres_bytes = block_n * K * 2;
+  const int bres_bytes = block_n * KB * 2;
   const int tail1 = tma_out ? AUX_BYTES_TMA : ((ep.mode == EPI_QUERY || ep.out_f32) ? AUX_BYTES_32 : AUX_BYTES_16);
   const int tail2 = tail1 + EPI_WARPS * TMA_TILE_BYTES;                    // second store tile per epilogue warp
   const int stream_stage = SMEM_A + block_n * BLOCK_K * 2;
@@ -679,7 +696,7 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
       configured[dev_id & 63] = cfg == cudaSuccess;                                                                        \
     }                                                                                                                      \
     if (cfg == cudaSuccess)                                                                                                \
-      linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmB, tmC, tmC2, Ri, Nout, K, block_n, br, stages, store_bufs, hi, ep); \
+      linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmA2, tmB, tmC, tmC2, Ri, Nout, K, K1 / BLOCK_K, KB / BLOCK_K, block_n, br, stages, store_bufs, hi, ep); \
   } while (0)
 #define PG_STORE16(RELU, GATE)                                                                                             \
   do {                                                                                                                     \
@@ -738,6 +755,19 @@ int msda_linear_accum_16(const void* x, const void* w, const float* bias, long l
   return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
+int msda_linear_accum2_16(const void* x1, int K1, const void* x2, int K2, const void* w, const float* bias, long long R, int Nout,
+                          const void* accum, void* out, int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!out || !accum || !x2) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  if (Nout % 8 || K2 <= 0 || K2 % pg::BLOCK_K) { snprintf(pg::t_err, sizeof(pg::t_err), "accumulating store needs Nout %% 8 == 0, K2 %% 64 == 0"); return MSDA_ERR_UNSUPPORTED; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.accum = accum;
+  return pg::launch(x1, w, R, K1 + K2, Nout, pg::pick_block_n(Nout, K1 + K2, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream),
+                    x2, K1, K1 + K2);
+}
+
 int msda_linear_act_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out, int relu,
                        const void* gate, int is_half, void* stream) {
   pg::t_err[0] = 0;
@@ -766,9 +796,19 @@ int msda_linear_act_bits_16(const void* x, const void* w, const float* bias, lon
   return pg::launch(x, w, R, K, Nout, pg::pick_block_n(Nout, K, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
+int msda_query_proj2_16(const void* query, const void* query_add, const void* w_cat, const float* bias_cat, const float* ref,
+                        int ref_dim, const int64_t* spatial_shapes, long long R, int K, int M, int L, int P, float* loc_out,
+                        float* aw_out, int is_half, void* stream);
+
 int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_cat, const float* ref, int ref_dim,
                        const int64_t* spatial_shapes, long long R, int K, int M, int L, int P, float* loc_out,
                        float* aw_out, int is_half, void* stream) {
+  return msda_query_proj2_16(query, nullptr, w_cat, bias_cat, ref, ref_dim, spatial_shapes, R, K, M, L, P, loc_out, aw_out, is_half, stream);
+}
+
+int msda_query_proj2_16(const void* query, const void* query_add, const void* w_cat, const float* bias_cat, const float* ref,
+                        int ref_dim, const int64_t* spatial_shapes, long long R, int K, int M, int L, int P, float* loc_out,
+                        float* aw_out, int is_half, void* stream) {
   pg::t_err[0] = 0;
   if (!ref || !spatial_shapes || !loc_out || !aw_out) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
   const int n_aw = M * L * P, n_loc = 2 * n_aw, lp = L * P;
@@ -781,8 +821,10 @@ int msda_query_proj_16(const void* query, const void* w_cat, const float* bias_c
   ep.mode = pg::EPI_QUERY;
   ep.bias = bias_cat; ep.loc_out = loc_out; ep.aw_out = aw_out; ep.ref = ref; ep.shapes = spatial_shapes;
   ep.ref_dim = ref_dim; ep.L = L; ep.P = P; ep.n_loc = n_loc; ep.n_aw = n_aw;
-  int rc = pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
-                      static_cast<cudaStream_t>(stream));
+  int rc = query_add ? pg::launch(query, w_cat, R, 2 * K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
+                                  static_cast<cudaStream_t>(stream), query_add, K, K)
+                     : pg::launch(query, w_cat, R, K, n_loc + n_aw, pg::pick_block_n(n_loc + n_aw, K, 32, true), is_half != 0, ep,
+                                  static_cast<cudaStream_t>(stream));
   if (rc == 0 && 32 % lp != 0) {   // softmax runs straddle the epilogue chunks: normalise the stored logits in place
     rc = pg::softmax_rows(aw_out, R * M, lp, static_cast<cudaStream_t>(stream));
   }

@@ -46,18 +46,21 @@ def linear16(x2d, w, bias_f32=None, row_mask=None, out_f32=False):
     return out
 
 
-def query_proj16(q2d, w_cat, bias_cat_f32, ref, ref_dim, spatial_shapes, M, L, P):
-    """-> (loc [R, M, L, P, 2] fp32, aw [R, M, L, P] fp32)."""
+def query_proj16(q2d, w_cat, bias_cat_f32, ref, ref_dim, spatial_shapes, M, L, P, q_add=None):
+    """-> (loc [R, M, L, P, 2] fp32, aw [R, M, L, P] fp32).  ``q_add`` [R, K]: the projection of ``q2d + q_add`` without
+    forming the sum (two activation operands against one resident copy of the weight: x1 W^T + x2 W^T in fp32)."""
     R, K = q2d.shape
     loc = torch.empty((R, M, L, P, 2), dtype=torch.float32, device=q2d.device)
     aw = torch.empty((R, M, L, P), dtype=torch.float32, device=q2d.device)
     if R == 0:
         return loc, aw
+    assert q_add is None or (q_add.shape == q2d.shape and q_add.dtype == q2d.dtype and q_add.is_contiguous())
     with torch.cuda.device(q2d.device):
-        rc = _lib.lib().msda_query_proj_16(q2d.data_ptr(), w_cat.data_ptr(), bias_cat_f32.data_ptr(), ref.data_ptr(), ref_dim,
-                                           spatial_shapes.data_ptr(), R, K, M, L, P, loc.data_ptr(), aw.data_ptr(),
-                                           1 if q2d.dtype == torch.float16 else 0, _stream(q2d))
-    _lib.check(rc, "msda_query_proj_16")
+        rc = _lib.lib().msda_query_proj2_16(q2d.data_ptr(), 0 if q_add is None else q_add.data_ptr(), w_cat.data_ptr(),
+                                            bias_cat_f32.data_ptr(), ref.data_ptr(), ref_dim, spatial_shapes.data_ptr(), R, K, M,
+                                            L, P, loc.data_ptr(), aw.data_ptr(), 1 if q2d.dtype == torch.float16 else 0,
+                                            _stream(q2d))
+    _lib.check(rc, "msda_query_proj2_16")
     return loc, aw
 
 
@@ -209,6 +212,8 @@ class Prepared:
             n = self.w_cat.shape[0]
             self.w_cat_t = torch.zeros((self.w_cat.shape[1], padded_k(n)), dtype=self.w_cat.dtype, device=self.w_cat.device)
             self.w_cat_t[:, :n] = self.w_cat.t()          # zero-padded along K to the GEMM's granularity
+            # [W_v^T | W_cat^T]: the value-projection and query-projection dgrads as ONE product over [grad_value | dq]
+            self.w_vq_t = torch.cat([self.w_v_t, self.w_cat_t], 1).contiguous()
 
 
 class FusedMSDeformAttnFunction(Function):
