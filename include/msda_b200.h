@@ -113,8 +113,10 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
  *                  per fp16 row <= 96), followed by one 128-byte tail whose first word receives the bits of max |grad_out|.
  *                  The call zeroes all of it on `stream`, measures the maximum and accumulates scale * contribution with
  *                  scale = the power of two f16acc_scale(max, Lq) (msda_common.cuh), chosen so that no partial sum can
- *                  overflow fp16 whatever the sampling pattern.  A rows_h that disagrees with the device-side shapes makes
- *                  the kernel write nothing and poison the tail (the consumer then yields NaN).
+ *                  overflow fp16 whatever the sampling pattern.  spatial_shapes_host = the caller's HOST copy of spatial_shapes
+ *                  (it sized the buffer from it; the replica layout is derived from it once per call instead of once per
+ *                  CTA); if it disagrees with the device-side shapes the kernel writes nothing and poisons the tail (the
+ *                  consumer then yields NaN).
  * Error vs fp32 accumulation: ~1e-3 of max |grad_value| (fp16 has 11 significand bits; the consumer rounds to bf16's 8
  * anyway) -- inside the 1e-2 bar of 16-bit storage, outside fp32's 1e-4, so fp32 storage never takes this path.
  * msda_cast_mask_h16 is the consumer: sum of replicas / scale -> [N*S, cols = M*D] 16-bit rows (out_f32 = 0; padded rows
@@ -122,8 +124,8 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
 long long msda_grad_value_h16_rows(const int64_t *spatial_shapes_host, int L, int Lq);
 int msda_backward_fusedq_h16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                              const float *loc, const float *aw, const void *grad_out, const float *ref, int ref_dim,
-                             int N, int S, int M, int D, int L, int Lq, int P, void *grad_value_h, long long rows_h,
-                             void *dq, int is_half, void *stream);
+                             int N, int S, int M, int D, int L, int Lq, int P, void *grad_value_h,
+                             const int64_t *spatial_shapes_host, void *dq, int is_half, void *stream);
 int msda_cast_mask_h16(const void *grad_value_h, const int64_t *spatial_shapes, const int64_t *level_start_index, int L,
                        int N, int S, int cols, int Lq, long long rows_h, const uint8_t *row_mask, void *out, int out_f32,
                        int is_half, void *stream);
@@ -145,7 +147,7 @@ int msda_backward_16_ws(const void *value, const int64_t *spatial_shapes, const 
  *   key "fwd_sample_batch"  : samples whose corner loads are issued together (1, 2 or 4)
  *   key "fwd_q_fast"        : 1 = lanes of a warp span consecutive queries of one head, 0 = heads
  *   key "bwd_q_fast"        : same for the backward kernel
- *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64)
+ *   key "fwd_passes" / "bwd_passes" : consecutive unit tiles per CTA (1..64; bwd_passes 0, the default, = by launch size)
  *   key "bwd_narrow"        : 16-bit storage, 1 = 4 channels per lane in the backward kernel (one full-line
  *                             reduction per corner), 0 = 8 channels per lane
  *   key "bwd_dots"          : 1 = the backward forms grad_sampling_loc / grad_attn_weight from the four corner dot products

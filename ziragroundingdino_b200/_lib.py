@@ -64,7 +64,7 @@ def lib():
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]
     L.msda_grad_value_h16_rows.restype = _ll
     L.msda_grad_value_h16_rows.argtypes = [_vp, _i, _i]
-    L.msda_backward_fusedq_h16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _ll, _vp, _i, _vp]
+    L.msda_backward_fusedq_h16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _vp, _i, _vp]
     L.msda_cast_mask_h16.argtypes = [_vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _vp, _vp, _i, _i, _vp]
     L.msda_linear_f32.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp, _vp]
     L.msda_query_proj_f32.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _vp]

@@ -147,10 +147,15 @@ def linear_accum2_16(x1, x2, w12, accum, out=None):
     return out
 
 
-# A/B switches (tests, measurements): `query = src + pos` as a second operand of the query projection instead of an
-# elementwise pass; the two input dgrads of the block as one K-concatenated product.
+# A/B switches (tests, measurements).
+# FOLD_POS (default on): `query = src + pos` as a second operand of the query projection instead of an elementwise pass --
+#   in the captured step the projection grows by 16 us and the 25 us add disappears (config 2: -54 us, config 4: -85 us),
+#   and the locations come from the exact sum (7e-7 from fp64 instead of 2e-3 for the rounded 16-bit sum).
+# DGRAD_CAT (default OFF, a measured loss): the block's two input dgrads as one K-concatenated product (K = 640).  It saves
+#   one read + write of the accumulator, but W no longer fits beside the ring at 256 columns, so two CTAs stream every
+#   activation tile: 62 us against 2 x 24 us at 4 images (config 2 +83 us, config 4 +213 us per step).
 FOLD_POS = os.environ.get("MSDA_B200_FOLD_POS", "1") != "0"
-DGRAD_CAT = os.environ.get("MSDA_B200_DGRAD_CAT", "1") != "0"
+DGRAD_CAT = os.environ.get("MSDA_B200_DGRAD_CAT", "0") == "1"
 
 
 class SelfAttnBlockFunction(Function):

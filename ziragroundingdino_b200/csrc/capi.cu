@@ -13,7 +13,7 @@ cudaError_t backward_f32acc(const VT*, const int64_t*, const int64_t*, const flo
 template <typename VT>
 cudaError_t backward_fused_q(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 template <typename VT>
-cudaError_t backward_fused_q_h16(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+cudaError_t backward_fused_q_h16(const VT*, const int64_t*, const int64_t*, const float*, const float*, const VT*, void*, const int64_t*, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 cudaError_t forward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t backward_f64(const double*, const int64_t*, const int64_t*, const double*, const double*, const double*, double*, double*, double*, int, int, int, int, int, int, int, cudaStream_t);
 }  // namespace msda
@@ -132,7 +132,8 @@ int msda_b200_set_tuning(const char* key, int value) {
     *slot = value;
     return MSDA_OK;
   }
-  if ((is_batch && value != 1 && value != 2 && value != 4) || (is_pass && (value < 1 || value > 64)) ||
+  const int pass_min = slot == &msda::g_tuning.bwd_passes ? 0 : 1;      // bwd_passes 0 = chosen by launch size
+  if ((is_batch && value != 1 && value != 2 && value != 4) || (is_pass && (value < pass_min || value > 64)) ||
       (!is_batch && !is_pass && value != 0 && value != 1))
     return fail(MSDA_ERR_UNSUPPORTED, "bad value %d for tuning key '%s'", value, key);
   *slot = value;
@@ -209,14 +210,17 @@ long long msda_grad_value_h16_rows(const int64_t* shapes_host, int L, int Lq) {
 
 int msda_backward_fusedq_h16(const void* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
                              const void* grad_out, const float* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
-                             void* gv_h, long long rows_h, void* dq, int is_half, void* stream) {
+                             void* gv_h, const int64_t* shapes_host, void* dq, int is_half, void* stream) {
   t_err[0] = 0;
   int rc = check_common(value, shapes, lstart, loc, aw, N, S, M, D, L, Lq, P, 2);
   if (rc) return rc;
-  if (!grad_out || !gv_h || !dq || !ref) return fail(MSDA_ERR_NULL_POINTER, "null pointer");
+  if (!grad_out || !gv_h || !dq || !ref || !shapes_host) return fail(MSDA_ERR_NULL_POINTER, "null pointer");
   if (D != 32 || L != 4 || P != 4 || (ref_dim != 2 && ref_dim != 4))
     return fail(MSDA_ERR_UNSUPPORTED, "fused query backward needs D=32, L=4, P=4 (got D=%d L=%d P=%d)", D, L, P);
-  if (rows_h < S || rows_h > 64ll * S) return fail(MSDA_ERR_BAD_SHAPE, "rows_h = %lld is not msda_grad_value_h16_rows() of S = %d", rows_h, S);
+  const long long rows_h = msda_grad_value_h16_rows(shapes_host, L, Lq);
+  long long s_host = 0;
+  for (int l = 0; l < L; ++l) s_host += shapes_host[2 * l] * shapes_host[2 * l + 1];
+  if (rows_h <= 0 || s_host != S) return fail(MSDA_ERR_BAD_SHAPE, "host copy of spatial_shapes sums to %lld rows, S = %d", s_host, S);
   if (rows_h * M * D >= (1ll << 31)) return fail(MSDA_ERR_BAD_SHAPE, "scaled-fp16 map of %lld rows does not fit 32-bit per-image indexing", rows_h);
   if (!aligned16(grad_out) || !aligned16(gv_h) || !aligned16(dq) || !aligned16(ref))
     return fail(MSDA_ERR_MISALIGNED, "pointers must be 16-byte aligned");
@@ -229,10 +233,10 @@ int msda_backward_fusedq_h16(const void* value, const int64_t* shapes, const int
   cudaError_t e;
   if (is_half)
     e = msda::backward_fused_q_h16<__half>(static_cast<const __half*>(value), shapes, lstart, loc, aw, static_cast<const __half*>(grad_out),
-                                           gv_h, rows_h, amax, ref, ref_dim, dq, 1, N, S, M, Lq, st);
+                                           gv_h, shapes_host, amax, ref, ref_dim, dq, 1, N, S, M, Lq, st);
   else
     e = msda::backward_fused_q_h16<__nv_bfloat16>(static_cast<const __nv_bfloat16*>(value), shapes, lstart, loc, aw,
-                                                  static_cast<const __nv_bfloat16*>(grad_out), gv_h, rows_h, amax, ref, ref_dim, dq, 0, N, S,
+                                                  static_cast<const __nv_bfloat16*>(grad_out), gv_h, shapes_host, amax, ref, ref_dim, dq, 0, N, S,
                                                   M, Lq, st);
   return cuda_status(e, "msda_backward_fusedq_h16 launch");
 }

@@ -21,7 +21,7 @@ struct Tuning {
   int fwd_q_fast = 1;        // lane groups of a warp span consecutive queries of one head
   int fwd_passes = 1;        // consecutive unit tiles handled by one CTA
   int bwd_q_fast = 1;
-  int bwd_passes = 1;
+  int bwd_passes = 0;        // 0 = by launch size (bwd_passes_auto()); 1..64 = fixed
   int bwd_narrow = 1;        // 16-bit storage: 4 channels per lane in the backward kernel (full-line reductions)
   int bwd_dots = 1;          // backward: per-sample sums from the four corner dot products (combine_dots) instead of per channel
                              // (measured -13 % on the scatter kernel, same parity: profiles/r2_scatter_variants.jsonl)
@@ -34,6 +34,16 @@ struct Tuning {
   int bwd_mma_min_units = 131072;   // ... when N*Lq*M is at least this (below it the reductions it saves do not pay for a launch)
 };
 extern Tuning g_tuning;
+// Unit tiles per CTA of the scatter kernel when the tuning key is 0.  A CTA's prologue (shapes, 1/W, 1/H, two barriers) is
+// paid per CTA, and a CTA with one tile lives ~17 us: two tiles per CTA measure -2 % on the fp32-accumulating kernel at
+// config 2's launch (937 -> 917 us; 3, 4: the same; 8: 932; 16: 969), four tiles -7 % on the scaled-fp16 one, which is
+// latency- rather than bandwidth-bound (893 -> 828 us; profiles/r2_bwd_passes.jsonl).  Small launches (the decoder's 1 800
+// tiles at 8 images) keep one tile per CTA so that the grid still covers the 444 resident CTAs several times.
+inline int bwd_passes_auto(long long tiles, bool f16acc) {
+  if (g_tuning.bwd_passes > 0) return g_tuning.bwd_passes;
+  if (tiles >= 8192) return f16acc ? 4 : 2;
+  return tiles >= 4096 ? 2 : 1;
+}
 extern long long g_launches;
 // scratch of the backward call in flight on this thread (set by msda_backward_16_ws around the launch; msda_core.cu)
 extern thread_local void* t_workspace;
@@ -143,20 +153,27 @@ __device__ __forceinline__ void red_add_v2h(__half* p, __half2 a, __half2 b) {
 // touches a pixel with at most one corner of weight <= 1), so every partial sum stays below Lq * s * amax < 60000 < the
 // fp16 maximum: the accumulation cannot overflow whatever the sampling pattern.  Producer and consumers call this with
 // the same (amax bits, Lq) and get the same scale.
-__host__ __device__ inline float f16acc_scale(uint32_t amax_bits, int Lq) {
-  float amax;
+__host__ __device__ inline uint32_t f16acc_bits(float x) {
 #ifdef __CUDA_ARCH__
-  amax = __uint_as_float(amax_bits);
+  return __float_as_uint(x);
 #else
-  memcpy(&amax, &amax_bits, 4);
+  uint32_t b; memcpy(&b, &x, 4); return b;
 #endif
-  if (!(amax > 0.f) || amax > 3.0e38f || Lq <= 0) return 1.f;     // zero, NaN or inf gradient: any scale will do
-  int e = 0, be = 0;
-  frexpf(amax, &e);                                               // amax < 2^e
-  frexpf(60000.f / static_cast<float>(Lq), &be);                  // 2^(be-1) <= 60000 / Lq
+}
+__host__ __device__ inline float f16acc_scale(uint32_t amax_bits, int Lq) {
+  if (amax_bits == 0u || amax_bits >= 0x7f800000u || Lq <= 0) return 1.f;   // zero, NaN or inf gradient: any scale will do
+  // integer form of frexp(): x = f * 2^e, f in [0.5, 1)  <=>  e = biased exponent - 126 (a subnormal maximum is treated as
+  // 2^-126: a smaller scale than necessary, never a larger one)
+  const int e = static_cast<int>(amax_bits >> 23) - 126;                                   // amax < 2^e
+  const int be = static_cast<int>(f16acc_bits(60000.f / static_cast<float>(Lq)) >> 23) - 126;   // 2^(be-1) <= 60000 / Lq
   int k = be - 1 - e;
   k = k < -120 ? -120 : (k > 120 ? 120 : k);
-  return ldexpf(1.f, k);
+  const uint32_t sb = static_cast<uint32_t>(127 + k) << 23;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(sb);
+#else
+  float r; memcpy(&r, &sb, 4); return r;
+#endif
 }
 
 // fp16 has 11 significand bits: a row that receives n contributions of similar size loses ~log2(n) of them, and the two

@@ -215,6 +215,7 @@ struct FuseQ {
   int is_half;
   uint32_t* amax;        // F16ACC: bits of max |grad_out| (written by grad_amax_kernel), else unused
   long long rows_h;      // F16ACC: rows per image of the scaled-fp16 map (levels with replicas), as the host sized it
+  int h_start[4], h_hw[4], h_mask[4];   // F16ACC: per level, first row of its replica block, H*W, replicas - 1 (host-computed)
 };
 
 // 3 resident CTAs per SM (<= 85 registers): the kernel needs its occupancy to keep enough reductions and corner loads in
@@ -253,7 +254,6 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   __shared__ float sScale;
   static_assert(!F16ACC || (FUSEQ && MODE == 0 && V::CH == 4 && sizeof(VT) == 2), "F16ACC: fused-query 16-bit kernel only");
   __shared__ int sHStart[MSDA_MAX_LEVELS], sHW[MSDA_MAX_LEVELS], sRepMask[MSDA_MAX_LEVELS];   // F16ACC: replica blocks of the map
-  __shared__ long long sRowsH;
   if (F16ACC && threadIdx.x == 32) sScale = f16acc_scale(*fq.amax, Lq);
   if (threadIdx.x < L) {
     sH[threadIdx.x] = static_cast<int>(shapes[2 * threadIdx.x]);
@@ -271,21 +271,17 @@ msda_bwd_vec_kernel(const VT* __restrict__ value, const int64_t* __restrict__ sh
   if (threadIdx.x == 0) {
     if (HITS) { plan_ranges(plan, sH, sW, sStart, L, S, mma_levels); sRedLevels = plan.first_level; }
     else sRedLevels = mma_mode == 1 ? coarse_first_level(sH, sW, sStart, L, S) : L;
-    if (F16ACC) {
-      long long at = 0;
-      for (int l = 0; l < L; ++l) {
-        const int hw = sH[l] * sW[l], k = f16acc_replicas(Lq, hw);
-        sHStart[l] = static_cast<int>(at); sHW[l] = hw; sRepMask[l] = k - 1;
-        at += static_cast<long long>(k) * hw;
-      }
-      sRowsH = at;
-    }
+  }
+  if (F16ACC && threadIdx.x < 4) {
+    // the replica layout comes from the HOST's copy of the shapes (it sized and zeroed the map, and a serial plan in every
+    // short-lived CTA costs more than it looks: the first version spent 0.9 warp-stalls per issue at this barrier)
+    sHStart[threadIdx.x] = fq.h_start[threadIdx.x]; sHW[threadIdx.x] = fq.h_hw[threadIdx.x]; sRepMask[threadIdx.x] = fq.h_mask[threadIdx.x];
   }
   __syncthreads();
   if constexpr (F16ACC) {
-    // the host sized (and zeroed) the map from ITS copy of the shapes: refuse to write into a buffer laid out differently,
-    // and poison the amax word so that the consumer produces NaN instead of silently wrong gradients
-    if (sRowsH != fq.rows_h) {
+    // refuse to write into a buffer laid out for other shapes than the device-side ones, and poison the amax word so that
+    // the consumer produces NaN instead of silently wrong gradients
+    if (sH[0] * sW[0] != sHW[0] || sH[1] * sW[1] != sHW[1] || sH[2] * sW[2] != sHW[2] || sH[3] * sW[3] != sHW[3]) {
       if (blockIdx.x == 0 && threadIdx.x == 0) atomicMax(fq.amax, 0xffffffffu);
       return;
     }
@@ -677,7 +673,7 @@ static cudaError_t launch_bwd_vec_t(const VT* value, const int64_t* shapes, cons
   constexpr int TILE = (32 / (D / V::CH)) * kWarpsPerBlock;
   const long long units = static_cast<long long>(N) * Lq * M;
   const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
-  const int passes = g_tuning.bwd_passes;
+  const int passes = bwd_passes_auto((units + TILE - 1) / TILE, false);
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   // 16-bit storage, D = 32: the coarse tail of the level list accumulates in tensor memory (msda_scatter_mma.cu); this
   // kernel then skips those reductions.  Both kernels derive the same split from the device-side shapes.
@@ -735,7 +731,7 @@ template <typename VT, int D>
 static cudaError_t launch_bwd_vec(const VT* value, const int64_t* shapes, const int64_t* lstart,
                                   const float* loc, const float* aw, const VT* grad_out, float* gv,
                                   float* gl, float* ga, int N, int S, int M, int L, int Lq, cudaStream_t st) {
-  const FuseQ none{nullptr, nullptr, 0, 0, nullptr, 0};
+  const FuseQ none{nullptr, nullptr, 0, 0, nullptr, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
   // narrow layout needs D/4 <= 16 lanes per unit
   if constexpr (Vec<VT>::CH == 8 && D <= 64) {
     if (g_tuning.bwd_narrow)
@@ -749,7 +745,7 @@ template <typename VT>
 cudaError_t backward_fused_q(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
                              const VT* grad_out, float* gv, const float* ref, int ref_dim, void* dq, int is_half, int N, int S,
                              int M, int Lq, cudaStream_t st) {
-  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, nullptr, 0};
+  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, nullptr, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
   return launch_bwd_vec_t<VT, 32, VecQ<VT>, true>(value, shapes, lstart, loc, aw, grad_out, gv, nullptr, nullptr, N, S, M, 4, Lq, st, fq);
 }
 template cudaError_t backward_fused_q<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, float*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
@@ -782,8 +778,8 @@ __global__ void __launch_bounds__(256) grad_amax_kernel(const uint4* __restrict_
 // (F16ACC).  gv_h [N*S*M*32] halves and the amax word must arrive zeroed.
 template <typename VT>
 cudaError_t backward_fused_q_h16(const VT* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
-                                 const VT* grad_out, void* gv_h, long long rows_h, uint32_t* amax, const float* ref, int ref_dim,
-                                 void* dq, int is_half, int N, int S, int M, int Lq, cudaStream_t st) {
+                                 const VT* grad_out, void* gv_h, const int64_t* shapes_host, uint32_t* amax, const float* ref,
+                                 int ref_dim, void* dq, int is_half, int N, int S, int M, int Lq, cudaStream_t st) {
   using V = VecQ<VT>;
   constexpr int D = 32;
   constexpr int TILE = (32 / (D / V::CH)) * kWarpsPerBlock;
@@ -794,17 +790,23 @@ cudaError_t backward_fused_q_h16(const VT* value, const int64_t* shapes, const i
   grad_amax_kernel<std::is_same<VT, __half>::value><<<ablocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(grad_out), n8, amax);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, amax, rows_h};
+  FuseQ fq{ref, static_cast<uint16_t*>(dq), ref_dim, is_half, amax, 0, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}};
+  for (int l = 0; l < 4; ++l) {
+    const long long hw = shapes_host[2 * l] * shapes_host[2 * l + 1];
+    const int k = f16acc_replicas(Lq, hw);
+    fq.h_start[l] = static_cast<int>(fq.rows_h); fq.h_hw[l] = static_cast<int>(hw); fq.h_mask[l] = k - 1;
+    fq.rows_h += hw * k;
+  }
   const int q_fast = (g_tuning.bwd_q_fast && TILE % M == 0) ? 1 : 0;
-  const int passes = g_tuning.bwd_passes;
+  const int passes = bwd_passes_auto((units + TILE - 1) / TILE, true);
   const long long blocks = (units + static_cast<long long>(TILE) * passes - 1) / (static_cast<long long>(TILE) * passes);
   msda_bwd_vec_kernel<VT, D, V, true, 0, false, true, true><<<dim3(static_cast<unsigned>(blocks)), kThreads, 0, st>>>(
       value, shapes, lstart, loc, aw, grad_out, static_cast<float*>(gv_h), nullptr, nullptr, S, M, 4, Lq, units, passes, q_fast, 0, 0,
       nullptr, fq);
   return cudaGetLastError();
 }
-template cudaError_t backward_fused_q_h16<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
-template cudaError_t backward_fused_q_h16<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, void*, long long, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_fused_q_h16<__nv_bfloat16>(const __nv_bfloat16*, const int64_t*, const int64_t*, const float*, const float*, const __nv_bfloat16*, void*, const int64_t*, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
+template cudaError_t backward_fused_q_h16<__half>(const __half*, const int64_t*, const int64_t*, const float*, const float*, const __half*, void*, const int64_t*, uint32_t*, const float*, int, void*, int, int, int, int, int, cudaStream_t);
 
 // Storage types whose locations / weights / gradients are fp32 (float, bf16, half).
 template <typename VT>

@@ -116,19 +116,19 @@ def backward_fusedq16(value, spatial_shapes, level_start_index, loc, aw, grad_co
 _H16_ROWS = {}
 
 
-def h16_rows(spatial_shapes, Lq):
+def h16_rows(spatial_shapes, Lq, with_host_array=False):
     """Rows per image of the scaled-fp16 grad_value map (levels with their replicas) for these shapes."""
     import ctypes
     from .ms_deform_attn import _host_shapes
     hs = _host_shapes(spatial_shapes)
-    rows = _H16_ROWS.get((hs, Lq))
-    if rows is None:
+    hit = _H16_ROWS.get((hs, Lq))
+    if hit is None:
         arr = (ctypes.c_int64 * (2 * len(hs)))(*[d for hw in hs for d in hw])
         rows = int(_lib.lib().msda_grad_value_h16_rows(arr, len(hs), Lq))
         if rows <= 0:
             raise RuntimeError("msda_grad_value_h16_rows: bad shapes %r" % (hs,))
-        _H16_ROWS[(hs, Lq)] = rows
-    return rows
+        hit = _H16_ROWS[(hs, Lq)] = (rows, arr)
+    return hit if with_host_array else hit[0]
 
 
 def backward_fusedq_h16(value, spatial_shapes, level_start_index, loc, aw, grad_core, ref, ref_dim):
@@ -136,13 +136,13 @@ def backward_fusedq_h16(value, spatial_shapes, level_start_index, loc, aw, grad_
     (the map buffer -- N * rows_h * M * D halves and a 128-byte tail holding max |grad_core| -- as an int16 tensor, dq_cat)."""
     N, S, M, D = value.shape
     Lq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
-    rows_h = h16_rows(spatial_shapes, Lq)
+    rows_h, shapes_host = h16_rows(spatial_shapes, Lq, with_host_array=True)
     buf = torch.empty((N * rows_h * M * D + 64,), dtype=torch.int16, device=value.device)
     dq = torch.empty((N * Lq, 3 * M * L * P), dtype=value.dtype, device=value.device)
     with torch.cuda.device(value.device):
         rc = _lib.lib().msda_backward_fusedq_h16(value.data_ptr(), spatial_shapes.data_ptr(), level_start_index.data_ptr(),
                                                  loc.data_ptr(), aw.data_ptr(), grad_core.data_ptr(), ref.data_ptr(), ref_dim, N, S,
-                                                 M, D, L, Lq, P, buf.data_ptr(), rows_h, dq.data_ptr(),
+                                                 M, D, L, Lq, P, buf.data_ptr(), shapes_host, dq.data_ptr(),
                                                  1 if value.dtype == torch.float16 else 0, _stream(value))
     _lib.check(rc, "msda_backward_fusedq_h16")
     return buf, dq
