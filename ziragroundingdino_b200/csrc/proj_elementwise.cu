@@ -362,7 +362,7 @@ int msda_cast_mask_h16(const void* gv_h, const int64_t* shapes, const int64_t* l
   const long long n8 = static_cast<long long>(N) * S * (cols / 8);
   const uint32_t* amax = reinterpret_cast<const uint32_t*>(static_cast<const char*>(gv_h) + 2ll * N * rows_h * cols);
   const long long per_image = (static_cast<long long>(S) * (cols / 8) + 255) / 256;
-  const dim3 blocks(static_cast<unsigned>(std::min<long long>(per_image, (148 * 8 + N - 1) / N)), static_cast<unsigned>(N));
+  const dim3 blocks(static_cast<unsigned>(std::max<long long>(1, std::min<long long>(per_image, (148 * 8 + N - 1) / N))), static_cast<unsigned>(N));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   ++msda::g_launches;
   if (out_f32)
