@@ -196,6 +196,13 @@ int msda_linear_accum_16(const void *x, const void *w, const float *bias, long l
  * (d value_proj input + d query, ms_deform_attn.py:286 and :290-293 backward) as one launch. */
 int msda_linear_accum2_16(const void *x1, int K1, const void *x2, int K2, const void *w, const float *bias, long long R,
                           int Nout, const void *accum, void *out, int is_half, void *stream);
+/* Projection + residual + LayerNorm in ONE launch (`src = norm1(src + output_proj(x))`, transformer_for_adapter.py:901-902 with
+ * ms_deform_attn.py:350): z = residual + x w^T + bias (stored, 16-bit: LayerNorm's saved input), y = LayerNorm(z) * gamma +
+ * beta with the statistics of the ROUNDED z (as msda_add_layernorm_fwd_16 computes them), mean / rstd [R] fp32 for
+ * msda_add_layernorm_bwd_16.  Nout in {128, 256} (a GEMM tile holds whole rows), K % 64 == 0. */
+int msda_linear_add_layernorm_16(const void *x, const void *w, const float *bias, long long R, int K, int Nout,
+                                 const void *residual, const float *gamma, const float *beta, float eps, void *z, void *y,
+                                 float *mean, float *rstd, int is_half, void *stream);
 /* FFN companions (row N1; reference transformer_for_adapter.py:876-885): out = relu(x W^T + bias) when relu != 0, and
  * out = (x W^T + bias) where gate > 0 else 0 when gate != NULL (gate: 16-bit [R, Nout]) -- the ReLU backward fused into
  * the dgrad GEMM of linear2.  16-bit output, leading dimension Nout; Nout <= 2048. */

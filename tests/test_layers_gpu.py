@@ -471,3 +471,77 @@ def test_encoder_block_operand_folds_match_the_separate_launches():
     dg = rel_err(res[True][1].cpu(), res[False][1].cpu())
     print("encoder block folds on vs off: max |dy| %.2e, rel d(src) %.2e" % (dy, dg))
     assert dy <= 6e-2 and dg < 4e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("R,K,Nout", [(1, 256, 256), (127, 256, 256), (1000, 256, 256), (4 * 22223 + 3, 256, 256), (300, 128, 128), (777, 512, 256)])
+def test_projection_residual_layernorm_in_one_launch(dtype, R, K, Nout):
+    """msda_linear_add_layernorm_16 (z = residual + x W^T + b stored, y = LayerNorm(z), mean, rstd) against fp64 on the same
+    16-bit operands, and against the two-launch form (msda_linear_16 + msda_add_layernorm_fwd_16): z within one 16-bit ulp
+    (the fused form does not round the projection before the add), y within a few ulps of O(1) values, statistics consistent
+    with the z it stored (the backward kernel reads exactly these)."""
+    from ziragroundingdino_b200 import blocks, fused
+    g = torch.Generator().manual_seed(R + K)
+    x = torch.randn(R, K, generator=g).to(dtype).to(DEV)
+    w = (torch.randn(Nout, K, generator=g) * 0.06).to(dtype).to(DEV)
+    bias = (torch.randn(Nout, generator=g) * 0.1).to(DEV)
+    res = torch.randn(R, Nout, generator=g).to(dtype).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(Nout, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(Nout, generator=g)).to(DEV)
+    eps = 1e-5
+    z, y, mean, rstd = blocks.linear_add_ln16(x, w, bias, res, gamma, beta, eps)
+    attn = fused.linear16(x, w, bias)
+    z0, y0, mean0, rstd0 = blocks._add_ln_fwd(res, attn, gamma, beta, eps)
+    ulp = 2 ** -8 if dtype == torch.bfloat16 else 2 ** -11
+    zt = res.double() + x.double() @ w.double().t() + bias.double()
+    zmax = zt.abs().max().item()
+    assert (z.double() - zt).abs().max().item() <= 1.01 * ulp * zmax
+    assert (z.float() - z0.float()).abs().max().item() <= 2 * ulp * zmax
+    # statistics of the stored z
+    zs = z.double()
+    m_ref, v_ref = zs.mean(1), zs.var(1, unbiased=False)
+    assert (mean.double() - m_ref).abs().max().item() < 1e-4
+    assert ((rstd.double() - (v_ref + eps).rsqrt()).abs() / (v_ref + eps).rsqrt()).max().item() < 1e-4
+    yt = (zs - m_ref[:, None]) * (v_ref[:, None] + eps).rsqrt() * gamma.double() + beta.double()
+    assert (y.double() - yt).abs().max().item() <= 2.5 * ulp * yt.abs().max().item()
+    assert (y.float() - y0.float()).abs().max().item() <= 8 * ulp * yt.abs().max().item()
+
+
+def test_encoder_block_with_layernorm_in_the_projection_matches_separate():
+    """blocks.OUT_LN (default on) against the projection + add+LayerNorm pair, forward output and input gradient of the
+    encoder's attention block."""
+    import ziragroundingdino_b200 as zb
+    from ziragroundingdino_b200 import blocks
+    torch.manual_seed(10)
+    C, FF, M, L, P, N = 256, 2048, 8, 4, 4, 2
+    shapes = [(20, 30), (10, 15), (5, 8), (3, 4)]
+    S = sum(h * w for h, w in shapes)
+    layer = zb.DeformableTransformerEncoderLayer(C, FF, 0.0, "relu", L, M, P)
+    with torch.no_grad():
+        layer.self_attn.sampling_offsets.weight.normal_(0, 0.01)
+        layer.self_attn.attention_weights.weight.normal_(0, 0.05)
+        layer.norm1.weight.normal_(1, 0.1); layer.norm1.bias.normal_(0, 0.1)
+    layer = layer.to(DEV).to(torch.bfloat16)
+    for p in layer.parameters():
+        p.requires_grad_(False)
+    sh = torch.tensor(shapes, device=DEV)
+    lsi = torch.cat([sh.new_zeros(1), (sh[:, 0] * sh[:, 1]).cumsum(0)[:-1]])
+    src0 = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    pos = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    refp = torch.rand(N, S, L, 2, device=DEV)
+    gy = torch.randn(N, S, C, device=DEV).to(torch.bfloat16)
+    res = {}
+    keep = blocks.OUT_LN
+    try:
+        for on in (True, False):
+            blocks.OUT_LN = on
+            x = src0.clone().requires_grad_(True)
+            y, _ = layer(x, pos, refp, sh, lsi, None)
+            y.backward(gy)
+            res[on] = (y.detach().float(), x.grad.float())
+    finally:
+        blocks.OUT_LN = keep
+    dy = (res[True][0] - res[False][0]).abs().max().item()
+    dg = rel_err(res[True][1].cpu(), res[False][1].cpu())
+    print("encoder block, LayerNorm in the projection on vs off: max |dy| %.2e, rel d(src) %.2e" % (dy, dg))
+    assert dy <= 6e-2 and dg < 2e-2

@@ -49,6 +49,7 @@ def lib():
     L.msda_linear_accum_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _i, _vp]
     L.msda_linear_accum2_16.argtypes = [_vp, _i, _vp, _i, _vp, _vp, _ll, _i, _vp, _vp, _i, _vp]
     L.msda_query_proj2_16.argtypes = [_vp, _vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]
+    L.msda_linear_add_layernorm_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, ctypes.c_float, _vp, _vp, _vp, _vp, _i, _vp]
     L.msda_linear_act_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp]
     L.msda_linear_act_bits_16.argtypes = [_vp, _vp, _vp, _ll, _i, _i, _vp, _vp, _vp, _i, _vp]
     L.msda_query_proj_16.argtypes = [_vp, _vp, _vp, _vp, _i, _vp, _ll, _i, _i, _i, _i, _vp, _vp, _i, _vp]

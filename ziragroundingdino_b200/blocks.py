@@ -108,6 +108,24 @@ def _add_ln_fwd(x2, r2, g32, b32, eps):
     return z, y, mean, rstd
 
 
+def linear_add_ln16(x2d, w, b32_bias, residual, g32, b32, eps):
+    """(z, y, mean, rstd) with z = residual + x2d @ w^T + bias and y = LayerNorm(z): the projection, the residual add and the
+    LayerNorm as ONE GEMM launch (msda_linear_add_layernorm_16; the statistics come from the rounded z it stores)."""
+    R, K = x2d.shape
+    Nout = w.shape[0]
+    assert x2d.is_contiguous() and w.is_contiguous() and residual.is_contiguous() and residual.shape == (R, Nout)
+    z, y = torch.empty_like(residual), torch.empty_like(residual)
+    mean = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    rstd = torch.empty(R, dtype=torch.float32, device=x2d.device)
+    with torch.cuda.device(x2d.device):
+        rc = _lib.lib().msda_linear_add_layernorm_16(x2d.data_ptr(), w.data_ptr(), 0 if b32_bias is None else b32_bias.data_ptr(), R, K,
+                                                     Nout, residual.data_ptr(), g32.data_ptr(), b32.data_ptr(), float(eps),
+                                                     z.data_ptr(), y.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                     1 if x2d.dtype == torch.float16 else 0, _stream(x2d))
+    _lib.check(rc, "msda_linear_add_layernorm_16")
+    return z, y, mean, rstd
+
+
 def _add_ln_bwd(dy2, z, g32, mean, rstd):
     R, C = z.shape
     dz = torch.empty_like(z)
@@ -154,6 +172,11 @@ def linear_accum2_16(x1, x2, w12, accum, out=None):
 # DGRAD_CAT (default OFF, a measured loss): the block's two input dgrads as one K-concatenated product (K = 640).  It saves
 #   one read + write of the accumulator, but W no longer fits beside the ring at 256 columns, so two CTAs stream every
 #   activation tile: 62 us against 2 x 24 us at 4 images (config 2 +83 us, config 4 +213 us per step).
+# OUT_LN (default on): `norm1(src + output_proj(core))` as one GEMM launch with the LayerNorm in its epilogue
+#   (msda_linear_add_layernorm_16) instead of the projection + the add+LayerNorm kernel: 49.9 us against 25.0 + 32.9 us at 4
+#   images (the K = 256 GEMMs are bound by their epilogue warps, and this epilogue makes two passes over the accumulator and
+#   issues two stores per column group, so the saving is the 91 MB round trip of the projection's output, not a kernel).
+OUT_LN = os.environ.get("MSDA_B200_OUT_LN", "1") != "0"
 FOLD_POS = os.environ.get("MSDA_B200_FOLD_POS", "1") != "0"
 DGRAD_CAT = os.environ.get("MSDA_B200_DGRAD_CAT", "0") == "1"
 
@@ -180,8 +203,11 @@ class SelfAttnBlockFunction(Function):
             loc, aw = fused.query_proj16(q2d, prep.w_cat, prep.b_cat, ref, ref_dim, spatial_shapes, M, L, P)
         loc, aw = loc.view(N, S, M, L, P, 2), aw.view(N, S, M, L, P)
         core = _C.ms_deform_attn_forward(value, spatial_shapes, level_start_index, loc, aw, im2col_step)
-        attn = fused.linear16(core.view(N * S, C), prep.w_o, prep.b_o)
-        z, y, mean, rstd = _add_ln_fwd(src2d, attn, g32, b32, eps)
+        if OUT_LN and C in (128, 256):
+            z, y, mean, rstd = linear_add_ln16(core.view(N * S, C), prep.w_o, prep.b_o, src2d, g32, b32, eps)
+        else:
+            attn = fused.linear16(core.view(N * S, C), prep.w_o, prep.b_o)
+            z, y, mean, rstd = _add_ln_fwd(src2d, attn, g32, b32, eps)
         ctx.dims = (N, S, C, M, L, P, ref_dim, im2col_step)
         ctx.prep = prep
         ctx.save_for_backward(row_mask, ref, spatial_shapes, level_start_index, value, loc, aw, z, g32, mean, rstd)

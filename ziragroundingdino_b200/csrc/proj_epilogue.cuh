@@ -42,6 +42,13 @@ struct EpiParams {
   // products of features [32g, 32g+32).  bias = [b_0 | b_f | b_b] (3F floats).
   //   branch  = s * (x W_b^T + b_b)            adapter = branch + x W_f^T + b_f           y = x W_0^T + b_0 + adapter
   //   loss_sums[0] += sum SmoothL1(branch), loss_sums[1] += sum SmoothL1(adapter)   (all rows, also masked ones)
+  // LN (see linear_tc_kernel): LayerNorm of the stored sum in the same launch
+  const float* ln_gamma;   // [Nout] fp32, null = off
+  const float* ln_beta;    // [Nout] fp32
+  float ln_eps;
+  void* ln_y;              // [R, out_ld] 16-bit: the normalised output
+  float* ln_mean;          // [R]
+  float* ln_rstd;          // [R]
   const float* scaling;    // device scalar s
   void* pre_out;           // [R, F] 16-bit: x W_b^T + b_b   (saved for backward; may be null)
   void* adapter_out;       // [R, F] 16-bit: adapter          (saved for backward; may be null)
@@ -125,6 +132,15 @@ __device__ __forceinline__ void pack_16_relu(const float (&v)[32], bool half_out
     o[i].y = pack16_relu(v[8 * i + 2], v[8 * i + 3], half_out);
     o[i].z = pack16_relu(v[8 * i + 4], v[8 * i + 5], half_out);
     o[i].w = pack16_relu(v[8 * i + 6], v[8 * i + 7], half_out);
+  }
+}
+
+__device__ __forceinline__ void unpack16x2(uint32_t w, bool half_in, float& a, float& b) {
+  if (half_in) {
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w));
+    a = t.x; b = t.y;
+  } else {
+    a = __uint_as_float(w << 16); b = __uint_as_float(w & 0xffff0000u);
   }
 }
 

@@ -59,7 +59,13 @@ bool g_tma_store = true;         // msda_b200_gemm_set_staged(0) turns the TMA-s
 bool g_staged_store = true;      // msda_b200_gemm_set_staged(0|1)   // msda_b200_set_tuning("gemm_resident", 0|1)
 
 // ---- the kernel -----------------------------------------------------------------------------------
-template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE, bool TMA_OUT>
+// LN (EPI_STORE through TMA, accumulate form, block_n == Nout <= 256 so that a tile holds whole rows): the launch also
+// performs the LayerNorm that follows the projection in the reference layer -- `src = norm1(src + output_proj(...))`,
+// transformer_for_adapter.py:901-902 -- on the rounded sum z = accum + x W^T + b it stores: row statistics are collected
+// while z is written, exchanged between the two warps of a lane quarter, and a second pass over the accumulator (still in
+// tensor memory) writes y = (z - mean) * rstd * gamma + beta through the second output map; mean / rstd go to ep.ln_mean /
+// ep.ln_rstd for the backward.
+template <int MODE, bool OUT_F32, bool HALF_OUT, bool RELU, bool GATE, bool TMA_OUT, bool LN = false>
 __global__ void __launch_bounds__(THREADS, 1)
 linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
@@ -116,6 +122,9 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < Nout; i += THREADS) s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
+  if constexpr (LN) {   // s_bias[256..511] = gamma, [512..767] = beta, [768..1279] = the statistics exchange (MAX_N = 2048 floats)
+    for (int i = threadIdx.x; i < Nout; i += THREADS) { s_bias[256 + i] = ep.ln_gamma[i]; s_bias[512 + i] = ep.ln_beta[i]; }
+  }
   if (MODE == EPI_QUERY && threadIdx.x < ep.L) {
     s_norm[2 * threadIdx.x] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x + 1]);      // 1/W
     s_norm[2 * threadIdx.x + 1] = 1.f / static_cast<float>(ep.shapes[2 * threadIdx.x]);      // 1/H
@@ -188,6 +197,19 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     float zsum_b = 0.f, zsum_o = 0.f;   // EPI_ZIRA: this thread's share of the two SmoothL1 sums
     for (int t = t_first; t < t_end; t += t_step) {
       const int m_idx = (b_resident ? t : t / num_n) * BLOCK_M, n_idx = b_resident ? n_fixed : (t % num_n) * block_n;
+      // LN: this row's residual columns (both 64-column groups of this warp) are fetched BEFORE the accumulator wait and kept
+      // for both passes -- the epilogue is otherwise a chain of exposed global-load latencies (measured: 10.8 us per tile)
+      uint4 ln_res0[8], ln_res1[8];
+      if constexpr (LN) {
+        const long long rr = static_cast<long long>(m_idx) + quarter * 32 + lane;
+        const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.accum) + rr * ep.out_ld + n_idx + chunk_par * 64);
+        const bool two = chunk_par * 64 + 128 < block_n;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          ln_res0[i] = rr < R ? __ldg(ap + i) : make_uint4(0u, 0u, 0u, 0u);
+          ln_res1[i] = (rr < R && two) ? __ldg(ap + 16 + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
       mbar_wait(tfull_bar + acc, acc_phase);
       tc_fence_after();
       const long long row = static_cast<long long>(m_idx) + quarter * 32 + lane;
@@ -232,6 +254,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // one or two store tiles per warp: with two, a step only waits for the store issued two steps ago
         uint8_t* tile0 = tma_tiles + (warp - 2) * store_bufs * TMA_TILE_BYTES;
         int buf = 0;
+        float ln_s1 = 0.f, ln_s2 = 0.f;
         uint4 gnext[8];
         const int g_j = lane & 7, g_rsub = lane >> 3;           // gate fetch: 8 lanes along a 128-byte row, 4 rows per instr
         auto gate_fetch = [&](int c) {
@@ -257,7 +280,14 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint4 gt[8];
           uint32_t gb[2] = {gb_next[0], gb_next[1]};
           uint4 ain[8];
-          if (!RELU && !GATE && ep.accum != nullptr) {   // this row's 64 columns of the tensor to accumulate onto
+          if constexpr (LN) {
+            const bool first = c0 == chunk_par * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              ain[i].x = first ? ln_res0[i].x : ln_res1[i].x; ain[i].y = first ? ln_res0[i].y : ln_res1[i].y;
+              ain[i].z = first ? ln_res0[i].z : ln_res1[i].z; ain[i].w = first ? ln_res0[i].w : ln_res1[i].w;
+            }
+          } else if (!RELU && !GATE && ep.accum != nullptr) {   // this row's 64 columns of the tensor to accumulate onto
             const uint4* ap = reinterpret_cast<const uint4*>(static_cast<const uint16_t*>(ep.accum) + row * ep.out_ld + gc);
 #pragma unroll
             for (int i = 0; i < 8; ++i) ain[i] = live ? ap[i] : make_uint4(0u, 0u, 0u, 0u);
@@ -314,6 +344,16 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             uint4 pk[4];
             pack_16(v, HALF_OUT, zero, pk);
+            if constexpr (LN) {      // statistics of the ROUNDED values, as LayerNorm on the stored z would see them
+              const uint32_t* pw = reinterpret_cast<const uint32_t*>(pk);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a, b;
+                unpack16x2(pw[j], HALF_OUT, a, b);
+                ln_s1 += a + b;
+                ln_s2 = fmaf(a, a, fmaf(b, b, ln_s2));
+              }
+            }
             if ((!GATE || bit_gate) && hf == 0) {   // wait as late as possible: the previous store's smem read overlaps this step's TMEM load + math
               if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
               __syncwarp();
@@ -325,6 +365,68 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
           if (lane == 0) tma_store_2d(&tmC, tile, gc, static_cast<int>(row0));
           if (store_bufs == 2) buf ^= 1;
+        }
+        if constexpr (LN) {
+          // the other half of this row's columns belongs to the partner warp of the lane quarter (warps w and w ^ 4 of the
+          // eight epilogue warps): exchange the partial sums through shared memory under a 64-thread named barrier
+          float* xch = s_bias + 768;
+          const int me = (warp - 2) * 32 + lane, other = ((warp - 2) ^ 4) * 32 + lane;
+          xch[2 * me] = ln_s1; xch[2 * me + 1] = ln_s2;
+          named_bar(1 + quarter, 64);
+          const float t1 = ln_s1 + xch[2 * other], t2 = ln_s2 + xch[2 * other + 1];
+          named_bar(1 + quarter, 64);          // the slots are rewritten by the next tile
+          const float inv_n = 1.f / static_cast<float>(Nout);
+          const float mean = t1 * inv_n;
+          const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.ln_eps);
+          if (chunk_par == 0 && live) { ep.ln_mean[row] = mean; ep.ln_rstd[row] = rstd; }
+          for (int c0 = chunk_par * 64; c0 < block_n; c0 += 128) {
+            const int gc = n_idx + c0;
+            uint8_t* tile = tile0 + buf * TMA_TILE_BYTES;
+            uint4 ain[8];
+            const bool first = c0 == chunk_par * 64;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              ain[i].x = first ? ln_res0[i].x : ln_res1[i].x; ain[i].y = first ? ln_res0[i].y : ln_res1[i].y;
+              ain[i].z = first ? ln_res0[i].z : ln_res1[i].z; ain[i].w = first ? ln_res0[i].w : ln_res1[i].w;
+            }
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              uint32_t r[32];
+              tmem_ld32(taddr + c0 + 32 * hf, r);
+              float v[32];
+              const float4* bp = reinterpret_cast<const float4*>(s_bias + gc + 32 * hf);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float4 bb = bp[i];
+                v[4 * i] = __uint_as_float(r[4 * i]) + bb.x; v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + bb.y;
+                v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + bb.z; v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + bb.w;
+              }
+              add_packed16(v, reinterpret_cast<const uint32_t*>(ain) + 16 * hf, HALF_OUT);
+              uint4 pk[4];
+              pack_16(v, HALF_OUT, false, pk);                      // z exactly as stored by the first pass
+              const uint32_t* pw = reinterpret_cast<const uint32_t*>(pk);
+              const float* gp = s_bias + 256 + gc + 32 * hf;
+              const float* btp = s_bias + 512 + gc + 32 * hf;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float a, b;
+                unpack16x2(pw[j], HALF_OUT, a, b);
+                v[2 * j] = fmaf((a - mean) * rstd, gp[2 * j], btp[2 * j]);
+                v[2 * j + 1] = fmaf((b - mean) * rstd, gp[2 * j + 1], btp[2 * j + 1]);
+              }
+              pack_16(v, HALF_OUT, false, pk);
+              if (hf == 0) {
+                if (lane == 0) { if (store_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
+                __syncwarp();
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(swz(tile, lane, 4 * hf + i)) = pk[i];
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tma_store_2d(&tmC2, tile, gc, static_cast<int>(row0));
+            if (store_bufs == 2) buf ^= 1;
+          }
         }
       } else if (TMA_OUT && MODE == EPI_QUERY) {
         // ---- fp32 sampling locations / softmax weights through TMA: 32 columns (128 bytes per row) per step
@@ -644,6 +746,10 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
       rc = make_map(&tmC, ep.out, R, ep.out_ld, 32, 64, ep.out_half ? 1 : 0);
       if (rc) return rc;
       tma_out = true;
+      if (ep.ln_gamma != nullptr) {
+        rc = make_map(&tmC2, ep.ln_y, R, ep.out_ld, 32, 64, ep.out_half ? 1 : 0);
+        if (rc) return rc;
+      }
     } else if (ep.mode == EPI_QUERY) {
       rc = make_map(&tmC, ep.loc_out, R, ep.n_loc, 32, 32, 2);
       if (rc) return rc;
@@ -698,19 +804,39 @@ static int launch(const void* x, const void* w, long long R, int K, int Nout, in
     if (cfg == cudaSuccess)                                                                                                \
       linear_tc_kernel<MODE, F32, HALF, RELU, GATE, TMA><<<grid, THREADS, smem, st>>>(tmA, tmA2, tmB, tmC, tmC2, Ri, Nout, K, K1 / BLOCK_K, KB / BLOCK_K, block_n, br, stages, store_bufs, hi, ep); \
   } while (0)
+#define PG_LAUNCH_LN(HALF)                                                                                                 \
+  do {                                                                                                                     \
+    static bool configured[64] = {};                                                                                       \
+    if (!configured[dev_id & 63]) {                                                                                        \
+      cfg = cudaFuncSetAttribute(linear_tc_kernel<EPI_STORE, false, HALF, false, false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem); \
+      configured[dev_id & 63] = cfg == cudaSuccess;                                                                        \
+    }                                                                                                                      \
+    if (cfg == cudaSuccess)                                                                                                \
+      linear_tc_kernel<EPI_STORE, false, HALF, false, false, true, true><<<grid, THREADS, smem, st>>>(tmA, tmA2, tmB, tmC, tmC2, Ri, Nout, K, K1 / BLOCK_K, KB / BLOCK_K, block_n, br, stages, store_bufs, hi, ep); \
+  } while (0)
 #define PG_STORE16(RELU, GATE)                                                                                             \
   do {                                                                                                                     \
     if (tma_out) { if (half_out) PG_LAUNCH(EPI_STORE, false, true, RELU, GATE, true); else PG_LAUNCH(EPI_STORE, false, false, RELU, GATE, true); } \
     else { if (half_out) PG_LAUNCH(EPI_STORE, false, true, RELU, GATE, false); else PG_LAUNCH(EPI_STORE, false, false, RELU, GATE, false); }       \
   } while (0)
   const bool half_out = ep.out_half != 0;
-  if (ep.mode == EPI_QUERY) { if (tma_out) PG_LAUNCH(EPI_QUERY, true, false, false, false, true); else PG_LAUNCH(EPI_QUERY, true, false, false, false, false); }
+  if (ep.ln_gamma != nullptr) {
+    // LayerNorm in the epilogue: whole rows in one tile, accumulate form, TMA stores
+    if (!(tma_out && ep.mode == EPI_STORE && block_n == Nout && Nout <= 256 && Nout % 128 == 0 && ep.accum && ep.ln_beta && ep.ln_y &&
+          ep.ln_mean && ep.ln_rstd && !ep.relu && !ep.gate && !ep.gate_bits && !ep.row_mask && ep.out_ld == Nout &&
+          (reinterpret_cast<uintptr_t>(ep.ln_y) & 15u) == 0)) {
+      snprintf(t_err, sizeof(t_err), "LayerNorm epilogue needs Nout in {128, 256} as one tile, an accumulate operand and TMA stores");
+      return MSDA_ERR_UNSUPPORTED;
+    }
+    if (half_out) PG_LAUNCH_LN(true); else PG_LAUNCH_LN(false);
+  } else if (ep.mode == EPI_QUERY) { if (tma_out) PG_LAUNCH(EPI_QUERY, true, false, false, false, true); else PG_LAUNCH(EPI_QUERY, true, false, false, false, false); }
   else if (ep.mode == EPI_ZIRA) { if (half_out) PG_LAUNCH(EPI_ZIRA, false, true, false, false, false); else PG_LAUNCH(EPI_ZIRA, false, false, false, false, false); }
   else if (ep.out_f32) PG_LAUNCH(EPI_STORE, true, false, false, false, false);
   else if (ep.gate || ep.gate_bits) PG_STORE16(false, true);
   else if (ep.relu) PG_STORE16(true, false);
   else PG_STORE16(false, false);
 #undef PG_STORE16
+#undef PG_LAUNCH_LN
 #undef PG_LAUNCH
   if (cfg != cudaSuccess) { snprintf(t_err, sizeof(t_err), "cudaFuncSetAttribute: %s", cudaGetErrorString(cfg)); return static_cast<int>(cfg); }
   cudaError_t e = cudaGetLastError();
@@ -766,6 +892,19 @@ int msda_linear_accum2_16(const void* x1, int K1, const void* x2, int K2, const 
   ep.out = out; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.accum = accum;
   return pg::launch(x1, w, R, K1 + K2, Nout, pg::pick_block_n(Nout, K1 + K2, 32, false), is_half != 0, ep, static_cast<cudaStream_t>(stream),
                     x2, K1, K1 + K2);
+}
+
+int msda_linear_add_layernorm_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, const void* residual,
+                                 const float* gamma, const float* beta, float eps, void* z, void* y, float* mean, float* rstd,
+                                 int is_half, void* stream) {
+  pg::t_err[0] = 0;
+  if (!residual || !gamma || !beta || !z || !y || !mean || !rstd) { snprintf(pg::t_err, sizeof(pg::t_err), "null pointer"); return MSDA_ERR_NULL_POINTER; }
+  pg::EpiParams ep;
+  memset(&ep, 0, sizeof(ep));
+  ep.mode = pg::EPI_STORE;
+  ep.out = z; ep.out_ld = Nout; ep.out_f32 = 0; ep.out_half = is_half; ep.bias = bias; ep.accum = residual;
+  ep.ln_gamma = gamma; ep.ln_beta = beta; ep.ln_eps = eps; ep.ln_y = y; ep.ln_mean = mean; ep.ln_rstd = rstd;
+  return pg::launch(x, w, R, K, Nout, Nout, is_half != 0, ep, static_cast<cudaStream_t>(stream));
 }
 
 int msda_linear_act_16(const void* x, const void* w, const float* bias, long long R, int K, int Nout, void* out, int relu,
