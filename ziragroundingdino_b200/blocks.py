@@ -174,8 +174,8 @@ def linear_accum2_16(x1, x2, w12, accum, out=None):
 #   activation tile: 62 us against 2 x 24 us at 4 images (config 2 +83 us, config 4 +213 us per step).
 # OUT_LN (default on): `norm1(src + output_proj(core))` as one GEMM launch with the LayerNorm in its epilogue
 #   (msda_linear_add_layernorm_16) instead of the projection + the add+LayerNorm kernel: 49.9 us against 25.0 + 32.9 us at 4
-#   images (the K = 256 GEMMs are bound by their epilogue warps, and this epilogue makes two passes over the accumulator and
-#   issues two stores per column group, so the saving is the 91 MB round trip of the projection's output, not a kernel).
+#   images (this epilogue makes two passes over the accumulator and issues four dependent stores per warp and tile, so it,
+#   not HBM, bounds the launch: the saving is most of the 91 MB round trip of the projection's output, not a whole kernel).
 OUT_LN = os.environ.get("MSDA_B200_OUT_LN", "1") != "0"
 FOLD_POS = os.environ.get("MSDA_B200_FOLD_POS", "1") != "0"
 DGRAD_CAT = os.environ.get("MSDA_B200_DGRAD_CAT", "0") == "1"
