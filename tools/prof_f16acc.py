@@ -28,5 +28,9 @@ acc = torch.randn(R, C, device=dev, generator=g).bfloat16()
 for _ in range(2):
     loc, aw = fused.query_proj16(src, wq, bq, ref.view(R, 4, 2), 2, inp["shapes"], 8, 4, 4, q_add=pos)
     out = blocks.linear_accum2_16(gv, dq, w12, acc, torch.empty_like(acc))
+wo = (torch.randn(C, C, device=dev, generator=g) * 0.06).bfloat16()
+gam, bet = torch.ones(C, device=dev), torch.zeros(C, device=dev)
+for _ in range(2):
+    z, y, mean, rstd = blocks.linear_add_ln16(gv, wo, None, src, gam, bet, 1e-5)
 torch.cuda.synchronize()
 print("done")
