@@ -122,7 +122,7 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   for (int i = threadIdx.x; i < Nout; i += THREADS) s_bias[i] = ep.bias ? ep.bias[i] : 0.f;
-  if constexpr (LN) {   // s_bias[256..511] = gamma, [512..767] = beta, [768..1279] = the statistics exchange (MAX_N = 2048 floats)
+  if constexpr (LN) {   // s_bias[256..511] = gamma, [512..767] = beta, [768..1791] = the statistics exchange, two buffers (MAX_N = 2048 floats)
     for (int i = threadIdx.x; i < Nout; i += THREADS) { s_bias[256 + i] = ep.ln_gamma[i]; s_bias[512 + i] = ep.ln_beta[i]; }
   }
   if (MODE == EPI_QUERY && threadIdx.x < ep.L) {
@@ -369,12 +369,13 @@ linear_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (LN) {
           // the other half of this row's columns belongs to the partner warp of the lane quarter (warps w and w ^ 4 of the
           // eight epilogue warps): exchange the partial sums through shared memory under a 64-thread named barrier
-          float* xch = s_bias + 768;
+          // (slots alternate with the accumulator buffer: a slot written for tile i is rewritten for tile i + 2, which its
+          // writer reaches only after the barrier of tile i + 1, i.e. after the partner has read tile i's slot)
+          float* xch = s_bias + 768 + acc * 512;
           const int me = (warp - 2) * 32 + lane, other = ((warp - 2) ^ 4) * 32 + lane;
           xch[2 * me] = ln_s1; xch[2 * me + 1] = ln_s2;
           named_bar(1 + quarter, 64);
           const float t1 = ln_s1 + xch[2 * other], t2 = ln_s2 + xch[2 * other + 1];
-          named_bar(1 + quarter, 64);          // the slots are rewritten by the next tile
           const float inv_n = 1.f / static_cast<float>(Nout);
           const float mean = t1 * inv_n;
           const float rstd = rsqrtf(fmaxf(t2 * inv_n - mean * mean, 0.f) + ep.ln_eps);
