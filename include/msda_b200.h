@@ -122,6 +122,9 @@ int msda_backward_fusedq_16(const void *value, const int64_t *spatial_shapes, co
  * msda_cast_mask_h16 is the consumer: sum of replicas / scale -> [N*S, cols = M*D] 16-bit rows (out_f32 = 0; padded rows
  * zeroed: backward of ms_deform_attn.py:287-288) or fp32 rows (out_f32 = 1). */
 long long msda_grad_value_h16_rows(const int64_t *spatial_shapes_host, int L, int Lq);
+/* The scale the scatter kernel and the consumer derive from the bits of max |grad_out| (host evaluation of the same inline
+ * function, for tests and diagnostics): a power of two s with s * max * Lq < 60000. */
+float msda_f16acc_scale(unsigned int amax_bits, int Lq);
 int msda_backward_fusedq_h16(const void *value, const int64_t *spatial_shapes, const int64_t *level_start_index,
                              const float *loc, const float *aw, const void *grad_out, const float *ref, int ref_dim,
                              int N, int S, int M, int D, int L, int Lq, int P, void *grad_value_h,

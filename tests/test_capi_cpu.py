@@ -224,3 +224,34 @@ def test_fusedq_gate_needs_k_multiple_of_64():
     assert fused.fusedq_ok(8, 4, 4, 32)
     assert not fused.fusedq_ok(6, 4, 4, 32)       # 288 columns: un-fused pair with the padded row
     assert not fused.fusedq_ok(8, 4, 4, 64)
+
+
+def test_scaled_fp16_map_layout_and_scale_host_side():
+    """Host logic of the opt-in scaled-fp16 accumulation (no GPU needed): the replicated map's row count for the Swin-T
+    800x1333 levels, and the overflow bound behind f16acc_scale() -- for any gradient magnitude and query count the scale is
+    a power of two with scale * max * Lq < 60000 (< the fp16 maximum 65504), and it is not needlessly small."""
+    import ctypes
+    import math
+    import struct
+    from ziragroundingdino_b200 import _lib
+    L = _lib.lib()
+    shapes = [(100, 167), (50, 84), (25, 42), (13, 21)]
+    arr = (ctypes.c_int64 * 8)(*[d for hw in shapes for d in hw])
+    assert L.msda_grad_value_h16_rows(arr, 4, 22223) == 16700 + 4200 + 4 * 1050 + 16 * 273       # replicas 1, 1, 4, 16
+    assert L.msda_grad_value_h16_rows(arr, 4, 900) == 22223                                       # decoder: no replicas
+    assert L.msda_grad_value_h16_rows(arr, 4, 0) == 0 and L.msda_grad_value_h16_rows(None, 4, 900) == 0
+    tiny = (ctypes.c_int64 * 8)(6, 5, 3, 3, 2, 2, 1, 1)
+    assert L.msda_grad_value_h16_rows(tiny, 4, 4000) == 32 * 30 + 64 * (9 + 4 + 1)               # 16*4000/30 = 2133 -> 32; the rest capped at 64
+    bits = lambda x: struct.unpack("<I", struct.pack("<f", x))[0]
+    for lq in (1, 7, 900, 22223, 153520, 1 << 20):
+        for e in range(-120, 121, 7):
+            for m in (1.0, 1.37, 1.999):
+                amax = m * 2.0 ** e
+                s = L.msda_f16acc_scale(bits(amax), lq)
+                assert s > 0 and math.frexp(s)[0] == 0.5, (amax, lq, s)                          # a power of two
+                amax32 = struct.unpack("<f", struct.pack("<f", amax))[0]
+                assert s * amax32 * lq < 60000.0, (amax, lq, s)
+                if 2.0 ** -100 < s < 2.0 ** 100:                                                   # not clamped: within 4x of the bound
+                    assert s * amax32 * lq * 4.0 >= 60000.0 * 0.999, (amax, lq, s)
+    for special in (0.0, float("inf"), float("nan")):
+        assert L.msda_f16acc_scale(bits(special), 900) == 1.0

@@ -63,6 +63,8 @@ def lib():
     L.msda_group_norm_fwd_16.argtypes = [_vp, _ll, _vp, _vp, _i, _ll, _i, _i, ctypes.c_float, _vp, _ll, _vp, _vp, _i, _vp]
     L.msda_group_norm_bwd_16.argtypes = [_vp, _ll, _vp, _ll, _vp, _vp, _i, _ll, _i, _i, _vp, _ll, _vp, _i, _vp]
     L.msda_backward_fusedq_16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _i, _i, _vp]
+    L.msda_f16acc_scale.restype = ctypes.c_float
+    L.msda_f16acc_scale.argtypes = [ctypes.c_uint32, _i]
     L.msda_grad_value_h16_rows.restype = _ll
     L.msda_grad_value_h16_rows.argtypes = [_vp, _i, _i]
     L.msda_backward_fusedq_h16.argtypes = [_vp] * 7 + [_i] * 8 + [_vp, _vp, _vp, _i, _vp]

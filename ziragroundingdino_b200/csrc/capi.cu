@@ -208,6 +208,8 @@ long long msda_grad_value_h16_rows(const int64_t* shapes_host, int L, int Lq) {
   return rows;
 }
 
+float msda_f16acc_scale(unsigned int amax_bits, int Lq) { return msda::f16acc_scale(amax_bits, Lq); }
+
 int msda_backward_fusedq_h16(const void* value, const int64_t* shapes, const int64_t* lstart, const float* loc, const float* aw,
                              const void* grad_out, const float* ref, int ref_dim, int N, int S, int M, int D, int L, int Lq, int P,
                              void* gv_h, const int64_t* shapes_host, void* dq, int is_half, void* stream) {
