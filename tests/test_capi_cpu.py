@@ -250,7 +250,8 @@ def test_scaled_fp16_map_layout_and_scale_host_side():
                 s = L.msda_f16acc_scale(bits(amax), lq)
                 assert s > 0 and math.frexp(s)[0] == 0.5, (amax, lq, s)                          # a power of two
                 amax32 = struct.unpack("<f", struct.pack("<f", amax))[0]
-                assert s * amax32 * lq < 60000.0, (amax, lq, s)
+                if amax32 * lq < 1e41:                  # beyond that (gradients near the fp32 maximum) the scale is clamped at 2^-126
+                    assert s * amax32 * lq < 60000.0, (amax, lq, s)
                 if 2.0 ** -100 < s < 2.0 ** 100:                                                   # not clamped: within 4x of the bound
                     assert s * amax32 * lq * 4.0 >= 60000.0 * 0.999, (amax, lq, s)
     for special in (0.0, float("inf"), float("nan")):

@@ -167,7 +167,7 @@ __host__ __device__ inline float f16acc_scale(uint32_t amax_bits, int Lq) {
   const int e = static_cast<int>(amax_bits >> 23) - 126;                                   // amax < 2^e
   const int be = static_cast<int>(f16acc_bits(60000.f / static_cast<float>(Lq)) >> 23) - 126;   // 2^(be-1) <= 60000 / Lq
   int k = be - 1 - e;
-  k = k < -120 ? -120 : (k > 120 ? 120 : k);
+  k = k < -126 ? -126 : (k > 126 ? 126 : k);       // a normal float; only max * Lq > 60000 * 2^126 (~5e42) meets the lower clamp
   const uint32_t sb = static_cast<uint32_t>(127 + k) << 23;
 #ifdef __CUDA_ARCH__
   return __uint_as_float(sb);
