@@ -545,3 +545,26 @@ def test_encoder_block_with_layernorm_in_the_projection_matches_separate():
     dg = rel_err(res[True][1].cpu(), res[False][1].cpu())
     print("encoder block, LayerNorm in the projection on vs off: max |dy| %.2e, rel d(src) %.2e" % (dy, dg))
     assert dy <= 6e-2 and dg < 2e-2
+
+
+@pytest.mark.parametrize("offset", [8.0, 50.0])
+def test_layernorm_epilogues_with_a_common_offset(offset):
+    """The fused LayerNorm epilogues (output projection, chained FFN) take the variance as E[z^2] - mean^2 in fp32 from ONE
+    pass over the row.  That form loses precision when |mean| >> std; this pins how much for rows that all carry a common
+    offset of 8 and of 50 standard deviations (LayerNorm inputs of the layers have |mean| / std < 1): rstd within 1e-3 of
+    the two-pass value of the stored z, y within a few 16-bit ulps."""
+    from ziragroundingdino_b200 import blocks
+    g = torch.Generator().manual_seed(7)
+    R, K, Nout = 1000, 256, 256
+    x = torch.randn(R, K, generator=g).to(torch.bfloat16).to(DEV)
+    w = (torch.randn(Nout, K, generator=g) * 0.06).to(torch.bfloat16).to(DEV)
+    res = (torch.randn(R, Nout, generator=g) + offset).to(torch.bfloat16).to(DEV)
+    gamma, beta = torch.ones(Nout, device=DEV), torch.zeros(Nout, device=DEV)
+    z, y, mean, rstd = blocks.linear_add_ln16(x, w, None, res, gamma, beta, 1e-5)
+    zs = z.double()
+    m_ref, r_ref = zs.mean(1), (zs.var(1, unbiased=False) + 1e-5).rsqrt()
+    e_r = ((rstd.double() - r_ref).abs() / r_ref).max().item()
+    yt = (zs - m_ref[:, None]) * r_ref[:, None]
+    e_y = (y.double() - yt).abs().max().item()
+    print("LayerNorm epilogue, common offset %g: rstd rel err %.2e, y abs err %.2e" % (offset, e_r, e_y))
+    assert e_r < 1e-3 and e_y < 4 * 2 ** -8 * yt.abs().max().item()
